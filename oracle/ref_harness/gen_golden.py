@@ -1,0 +1,277 @@
+"""TEST INFRASTRUCTURE ONLY — generate the golden fixtures under tests/golden/ by running the
+UNMODIFIED reference (apps/problem.py orig, apps/problem.py perturb, apps/adjoint.py) on small hex
+meshes produced by adfvm_b200.hexmesh. Needs /root/reference; the fixtures travel, this does not.
+
+usage: python oracle/ref_harness/gen_golden.py [case ...] [--fp32]
+Each case leaves tests/golden/<case>.{npz,json}: every compiled-function call the reference made
+(positional inputs, options, outputs), the static problem description, and objective.txt lines.
+"""
+import json
+import os
+import shutil
+import subprocess
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, HERE)
+from adfvm_b200 import hexmesh  # noqa: E402
+from adfvm_b200.metrics import build_mesh  # noqa: E402
+import foam_io  # noqa: E402
+
+SCRATCH = os.environ.get("ADFVM_GOLDEN_SCRATCH", "/tmp/adfvm_golden")
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+CASEFILE_HEAD = '''import numpy as np
+from adFVM import config
+from adFVM.density import RCF
+from adFVM.mesh import Mesh
+from adpy import tensor
+
+def _allreduce(x):
+    inputs = (x,)
+    outputs = tuple([tensor.Zeros(y.shape) for y in inputs])
+    (x,) = tensor.ExternalFunctionOp('mpi_allreduce', inputs, outputs).outputs
+    return x
+'''
+
+OBJ_CELL_TV = '''
+def _objTV(U, T, p, volumes):
+    return (T*volumes).sum()
+def objective(fields, solver):
+    U, T, p = fields
+    mesh = solver.mesh.symMesh
+    obj = tensor.Zeros((1,1))
+    obj = tensor.Kernel(_objTV)(mesh.nInternalCells, (obj,))(U, T, p, mesh.volumes)
+    return _allreduce(obj)
+'''
+
+OBJ_PATCH_PA = '''
+def _objPA(U, T, p, *mesh, **options):
+    mesh = Mesh.container(mesh)
+    p0 = p.extract(mesh.neighbour)
+    return (p0*mesh.areas).sum()
+def objective(fields, solver):
+    U, T, p = fields
+    mesh = solver.mesh.symMesh
+    patch = mesh.boundary['{patch}']
+    startFace, nFaces = patch['startFace'], patch['nFaces']
+    meshArgs = [x[startFace] for x in mesh.getTensor()]
+    obj = tensor.Zeros((1,1))
+    obj = tensor.Kernel(_objPA)(nFaces, (obj,))(U, T, p, *meshArgs)
+    return _allreduce(obj)
+'''
+
+# the drag objective of reference templates/cylinder_test.py:9-36
+OBJ_DRAG = '''
+def _objDrag(U, T, p, *mesh, **options):
+    solver = options['solver']
+    mesh = Mesh.container(mesh)
+    U0 = U.extract(mesh.neighbour)[0]
+    U0i = U.extract(mesh.owner)[0]
+    p0 = p.extract(mesh.neighbour)
+    T0 = T.extract(mesh.neighbour)
+    nx = mesh.normals[0]
+    mungUx = solver.mu(T0)*(U0-U0i)/mesh.deltas
+    drag = (p0*nx-mungUx)*mesh.areas
+    return drag.sum()
+def objective(fields, solver):
+    U, T, p = fields
+    mesh = solver.mesh.symMesh
+    patch = mesh.boundary['{patch}']
+    startFace, nFaces = patch['startFace'], patch['nFaces']
+    meshArgs = [x[startFace] for x in mesh.getTensor()]
+    obj = tensor.Zeros((1,1))
+    obj = tensor.Kernel(_objDrag)(nFaces, (obj,))(U, T, p, *meshArgs, solver=solver)
+    return _allreduce(obj)
+'''
+
+CASEFILE_TAIL = '''
+primal = RCF('{case}/', objective=objective, fixedTimeStep=True{rcf_extra})
+
+def perturb(fields, mesh, t):
+    x = mesh.cellCentres[:mesh.nInternalCells]
+    mid = np.array({mid})
+    G = {amp}*np.exp(-{width}*np.linalg.norm(x-mid, axis=1, keepdims=1)**2)
+    rho = G
+    rhoU = np.zeros((mesh.nInternalCells, 3))
+    rhoU[:, 0] += G.flatten()*100
+    rhoE = G*2e5
+    return rho, rhoU, rhoE
+
+parameters = 'source'
+nSteps = {nSteps}
+writeInterval = {writeInterval}
+startTime = 0.0
+dt = {dt}
+'''
+
+
+def smooth_fields(cc, lo, hi):
+    s3 = (cc - np.asarray(lo)) / (np.asarray(hi) - np.asarray(lo))
+    s = np.sin(2 * np.pi * s3[:, 0]) * np.cos(2 * np.pi * s3[:, 1]) * np.sin(2 * np.pi * s3[:, 2])
+    U = np.stack([100 + 10 * s, 50 - 5 * s, 20 + 2 * s], axis=1)
+    T = (300 + 10 * s).reshape(-1, 1)
+    p = (101325 + 1000 * s).reshape(-1, 1)
+    return U, T, p
+
+
+def case_box_cyclic():
+    """3-D periodic box, smoothly warped (non-orthogonal), Sutherland viscosity, objective sum T*V."""
+    lo, hi = (0., 0., 0.), (1., 1., 1.)
+    poly = hexmesh.box_mesh((6, 5, 4), lo, hi, warp=hexmesh.sine_warp(0.03, lo, hi))
+    m = build_mesh(poly)
+    U, T, p = smooth_fields(m.cellCentres[:m.nInternalCells], lo, hi)
+    bf = {k: {"type": "cyclic"} for k in poly.boundary}
+    return dict(poly=poly, fields={"U": (U, bf), "T": (T, bf), "p": (p, bf)}, objective=OBJ_CELL_TV,
+                obj_spec={"kind": "cell_TV"}, rcf_extra="", mid="[0.5,0.5,0.5]", amp="1e2", width="50", nSteps=4, writeInterval=2, dt=1e-6)
+
+
+def case_tube():
+    """Sod tube geometry (reference cases/shockTube/constant/polyMesh/blockMeshDict), 100 cells,
+    tanh-smoothed IC (the sharp IC NaNs in the reference), inviscid."""
+    lo, hi = (-5., -1., -1.), (5., 1., 1.)
+    poly = hexmesh.box_mesh((100, 1, 1), lo, hi, patches=[
+        ("sides", "patch", ["x+", "x-"], {}),
+        ("empty", "empty", ["y-", "z+", "y+", "z-"], {})])
+    m = build_mesh(poly)
+    x = m.cellCentres[:m.nInternalCells, 0]
+    sig = 0.5 * (1 - np.tanh(x / 0.3))
+    pr = 1e4 + 9e4 * sig
+    rho = 0.125 + 0.875 * sig
+    R = 1004.5 - 1004.5 / 1.4
+    T = (pr / (rho * R)).reshape(-1, 1)
+    U = np.zeros((len(x), 3))
+    bf = {"sides": {"type": "zeroGradient"}, "empty": {"type": "empty"}}
+    return dict(poly=poly, fields={"U": (U, bf), "T": (T, bf), "p": (pr.reshape(-1, 1), bf)},
+                objective=OBJ_PATCH_PA.format(patch="sides"),
+                obj_spec={"kind": "patch_pA", "patch": "sides"}, rcf_extra=", mu=lambda T: 0.",
+                mid="[-4.5,0.,0.]", amp="1e3", width="25", nSteps=6, writeInterval=3, dt=1e-5)
+
+
+def case_box_walls():
+    """Graded channel: total-pressure inlet (CBC_TOTAL_PT, characteristic flux), fixedValue-p outlet,
+    symmetryPlane floor, no-slip isothermal lid (fixedValue U, T), cyclic span; constant viscosity;
+    drag objective on the lid (reference templates/cylinder_test.py:9-36)."""
+    lo, hi = (0., 0., 0.), (2., 1., 0.5)
+    poly = hexmesh.box_mesh((8, 6, 3), lo, hi, grading=(1.0, 0.4, 1.0), patches=[
+        ("inlet", "patch", ["x-"], {}),
+        ("outlet", "patch", ["x+"], {}),
+        ("floor", "symmetryPlane", ["y-"], {}),
+        ("lid", "patch", ["y+"], {}),
+        ("z1", "cyclic", ["z-"], {"neighbourPatch": "z2"}),
+        ("z2", "cyclic", ["z+"], {"neighbourPatch": "z1"})])
+    m = build_mesh(poly)
+    cc = m.cellCentres[:m.nInternalCells]
+    s3 = (cc - np.asarray(lo)) / (np.asarray(hi) - np.asarray(lo))
+    s = np.sin(2 * np.pi * s3[:, 0]) * np.cos(np.pi * s3[:, 1]) * np.cos(2 * np.pi * s3[:, 2])
+    U = np.stack([60 * (1 - s3[:, 1] ** 2) + 3 * s, 2 * s, 1 * s], axis=1)
+    T = (300 + 5 * s).reshape(-1, 1)
+    p = (101325 + 500 * s).reshape(-1, 1)
+    cyc = {"z1": {"type": "cyclic"}, "z2": {"type": "cyclic"}}
+    nin = poly.boundary["inlet"]["nFaces"]
+    nlid = poly.boundary["lid"]["nFaces"]
+    ptv = 103000. + 100. * np.sin(np.arange(nin)).reshape(-1, 1)
+    Ulid = np.zeros((nlid, 3)); Ulid[:, 0] = 1.0 + 0.1 * np.cos(np.arange(nlid))
+    bU = dict(cyc, inlet={"type": "calculated"}, outlet={"type": "zeroGradient"},
+              floor={"type": "symmetryPlane"}, lid={"type": "fixedValue", "value": Ulid})
+    bT = dict(cyc, inlet={"type": "calculated"}, outlet={"type": "zeroGradient"},
+              floor={"type": "symmetryPlane"}, lid={"type": "fixedValue", "value": "uniform 310"})
+    bp = dict(cyc, inlet={"type": "CBC_TOTAL_PT", "Tt": "uniform 305", "pt": "uniform 103000", "value": "uniform 101325"},
+              outlet={"type": "fixedValue", "value": "uniform 101000"},
+              floor={"type": "symmetryPlane"}, lid={"type": "zeroGradient"})
+    return dict(poly=poly, fields={"U": (U, bU), "T": (T, bT), "p": (p, bp)},
+                objective=OBJ_DRAG.format(patch="lid"),
+                obj_spec={"kind": "drag", "patch": "lid", "direction": 0}, rcf_extra=", mu=lambda T: 2.5e-5",
+                mid="[1.0,0.5,0.25]", amp="1e2", width="20", nSteps=4, writeInterval=2, dt=2e-6)
+
+
+def case_box_upt():
+    """Warped box: CBC_UPT inlet with the Lax-Friedrichs boundary Riemann solver (as
+    templates/cylinder_test.py:38-43), zeroGradient outlet, slip + empty walls, cyclic span,
+    Sutherland viscosity, pressure-force objective on the outlet."""
+    lo, hi = (0., 0., 0.), (1., 0.5, 0.5)
+    poly = hexmesh.box_mesh((7, 4, 3), lo, hi, warp=hexmesh.sine_warp(0.02, lo, hi), patches=[
+        ("left", "patch", ["x-"], {}),
+        ("right", "patch", ["x+"], {}),
+        ("down", "patch", ["y-"], {}),
+        ("up", "empty", ["y+"], {}),
+        ("z1", "cyclic", ["z-"], {"neighbourPatch": "z2"}),
+        ("z2", "cyclic", ["z+"], {"neighbourPatch": "z1"})])
+    m = build_mesh(poly)
+    U, T, p = smooth_fields(m.cellCentres[:m.nInternalCells], lo, hi)
+    U[:, 0] -= 60.
+    cyc = {"z1": {"type": "cyclic"}, "z2": {"type": "cyclic"}}
+    nl = poly.boundary["left"]["nFaces"]
+    U0 = np.zeros((nl, 3)); U0[:, 0] = 40 + np.sin(np.arange(nl)); U0[:, 1] = 50.
+    bU = dict(cyc, left={"type": "calculated"}, right={"type": "zeroGradient"}, down={"type": "slip"}, up={"type": "empty"})
+    bT = dict(cyc, left={"type": "calculated"}, right={"type": "zeroGradient"}, down={"type": "zeroGradient"}, up={"type": "empty"})
+    bp = dict(cyc, left={"type": "CBC_UPT", "U0": "uniform (40 50 0)", "T0": "uniform 300", "p0": "uniform 101825",
+                         "value": "uniform 101825"},
+              right={"type": "zeroGradient"}, down={"type": "zeroGradient"}, up={"type": "empty"})
+    return dict(poly=poly, fields={"U": (U, bU), "T": (T, bT), "p": (p, bp)},
+                objective=OBJ_PATCH_PA.format(patch="right"), obj_spec={"kind": "patch_pA", "patch": "right"},
+                rcf_extra=", boundaryRiemannSolver='eulerLaxFriedrichs'",
+                mid="[0.5,0.25,0.25]", amp="1e2", width="60", nSteps=4, writeInterval=2, dt=1e-6)
+
+
+CASES = {"box_cyclic": case_box_cyclic, "tube": case_tube, "box_walls": case_box_walls, "box_upt": case_box_upt}
+
+
+def run(cmd, cwd):
+    print("+", " ".join(cmd), flush=True)
+    subprocess.check_call(cmd, cwd=cwd)
+
+
+def generate(name, fp32=False):
+    c = CASES[name]()
+    tag = name + ("_fp32" if fp32 else "")
+    case = os.path.join(SCRATCH, tag)
+    if os.path.exists(case):
+        shutil.rmtree(case)
+    os.makedirs(case)
+    foam_io.write_polymesh(case, c["poly"])
+    for fname, (internal, bf) in c["fields"].items():
+        foam_io.write_field(case, "0", fname, internal, bf)
+    casefile = os.path.join(case, "casefile.py")
+    with open(casefile, "w") as f:
+        f.write(CASEFILE_HEAD + c["objective"] + CASEFILE_TAIL.format(
+            case=case, rcf_extra=c["rcf_extra"], mid=c["mid"], amp=c["amp"], width=c["width"],
+            nSteps=c["nSteps"], writeInterval=c["writeInterval"], dt=c["dt"]))
+    runner = os.path.join(HERE, "run_ref.py")
+    flag = ["--fp32"] if fp32 else []
+    py = sys.executable
+    run([py, runner, "problem", os.path.join(case, "rec_orig.npz")] + flag + ["--", casefile, "-c"], case)
+    run([py, runner, "problem", os.path.join(case, "rec_perturb.npz")] + flag + ["--", casefile, "-c", "perturb"], case)
+    run([py, runner, "adjoint", os.path.join(case, "rec_adjoint.npz")] + flag + ["--", casefile, "-c"], case)
+
+    # merge into one fixture
+    out = {}
+    meta = {"case": name, "fp32": fp32, "runs": {}}
+    for runname in ("orig", "perturb", "adjoint"):
+        z = np.load(os.path.join(case, "rec_%s.npz" % runname))
+        with open(os.path.join(case, "rec_%s.json" % runname)) as f:
+            j = json.load(f)
+        meta["spec"] = j["spec"]
+        meta["spec"]["objective"] = c["obj_spec"]
+        meta["runs"][runname] = j["calls"]
+        for k in z.files:
+            out["%s__%s" % (runname, k)] = z[k]
+    with open(os.path.join(case, "objective.txt")) as f:
+        meta["objective_txt"] = f.read().strip().split("\n")
+    meta["casefile"] = {k: c[k] for k in ("nSteps", "writeInterval", "dt", "mid", "amp", "width", "rcf_extra")}
+    os.makedirs(GOLDEN, exist_ok=True)
+    np.savez_compressed(os.path.join(GOLDEN, tag + ".npz"), **out)
+    with open(os.path.join(GOLDEN, tag + ".json"), "w") as f:
+        json.dump(meta, f, indent=1)
+    print("wrote", tag, meta["objective_txt"])
+
+
+if __name__ == "__main__":
+    args = [a for a in sys.argv[1:] if not a.startswith("--")]
+    fp32 = "--fp32" in sys.argv
+    for nm in (args or list(CASES)):
+        generate(nm, fp32=fp32)
