@@ -1,0 +1,88 @@
+"""ctypes binding of the C ABI declared in include/adfvm_b200.h.
+
+The product library is `adfvm_b200/csrc/libadfvm_b200.so` (CUDA, sm_100a). There is NO CPU fallback:
+if it is missing or no CUDA device is usable, loading / context creation raises. (tests/hostsim builds a
+CPU simulator of the device code with the same ABI; only tests pass its path explicitly.)
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+DEFAULT_LIB = os.path.join(HERE, "csrc", "libadfvm_b200.so")
+
+# enums of include/adfvm_b200.h
+MU_CONSTANT, MU_SUTHERLAND = 0, 1
+RIEMANN = {"eulerRoe": 0, "eulerLaxFriedrichs": 1}
+PATCH_WALL, PATCH_CYCLIC, PATCH_SYMMETRY, PATCH_EMPTY, PATCH_CHARACTERISTIC, PATCH_PROCESSOR, PATCH_PROCESSOR_CYCLIC = range(7)
+BC_CALCULATED, BC_CYCLIC, BC_ZEROGRADIENT, BC_FIXEDVALUE, BC_SYMMETRY, BC_CBC_UPT, BC_CBC_TOTAL_PT, BC_PROCESSOR = range(8)
+KEY_VALUE_U, KEY_VALUE_T, KEY_VALUE_P, KEY_U0, KEY_T0, KEY_P0, KEY_TT, KEY_PT, KEY_DIRECTION = range(9)
+OBJ_NONE, OBJ_CELL_TV, OBJ_PATCH_PA, OBJ_DRAG = range(4)
+RETURN_STATIC, ZERO_STATIC, REPLACE_STATIC, RETURN_REUSABLE, REPLACE_REUSABLE = 1, 2, 4, 8, 16
+
+
+class Patch(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("startFace", "nFaces", "cellStartFace", "mesh_type", "bc_U", "bc_T", "bc_p",
+                                         "neighbour_patch", "peer_rank", "tag")]
+
+
+class AdfvmError(RuntimeError):
+    pass
+
+
+EXPORTS = ["adfvm_last_error", "adfvm_version", "adfvm_is_cuda", "adfvm_create", "adfvm_destroy", "adfvm_set_physics",
+           "adfvm_set_mesh", "adfvm_set_bc_value", "adfvm_set_objective", "adfvm_set_source", "adfvm_primal",
+           "adfvm_primal_grad", "adfvm_primal_step_resident", "adfvm_adjoint_step_resident", "adfvm_get_dtc_obj",
+           "adfvm_get_state", "adfvm_sync", "adfvm_launch_count", "adfvm_device_bytes", "adfvm_comm_unique_id",
+           "adfvm_comm_init"]
+
+
+class Lib:
+    def __init__(self, path=None):
+        path = path or DEFAULT_LIB
+        if not os.path.exists(path):
+            raise AdfvmError("native library %s not found: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                             "(there is no CPU fallback)" % path)
+        self.path = path
+        self.dll = C.CDLL(path)
+        d = self.dll
+        vp, i32, f64 = C.c_void_p, C.c_int32, C.c_double
+        d.adfvm_last_error.restype = C.c_char_p
+        d.adfvm_create.argtypes = [C.POINTER(vp), C.c_int, C.c_int, vp]
+        d.adfvm_destroy.argtypes = [vp]
+        d.adfvm_set_physics.argtypes = [vp, f64, f64, f64, C.c_int, f64, C.c_int, C.c_int]
+        d.adfvm_set_mesh.argtypes = [vp, C.POINTER(i32)] + [vp] * 10 + [vp] * 5 + [i32, C.POINTER(Patch)]
+        d.adfvm_set_bc_value.argtypes = [vp, i32, i32, vp]
+        d.adfvm_set_objective.argtypes = [vp, i32, i32, i32]
+        d.adfvm_set_source.argtypes = [vp, vp, vp, vp]
+        d.adfvm_primal.argtypes = [vp, vp, vp, vp, f64, i32, vp, vp, vp, vp, vp]
+        d.adfvm_primal_grad.argtypes = [vp, vp, vp, vp, f64, vp, vp, vp, f64, f64, i32, vp, vp, vp, vp, vp, vp]
+        d.adfvm_primal_step_resident.argtypes = [vp, f64]
+        d.adfvm_adjoint_step_resident.argtypes = [vp, f64, f64, i32]
+        d.adfvm_get_dtc_obj.argtypes = [vp, C.POINTER(f64), C.POINTER(f64)]
+        d.adfvm_get_state.argtypes = [vp, vp, vp, vp]
+        d.adfvm_sync.argtypes = [vp]
+        d.adfvm_launch_count.argtypes = [vp]; d.adfvm_launch_count.restype = C.c_int64
+        d.adfvm_device_bytes.argtypes = [vp]; d.adfvm_device_bytes.restype = C.c_int64
+        d.adfvm_comm_unique_id.argtypes = [vp]
+        d.adfvm_comm_init.argtypes = [vp, vp, i32, i32]
+
+    @property
+    def is_cuda(self):
+        return bool(self.dll.adfvm_is_cuda())
+
+    def check(self, rc):
+        if rc != 0:
+            raise AdfvmError(self.dll.adfvm_last_error().decode())
+
+
+_default = None
+
+
+def default_lib():
+    """The CUDA product library; raises if it has not been built."""
+    global _default
+    if _default is None:
+        _default = Lib(DEFAULT_LIB)
+    return _default

@@ -1,0 +1,519 @@
+// Per-element bodies (functors) of every kernel on the residual path and of its reverse sweep.
+// A body is a plain struct of pointers + an `operator()(int i)`; the CUDA side wraps it in a
+// __global__ grid-stride launcher (fvm_cuda_exec.cuh), the CPU test simulator in a for loop.
+//
+// Device data layout (all SoA, component-major, 32-element padded strides):
+//   W  [5][sC]   conserved state (rho, rhoU_x, rhoU_y, rhoU_z, rhoE), internal cells
+//   Q  [5][sN]   primitive state (U_x, U_y, U_z, T, p), internal + ghost cells
+//   G  [15][sN]  gradients: dU_i/dx_j at 3*i+j, dT/dx_j at 9+j, dp/dx_j at 12+j
+//   face metrics [k][sF]; cell connectivity [6][sC]
+// Every scatter of the reference (Tensor.collate -> atomicAdd, adpy/adpy/tensor.py:393-394) is turned
+// into a cell-centred gather over the six faces of the hexahedron, so all sums have a fixed order:
+// results are bitwise reproducible run to run, primal and adjoint.
+#pragma once
+#include "fvm_math.h"
+
+namespace fvm {
+
+enum BCType { BC_CALCULATED = 0, BC_CYCLIC = 1, BC_ZEROGRADIENT = 2, BC_FIXEDVALUE = 3, BC_SYMMETRY = 4,
+              BC_CBC_UPT = 5, BC_CBC_TOTAL_PT = 6, BC_PROCESSOR = 7 };
+enum ObjKind { OBJ_NONE = 0, OBJ_CELL_TV = 1, OBJ_PATCH_PA = 2, OBJ_DRAG = 3 };
+enum { MAX_PATCHES = 255 };
+
+template <typename R> struct PatchDev {
+    int startFace, nFaces, cellStartFace;
+    int kind;                 // FaceKind used by the flux
+    int bc[3];                // BCType of U, T, p
+    int gbc;                  // BC_CYCLIC or BC_ZEROGRADIENT (gradient fields) / BC_PROCESSOR
+    int nbrStartFace, nbrCellStartFace;   // cyclic partner
+    // SoA value arrays [d][nFaces] (NULL when the BC has no such input, adFVM/BCs.py createInput)
+    const R *valU, *valT, *valp, *U0, *T0, *p0, *Tt, *pt, *dir;
+};
+
+template <typename R> struct MeshDev {
+    int nCells, nFaces, nInternalCells, nInternalFaces, nLocalCells, nRemoteCells, nLocalFaces, nGhostCells;
+    int sC, sN, sF;
+    const R *area, *normal, *weight, *delta, *dunit, *linw, *quadw, *vol;
+    const int *owner, *neigh, *cellFaces, *cellNbr;
+    const unsigned char *cellOwner;      // bit j set: the cell owns its j-th face
+    const unsigned char *bpatch;         // [nGhostCells] patch index of each boundary face
+    const PatchDev<R>* patches;
+    int nPatches;
+};
+
+template <typename R> struct ObjDev { int kind, patch, dir; };
+
+// ------------------------------------------------------------------------------------------ loads
+template <typename R> FVM_HD void load_prim(const R* Q, int sN, int c, Prim<R>& q) {
+    q.U[0] = Q[c]; q.U[1] = Q[sN + c]; q.U[2] = Q[2 * sN + c]; q.T = Q[3 * sN + c]; q.p = Q[4 * sN + c];
+}
+template <typename R> FVM_HD void store_prim(R* Q, int sN, int c, const Prim<R>& q) {
+    Q[c] = q.U[0]; Q[sN + c] = q.U[1]; Q[2 * sN + c] = q.U[2]; Q[3 * sN + c] = q.T; Q[4 * sN + c] = q.p;
+}
+template <typename R> FVM_HD void add_prim(R* Q, int sN, int c, const Prim<R>& q) {
+    Q[c] += q.U[0]; Q[sN + c] += q.U[1]; Q[2 * sN + c] += q.U[2]; Q[3 * sN + c] += q.T; Q[4 * sN + c] += q.p;
+}
+template <typename R> FVM_HD void load_grad(const R* G, int sN, int c, Grad<R>& g) {
+    for (int k = 0; k < 9; k++) g.U[k] = G[k * sN + c];
+    for (int k = 0; k < 3; k++) { g.T[k] = G[(9 + k) * sN + c]; g.p[k] = G[(12 + k) * sN + c]; }
+}
+template <typename R> FVM_HD void store_grad(R* G, int sN, int c, const Grad<R>& g) {
+    for (int k = 0; k < 9; k++) G[k * sN + c] = g.U[k];
+    for (int k = 0; k < 3; k++) { G[(9 + k) * sN + c] = g.T[k]; G[(12 + k) * sN + c] = g.p[k]; }
+}
+template <typename R> FVM_HD void load_geom(const MeshDev<R>& m, int f, Geom<R>& g) {
+    const int s = m.sF;
+    g.area = m.area[f]; g.delta = m.delta[f];
+    for (int k = 0; k < 3; k++) { g.n[k] = m.normal[k * s + f]; g.d[k] = m.dunit[k * s + f]; }
+    g.lw[0] = m.linw[f]; g.lw[1] = m.linw[s + f];
+    for (int k = 0; k < 3; k++) { g.qw[0][k] = m.quadw[k * s + f]; g.qw[1][k] = m.quadw[(3 + k) * s + f]; }
+}
+template <typename R> FVM_HD int face_kind(const MeshDev<R>& m, int f) {
+    return f < m.nInternalFaces ? (int)FACE_COUPLED : m.patches[m.bpatch[f - m.nInternalFaces]].kind;
+}
+
+// halo buffers are patch-major: for each processor patch (in face order) a block [ncomp][nFaces_p], so that one
+// patch is one contiguous message. Offset of component 0 of remote face r; component stride returned in cs.
+template <typename R> FVM_HD long halo_offset(const MeshDev<R>& m, int r, int ncomp, int& cs) {
+    const int f = m.nLocalFaces + r;
+    const PatchDev<R>& P = m.patches[m.bpatch[f - m.nInternalFaces]];
+    cs = P.nFaces;
+    return (long)(P.startFace - m.nLocalFaces) * ncomp + (f - P.startFace);
+}
+
+// ------------------------------------------------------------------------------------------ a1
+// conserved -> primitive on internal cells (adFVM/density.py:162-171)
+template <typename R> struct PrimitiveBody {
+    Phys<R> ph; int sC, sN; const R* W; R* Q;
+    FVM_HD void operator()(int c) const {
+        R rhoU[3] = {W[sC + c], W[2 * sC + c], W[3 * sC + c]};
+        Prim<R> q; primitive(ph, W[c], rhoU, W[4 * sC + c], q);
+        store_prim(Q, sN, c, q);
+    }
+};
+
+// ------------------------------------------------------------------------------------------ a2/a3
+// Ghost rows of U,T,p for all LOCAL boundary faces in one launch. Every BC reads internal cells only and
+// writes its own ghost row, so the patch order of the reference (sorted names, then characteristic,
+// adFVM/field.py:148-156, adFVM/density.py:333-337,416-418) does not affect the result.
+template <typename R> struct GhostPrimBody {
+    Phys<R> ph; MeshDev<R> m; R* Q;
+    FVM_HD void operator()(int b) const {
+        const int f = m.nInternalFaces + b, g = m.nInternalCells + b;
+        const PatchDev<R>& P = m.patches[m.bpatch[b]];
+        const int i = f - P.startFace, nf = P.nFaces, sN = m.sN;
+        const int own = m.owner[f];
+        // U
+        switch (P.bc[0]) {
+        case BC_CYCLIC: { int s = m.owner[P.nbrStartFace + i]; for (int k = 0; k < 3; k++) Q[k * sN + g] = Q[k * sN + s]; } break;
+        case BC_ZEROGRADIENT: for (int k = 0; k < 3; k++) Q[k * sN + g] = Q[k * sN + own]; break;
+        case BC_FIXEDVALUE: for (int k = 0; k < 3; k++) Q[k * sN + g] = P.valU[k * nf + i]; break;
+        case BC_SYMMETRY: {
+            R u[3] = {Q[own], Q[sN + own], Q[2 * sN + own]};
+            R n[3] = {m.normal[f], m.normal[m.sF + f], m.normal[2 * m.sF + f]};
+            R un = dot3(u, n);
+            for (int k = 0; k < 3; k++) Q[k * sN + g] = u[k] - un * n[k];
+        } break;
+        default: break;
+        }
+        // T, p
+        for (int fld = 1; fld < 3; fld++) {
+            const int k = 2 + fld;
+            switch (P.bc[fld]) {
+            case BC_CYCLIC: Q[k * sN + g] = Q[k * sN + m.owner[P.nbrStartFace + i]]; break;
+            case BC_ZEROGRADIENT: case BC_SYMMETRY: Q[k * sN + g] = Q[k * sN + own]; break;
+            case BC_FIXEDVALUE: Q[k * sN + g] = (fld == 1 ? P.valT : P.valp)[i]; break;
+            default: break;
+            }
+        }
+        // characteristic BCs hang off the p field (adFVM/BCs.py:139-184)
+        if (P.bc[2] == BC_CBC_UPT) {
+            for (int k = 0; k < 3; k++) Q[k * sN + g] = P.U0[k * nf + i];
+            Q[3 * sN + g] = P.T0[i]; Q[4 * sN + g] = P.p0[i];
+        } else if (P.bc[2] == BC_CBC_TOTAL_PT) {
+            R d[3];
+            for (int k = 0; k < 3; k++) d[k] = P.dir ? P.dir[k * nf + i] : m.normal[k * m.sF + f];
+            R u[3] = {Q[own], Q[sN + own], Q[2 * sN + own]};
+            R To = Q[3 * sN + own];
+            R Un = dot3(u, d);
+            R Tt = P.Tt[i];
+            for (int k = 0; k < 3; k++) Q[k * sN + g] = Un * d[k];
+            Q[3 * sN + g] = Tt - R(0.5) * Un * Un / ph.Cp;
+            Q[4 * sN + g] = P.pt[i] * pow(To / Tt, ph.gamma / (ph.gamma - R(1)));
+        }
+    }
+};
+
+// ghost rows of gradU, gradT, gradp: cyclic copies the partner's owner row, everything else the own
+// owner row (gradient fields carry the mesh default boundary: adFVM/density.py:133, mesh.py:702-711)
+template <typename R> struct GhostGradBody {
+    MeshDev<R> m; R* G;
+    FVM_HD void operator()(int b) const {
+        const int f = m.nInternalFaces + b, g = m.nInternalCells + b;
+        const PatchDev<R>& P = m.patches[m.bpatch[b]];
+        int s = (P.gbc == BC_CYCLIC) ? m.owner[P.nbrStartFace + (f - P.startFace)] : m.owner[f];
+        for (int k = 0; k < 15; k++) G[k * m.sN + g] = G[k * m.sN + s];
+    }
+};
+
+// ------------------------------------------------------------------------------------------ a4
+// Green-Gauss cell gradient (adFVM/op.py:45-63)
+template <typename R> struct GradCellBody {
+    MeshDev<R> m; const R* Q; R* G;
+    FVM_HD void operator()(int c) const {
+        Prim<R> qc; load_prim(Q, m.sN, c, qc);
+        Grad<R> g; zero(g);
+        const unsigned ob = m.cellOwner[c];
+        for (int j = 0; j < 6; j++) {
+            const int f = m.cellFaces[j * m.sC + c], nb = m.cellNbr[j * m.sC + c];
+            const bool own = (ob >> j) & 1u;
+            const R S = m.area[f], w = m.weight[f];
+            const R sg = own ? S : -S;
+            const R SN[3] = {sg * m.normal[f], sg * m.normal[m.sF + f], sg * m.normal[2 * m.sF + f]};
+            const R wp = own ? R(1) - w : w;
+            Prim<R> qn; load_prim(Q, m.sN, nb, qn);
+            const R a = R(1) - wp;
+            for (int i = 0; i < 3; i++) {
+                R pf = qc.U[i] * a + qn.U[i] * wp;
+                for (int k = 0; k < 3; k++) g.U[3 * i + k] += pf * SN[k];
+            }
+            R tf = qc.T * a + qn.T * wp, pf = qc.p * a + qn.p * wp;
+            for (int k = 0; k < 3; k++) { g.T[k] += tf * SN[k]; g.p[k] += pf * SN[k]; }
+        }
+        const R iv = R(1) / m.vol[c];
+        for (int k = 0; k < 9; k++) g.U[k] = g.U[k] * iv;       // reference divides (gradPhi/volumes)
+        for (int k = 0; k < 3; k++) { g.T[k] = g.T[k] * iv; g.p[k] = g.p[k] * iv; }
+        store_grad(G, m.sN, c, g);
+    }
+};
+
+// ------------------------------------------------------------------------------------------ a8-a12
+// Residual of one cell (gather over its 6 faces: internal, coupled, characteristic, boundary) fused with the
+// RK stage update (adFVM/timestep.py:35-45) and with the primitive conversion of the NEW state for the
+// next stage. Returns the cell's dtc (sum_f wave*A/V) for the max-reduction (adFVM/density.py:405-413).
+template <typename R> struct FluxUpdateBody {
+    Phys<R> ph; MeshDev<R> m;
+    const R *Q, *G;            // this stage's primitives / gradients (ghosts filled)
+    const R *W0, *W1, *W2;     // previous stage states (W1/W2 may be NULL when their alpha is 0)
+    R a0, a1, a2, beta, dt;
+    const R* S;                // source terms [5][sC]
+    R* Wn;                     // new state
+    R* Qn;                     // primitives of the new state (may be NULL)
+    FVM_HD R operator()(int c) const {
+        Prim<R> qc; Grad<R> gc;
+        load_prim(Q, m.sN, c, qc); load_grad(G, m.sN, c, gc);
+        R res[5] = {0, 0, 0, 0, 0}, dtc = 0;
+        const unsigned ob = m.cellOwner[c];
+        const R iv = R(1) / m.vol[c];
+        for (int j = 0; j < 6; j++) {
+            const int f = m.cellFaces[j * m.sC + c], nb = m.cellNbr[j * m.sC + c];
+            const bool own = (ob >> j) & 1u;
+            Geom<R> gm; load_geom(m, f, gm);
+            Prim<R> qn; Grad<R> gn;
+            load_prim(Q, m.sN, nb, qn); load_grad(G, m.sN, nb, gn);
+            Flux5<R> F; R wave;
+            R s = gm.area * iv;
+            if (own) {
+                face_flux(ph, face_kind(m, f), gm, qc, gc, qn, gn, F, wave);
+            } else {
+                face_flux(ph, (int)FACE_COUPLED, gm, qn, gn, qc, gc, F, wave);
+                s = -s;
+            }
+            res[0] += F.rho * s; res[1] += F.rhoU[0] * s; res[2] += F.rhoU[1] * s; res[3] += F.rhoU[2] * s;
+            res[4] += F.rhoE * s;
+            dtc += wave * (gm.area * iv);
+        }
+        R wn[5];
+        for (int k = 0; k < 5; k++) {
+            R v = a0 * W0[k * m.sC + c];
+            if (W1) v += a1 * W1[k * m.sC + c];
+            if (W2) v += a2 * W2[k * m.sC + c];
+            v += -beta * (res[k] - S[k * m.sC + c]) * dt;
+            wn[k] = v;
+            Wn[k * m.sC + c] = v;
+        }
+        if (Qn) { Prim<R> q; primitive(ph, wn[0], wn + 1, wn[4], q); store_prim(Qn, m.sN, c, q); }
+        return dtc;
+    }
+};
+
+// ------------------------------------------------------------------------------------------ a13
+// objective contributions; reduced with a fixed-order tree
+template <typename R> struct ObjectiveBody {
+    Phys<R> ph; MeshDev<R> m; ObjDev<R> o; const R* Q;
+    FVM_HD R operator()(int i) const {
+        if (o.kind == OBJ_CELL_TV) return Q[3 * m.sN + i] * m.vol[i];
+        const PatchDev<R>& P = m.patches[o.patch];
+        const int f = P.startFace + i, g = m.neigh[f];
+        if (o.kind == OBJ_PATCH_PA) return Q[4 * m.sN + g] * m.area[f];
+        // drag (reference templates/cylinder_test.py:9-19)
+        const int own = m.owner[f];
+        R mu = viscosity(ph, Q[3 * m.sN + g]);
+        R mung = mu * (Q[o.dir * m.sN + g] - Q[o.dir * m.sN + own]) / m.delta[f];
+        return (Q[4 * m.sN + g] * m.normal[o.dir * m.sF + f] - mung) * m.area[f];
+    }
+};
+// adjoint of the objective w.r.t. the ghost row of boundary face f (scaled by obja) ...
+template <typename R> FVM_HD void objective_ghost_adj(const Phys<R>& ph, const MeshDev<R>& m, const ObjDev<R>& o, const R* Q,
+                                                      R obja, int f, Prim<R>& qb) {
+    if (o.kind != OBJ_PATCH_PA && o.kind != OBJ_DRAG) return;
+    const PatchDev<R>& P = m.patches[o.patch];
+    if (f < P.startFace || f >= P.startFace + P.nFaces) return;
+    const int g = m.neigh[f];
+    if (o.kind == OBJ_PATCH_PA) { qb.p += obja * m.area[f]; return; }
+    const int own = m.owner[f];
+    R Tg = Q[3 * m.sN + g];
+    R mu = viscosity(ph, Tg);
+    R du = Q[o.dir * m.sN + g] - Q[o.dir * m.sN + own];
+    R A = m.area[f], idel = R(1) / m.delta[f];
+    qb.p += obja * m.normal[o.dir * m.sF + f] * A;
+    qb.U[o.dir] += -obja * mu * idel * A;
+    qb.T += -obja * viscosity_dT(ph, Tg, mu) * du * idel * A;
+}
+// ... and w.r.t. the owner cell of boundary face f
+template <typename R> FVM_HD void objective_owner_adj(const Phys<R>& ph, const MeshDev<R>& m, const ObjDev<R>& o, const R* Q,
+                                                      R obja, int f, Prim<R>& qb) {
+    if (o.kind != OBJ_DRAG) return;
+    const PatchDev<R>& P = m.patches[o.patch];
+    if (f < P.startFace || f >= P.startFace + P.nFaces) return;
+    R mu = viscosity(ph, Q[3 * m.sN + m.neigh[f]]);
+    qb.U[o.dir] += obja * mu * m.area[f] / m.delta[f];
+}
+
+// ========================================================================================== reverse
+// A. adjoint of the flux+scatter (+ RK residual weight): for each cell, the part of every adjacent face's VJP
+// that lands on this cell; for boundary faces also the ghost row's part (exclusive writer = the owner).
+//   abar   = adjoint of the stage OUTPUT state, [5][sC]
+//   coef   = -beta_ii * dt   (d W_new / d residual)
+template <typename R> struct FluxGradBody {
+    Phys<R> ph; MeshDev<R> m;
+    const R *Q, *G; const R* abar; R coef;
+    R *Qb, *Gb;                // outputs [5][sN], [15][sN] (overwritten)
+    FVM_HD void operator()(int c) const {
+        Prim<R> qc; Grad<R> gc;
+        load_prim(Q, m.sN, c, qc); load_grad(G, m.sN, c, gc);
+        const R iv = coef / m.vol[c];
+        R rc[5];
+        for (int k = 0; k < 5; k++) rc[k] = abar[k * m.sC + c] * iv;
+        Prim<R> qb; Grad<R> gb; zero(qb); zero(gb);
+        const unsigned ob = m.cellOwner[c];
+        for (int j = 0; j < 6; j++) {
+            const int f = m.cellFaces[j * m.sC + c], nb = m.cellNbr[j * m.sC + c];
+            const bool own = (ob >> j) & 1u;
+            Geom<R> gm; load_geom(m, f, gm);
+            Prim<R> qn; Grad<R> gn;
+            load_prim(Q, m.sN, nb, qn); load_grad(G, m.sN, nb, gn);
+            Flux5<R> Fb;
+            if (f < m.nInternalFaces) {
+                const R ivn = coef / m.vol[nb];
+                R d[5];
+                for (int k = 0; k < 5; k++) {
+                    R rn = abar[k * m.sC + nb] * ivn;
+                    d[k] = gm.area * (own ? rc[k] - rn : rn - rc[k]);
+                }
+                Fb.rho = d[0]; Fb.rhoU[0] = d[1]; Fb.rhoU[1] = d[2]; Fb.rhoU[2] = d[3]; Fb.rhoE = d[4];
+                Prim<R> qx; Grad<R> gx; zero(qx); zero(gx);     // other side's share: discarded
+                if (own) face_flux_vjp(ph, (int)FACE_COUPLED, gm, qc, gc, qn, gn, Fb, qb, gb, qx, gx);
+                else     face_flux_vjp(ph, (int)FACE_COUPLED, gm, qn, gn, qc, gc, Fb, qx, gx, qb, gb);
+            } else {
+                Fb.rho = gm.area * rc[0]; Fb.rhoU[0] = gm.area * rc[1]; Fb.rhoU[1] = gm.area * rc[2];
+                Fb.rhoU[2] = gm.area * rc[3]; Fb.rhoE = gm.area * rc[4];
+                Prim<R> qg; Grad<R> gg; zero(qg); zero(gg);
+                face_flux_vjp(ph, face_kind(m, f), gm, qc, gc, qn, gn, Fb, qb, gb, qg, gg);
+                store_prim(Qb, m.sN, nb, qg); store_grad(Gb, m.sN, nb, gg);
+            }
+        }
+        store_prim(Qb, m.sN, c, qb); store_grad(Gb, m.sN, c, gb);
+    }
+};
+
+// B. adjoint of the gradient ghost fill, gathered per boundary-adjacent cell (list bcells):
+// Gb[c] += Gb[ghost rows that copied from c]. Processor faces add the rows received from the peer.
+template <typename R> struct GhostGradAdjBody {
+    MeshDev<R> m; const int* bcells; R* Gb; const R* recvG;   // recvG: patch-major halo buffer or NULL
+    FVM_HD void operator()(int i) const {
+        const int c = bcells[i];
+        R acc[15];
+        for (int k = 0; k < 15; k++) acc[k] = R(0);
+        bool any = false;
+        for (int j = 0; j < 6; j++) {
+            const int f = m.cellFaces[j * m.sC + c];
+            if (f < m.nInternalFaces) continue;
+            if (f >= m.nLocalFaces) {
+                if (recvG) { int cs; const long o = halo_offset(m, f - m.nLocalFaces, 15, cs); for (int k = 0; k < 15; k++) acc[k] += recvG[o + (long)k * cs]; any = true; }
+                continue;
+            }
+            const PatchDev<R>& P = m.patches[m.bpatch[f - m.nInternalFaces]];
+            const int g = (P.gbc == BC_CYCLIC) ? P.nbrCellStartFace + (f - P.startFace) : m.nInternalCells + (f - m.nInternalFaces);
+            for (int k = 0; k < 15; k++) acc[k] += Gb[k * m.sN + g];
+            any = true;
+        }
+        if (any) for (int k = 0; k < 15; k++) Gb[k * m.sN + c] += acc[k];
+    }
+};
+
+// C. adjoint of gradCell: Qb[c] += sum over faces of (own-gradient share + neighbour-gradient share);
+// ghost rows receive their share from the owning cell.
+template <typename R> struct GradCellAdjBody {
+    MeshDev<R> m; const R* Gb; R* Qb;
+    FVM_HD void operator()(int c) const {
+        Grad<R> gc; load_grad(Gb, m.sN, c, gc);
+        const R ivc = R(1) / m.vol[c];
+        Prim<R> acc; zero(acc);
+        const unsigned ob = m.cellOwner[c];
+        for (int j = 0; j < 6; j++) {
+            const int f = m.cellFaces[j * m.sC + c], nb = m.cellNbr[j * m.sC + c];
+            const bool own = (ob >> j) & 1u;
+            const R S = m.area[f], w = m.weight[f];
+            const R sg = own ? S : -S;
+            const R SN[3] = {sg * m.normal[f], sg * m.normal[m.sF + f], sg * m.normal[2 * m.sF + f]};
+            const R wp = own ? R(1) - w : w;
+            const R a = R(1) - wp;
+            // this cell's gradient: phiF = phi_c*a + phi_nb*wp
+            Prim<R> t;
+            for (int i = 0; i < 3; i++) t.U[i] = (SN[0] * gc.U[3 * i] + SN[1] * gc.U[3 * i + 1] + SN[2] * gc.U[3 * i + 2]) * ivc;
+            t.T = dot3(SN, gc.T) * ivc; t.p = dot3(SN, gc.p) * ivc;
+            for (int i = 0; i < 3; i++) acc.U[i] += a * t.U[i];
+            acc.T += a * t.T; acc.p += a * t.p;
+            if (nb >= m.nInternalCells) {
+                Prim<R> gq;
+                for (int i = 0; i < 3; i++) gq.U[i] = wp * t.U[i];
+                gq.T = wp * t.T; gq.p = wp * t.p;
+                add_prim(Qb, m.sN, nb, gq);
+            } else {
+                // neighbour's gradient used phi_c with weight (1 - wp) and normal -SN
+                Grad<R> gn; load_grad(Gb, m.sN, nb, gn);
+                const R ivn = -a / m.vol[nb];
+                for (int i = 0; i < 3; i++) acc.U[i] += (SN[0] * gn.U[3 * i] + SN[1] * gn.U[3 * i + 1] + SN[2] * gn.U[3 * i + 2]) * ivn;
+                acc.T += dot3(SN, gn.T) * ivn; acc.p += dot3(SN, gn.p) * ivn;
+            }
+        }
+        add_prim(Qb, m.sN, c, acc);
+    }
+};
+
+// E. adjoint of the U,T,p ghost fill (+ objective seeds on boundary faces), gathered per boundary-adjacent cell.
+template <typename R> struct GhostPrimAdjBody {
+    Phys<R> ph; MeshDev<R> m; ObjDev<R> o; R obja;   // obja == 0 on stages that do not carry the objective
+    const int* bcells; const R* Q; R* Qb; const R* recvQ;   // recvQ: patch-major halo buffer or NULL
+    FVM_HD void ghost_total(int f, Prim<R>& q) const {
+        load_prim(Qb, m.sN, m.nInternalCells + (f - m.nInternalFaces), q);
+        if (obja != R(0)) objective_ghost_adj(ph, m, o, Q, obja, f, q);
+    }
+    FVM_HD void operator()(int i) const {
+        const int c = bcells[i];
+        Prim<R> acc; zero(acc);
+        for (int j = 0; j < 6; j++) {
+            const int f = m.cellFaces[j * m.sC + c];
+            if (f < m.nInternalFaces) continue;
+            if (f >= m.nLocalFaces) {
+                if (recvQ) { int n; const long r = halo_offset(m, f - m.nLocalFaces, 5, n);
+                    acc.U[0] += recvQ[r]; acc.U[1] += recvQ[n + r]; acc.U[2] += recvQ[2 * (long)n + r];
+                    acc.T += recvQ[3 * (long)n + r]; acc.p += recvQ[4 * (long)n + r]; }
+                continue;
+            }
+            const PatchDev<R>& P = m.patches[m.bpatch[f - m.nInternalFaces]];
+            const int idx = f - P.startFace;
+            Prim<R> own, par; bool have_own = false, have_par = false;
+            // U
+            if (P.bc[0] == BC_CYCLIC) { ghost_total(P.nbrStartFace + idx, par); have_par = true; for (int k = 0; k < 3; k++) acc.U[k] += par.U[k]; }
+            else if (P.bc[0] == BC_ZEROGRADIENT) { ghost_total(f, own); have_own = true; for (int k = 0; k < 3; k++) acc.U[k] += own.U[k]; }
+            else if (P.bc[0] == BC_SYMMETRY) {
+                ghost_total(f, own); have_own = true;
+                R n[3] = {m.normal[f], m.normal[m.sF + f], m.normal[2 * m.sF + f]};
+                R un = dot3(own.U, n);
+                for (int k = 0; k < 3; k++) acc.U[k] += own.U[k] - un * n[k];
+            }
+            // T, p
+            for (int fld = 1; fld < 3; fld++) {
+                const int bc = P.bc[fld];
+                R v = R(0);
+                if (bc == BC_CYCLIC) { if (!have_par) { ghost_total(P.nbrStartFace + idx, par); have_par = true; } v = (fld == 1) ? par.T : par.p; }
+                else if (bc == BC_ZEROGRADIENT || bc == BC_SYMMETRY) { if (!have_own) { ghost_total(f, own); have_own = true; } v = (fld == 1) ? own.T : own.p; }
+                if (fld == 1) acc.T += v; else acc.p += v;
+            }
+            if (P.bc[2] == BC_CBC_TOTAL_PT) {              // adFVM/BCs.py:178-184
+                if (!have_own) { ghost_total(f, own); have_own = true; }
+                R d[3];
+                for (int k = 0; k < 3; k++) d[k] = P.dir ? P.dir[k * P.nFaces + idx] : m.normal[k * m.sF + f];
+                R u[3] = {Q[c], Q[m.sN + c], Q[2 * m.sN + c]};
+                R To = Q[3 * m.sN + c], Tt = P.Tt[idx];
+                R Un = dot3(u, d);
+                R Unb = dot3(own.U, d) - own.T * Un / ph.Cp;
+                for (int k = 0; k < 3; k++) acc.U[k] += Unb * d[k];
+                R ex = ph.gamma / (ph.gamma - R(1));
+                acc.T += own.p * P.pt[idx] * ex * pow(To / Tt, ex - R(1)) / Tt;
+            }
+            if (obja != R(0)) objective_owner_adj(ph, m, o, Q, obja, f, acc);
+        }
+        add_prim(Qb, m.sN, c, acc);
+    }
+};
+
+// F. adjoint of primitive() + adjoint of the RK combination: a_s = sum_k alpha_k * a_{k} + dQ/dW^T Qb
+// (+ optional cell objective seed, + on the last reverse stage the source-term gradient accumulation).
+template <typename R> struct PrimAdjUpdateBody {
+    Phys<R> ph; MeshDev<R> m;
+    const R* W;                // stage state the residual was evaluated at
+    const R* Qb;
+    const R *A1, *A2, *A3;     // adjoints of later stage outputs (NULL when coefficient is 0)
+    R c1, c2, c3;
+    R objT;                    // obja for OBJ_CELL_TV on the objective stage, else 0
+    R* Aout;                   // [5][sC]
+    // source gradient accumulation (only when Sb != NULL): Sb += s1*A1 + s2*A2 + s3*A3
+    R* Sb; R s1, s2, s3;
+    FVM_HD void operator()(int c) const {
+        const int sC = m.sC;
+        Prim<R> qb; load_prim(Qb, m.sN, c, qb);
+        if (objT != R(0)) qb.T += objT * m.vol[c];
+        R rhoU[3] = {W[sC + c], W[2 * sC + c], W[3 * sC + c]};
+        R out[5] = {0, 0, 0, 0, 0};
+        primitive_vjp(ph, W[c], rhoU, W[4 * sC + c], qb, out[0], out + 1, out[4]);
+        for (int k = 0; k < 5; k++) {
+            R v = out[k];
+            R x1 = A1 ? A1[k * sC + c] : R(0), x2 = A2 ? A2[k * sC + c] : R(0), x3 = A3 ? A3[k * sC + c] : R(0);
+            if (A1) v += c1 * x1;
+            if (A2) v += c2 * x2;
+            if (A3) v += c3 * x3;
+            Aout[k * sC + c] = v;
+            if (Sb) Sb[k * sC + c] += s1 * x1 + s2 * x2 + s3 * x3;
+        }
+    }
+};
+
+// ------------------------------------------------------------------------------------------ layout helpers
+// AoS host layout ([n][d] row-major, what the reference passes) <-> SoA device layout
+template <typename R> struct AosToSoaBody {
+    const R* src; R* dst; int d, stride;
+    FVM_HD void operator()(int i) const { for (int k = 0; k < d; k++) dst[k * stride + i] = src[i * d + k]; }
+};
+template <typename R> struct SoaToAosBody {
+    const R* src; R* dst; int d, stride;
+    FVM_HD void operator()(int i) const { for (int k = 0; k < d; k++) dst[i * d + k] = src[k * stride + i]; }
+};
+// processor-patch halo: pack owner rows of the remote faces / unpack into ghost rows (adFVM/cpp/parallel.cpp:116-133)
+template <typename R> struct HaloPackBody {
+    MeshDev<R> m; const R* X; int ncomp; R* buf;
+    FVM_HD void operator()(int r) const {
+        const int own = m.owner[m.nLocalFaces + r];
+        int cs; const long o = halo_offset(m, r, ncomp, cs);
+        for (int k = 0; k < ncomp; k++) buf[o + (long)k * cs] = X[k * m.sN + own];
+    }
+};
+template <typename R> struct HaloUnpackBody {
+    MeshDev<R> m; R* X; int ncomp; const R* buf;
+    FVM_HD void operator()(int r) const {
+        int cs; const long o = halo_offset(m, r, ncomp, cs);
+        for (int k = 0; k < ncomp; k++) X[k * m.sN + m.nLocalCells + r] = buf[o + (long)k * cs];
+    }
+};
+// reverse halo: ghost-row adjoints of the remote faces -> send buffer
+template <typename R> struct HaloPackGhostBody {
+    MeshDev<R> m; const R* X; int ncomp; R* buf;
+    FVM_HD void operator()(int r) const {
+        int cs; const long o = halo_offset(m, r, ncomp, cs);
+        for (int k = 0; k < ncomp; k++) buf[o + (long)k * cs] = X[k * m.sN + m.nLocalCells + r];
+    }
+};
+
+}  // namespace fvm

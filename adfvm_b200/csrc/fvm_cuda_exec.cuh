@@ -1,0 +1,95 @@
+// CUDA executor: wraps the per-element bodies of fvm_bodies.h in sm_100a kernels on one stream.
+// One thread per cell / face; 128-thread CTAs (the flux bodies are register-heavy fp64 code: 128 threads keep
+// >= 2 CTAs resident per SM within the 64K-register file), grids sized by the element count so
+// the 148 SMs stay covered by several waves; reductions are two-pass fixed-order trees (deterministic).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdexcept>
+#include <string>
+
+namespace fvm {
+
+#define FVM_CUDA_CHECK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) \
+    throw std::runtime_error(std::string("CUDA error: ") + cudaGetErrorString(e_) + " at " #x); } while (0)
+
+enum { kBlock = 128, kRedBlock = 256, kRedMaxBlocks = 148 * 8 };
+
+template <class Body> __global__ void __launch_bounds__(kBlock) k_run(const Body b, int n) {
+    const int i = blockIdx.x * kBlock + threadIdx.x;
+    if (i < n) b(i);
+}
+template <class Body> __global__ void __launch_bounds__(kBlock) k_run_discard(const Body b, int n) {
+    const int i = blockIdx.x * kBlock + threadIdx.x;
+    if (i < n) (void)b(i);
+}
+
+struct OpSum { template <typename R> __device__ static R id() { return R(0); } template <typename R> __device__ static R op(R a, R b) { return a + b; } };
+struct OpMax { template <typename R> __device__ static R id() { return R(-1e30); } template <typename R> __device__ static R op(R a, R b) { return a > b ? a : b; } };
+
+// pass 1: block b owns elements b*kRedBlock + t + k*gridDim*kRedBlock (fixed assignment -> fixed order)
+template <typename R, class Op, class Body> __global__ void __launch_bounds__(kRedBlock) k_reduce1(const Body b, int n, R* partial) {
+    __shared__ R sm[kRedBlock];
+    R acc = Op::template id<R>();
+    for (long i = (long)blockIdx.x * kRedBlock + threadIdx.x; i < n; i += (long)gridDim.x * kRedBlock)
+        acc = Op::op(acc, b((int)i));
+    sm[threadIdx.x] = acc;
+    __syncthreads();
+    for (int s = kRedBlock / 2; s > 0; s >>= 1) {
+        if ((int)threadIdx.x < s) sm[threadIdx.x] = Op::op(sm[threadIdx.x], sm[threadIdx.x + s]);
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) partial[blockIdx.x] = sm[0];
+}
+template <typename R, class Op> __global__ void __launch_bounds__(kRedBlock) k_reduce2(const R* partial, int nb, R* out) {
+    __shared__ R sm[kRedBlock];
+    R acc = Op::template id<R>();
+    for (int i = threadIdx.x; i < nb; i += kRedBlock) acc = Op::op(acc, partial[i]);
+    sm[threadIdx.x] = acc;
+    __syncthreads();
+    for (int s = kRedBlock / 2; s > 0; s >>= 1) {
+        if ((int)threadIdx.x < s) sm[threadIdx.x] = Op::op(sm[threadIdx.x], sm[threadIdx.x + s]);
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *out = sm[0];
+}
+
+struct CudaExec {
+    cudaStream_t stream = 0;
+    int device = 0;
+    void* partial = nullptr;     // reduction scratch (kRedMaxBlocks doubles)
+
+    void init(int dev, void* strm) {
+        device = dev;
+        FVM_CUDA_CHECK(cudaSetDevice(dev));
+        stream = (cudaStream_t)strm;
+        FVM_CUDA_CHECK(cudaMalloc(&partial, kRedMaxBlocks * sizeof(double)));
+    }
+    void* stream_handle() const { return (void*)stream; }
+    void* alloc(size_t bytes) { void* p = nullptr; FVM_CUDA_CHECK(cudaMalloc(&p, bytes ? bytes : 1)); return p; }
+    void free(void* p) { cudaFree(p); }
+    void zero(void* p, size_t bytes) { if (bytes) FVM_CUDA_CHECK(cudaMemsetAsync(p, 0, bytes, stream)); }
+    void upload(void* dst, const void* src, size_t bytes) { if (bytes) FVM_CUDA_CHECK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, stream)); }
+    void download(void* dst, const void* src, size_t bytes) { if (bytes) FVM_CUDA_CHECK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, stream)); }
+    void sync() { FVM_CUDA_CHECK(cudaStreamSynchronize(stream)); }
+
+    template <class Body> void run(int n, const Body& b) {
+        k_run<Body><<<(n + kBlock - 1) / kBlock, kBlock, 0, stream>>>(b, n);
+        FVM_CUDA_CHECK(cudaPeekAtLastError());
+    }
+    template <class Body> void run_discard(int n, const Body& b) {
+        k_run_discard<Body><<<(n + kBlock - 1) / kBlock, kBlock, 0, stream>>>(b, n);
+        FVM_CUDA_CHECK(cudaPeekAtLastError());
+    }
+    template <typename R, class Op, class Body> void reduce(int n, const Body& b, R* out) {
+        int nb = (n + kRedBlock - 1) / kRedBlock;
+        if (nb > kRedMaxBlocks) nb = kRedMaxBlocks;
+        if (nb < 1) nb = 1;
+        k_reduce1<R, Op, Body><<<nb, kRedBlock, 0, stream>>>(b, n, (R*)partial);
+        k_reduce2<R, Op><<<1, kRedBlock, 0, stream>>>((const R*)partial, nb, out);
+        FVM_CUDA_CHECK(cudaPeekAtLastError());
+    }
+    template <class Body, typename R> void reduce_sum(int n, const Body& b, R* out) { reduce<R, OpSum, Body>(n, b, out); }
+    template <class Body, typename R> void reduce_max(int n, const Body& b, R* out) { reduce<R, OpMax, Body>(n, b, out); }
+};
+
+}  // namespace fvm

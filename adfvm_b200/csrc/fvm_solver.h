@@ -1,0 +1,358 @@
+// Step orchestration of the residual hot path and its reverse sweep, templated on the scalar type and on an
+// executor (CUDA streams/kernels in the product, plain loops in the CPU test simulator).
+//
+// Mirrors, per call, what the reference's generated `Function_primal` / `Function_primal_grad` do
+// (call sequence verified from generated code): for each of the 3 SSPRK stages
+// primitive -> halo+BC ghost fill -> [objective on stage 1] -> gradCell -> halo+BC ghost fill of gradients ->
+// flux over all face classes -> [max dtc on stage 1] -> RK update; and for the adjoint the same forward
+// sweep keeping every stage's state, followed by the reverse sweep stage 3 -> 1.
+#pragma once
+#include <stdexcept>
+#include <string>
+#include <vector>
+#include <cstring>
+#include "fvm_bodies.h"
+
+namespace fvm {
+
+static inline int pad32(long n) { return (int)(((n + 31) / 32) * 32); }
+
+// SSPRK3 (adFVM/timestep.py:17-25)
+static const double RK_ALPHA[3][3] = {{1., 0., 0.}, {3. / 4, 1. / 4, 0.}, {1. / 3, 0., 2. / 3}};
+static const double RK_BETA[3] = {1., 1. / 4, 2. / 3};
+
+struct PatchHost {
+    int startFace, nFaces, cellStartFace;
+    int meshType;          // 0 patch/wall-like, 1 cyclic, 2 symmetryPlane, 3 empty, 4 characteristic, 5 processor, 6 processorCyclic
+    int bc[3];             // BCType for U,T,p
+    int nbrPatch;          // cyclic partner index or -1
+    int peer;              // processor patches: neighbour rank
+    int tag;               // processor patches: ordering tag shared by both sides (adFVM/mesh.py:746-756)
+};
+
+// Exchange of processor-patch rows between ranks. send/recv are in executor memory, laid out patch-major:
+// for each remote patch p (in face order) a block [ncomp][nFaces_p].
+template <typename R> struct HaloComm {
+    virtual ~HaloComm() {}
+    virtual void exchange(const R* send, R* recv, int ncomp, const std::vector<PatchHost>& remote, void* stream) = 0;
+    virtual double allreduce_sum(double v) = 0;
+    virtual double allreduce_max(double v) = 0;
+};
+
+template <typename R, class Exec> class Solver {
+public:
+    Exec ex;
+    Phys<R> ph;
+    MeshDev<R> m;
+    ObjDev<R> obj;
+    std::vector<PatchHost> patches;          // all patches, local (sorted-name order as given) then remote
+    std::vector<PatchDev<R>> patches_dev_h;  // host mirror of the device table
+    HaloComm<R>* comm = nullptr;
+    long launches = 0;                        // kernels launched so far (bench "gpu_launches")
+    long bytes_allocated = 0;
+
+    // device buffers
+    R *W[4] = {0, 0, 0, 0}, *Q[3] = {0, 0, 0}, *G[3] = {0, 0, 0}, *S = 0, *red = 0;
+    R *A[4] = {0, 0, 0, 0}, *Qb = 0, *Gb = 0, *Sb = 0;
+    R *sendbuf = 0, *recvbuf = 0, *stage_aos = 0;
+    int *bcells = 0; int nBcells = 0;
+    bool have_mesh = false, have_state = false, adjoint_ready = false;
+    std::vector<void*> owned;                 // everything to free
+
+    explicit Solver(const Exec& e) : ex(e) {
+        std::memset(&m, 0, sizeof(m)); std::memset(&ph, 0, sizeof(ph)); obj.kind = OBJ_NONE; obj.patch = 0; obj.dir = 0;
+    }
+    ~Solver() { for (void* p : owned) ex.free(p); }
+
+    template <typename T> T* dalloc(size_t n) {
+        T* p = (T*)ex.alloc(n * sizeof(T)); ex.zero(p, n * sizeof(T)); owned.push_back(p);
+        bytes_allocated += (long)(n * sizeof(T)); return p;
+    }
+    template <class B> void run(int n, const B& b) { if (n > 0) { ex.run(n, b); launches++; } }
+
+    // ---- host AoS [n][d] -> device SoA [d][stride]
+    R* upload_aos(const R* host, long n, int d, int stride, R* dst = nullptr) {
+        if (!dst) dst = dalloc<R>((size_t)d * stride);
+        if (n == 0) return dst;
+        if (d == 1) { ex.upload(dst, host, n * sizeof(R)); return dst; }
+        R* tmp = (R*)ex.alloc((size_t)n * d * sizeof(R));
+        ex.upload(tmp, host, (size_t)n * d * sizeof(R));
+        run((int)n, AosToSoaBody<R>{tmp, dst, d, stride});
+        ex.sync(); ex.free(tmp);
+        return dst;
+    }
+    void download_aos(R* host, const R* src, long n, int d, int stride) {
+        if (n == 0) return;
+        if (d == 1) { ex.download(host, src, n * sizeof(R)); return; }
+        R* tmp = (R*)ex.alloc((size_t)n * d * sizeof(R));
+        run((int)n, SoaToAosBody<R>{src, tmp, d, stride});
+        ex.download(host, tmp, (size_t)n * d * sizeof(R));
+        ex.sync(); ex.free(tmp);
+    }
+
+    void set_physics(double gamma, double Cp, double Pr, int mu_law, double mu_value, int riemann, int briemann) {
+        ph.gamma = (R)gamma; ph.Cp = (R)Cp; ph.Pr = (R)Pr; ph.Cv = (R)(Cp / gamma);
+        ph.small = sizeof(R) == 8 ? (R)1e-30 : (R)1e-9;
+        ph.mu_law = mu_law; ph.mu_value = (R)mu_value; ph.riemann = riemann; ph.boundary_riemann = briemann;
+    }
+
+    // ---- mesh: the 10 gradFields + 5 intFields + 8 constants of adFVM/mesh.py:27-37 as the reference passes them
+    void set_mesh(const int* sizes, const R* areas, const R* volumesL, const R* volumesR, const R* weights, const R* deltas,
+                  const R* normals, const R* deltasUnit, const R* linearWeights, const R* quadraticWeights, const R* volumes,
+                  const int* owner, const int* neighbour, const int* cellFaces, const int* cellNeighbours, const int* cellOwner,
+                  const std::vector<PatchHost>& patches_in) {
+        if (have_mesh) throw std::runtime_error("mesh already set (create a new context)");
+        m.nCells = sizes[0]; m.nFaces = sizes[1]; m.nInternalCells = sizes[2]; m.nInternalFaces = sizes[3];
+        m.nLocalCells = sizes[4]; m.nRemoteCells = sizes[5]; m.nLocalFaces = sizes[6]; m.nGhostCells = sizes[7];
+        const int C = m.nInternalCells, F = m.nFaces, Fi = m.nInternalFaces, N = m.nCells;
+        if (N != C + (F - Fi) || m.nGhostCells != F - Fi || m.nRemoteCells != N - m.nLocalCells ||
+            m.nLocalFaces != m.nLocalCells - C + Fi)
+            throw std::runtime_error("inconsistent mesh size constants");
+        // the kernels use V[owner]/V[neighbour] for volumesL/volumesR; reject inputs where they differ
+        for (long f = 0; f < F; f++) if (volumesL[f] != volumes[owner[f]]) throw std::runtime_error("volumesL != volumes[owner] (perturbed volume arrays are not supported)");
+        for (long f = 0; f < Fi; f++) if (volumesR[f] != volumes[neighbour[f]]) throw std::runtime_error("volumesR != volumes[neighbour]");
+        m.sC = pad32(C); m.sN = pad32(N); m.sF = pad32(F);
+        m.area = upload_aos(areas, F, 1, m.sF); m.weight = upload_aos(weights, F, 1, m.sF);
+        m.delta = upload_aos(deltas, F, 1, m.sF); m.normal = upload_aos(normals, F, 3, m.sF);
+        m.dunit = upload_aos(deltasUnit, F, 3, m.sF); m.linw = upload_aos(linearWeights, F, 2, m.sF);
+        m.quadw = upload_aos(quadraticWeights, F, 6, m.sF); m.vol = upload_aos(volumes, C, 1, m.sC);
+        int* d_owner = dalloc<int>(m.sF); ex.upload(d_owner, owner, (size_t)F * 4); m.owner = d_owner;
+        int* d_neigh = dalloc<int>(m.sF); ex.upload(d_neigh, neighbour, (size_t)F * 4); m.neigh = d_neigh;
+        // connectivity: transpose on the host (ints, one-off)
+        std::vector<int> cf((size_t)6 * m.sC, 0), cn((size_t)6 * m.sC, 0);
+        std::vector<unsigned char> co(m.sC, 0);
+        std::vector<int> bc_list;
+        for (long c = 0; c < C; c++) {
+            bool b = false; unsigned bits = 0;
+            for (int j = 0; j < 6; j++) {
+                int f = cellFaces[c * 6 + j], nb = cellNeighbours[c * 6 + j];
+                if (f < 0 || f >= F || nb < 0 || nb >= N) throw std::runtime_error("cellFaces/cellNeighbours out of range");
+                cf[(size_t)j * m.sC + c] = f; cn[(size_t)j * m.sC + c] = nb;
+                if (cellOwner[c * 6 + j]) bits |= 1u << j;
+                if (nb >= C) b = true;
+            }
+            co[c] = (unsigned char)bits;
+            if (b) bc_list.push_back((int)c);
+        }
+        int* d_cf = dalloc<int>(cf.size()); ex.upload(d_cf, cf.data(), cf.size() * 4); m.cellFaces = d_cf;
+        int* d_cn = dalloc<int>(cn.size()); ex.upload(d_cn, cn.data(), cn.size() * 4); m.cellNbr = d_cn;
+        unsigned char* d_co = dalloc<unsigned char>(co.size()); ex.upload(d_co, co.data(), co.size()); m.cellOwner = d_co;
+        nBcells = (int)bc_list.size();
+        bcells = dalloc<int>(nBcells + 1); ex.upload(bcells, bc_list.data(), (size_t)nBcells * 4);
+        // patches
+        patches = patches_in;
+        if ((int)patches.size() > MAX_PATCHES) throw std::runtime_error("too many patches");
+        std::vector<unsigned char> bp(m.nGhostCells + 1, 255);
+        patches_dev_h.assign(patches.size(), PatchDev<R>());
+        for (size_t p = 0; p < patches.size(); p++) {
+            const PatchHost& h = patches[p]; PatchDev<R>& d = patches_dev_h[p];
+            std::memset(&d, 0, sizeof(d));
+            d.startFace = h.startFace; d.nFaces = h.nFaces; d.cellStartFace = h.cellStartFace;
+            if (h.nFaces && (h.startFace < Fi || h.startFace + h.nFaces > F || h.cellStartFace != h.startFace - Fi + C))
+                throw std::runtime_error("patch face range out of bounds");
+            const bool coupled = (h.meshType == 1 || h.meshType == 5 || h.meshType == 6);
+            d.kind = coupled ? FACE_COUPLED : (h.meshType == 4 ? FACE_CHARACTERISTIC : FACE_BOUNDARY);
+            for (int k = 0; k < 3; k++) d.bc[k] = h.bc[k];
+            d.gbc = (h.meshType == 1) ? BC_CYCLIC : ((h.meshType == 5 || h.meshType == 6) ? BC_PROCESSOR : BC_ZEROGRADIENT);
+            if (h.meshType == 1) {
+                if (h.nbrPatch < 0 || h.nbrPatch >= (int)patches.size() || patches[h.nbrPatch].nFaces != h.nFaces)
+                    throw std::runtime_error("cyclic patch without a matching neighbourPatch");
+                d.nbrStartFace = patches[h.nbrPatch].startFace; d.nbrCellStartFace = patches[h.nbrPatch].cellStartFace;
+            }
+            for (int i = 0; i < h.nFaces; i++) bp[h.startFace - Fi + i] = (unsigned char)p;
+        }
+        for (int b = 0; b < m.nGhostCells; b++) if (bp[b] == 255) throw std::runtime_error("boundary face not covered by any patch");
+        unsigned char* d_bp = dalloc<unsigned char>(bp.size()); ex.upload(d_bp, bp.data(), bp.size()); m.bpatch = d_bp;
+        m.nPatches = (int)patches.size();
+        patches_dev = dalloc<PatchDev<R>>(patches.size() + 1);
+        m.patches = patches_dev;
+        push_patches();
+        // state + work buffers
+        for (int k = 0; k < 4; k++) W[k] = dalloc<R>((size_t)5 * m.sC);
+        for (int k = 0; k < 2; k++) Q[k] = dalloc<R>((size_t)5 * m.sN);
+        G[0] = dalloc<R>((size_t)15 * m.sN);
+        S = dalloc<R>((size_t)5 * m.sC);
+        red = dalloc<R>(8);
+        stage_aos = dalloc<R>((size_t)5 * m.sC);
+        if (m.nRemoteCells > 0) { sendbuf = dalloc<R>((size_t)15 * m.nRemoteCells); recvbuf = dalloc<R>((size_t)15 * m.nRemoteCells); }
+        ex.sync();
+        have_mesh = true;
+    }
+    PatchDev<R>* patches_dev = nullptr;
+    void push_patches() { ex.upload(patches_dev, patches_dev_h.data(), patches_dev_h.size() * sizeof(PatchDev<R>)); ex.sync(); }
+
+    // BC value arrays (static inputs created by BoundaryCondition.createInput, adFVM/BCs.py:45-54); host AoS [nFaces][d]
+    enum BCKey { KEY_VALUE_U = 0, KEY_VALUE_T, KEY_VALUE_P, KEY_U0, KEY_T0, KEY_P0, KEY_TT, KEY_PT, KEY_DIR };
+    void set_bc_value(int patch, int key, const R* host) {
+        if (patch < 0 || patch >= (int)patches.size()) throw std::runtime_error("bad patch index");
+        const int n = patches[patch].nFaces;
+        const int d = (key == KEY_VALUE_U || key == KEY_U0 || key == KEY_DIR) ? 3 : 1;
+        PatchDev<R>& pd = patches_dev_h[patch];
+        const R** slot;
+        switch (key) {
+        case KEY_VALUE_U: slot = &pd.valU; break; case KEY_VALUE_T: slot = &pd.valT; break; case KEY_VALUE_P: slot = &pd.valp; break;
+        case KEY_U0: slot = &pd.U0; break; case KEY_T0: slot = &pd.T0; break; case KEY_P0: slot = &pd.p0; break;
+        case KEY_TT: slot = &pd.Tt; break; case KEY_PT: slot = &pd.pt; break; case KEY_DIR: slot = &pd.dir; break;
+        default: throw std::runtime_error("bad BC key");
+        }
+        R* dst = const_cast<R*>(*slot);
+        dst = upload_aos(host, n, d, n > 0 ? n : 1, dst);
+        *slot = dst;
+        push_patches();
+    }
+    void check_bcs() const {
+        for (size_t p = 0; p < patches.size(); p++) {
+            const PatchDev<R>& d = patches_dev_h[p];
+            if (d.nFaces == 0) continue;
+            if ((d.bc[0] == BC_FIXEDVALUE && !d.valU) || (d.bc[1] == BC_FIXEDVALUE && !d.valT) || (d.bc[2] == BC_FIXEDVALUE && !d.valp) ||
+                (d.bc[2] == BC_CBC_UPT && !(d.U0 && d.T0 && d.p0)) || (d.bc[2] == BC_CBC_TOTAL_PT && !(d.Tt && d.pt)))
+                throw std::runtime_error("boundary condition input array missing for patch " + std::to_string(p));
+        }
+    }
+    void set_objective(int kind, int patch, int dir) {
+        if (kind != OBJ_NONE && kind != OBJ_CELL_TV && (patch < 0 || patch >= (int)patches.size())) throw std::runtime_error("objective patch out of range");
+        obj.kind = kind; obj.patch = patch; obj.dir = dir;
+    }
+    void set_source(const R* s_rho, const R* s_rhoU, const R* s_rhoE) {
+        const int C = m.nInternalCells;
+        upload_aos(s_rho, C, 1, m.sC, S); upload_aos(s_rhoU, C, 3, m.sC, S + m.sC); upload_aos(s_rhoE, C, 1, m.sC, S + 4 * (size_t)m.sC);
+    }
+    void set_state(const R* rho, const R* rhoU, const R* rhoE) { put5(W[0], rho, rhoU, rhoE); have_state = true; }
+    void get_state(R* rho, R* rhoU, R* rhoE) { get5(W[0], rho, rhoU, rhoE); }
+    void put5(R* dst, const R* a, const R* b, const R* c) {
+        const int C = m.nInternalCells;
+        ex.upload(dst, a, (size_t)C * sizeof(R));
+        ex.upload(stage_aos, b, (size_t)3 * C * sizeof(R));
+        run(C, AosToSoaBody<R>{stage_aos, dst + m.sC, 3, m.sC});
+        ex.upload(dst + 4 * (size_t)m.sC, c, (size_t)C * sizeof(R));
+    }
+    void get5(const R* src, R* a, R* b, R* c) {
+        const int C = m.nInternalCells;
+        ex.download(a, src, (size_t)C * sizeof(R));
+        run(C, SoaToAosBody<R>{src + m.sC, stage_aos, 3, m.sC});
+        ex.download(b, stage_aos, (size_t)3 * C * sizeof(R));
+        ex.download(c, src + 4 * (size_t)m.sC, (size_t)C * sizeof(R));
+        ex.sync();
+    }
+
+    // ---- processor-patch halo (replaces adFVM/cpp/parallel.cpp Function_mpi_init/mpi/mpi_end)
+    std::vector<PatchHost> remote_patches() const {
+        std::vector<PatchHost> r;
+        for (const PatchHost& p : patches) if (p.meshType == 5 || p.meshType == 6) r.push_back(p);
+        return r;
+    }
+    void halo(R* X, int ncomp) {
+        if (m.nRemoteCells == 0) return;
+        if (!comm) throw std::runtime_error("mesh has processor patches but no communicator was attached");
+        run(m.nRemoteCells, HaloPackBody<R>{m, X, ncomp, sendbuf});
+        comm->exchange(sendbuf, recvbuf, ncomp, remote_patches(), ex.stream_handle());
+        run(m.nRemoteCells, HaloUnpackBody<R>{m, X, ncomp, recvbuf});
+    }
+    const R* halo_reverse(const R* Xb, int ncomp) {
+        if (m.nRemoteCells == 0) return nullptr;
+        if (!comm) throw std::runtime_error("mesh has processor patches but no communicator was attached");
+        run(m.nRemoteCells, HaloPackGhostBody<R>{m, Xb, ncomp, sendbuf});
+        comm->exchange(sendbuf, recvbuf, ncomp, remote_patches(), ex.stream_handle());
+        return recvbuf;
+    }
+
+    // ---- one residual stage + RK update
+    void stage(int s, R dt, R* Qs, R* Gs, R* Qnext, bool want_dtc_obj) {
+        const int C = m.nInternalCells, nLB = m.nLocalFaces - m.nInternalFaces;
+        if (s == 0) run(C, PrimitiveBody<R>{ph, m.sC, m.sN, W[0], Qs});
+        run(nLB, GhostPrimBody<R>{ph, m, Qs});
+        halo(Qs, 5);
+        if (want_dtc_obj) {
+            if (obj.kind == OBJ_NONE) ex.zero(red + 1, sizeof(R));
+            else {
+                int n = (obj.kind == OBJ_CELL_TV) ? C : patches[obj.patch].nFaces;
+                ex.reduce_sum(n, ObjectiveBody<R>{ph, m, obj, Qs}, red + 1); launches += 2;
+            }
+        }
+        run(C, GradCellBody<R>{m, Qs, Gs});
+        run(nLB, GhostGradBody<R>{m, Gs});
+        halo(Gs, 15);
+        FluxUpdateBody<R> fb;
+        fb.ph = ph; fb.m = m; fb.Q = Qs; fb.G = Gs;
+        fb.W0 = W[0]; fb.W1 = RK_ALPHA[s][1] != 0. ? W[1] : nullptr; fb.W2 = RK_ALPHA[s][2] != 0. ? W[2] : nullptr;
+        fb.a0 = (R)RK_ALPHA[s][0]; fb.a1 = (R)RK_ALPHA[s][1]; fb.a2 = (R)RK_ALPHA[s][2];
+        fb.beta = (R)RK_BETA[s]; fb.dt = dt; fb.S = S; fb.Wn = W[s + 1]; fb.Qn = Qnext;
+        if (want_dtc_obj) { ex.reduce_max(C, fb, red); launches += 2; }
+        else { ex.run_discard(C, fb); launches++; }
+    }
+
+    // primal step; state W[0] -> W[0]. keep=true keeps every stage (Q[s], G[s], W[s]) for the reverse sweep.
+    void primal_step(R dt, bool keep = false) {
+        if (!have_mesh || !have_state) throw std::runtime_error("mesh/state not set");
+        check_bcs();
+        if (keep) ensure_adjoint_buffers();
+        for (int s = 0; s < 3; s++) {
+            R* Qs = keep ? Q[s] : Q[s % 2];
+            R* Gs = keep ? G[s] : G[0];
+            R* Qn = (s < 2) ? (keep ? Q[s + 1] : Q[(s + 1) % 2]) : nullptr;
+            stage(s, dt, Qs, Gs, Qn, s == 1);
+        }
+        if (!keep) { R* t = W[0]; W[0] = W[3]; W[3] = t; }
+    }
+    // dtc (max over ranks not applied here: the reference returns the rank-local max, adFVM/density.py:405-413)
+    // and objective (allreduce-summed like mpi_allreduce, adFVM/cpp/parallel.cpp:214-232)
+    void get_dtc_obj(double* dtc, double* objective) {
+        R h[2]; ex.download(h, red, 2 * sizeof(R)); ex.sync();
+        *dtc = (double)h[0];
+        *objective = comm ? comm->allreduce_sum((double)h[1]) : (double)h[1];
+    }
+
+    void ensure_adjoint_buffers() {
+        if (adjoint_ready) return;
+        Q[2] = dalloc<R>((size_t)5 * m.sN);
+        G[1] = dalloc<R>((size_t)15 * m.sN); G[2] = dalloc<R>((size_t)15 * m.sN);
+        for (int k = 0; k < 4; k++) A[k] = dalloc<R>((size_t)5 * m.sC);
+        Qb = dalloc<R>((size_t)5 * m.sN); Gb = dalloc<R>((size_t)15 * m.sN);
+        Sb = dalloc<R>((size_t)5 * m.sC);
+        adjoint_ready = true;
+    }
+
+    // adjoint step (Function_primal_grad for parameters='source'): W[0] must hold the state at the START of the
+    // step; adjoint of the step output in (rhoa, rhoUa, rhoEa); result: adjoint w.r.t. the start state in A[0],
+    // source-term gradient accumulated into Sb (static accumulator semantics, adpy/adpy/variable.py:484-490).
+    void adjoint_step(R dt, const R* rhoa, const R* rhoUa, const R* rhoEa, R obja) {
+        ensure_adjoint_buffers();
+        put5(A[3], rhoa, rhoUa, rhoEa);
+        adjoint_step_resident(dt, obja, false);
+    }
+    // same on resident data: adjoint input already in A[3] (chain: take the previous call's result A[0])
+    void adjoint_step_resident(R dt, R obja, bool chain) {
+        ensure_adjoint_buffers();
+        if (chain) { R* t = A[0]; A[0] = A[3]; A[3] = t; }
+        primal_step(dt, true);
+        const int C = m.nInternalCells;
+        for (int s = 2; s >= 0; s--) {
+            const R coef = (R)(-RK_BETA[s]) * dt;
+            run(C, FluxGradBody<R>{ph, m, Q[s], G[s], A[s + 1], coef, Qb, Gb});
+            const R* rG = halo_reverse(Gb, 15);
+            run(nBcells, GhostGradAdjBody<R>{m, bcells, Gb, rG});
+            run(C, GradCellAdjBody<R>{m, Gb, Qb});
+            const R* rQ = halo_reverse(Qb, 5);
+            const R oa = (s == 1) ? obja : R(0);
+            run(nBcells, GhostPrimAdjBody<R>{ph, m, obj, oa, bcells, Q[s], Qb, rQ});
+            PrimAdjUpdateBody<R> pb;
+            pb.ph = ph; pb.m = m; pb.W = W[s]; pb.Qb = Qb;
+            // a_s = sum_{k>=s} alpha[k][s] * a_{k+1}
+            pb.A1 = (s <= 0 && RK_ALPHA[0][s] != 0.) ? A[1] : nullptr; pb.c1 = (R)(s <= 0 ? RK_ALPHA[0][s] : 0.);
+            pb.A2 = (s <= 1 && RK_ALPHA[1][s] != 0.) ? A[2] : nullptr; pb.c2 = (R)(s <= 1 ? RK_ALPHA[1][s] : 0.);
+            pb.A3 = (RK_ALPHA[2][s] != 0.) ? A[3] : nullptr; pb.c3 = (R)RK_ALPHA[2][s];
+            pb.objT = (s == 1 && obj.kind == OBJ_CELL_TV) ? obja : R(0);
+            pb.Aout = A[s];
+            pb.Sb = (s == 0) ? Sb : nullptr;
+            pb.s1 = (R)RK_BETA[0] * dt; pb.s2 = (R)RK_BETA[1] * dt; pb.s3 = (R)RK_BETA[2] * dt;
+            run(C, pb);
+        }
+    }
+    void get_adjoint(R* rhoa, R* rhoUa, R* rhoEa) { get5(A[0], rhoa, rhoUa, rhoEa); }
+    void get_source_grad(R* a, R* b, R* c, bool zero_after) {
+        get5(Sb, a, b, c);
+        if (zero_after) ex.zero(Sb, (size_t)5 * m.sC * sizeof(R));
+    }
+};
+
+}  // namespace fvm

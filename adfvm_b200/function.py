@@ -1,0 +1,341 @@
+"""Host-side mirror of the reference's compiled-function objects for the residual hot path.
+
+In the reference `solver.map` / `adjoint.map` are `adpy.variable.Function` instances whose `__call__`
+forwards a long positional list of numpy arrays / ints plus option kwargs to the generated
+`graph_N.Function_primal` / `Function_primal_grad` (adpy/adpy/variable.py:533-538). `PrimalFunction` and
+`AdjointFunction` below are callable with exactly that positional list and those kwargs and return exactly
+those tuples, but land in the C ABI of include/adfvm_b200.h (hand-written sm_100a kernels).
+
+What the reference bakes into generated code at compile time (patch types, BC classes, gas constants, the
+objective) is passed once as a `spec` dict — `spec_from_solver(primal)` reads it off a reference `RCF`
+object, tests read it from the golden fixtures:
+
+  spec = {Cp, gamma, Pr, mu: {law: sutherland|constant, value}, riemannSolver, boundaryRiemannSolver,
+          timeIntegrator: 'SSPRK', sortedPatches: [...],
+          patches: [{name, type, startFace, nFaces, cellStartFace, neighbourPatch?, myProcNo?, neighbProcNo?, tag?}],
+          BCs: {U|T|p: {patch: {type, keys}}}, objective: {kind: none|cell_TV|patch_pA|drag, patch?, direction?}}
+
+Positional layout (adFVM/solver.py:312-317, adFVM/mesh.py:870-881, adFVM/field.py:141-146,
+adFVM/density.py:108-110): 0-2 state | 3 dt | 4-13 gradFields | 14-18 intFields | 19-26 constants |
+3 ints per sorted local patch | 3 source arrays | BC value arrays (U,T,p then gradient fields) | extraArgs.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib as L
+
+GRAD_FIELDS = ["areas", "volumesL", "volumesR", "weights", "deltas", "normals", "deltasUnit",
+               "linearWeights", "quadraticWeights", "volumes"]
+GRAD_FIELD_DIMS = [(1,), (1,), (1,), (1,), (1,), (3,), (3,), (2,), (2, 3), (1,)]
+INT_FIELDS = ["owner", "neighbour", "cellFaces", "cellNeighbours", "cellOwner"]
+CONSTANTS = ["nCells", "nFaces", "nInternalCells", "nInternalFaces",
+             "nLocalCells", "nRemoteCells", "nLocalFaces", "nGhostCells"]
+
+_MESH_TYPE = {"cyclic": L.PATCH_CYCLIC, "slidingPeriodic1D": None, "symmetryPlane": L.PATCH_SYMMETRY,
+              "empty": L.PATCH_EMPTY, "characteristic": L.PATCH_CHARACTERISTIC, "processor": L.PATCH_PROCESSOR,
+              "processorCyclic": L.PATCH_PROCESSOR_CYCLIC}
+_BC_TYPE = {"cyclic": L.BC_CYCLIC, "zeroGradient": L.BC_ZEROGRADIENT, "empty": L.BC_ZEROGRADIENT,
+            "inletOutlet": L.BC_ZEROGRADIENT, "fixedValue": L.BC_FIXEDVALUE, "symmetryPlane": L.BC_SYMMETRY,
+            "slip": L.BC_SYMMETRY, "calculated": L.BC_CALCULATED, "CBC_UPT": L.BC_CBC_UPT,
+            "CBC_TOTAL_PT": L.BC_CBC_TOTAL_PT, "processor": L.BC_PROCESSOR, "processorCyclic": L.BC_PROCESSOR}
+_BC_KEY = {("U", "value"): (L.KEY_VALUE_U, 3), ("T", "value"): (L.KEY_VALUE_T, 1), ("p", "value"): (L.KEY_VALUE_P, 1),
+           ("p", "U0"): (L.KEY_U0, 3), ("p", "T0"): (L.KEY_T0, 1), ("p", "p0"): (L.KEY_P0, 1),
+           ("p", "Tt"): (L.KEY_TT, 1), ("p", "pt"): (L.KEY_PT, 1), ("p", "direction"): (L.KEY_DIRECTION, 3)}
+_OBJ_KIND = {"none": L.OBJ_NONE, "cell_TV": L.OBJ_CELL_TV, "patch_pA": L.OBJ_PATCH_PA, "drag": L.OBJ_DRAG}
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+class _Context:
+    """Owns one adfvm_ctx: device-resident mesh, BC, source and state of one rank."""
+
+    def __init__(self, spec, precision, device, stream, lib):
+        self.spec = spec
+        self.lib = lib or L.default_lib()
+        self.dtype = np.dtype(precision)
+        if self.dtype not in (np.dtype(np.float32), np.dtype(np.float64)):
+            raise TypeError("precision must be float32 or float64")
+        if spec.get("timeIntegrator", "SSPRK") != "SSPRK":
+            raise NotImplementedError("only the 3-stage SSPRK integrator is supported (the reference's euler "
+                                      "integrator cannot compile either, SURVEY §3.1)")
+        self.ctx = C.c_void_p()
+        self.lib.check(self.lib.dll.adfvm_create(C.byref(self.ctx), int(device), self.dtype.itemsize,
+                                                  C.c_void_p(stream) if stream else None))
+        mu = spec["mu"]
+        law = L.MU_SUTHERLAND if mu["law"] == "sutherland" else L.MU_CONSTANT
+        self.lib.check(self.lib.dll.adfvm_set_physics(
+            self.ctx, float(spec["gamma"]), float(spec["Cp"]), float(spec["Pr"]), law, float(mu.get("value", 0.)),
+            L.RIEMANN[spec["riemannSolver"]], L.RIEMANN[spec["boundaryRiemannSolver"]]))
+        self.sorted = list(spec["sortedPatches"])
+        byname = {p["name"]: p for p in spec["patches"]}
+        remote = [p["name"] for p in spec["patches"] if p["type"] in ("processor", "processorCyclic")]
+        self.patch_names = self.sorted + [n for n in remote if n not in self.sorted]
+        self.patch = byname
+        self.static_loaded = False
+        self.sizes = None
+
+    def close(self):
+        if self.ctx:
+            self.lib.dll.adfvm_destroy(self.ctx)
+            self.ctx = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- argument checking in the spirit of getArray (adpy/adpy/cpp/include/interface.hpp:29-52)
+    def _arr(self, a, shape_tail, what, rows=None):
+        if not isinstance(a, np.ndarray):
+            raise TypeError("%s: expected a numpy array" % what)
+        if a.dtype != self.dtype:
+            raise TypeError("%s: dtype %s, expected %s" % (what, a.dtype, self.dtype))
+        if not a.flags["C_CONTIGUOUS"]:
+            raise ValueError("%s: array must be C-contiguous" % what)
+        if tuple(a.shape[1:]) != tuple(shape_tail):
+            raise ValueError("%s: trailing dims %s, expected %s" % (what, a.shape[1:], tuple(shape_tail)))
+        if rows is not None and a.shape[0] != rows:
+            raise ValueError("%s: %d rows, expected %d" % (what, a.shape[0], rows))
+        return a
+
+    def _iarr(self, a, what, rows, cols=None):
+        if not isinstance(a, np.ndarray) or a.dtype != np.int32 or not a.flags["C_CONTIGUOUS"]:
+            raise TypeError("%s: expected a C-contiguous int32 array" % what)
+        if a.shape[0] != rows or (cols is not None and (a.ndim != 2 or a.shape[1] != cols)):
+            raise ValueError("%s: bad shape %s" % (what, a.shape))
+        return a
+
+    def parse(self, inputs):
+        """Split the positional list; returns dict with state, dt, mesh arrays, sizes, source, bc arrays, rest."""
+        k = 4
+        if len(inputs) < 27:
+            raise TypeError("expected at least 27 positional inputs, got %d" % len(inputs))
+        out = {"state": inputs[0:3], "dt": inputs[3]}
+        mesh = {}
+        for name in GRAD_FIELDS + INT_FIELDS:
+            mesh[name] = inputs[k]; k += 1
+        sizes = [int(inputs[k + i]) for i in range(8)]; k += 8
+        triples = {}
+        for pid in self.sorted:
+            triples[pid] = (int(inputs[k]), int(inputs[k + 1]), int(inputs[k + 2])); k += 3
+        source = inputs[k:k + 3]; k += 3
+        bcs = []
+        for field in ("U", "T", "p"):
+            for pid in self.sorted:
+                for key in self.spec["BCs"][field][pid]["keys"]:
+                    bcs.append((field, pid, key, inputs[k])); k += 1
+        out.update(mesh=mesh, sizes=sizes, triples=triples, source=source, bcs=bcs, rest=list(inputs[k:]))
+        return out
+
+    def load_static(self, P):
+        d = self.lib.dll
+        sizes = P["sizes"]
+        nCells, nFaces, C_, Fi = sizes[0], sizes[1], sizes[2], sizes[3]
+        m = P["mesh"]
+        rows = {"areas": nFaces, "volumesL": nFaces, "volumesR": Fi, "weights": nFaces, "deltas": nFaces,
+                "normals": nFaces, "deltasUnit": nFaces, "linearWeights": nFaces, "quadraticWeights": nFaces,
+                "volumes": C_}
+        for name, dims in zip(GRAD_FIELDS, GRAD_FIELD_DIMS):
+            self._arr(m[name], dims, "mesh." + name, rows[name])
+        self._iarr(m["owner"], "mesh.owner", nFaces)
+        self._iarr(m["neighbour"], "mesh.neighbour", nFaces)
+        for name in ("cellFaces", "cellNeighbours", "cellOwner"):
+            self._iarr(m[name], "mesh." + name, C_, 6)
+        table = (L.Patch * len(self.patch_names))()
+        index = {n: i for i, n in enumerate(self.patch_names)}
+        for i, pid in enumerate(self.patch_names):
+            p = self.patch[pid]
+            if pid in P["triples"] and P["triples"][pid] != (p["startFace"], p["nFaces"], p["cellStartFace"]):
+                raise ValueError("patch %s: (startFace,nFaces,cellStartFace) %s differs from the compiled spec"
+                                 % (pid, P["triples"][pid]))
+            if p["type"] == "slidingPeriodic1D":
+                raise NotImplementedError("slidingPeriodic1D patches (dynamic mesh) are outside the hot path")
+            t = table[i]
+            t.startFace, t.nFaces, t.cellStartFace = p["startFace"], p["nFaces"], p["cellStartFace"]
+            t.mesh_type = _MESH_TYPE.get(p["type"], L.PATCH_WALL)
+            remote = p["type"] in ("processor", "processorCyclic")
+            for fld, attr in (("U", "bc_U"), ("T", "bc_T"), ("p", "bc_p")):
+                bct = p["type"] if remote else self.spec["BCs"][fld][pid]["type"]
+                if bct not in _BC_TYPE:
+                    raise NotImplementedError("boundary condition %r (patch %s) has no class in the reference "
+                                              "BCs.py either" % (bct, pid))
+                setattr(t, attr, _BC_TYPE[bct])
+            t.neighbour_patch = index[p["neighbourPatch"]] if p["type"] == "cyclic" else -1
+            t.peer_rank = int(p.get("neighbProcNo", -1)) if remote else -1
+            t.tag = int(p.get("tag", 0))
+        csizes = (C.c_int32 * 8)(*sizes)
+        self.lib.check(d.adfvm_set_mesh(
+            self.ctx, csizes, *[_ptr(m[n]) for n in GRAD_FIELDS], *[_ptr(m[n]) for n in INT_FIELDS],
+            len(self.patch_names), table))
+        self.sizes = sizes
+        self.patch_index = index
+        o = self.spec.get("objective") or {"kind": "none"}
+        self.lib.check(d.adfvm_set_objective(self.ctx, _OBJ_KIND[o["kind"]],
+                                             index.get(o.get("patch"), 0), int(o.get("direction", 0))))
+        self.load_replaceable(P)
+        self.static_loaded = True
+
+    def load_replaceable(self, P):
+        """source terms + BC value arrays: static in the reference, but re-settable here (fixes the
+        silent GPU-perturb bug noted at apps/problem.py:109-110)."""
+        d = self.lib.dll
+        C_ = P["sizes"][2]
+        s = P["source"]
+        self._arr(s[0], (1,), "source rho", C_); self._arr(s[1], (3,), "source rhoU", C_)
+        self._arr(s[2], (1,), "source rhoE", C_)
+        self.lib.check(d.adfvm_set_source(self.ctx, _ptr(s[0]), _ptr(s[1]), _ptr(s[2])))
+        for field, pid, key, arr in P["bcs"]:
+            if (field, key) not in _BC_KEY:
+                raise NotImplementedError("BC input %s.%s" % (field, key))
+            kid, dim = _BC_KEY[(field, key)]
+            self._arr(arr, (dim,), "BC %s.%s.%s" % (field, pid, key), self.patch[pid]["nFaces"])
+            self.lib.check(d.adfvm_set_bc_value(self.ctx, self.patch_index[pid], kid, _ptr(arr)))
+
+    def attach_comm(self, unique_id: bytes, rank: int, nranks: int):
+        buf = C.create_string_buffer(unique_id, 128)
+        self.lib.check(self.lib.dll.adfvm_comm_init(self.ctx, buf, rank, nranks))
+
+
+class PrimalFunction:
+    """Drop-in for `solver.map` (Function('primal', ...), adFVM/density.py:101-105)."""
+    name = "primal"
+    defaultOptions = {"return_static": True, "zero_static": False, "replace_static": False,
+                      "return_reusable": True, "replace_reusable": False}   # adpy/adpy/variable.py:282-287
+
+    def __init__(self, spec, precision=np.float64, device=0, stream=None, lib=None):
+        self.c = _Context(spec, precision, device, stream, lib)
+
+    def _prepare(self, inputs, options):
+        opts = dict(self.defaultOptions)
+        for k in options:
+            if k not in opts:
+                raise TypeError("unknown option %r" % k)
+        opts.update(options)
+        P = self.c.parse(inputs)
+        if not self.c.static_loaded:
+            self.c.load_static(P)
+        elif opts["replace_static"] or opts["replace_reusable"]:
+            self.c.load_replaceable(P)
+        if P["sizes"] != self.c.sizes:
+            raise ValueError("mesh size constants changed between calls")
+        return P, opts
+
+    def __call__(self, *inputs, **options):
+        c = self.c
+        P, opts = self._prepare(inputs, options)
+        if P["rest"]:
+            raise NotImplementedError("extraArgs are not supported on the hot path")
+        C_ = c.sizes[2]
+        rho, rhoU, rhoE = P["state"]
+        c._arr(rho, (1,), "rho", C_); c._arr(rhoU, (3,), "rhoU", C_); c._arr(rhoE, (1,), "rhoE", C_)
+        dt = c._arr(P["dt"], (1,), "dt", 1)
+        flags = (L.RETURN_REUSABLE if opts["return_reusable"] else 0) | (L.REPLACE_REUSABLE if opts["replace_reusable"] else 0)
+        outs = [None, None, None]
+        if opts["return_reusable"]:
+            outs = [np.empty((C_, 1), c.dtype), np.empty((C_, 3), c.dtype), np.empty((C_, 1), c.dtype)]
+        dtc, obj = np.zeros((1, 1), c.dtype), np.zeros((1, 1), c.dtype)
+        c.lib.check(c.lib.dll.adfvm_primal(c.ctx, _ptr(rho), _ptr(rhoU), _ptr(rhoE), float(dt[0, 0]), flags,
+                                           _ptr(outs[0]), _ptr(outs[1]), _ptr(outs[2]), _ptr(dtc), _ptr(obj)))
+        return (outs[0], outs[1], outs[2], dtc, obj)
+
+    def grad(self):
+        """Counterpart of `primal.map.grad()` (adpy/adpy/variable.py:322-343): the reverse-mode function of
+        this step for parameters='source' (apps/adjoint.py:94-126)."""
+        return AdjointFunction(self)
+
+    # resident stepping used by the benchmark and by long runs between report steps
+    def step_resident(self, dt):
+        self.c.lib.check(self.c.lib.dll.adfvm_primal_step_resident(self.c.ctx, float(dt)))
+
+    def dtc_obj(self):
+        a, b = C.c_double(), C.c_double()
+        self.c.lib.check(self.c.lib.dll.adfvm_get_dtc_obj(self.c.ctx, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def sync(self):
+        self.c.lib.check(self.c.lib.dll.adfvm_sync(self.c.ctx))
+
+    @property
+    def launches(self):
+        return int(self.c.lib.dll.adfvm_launch_count(self.c.ctx))
+
+    @property
+    def device_bytes(self):
+        return int(self.c.lib.dll.adfvm_device_bytes(self.c.ctx))
+
+
+class AdjointFunction:
+    """Drop-in for `adjoint.map` (Function('primal_grad', ...), apps/adjoint.py:124-126) with
+    parameters='source': inputs = primal inputs + [rhoa, rhoUa, rhoEa, dtca, obja] + [scaling];
+    returns (rhoa', rhoUa', rhoEa', dJ/dS_rho, dJ/dS_rhoU, dJ/dS_rhoE); the three gradients are None unless
+    return_static (static accumulators, zeroed on zero_static)."""
+    name = "primal_grad"
+    defaultOptions = PrimalFunction.defaultOptions
+
+    def __init__(self, primal):
+        self.primal = primal
+        self.c = primal.c
+
+    def __call__(self, *inputs, **options):
+        c = self.c
+        P, opts = self.primal._prepare(inputs, options)
+        rest = P["rest"]
+        if len(rest) != 6:
+            raise TypeError("primal_grad expects primal inputs + 5 adjoint seeds + scaling (got %d extra)" % len(rest))
+        C_ = c.sizes[2]
+        rho, rhoU, rhoE = P["state"]
+        c._arr(rho, (1,), "rho", C_); c._arr(rhoU, (3,), "rhoU", C_); c._arr(rhoE, (1,), "rhoE", C_)
+        dt = c._arr(P["dt"], (1,), "dt", 1)
+        ra, rUa, rEa = rest[0:3]
+        c._arr(ra, (1,), "rhoa", C_); c._arr(rUa, (3,), "rhoUa", C_); c._arr(rEa, (1,), "rhoEa", C_)
+        dtca = float(c._arr(rest[3], (1,), "dtca", 1)[0, 0]); obja = float(c._arr(rest[4], (1,), "obja", 1)[0, 0])
+        flags = (L.RETURN_STATIC if opts["return_static"] else 0) | (L.ZERO_STATIC if opts["zero_static"] else 0)
+        outs = [np.empty((C_, 1), c.dtype), np.empty((C_, 3), c.dtype), np.empty((C_, 1), c.dtype)]
+        grads = [None, None, None]
+        if opts["return_static"]:
+            grads = [np.empty((C_, 1), c.dtype), np.empty((C_, 3), c.dtype), np.empty((C_, 1), c.dtype)]
+        c.lib.check(c.lib.dll.adfvm_primal_grad(
+            c.ctx, _ptr(rho), _ptr(rhoU), _ptr(rhoE), float(dt[0, 0]), _ptr(ra), _ptr(rUa), _ptr(rEa), dtca, obja, flags,
+            _ptr(outs[0]), _ptr(outs[1]), _ptr(outs[2]), _ptr(grads[0]), _ptr(grads[1]), _ptr(grads[2])))
+        return tuple(outs + grads)
+
+    def step_resident(self, dt, obja=1.0, chain=True):
+        self.c.lib.check(self.c.lib.dll.adfvm_adjoint_step_resident(self.c.ctx, float(dt), float(obja), int(chain)))
+
+
+def spec_from_solver(primal, objective):
+    """Build the static spec from a reference `RCF` object (adFVM/density.py) after `readFields`.
+    `objective` is one of the supported objective dicts (the reference takes arbitrary adpy-DSL code here)."""
+    mesh = primal.mesh
+    patches = []
+    for pid in list(mesh.sortedPatches) + list(mesh.remotePatches):
+        p = mesh.boundary[pid]
+        d = {"name": pid, "type": p["type"], "startFace": int(p["startFace"]), "nFaces": int(p["nFaces"]),
+             "cellStartFace": int(p["cellStartFace"])}
+        for k in ("neighbourPatch", "myProcNo", "neighbProcNo", "referPatch"):
+            if k in p:
+                d[k] = p[k] if isinstance(p[k], str) else int(p[k])
+        if pid in mesh.remotePatches:
+            d["tag"] = int(mesh.getProcessorPatchInfo(pid)[2])
+        patches.append(d)
+    bcs = {phi.name: {pid: {"type": bc.__class__.__name__, "keys": list(bc.keys)} for pid, bc in phi.phi.BC.items()}
+           for phi in primal.fields}
+    T = np.array([250., 300., 400.])
+    muv = np.asarray(primal.mu(T), np.float64) * np.ones(3)
+    if np.allclose(muv, 1.4792e-06 * T ** 1.5 / (T + 116.), rtol=1e-14, atol=0):
+        mu = {"law": "sutherland"}
+    elif np.all(muv == muv[0]):
+        mu = {"law": "constant", "value": float(muv[0])}
+    else:
+        raise NotImplementedError("viscosity law must be constant or Sutherland")
+    return {"Cp": primal.Cp, "gamma": primal.gamma, "Pr": primal.Pr, "mu": mu,
+            "riemannSolver": primal.riemannSolver.__name__,
+            "boundaryRiemannSolver": primal.boundaryRiemannSolver.__name__,
+            "timeIntegrator": primal.timeIntegrator, "patches": patches, "BCs": bcs,
+            "sortedPatches": list(mesh.sortedPatches), "objective": objective}

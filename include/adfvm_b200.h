@@ -1,0 +1,120 @@
+/* adfvm_b200 — C ABI of the B200-native adFVM residual + discrete-adjoint hot path.
+ *
+ * This is the drop-in boundary: what the reference reaches today through its generated CPython module
+ * `graph_N.so` (`Function_primal`, `Function_primal_grad`, `initialize`) plus the halo externals of
+ * adFVM/cpp/parallel.cpp. Plain pointers and sizes only; all array arguments are HOST pointers in the
+ * reference's own layout (C-contiguous row-major AoS `[n][d]`, scalar = float or double chosen at
+ * adfvm_create, int32 indices) exactly as `solver.map(*inputs)` passes them (adFVM/solver.py:312-323).
+ * Device residency, SoA re-layout, streams and kernels are internal.
+ *
+ * Every function returns 0 on success; on failure a non-zero code, and adfvm_last_error() describes it
+ * (the reference aborts on C asserts / gpuErrorCheck exit, adpy/adpy/cpp/include/gpu.hpp:13-23; raising a
+ * Python exception from the binding is strictly better). No call returns partial results.
+ * Paths cited below are relative to the reference tree.
+ */
+#ifndef ADFVM_B200_H
+#define ADFVM_B200_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct adfvm_ctx adfvm_ctx;
+
+/* enums shared with the Python host layer (adfvm_b200/function.py) */
+enum { ADFVM_MU_CONSTANT = 0, ADFVM_MU_SUTHERLAND = 1 };                 /* RCF `mu`, adFVM/density.py:25-31 */
+enum { ADFVM_RIEMANN_ROE = 0, ADFVM_RIEMANN_LAXFRIEDRICHS = 1 };          /* adFVM/riemann.py */
+enum { ADFVM_PATCH_WALL = 0, ADFVM_PATCH_CYCLIC = 1, ADFVM_PATCH_SYMMETRY = 2, ADFVM_PATCH_EMPTY = 3,
+       ADFVM_PATCH_CHARACTERISTIC = 4, ADFVM_PATCH_PROCESSOR = 5, ADFVM_PATCH_PROCESSOR_CYCLIC = 6 };
+enum { ADFVM_BC_CALCULATED = 0, ADFVM_BC_CYCLIC = 1, ADFVM_BC_ZEROGRADIENT = 2, ADFVM_BC_FIXEDVALUE = 3,
+       ADFVM_BC_SYMMETRY = 4, ADFVM_BC_CBC_UPT = 5, ADFVM_BC_CBC_TOTAL_PT = 6, ADFVM_BC_PROCESSOR = 7 };   /* adFVM/BCs.py */
+enum { ADFVM_KEY_VALUE_U = 0, ADFVM_KEY_VALUE_T = 1, ADFVM_KEY_VALUE_P = 2, ADFVM_KEY_U0 = 3, ADFVM_KEY_T0 = 4,
+       ADFVM_KEY_P0 = 5, ADFVM_KEY_TT = 6, ADFVM_KEY_PT = 7, ADFVM_KEY_DIRECTION = 8 };                     /* createInput keys */
+enum { ADFVM_OBJ_NONE = 0, ADFVM_OBJ_CELL_TV = 1, ADFVM_OBJ_PATCH_PA = 2, ADFVM_OBJ_DRAG = 3 };
+/* option bits of adfvm_primal / adfvm_primal_grad == the kwargs of Function.__call__, adpy/adpy/variable.py:282-287 */
+enum { ADFVM_RETURN_STATIC = 1, ADFVM_ZERO_STATIC = 2, ADFVM_REPLACE_STATIC = 4, ADFVM_RETURN_REUSABLE = 8,
+       ADFVM_REPLACE_REUSABLE = 16 };
+
+/* one boundary patch: the (startFace, nFaces, cellStartFace) triple of Mesh.getScalar (adFVM/mesh.py:874-881) plus
+ * what the reference bakes into the generated code from mesh.boundary / field BC dicts at compile time */
+typedef struct adfvm_patch {
+    int32_t startFace, nFaces, cellStartFace;
+    int32_t mesh_type;        /* ADFVM_PATCH_* (mesh.boundary[patch]['type']) */
+    int32_t bc_U, bc_T, bc_p; /* ADFVM_BC_*   (CellField.BC classes, adFVM/field.py:123-139) */
+    int32_t neighbour_patch;  /* cyclic: index of neighbourPatch in this table, else -1 */
+    int32_t peer_rank;        /* processor patches: neighbProcNo, else -1 */
+    int32_t tag;              /* processor patches: message ordering tag (adFVM/mesh.py:746-756), else 0 */
+} adfvm_patch;
+
+const char* adfvm_last_error(void);
+int adfvm_version(void);
+/* 1 if this library launches CUDA kernels (the product), 0 for the CPU test simulator built under tests/hostsim */
+int adfvm_is_cuda(void);
+
+/* replaces graph_N.initialize(localRank, mesh): adpy/adpy/cpp/module/graph.cpp:16-30 -> cudaSetDevice + external_init.
+ * scalar_bytes: 8 (fp64, `--gpu_double`) or 4 (fp32, the reference's GPU default, README.md:87-91).
+ * stream: a cudaStream_t to launch on (e.g. torch's current stream) or NULL for the default stream. */
+int adfvm_create(adfvm_ctx** ctx, int device, int scalar_bytes, void* stream);
+int adfvm_destroy(adfvm_ctx* ctx);
+
+/* RCF constants (adFVM/density.py:22-39) */
+int adfvm_set_physics(adfvm_ctx* ctx, double gamma, double Cp, double Pr, int mu_law, double mu_value,
+                      int riemann_solver, int boundary_riemann_solver);
+
+/* static inputs 4..26(+3/patch) of `primal`: Mesh.gradFields, Mesh.intFields, Mesh.constants, patch table.
+ * sizes = {nCells, nFaces, nInternalCells, nInternalFaces, nLocalCells, nRemoteCells, nLocalFaces, nGhostCells}.
+ * Uploaded once (the reference's "static" arrays, adpy/adpy/cpp/include/common.hpp:315-327). */
+int adfvm_set_mesh(adfvm_ctx* ctx, const int32_t sizes[8],
+                   const void* areas, const void* volumesL, const void* volumesR, const void* weights,
+                   const void* deltas, const void* normals, const void* deltasUnit, const void* linearWeights,
+                   const void* quadraticWeights, const void* volumes,
+                   const int32_t* owner, const int32_t* neighbour, const int32_t* cellFaces,
+                   const int32_t* cellNeighbours, const int32_t* cellOwner,
+                   int32_t nPatches, const adfvm_patch* patches);
+/* BC value arrays ([nFaces][d], static inputs after the source terms; adFVM/BCs.py:45-54). May be called again
+ * later: this is the explicit "invalidate static data" the reference lacks on GPU (apps/problem.py:109-110). */
+int adfvm_set_bc_value(adfvm_ctx* ctx, int32_t patch, int32_t key, const void* values);
+/* objective evaluated on the stage-1 state (adFVM/density.py:412-413); see DESIGN.md for the supported kinds */
+int adfvm_set_objective(adfvm_ctx* ctx, int32_t kind, int32_t patch, int32_t direction);
+/* source terms [C][1],[C][3],[C][1] (Solver.sourceTerms, adFVM/solver.py:116-133); static, re-settable */
+int adfvm_set_source(adfvm_ctx* ctx, const void* S_rho, const void* S_rhoU, const void* S_rhoE);
+
+/* == Function_primal (adpy/adpy/variable.py:360-504 as instantiated by adFVM/density.py:101-105) ==
+ * rho,rhoU,rhoE: state in; read only if ADFVM_REPLACE_REUSABLE or no state is resident yet (reuse ids primal_0..2).
+ * *_out: written only if ADFVM_RETURN_REUSABLE (may be NULL otherwise). dtc/obj: one scalar each, always written
+ * (dtc = rank-local max over cells, obj = objective summed over ranks), in the context's scalar type. */
+int adfvm_primal(adfvm_ctx* ctx, const void* rho, const void* rhoU, const void* rhoE, double dt, int32_t options,
+                 void* rho_out, void* rhoU_out, void* rhoE_out, void* dtc_out, void* obj_out);
+
+/* == Function_primal_grad for parameters='source' (apps/adjoint.py:94-126, 268-291) ==
+ * state at the START of the step, adjoint of the step OUTPUT (volume-weighted, as the reference carries it),
+ * dtca (ignored: max-reduce has no gradient, adpy/adpy/scalar.py:306-311), obja.
+ * Always writes the new adjoint fields; the source-term gradients are static accumulators: written to grad_*
+ * only with ADFVM_RETURN_STATIC and zeroed only with ADFVM_ZERO_STATIC (adpy/adpy/variable.py:484-490). */
+int adfvm_primal_grad(adfvm_ctx* ctx, const void* rho, const void* rhoU, const void* rhoE, double dt,
+                      const void* rhoa, const void* rhoUa, const void* rhoEa, double dtca, double obja, int32_t options,
+                      void* rhoa_out, void* rhoUa_out, void* rhoEa_out,
+                      void* grad_S_rho, void* grad_S_rhoU, void* grad_S_rhoE);
+
+/* device-resident stepping (no host transfers): what Solver.run does between report steps (return_reusable=0) */
+int adfvm_primal_step_resident(adfvm_ctx* ctx, double dt);
+/* adjoint step on resident data; chain!=0 feeds the previous call's output adjoint back in as this call's input */
+int adfvm_adjoint_step_resident(adfvm_ctx* ctx, double dt, double obja, int32_t chain);
+int adfvm_get_dtc_obj(adfvm_ctx* ctx, double* dtc, double* obj);
+int adfvm_get_state(adfvm_ctx* ctx, void* rho, void* rhoU, void* rhoE);
+int adfvm_sync(adfvm_ctx* ctx);
+/* kernels launched by this context so far */
+int64_t adfvm_launch_count(adfvm_ctx* ctx);
+/* bytes of device memory held by the context */
+int64_t adfvm_device_bytes(adfvm_ctx* ctx);
+
+/* multi-GPU halo: replaces Function_mpi_init / Function_mpi / Function_mpi_end and their _grad twins
+ * (adFVM/cpp/parallel.cpp:31-209) and Function_mpi_allreduce (:214-232) with NCCL point-to-point over NVLink.
+ * id: 128-byte ncclUniqueId produced on rank 0 and distributed by the host layer (torch.distributed). */
+int adfvm_comm_unique_id(void* id128);
+int adfvm_comm_init(adfvm_ctx* ctx, const void* id128, int32_t rank, int32_t nranks);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -177,7 +177,7 @@ def case_box_walls():
     ptv = 103000. + 100. * np.sin(np.arange(nin)).reshape(-1, 1)
     Ulid = np.zeros((nlid, 3)); Ulid[:, 0] = 1.0 + 0.1 * np.cos(np.arange(nlid))
     bU = dict(cyc, inlet={"type": "calculated"}, outlet={"type": "zeroGradient"},
-              floor={"type": "symmetryPlane"}, lid={"type": "fixedValue", "value": Ulid})
+              floor={"type": "symmetryPlane"}, lid={"type": "fixedValue", "value": "uniform (1.5 0 0)"})
     bT = dict(cyc, inlet={"type": "calculated"}, outlet={"type": "zeroGradient"},
               floor={"type": "symmetryPlane"}, lid={"type": "fixedValue", "value": "uniform 310"})
     bp = dict(cyc, inlet={"type": "CBC_TOTAL_PT", "Tt": "uniform 305", "pt": "uniform 103000", "value": "uniform 101325"},
