@@ -1,0 +1,146 @@
+"""Synthetic cases in the reference's own input format: mesh arrays, initial fields, the static `spec`
+and the positional argument list `solver.map(*inputs)` would receive (adFVM/solver.py:312-317).
+
+Used by the parity tests, `__graft_entry__.smoke()` and `bench.py` (hex box [0,1]^3, N^3 cells,
+cyclic in x,y,z, smooth sinusoidal U/T/p, Gaussian source perturbation, objective sum T*V), plus a walled
+variant exercising the other boundary conditions.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from . import hexmesh
+from .metrics import build_mesh, GRAD_FIELDS, INT_FIELDS
+
+
+class Case:
+    """mesh: metrics.MeshData; spec: dict; fields: (rho, rhoU, rhoE) conservative initial state;
+    source: 3 arrays; bcvals: {(field, patch, key): array}"""
+
+    def __init__(self, mesh, spec, state, source, bcvals, dt, dtype=np.float64):
+        self.mesh, self.spec, self.dt = mesh, spec, dt
+        self.dtype = np.dtype(dtype)
+        c = lambda a: np.ascontiguousarray(a, self.dtype)
+        self.state = [c(s) for s in state]
+        self.source = [c(s) for s in source]
+        self.bcvals = {k: c(v) for k, v in bcvals.items()}
+        self._static = None
+
+    def static_inputs(self):
+        if self._static is None:
+            m = self.mesh
+            t = [np.ascontiguousarray(getattr(m, a), self.dtype) for a in GRAD_FIELDS] + \
+                [np.ascontiguousarray(getattr(m, a), np.int32) for a in INT_FIELDS]
+            bc = []
+            for field in ("U", "T", "p"):
+                for pid in self.spec["sortedPatches"]:
+                    for key in self.spec["BCs"][field][pid]["keys"]:
+                        bc.append(self.bcvals[(field, pid, key)])
+            self._static = (t + m.getScalar(), self.source, bc)
+        return self._static
+
+    def inputs(self, state=None, dt=None):
+        """positional list for `primal`"""
+        mesh_args, source, bc = self.static_inputs()
+        st = self.state if state is None else state
+        return list(st) + [np.array([[self.dt if dt is None else dt]], self.dtype)] + mesh_args + list(source) + bc
+
+    def adjoint_inputs(self, state, adj, obja=1.0, dtca=0.0, scaling=0.0, dt=None):
+        """positional list for `primal_grad` (apps/adjoint.py:272-280)"""
+        a = lambda v: np.array([[v]], self.dtype)
+        return self.inputs(state, dt) + list(adj) + [a(dtca), a(obja)] + [a(scaling)]
+
+
+def conservative(U, T, p, gamma=1.4, Cp=1004.5):
+    """adFVM/density.py:173-181"""
+    Cv = Cp / gamma
+    e = Cv * T
+    rho = p / (e * (gamma - 1))
+    rhoE = rho * (e + 0.5 * (U * U).sum(axis=1, keepdims=True))
+    return rho, U * rho, rhoE
+
+
+def _spec(mesh, bcs, objective, mu=None, briemann="eulerRoe", Cp=1004.5, gamma=1.4, Pr=0.7):
+    patches = []
+    for pid in mesh.sortedPatches + mesh.remotePatches:
+        p = mesh.boundary[pid]
+        d = {"name": pid, "type": p["type"], "startFace": p["startFace"], "nFaces": p["nFaces"],
+             "cellStartFace": p["cellStartFace"]}
+        for k in ("neighbourPatch", "myProcNo", "neighbProcNo", "referPatch", "tag"):
+            if k in p:
+                d[k] = p[k]
+        patches.append(d)
+    return {"Cp": Cp, "gamma": gamma, "Pr": Pr, "mu": mu or {"law": "sutherland"}, "riemannSolver": "eulerRoe",
+            "boundaryRiemannSolver": briemann, "timeIntegrator": "SSPRK", "patches": patches, "BCs": bcs,
+            "sortedPatches": list(mesh.sortedPatches), "objective": objective}
+
+
+def smooth_state(cc, lo=(0., 0., 0.), hi=(1., 1., 1.)):
+    """s = sin2πx·cos2πy·sin2πz; U=(100+10s, 50−5s, 20+2s), T=300+10s, p=101325+1000s"""
+    s3 = (cc - np.asarray(lo)) / (np.asarray(hi) - np.asarray(lo))
+    s = np.sin(2 * np.pi * s3[:, 0]) * np.cos(2 * np.pi * s3[:, 1]) * np.sin(2 * np.pi * s3[:, 2])
+    U = np.stack([100 + 10 * s, 50 - 5 * s, 20 + 2 * s], axis=1)
+    return U, (300 + 10 * s).reshape(-1, 1), (101325 + 1000 * s).reshape(-1, 1)
+
+
+def gaussian_source(cc, mid=(0.5, 0.5, 0.5), amp=1e2, width=50.):
+    """G = 1e2·exp(−50|x−½|²) → (G, (100G,0,0), 2e5·G)"""
+    G = amp * np.exp(-width * ((cc - np.asarray(mid)) ** 2).sum(axis=1, keepdims=True))
+    rhoU = np.zeros((len(cc), 3)); rhoU[:, 0] = 100 * G[:, 0]
+    return G, rhoU, 2e5 * G
+
+
+def periodic_box(n, dtype=np.float64, warp=0.0, dt=None, mesh=None):
+    """The §8(d) benchmark workload: n^3 (or (nx,ny,nz)) periodic unit box."""
+    if isinstance(n, int):
+        n = (n, n, n)
+    if mesh is None:
+        poly = hexmesh.box_mesh(n, warp=hexmesh.sine_warp(warp) if warp else None)
+        mesh = build_mesh(poly)
+    C = mesh.nInternalCells
+    cc = mesh.cellCentres[:C]
+    U, T, p = smooth_state(cc)
+    bcs = {f: {pid: {"type": "cyclic", "keys": []} for pid in mesh.sortedPatches} for f in ("U", "T", "p")}
+    spec = _spec(mesh, bcs, {"kind": "cell_TV"})
+    if dt is None:
+        dt = 1e-6 * 48. / max(n)        # dt = 1e-6 at 48^3, scaled ∝ 1/N
+    return Case(mesh, spec, conservative(U, T, p), gaussian_source(cc), {}, dt, dtype)
+
+
+def walled_box(n=(8, 6, 4), dtype=np.float64, warp=0.02, dt=2e-6, nonuniform=True):
+    """Channel exercising every supported BC: CBC_TOTAL_PT inlet, fixedValue-p outlet, symmetryPlane floor,
+    no-slip isothermal lid (fixedValue U,T), one cyclic pair; constant viscosity; drag objective on the lid.
+    With nonuniform=True the BC value arrays vary face by face (the reference's readers cannot express
+    that — SURVEY H6 — so it is checked against the oracle only)."""
+    lo, hi = (0., 0., 0.), (2., 1., 0.5)
+    poly = hexmesh.box_mesh(n, lo, hi, grading=(1.0, 0.4, 1.0), warp=hexmesh.sine_warp(warp, lo, hi) if warp else None,
+                            patches=[("inlet", "patch", ["x-"], {}), ("outlet", "patch", ["x+"], {}),
+                                     ("floor", "symmetryPlane", ["y-"], {}), ("lid", "patch", ["y+"], {}),
+                                     ("z1", "cyclic", ["z-"], {"neighbourPatch": "z2"}),
+                                     ("z2", "cyclic", ["z+"], {"neighbourPatch": "z1"})])
+    mesh = build_mesh(poly)
+    mesh.boundary["inlet"]["type"] = "characteristic"       # what CBC_TOTAL_PT.__init__ does (BCs.py:167)
+    C = mesh.nInternalCells
+    cc = mesh.cellCentres[:C]
+    s3 = (cc - np.asarray(lo)) / (np.asarray(hi) - np.asarray(lo))
+    s = np.sin(2 * np.pi * s3[:, 0]) * np.cos(np.pi * s3[:, 1]) * np.cos(2 * np.pi * s3[:, 2])
+    U = np.stack([60 * (1 - s3[:, 1] ** 2) + 3 * s, 2 * s, 1 * s], axis=1)
+    T = (300 + 5 * s).reshape(-1, 1)
+    p = (101325 + 500 * s).reshape(-1, 1)
+    cyc = {"z1": {"type": "cyclic", "keys": []}, "z2": {"type": "cyclic", "keys": []}}
+    k0 = {"keys": []}
+    bcs = {"U": dict(cyc, inlet=dict(type="calculated", **k0), outlet=dict(type="zeroGradient", **k0),
+                     floor=dict(type="symmetryPlane", **k0), lid={"type": "fixedValue", "keys": ["value"]}),
+           "T": dict(cyc, inlet=dict(type="calculated", **k0), outlet=dict(type="zeroGradient", **k0),
+                     floor=dict(type="symmetryPlane", **k0), lid={"type": "fixedValue", "keys": ["value"]}),
+           "p": dict(cyc, inlet={"type": "CBC_TOTAL_PT", "keys": ["Tt", "pt"]},
+                     outlet={"type": "fixedValue", "keys": ["value"]},
+                     floor=dict(type="symmetryPlane", **k0), lid=dict(type="zeroGradient", **k0))}
+    nin, nout, nlid = (mesh.boundary[k]["nFaces"] for k in ("inlet", "outlet", "lid"))
+    v = (lambda n_: np.sin(1.0 + np.arange(n_))) if nonuniform else (lambda n_: np.zeros(n_))
+    Ulid = np.zeros((nlid, 3)); Ulid[:, 0] = 1.5 + 0.2 * v(nlid)
+    bcvals = {("U", "lid", "value"): Ulid, ("T", "lid", "value"): (310 + 2 * v(nlid)).reshape(-1, 1),
+              ("p", "outlet", "value"): (101000 + 50 * v(nout)).reshape(-1, 1),
+              ("p", "inlet", "Tt"): (305 + v(nin)).reshape(-1, 1), ("p", "inlet", "pt"): (103000 + 100 * v(nin)).reshape(-1, 1)}
+    spec = _spec(mesh, bcs, {"kind": "drag", "patch": "lid", "direction": 0}, mu={"law": "constant", "value": 2.5e-5})
+    return Case(mesh, spec, conservative(U, T, p), gaussian_source(cc, (1.0, 0.5, 0.25), 1e2, 20.), bcvals, dt, dtype)

@@ -84,6 +84,7 @@ template <typename R> FVM_HD long halo_offset(const MeshDev<R>& m, int r, int nc
 // ------------------------------------------------------------------------------------------ a1
 // conserved -> primitive on internal cells (adFVM/density.py:162-171)
 template <typename R> struct PrimitiveBody {
+    static constexpr const char* kName = "primitive";
     Phys<R> ph; int sC, sN; const R* W; R* Q;
     FVM_HD void operator()(int c) const {
         R rhoU[3] = {W[sC + c], W[2 * sC + c], W[3 * sC + c]};
@@ -97,6 +98,7 @@ template <typename R> struct PrimitiveBody {
 // writes its own ghost row, so the patch order of the reference (sorted names, then characteristic,
 // adFVM/field.py:148-156, adFVM/density.py:333-337,416-418) does not affect the result.
 template <typename R> struct GhostPrimBody {
+    static constexpr const char* kName = "ghost_prim";
     Phys<R> ph; MeshDev<R> m; R* Q;
     FVM_HD void operator()(int b) const {
         const int f = m.nInternalFaces + b, g = m.nInternalCells + b;
@@ -147,6 +149,7 @@ template <typename R> struct GhostPrimBody {
 // ghost rows of gradU, gradT, gradp: cyclic copies the partner's owner row, everything else the own
 // owner row (gradient fields carry the mesh default boundary: adFVM/density.py:133, mesh.py:702-711)
 template <typename R> struct GhostGradBody {
+    static constexpr const char* kName = "ghost_grad";
     MeshDev<R> m; R* G;
     FVM_HD void operator()(int b) const {
         const int f = m.nInternalFaces + b, g = m.nInternalCells + b;
@@ -159,6 +162,7 @@ template <typename R> struct GhostGradBody {
 // ------------------------------------------------------------------------------------------ a4
 // Green-Gauss cell gradient (adFVM/op.py:45-63)
 template <typename R> struct GradCellBody {
+    static constexpr const char* kName = "grad_cell";
     MeshDev<R> m; const R* Q; R* G;
     FVM_HD void operator()(int c) const {
         Prim<R> qc; load_prim(Q, m.sN, c, qc);
@@ -192,6 +196,7 @@ template <typename R> struct GradCellBody {
 // RK stage update (adFVM/timestep.py:35-45) and with the primitive conversion of the NEW state for the
 // next stage. Returns the cell's dtc (sum_f wave*A/V) for the max-reduction (adFVM/density.py:405-413).
 template <typename R> struct FluxUpdateBody {
+    static constexpr const char* kName = "flux_update";
     Phys<R> ph; MeshDev<R> m;
     const R *Q, *G;            // this stage's primitives / gradients (ghosts filled)
     const R *W0, *W1, *W2;     // previous stage states (W1/W2 may be NULL when their alpha is 0)
@@ -240,6 +245,7 @@ template <typename R> struct FluxUpdateBody {
 // ------------------------------------------------------------------------------------------ a13
 // objective contributions; reduced with a fixed-order tree
 template <typename R> struct ObjectiveBody {
+    static constexpr const char* kName = "objective";
     Phys<R> ph; MeshDev<R> m; ObjDev<R> o; const R* Q;
     FVM_HD R operator()(int i) const {
         if (o.kind == OBJ_CELL_TV) return Q[3 * m.sN + i] * m.vol[i];
@@ -286,6 +292,7 @@ template <typename R> FVM_HD void objective_owner_adj(const Phys<R>& ph, const M
 //   abar   = adjoint of the stage OUTPUT state, [5][sC]
 //   coef   = -beta_ii * dt   (d W_new / d residual)
 template <typename R> struct FluxGradBody {
+    static constexpr const char* kName = "flux_grad";
     Phys<R> ph; MeshDev<R> m;
     const R *Q, *G; const R* abar; R coef;
     R *Qb, *Gb;                // outputs [5][sN], [15][sN] (overwritten)
@@ -330,6 +337,7 @@ template <typename R> struct FluxGradBody {
 // B. adjoint of the gradient ghost fill, gathered per boundary-adjacent cell (list bcells):
 // Gb[c] += Gb[ghost rows that copied from c]. Processor faces add the rows received from the peer.
 template <typename R> struct GhostGradAdjBody {
+    static constexpr const char* kName = "ghost_grad_adj";
     MeshDev<R> m; const int* bcells; R* Gb; const R* recvG;   // recvG: patch-major halo buffer or NULL
     FVM_HD void operator()(int i) const {
         const int c = bcells[i];
@@ -355,6 +363,7 @@ template <typename R> struct GhostGradAdjBody {
 // C. adjoint of gradCell: Qb[c] += sum over faces of (own-gradient share + neighbour-gradient share);
 // ghost rows receive their share from the owning cell.
 template <typename R> struct GradCellAdjBody {
+    static constexpr const char* kName = "grad_cell_adj";
     MeshDev<R> m; const R* Gb; R* Qb;
     FVM_HD void operator()(int c) const {
         Grad<R> gc; load_grad(Gb, m.sN, c, gc);
@@ -394,6 +403,7 @@ template <typename R> struct GradCellAdjBody {
 
 // E. adjoint of the U,T,p ghost fill (+ objective seeds on boundary faces), gathered per boundary-adjacent cell.
 template <typename R> struct GhostPrimAdjBody {
+    static constexpr const char* kName = "ghost_prim_adj";
     Phys<R> ph; MeshDev<R> m; ObjDev<R> o; R obja;   // obja == 0 on stages that do not carry the objective
     const int* bcells; const R* Q; R* Qb; const R* recvQ;   // recvQ: patch-major halo buffer or NULL
     FVM_HD void ghost_total(int f, Prim<R>& q) const {
@@ -453,6 +463,7 @@ template <typename R> struct GhostPrimAdjBody {
 // F. adjoint of primitive() + adjoint of the RK combination: a_s = sum_k alpha_k * a_{k} + dQ/dW^T Qb
 // (+ optional cell objective seed, + on the last reverse stage the source-term gradient accumulation).
 template <typename R> struct PrimAdjUpdateBody {
+    static constexpr const char* kName = "prim_adj_update";
     Phys<R> ph; MeshDev<R> m;
     const R* W;                // stage state the residual was evaluated at
     const R* Qb;
@@ -484,15 +495,18 @@ template <typename R> struct PrimAdjUpdateBody {
 // ------------------------------------------------------------------------------------------ layout helpers
 // AoS host layout ([n][d] row-major, what the reference passes) <-> SoA device layout
 template <typename R> struct AosToSoaBody {
+    static constexpr const char* kName = "aos_to_soa";
     const R* src; R* dst; int d, stride;
     FVM_HD void operator()(int i) const { for (int k = 0; k < d; k++) dst[k * stride + i] = src[i * d + k]; }
 };
 template <typename R> struct SoaToAosBody {
+    static constexpr const char* kName = "soa_to_aos";
     const R* src; R* dst; int d, stride;
     FVM_HD void operator()(int i) const { for (int k = 0; k < d; k++) dst[i * d + k] = src[k * stride + i]; }
 };
 // processor-patch halo: pack owner rows of the remote faces / unpack into ghost rows (adFVM/cpp/parallel.cpp:116-133)
 template <typename R> struct HaloPackBody {
+    static constexpr const char* kName = "halo_pack";
     MeshDev<R> m; const R* X; int ncomp; R* buf;
     FVM_HD void operator()(int r) const {
         const int own = m.owner[m.nLocalFaces + r];
@@ -501,6 +515,7 @@ template <typename R> struct HaloPackBody {
     }
 };
 template <typename R> struct HaloUnpackBody {
+    static constexpr const char* kName = "halo_unpack";
     MeshDev<R> m; R* X; int ncomp; const R* buf;
     FVM_HD void operator()(int r) const {
         int cs; const long o = halo_offset(m, r, ncomp, cs);
@@ -509,6 +524,7 @@ template <typename R> struct HaloUnpackBody {
 };
 // reverse halo: ghost-row adjoints of the remote faces -> send buffer
 template <typename R> struct HaloPackGhostBody {
+    static constexpr const char* kName = "halo_pack_ghost";
     MeshDev<R> m; const R* X; int ncomp; R* buf;
     FVM_HD void operator()(int r) const {
         int cs; const long o = halo_offset(m, r, ncomp, cs);

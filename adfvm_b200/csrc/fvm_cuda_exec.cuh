@@ -6,6 +6,8 @@
 #include <cuda_runtime.h>
 #include <stdexcept>
 #include <string>
+#include <vector>
+#include <map>
 
 namespace fvm {
 
@@ -57,12 +59,40 @@ struct CudaExec {
     cudaStream_t stream = 0;
     int device = 0;
     void* partial = nullptr;     // reduction scratch (kRedMaxBlocks doubles)
+    // optional per-kernel timing (bench.py roofline leg): CUDA events around every launch on the launching stream
+    struct Rec { const char* name; cudaEvent_t a, b; };
+    struct Timing { bool on = false; std::vector<Rec> recs; std::map<std::string, std::pair<double, long>> acc; };
+    Timing* timing = nullptr;    // shared by copies of the executor
+    void tic(const char* name) {
+        if (!timing || !timing->on) return;
+        Rec r; r.name = name; cudaEventCreate(&r.a); cudaEventCreate(&r.b); cudaEventRecord(r.a, stream); timing->recs.push_back(r);
+    }
+    void toc() { if (timing && timing->on) cudaEventRecord(timing->recs.back().b, stream); }
+    void timing_enable(bool on) { timing_collect(); if (timing) { timing->on = on; if (on) timing->acc.clear(); } }
+    std::string timing_report() {
+        timing_collect();
+        std::string out;
+        if (timing) for (auto& kv : timing->acc)
+            out += kv.first + " " + std::to_string(kv.second.second) + " " + std::to_string(kv.second.first) + "\n";
+        return out;
+    }
+    void timing_collect() {
+        if (!timing) return;
+        cudaStreamSynchronize(stream);
+        for (Rec& r : timing->recs) {
+            float ms = 0; cudaEventElapsedTime(&ms, r.a, r.b);
+            auto& e = timing->acc[r.name]; e.first += ms; e.second += 1;
+            cudaEventDestroy(r.a); cudaEventDestroy(r.b);
+        }
+        timing->recs.clear();
+    }
 
     void init(int dev, void* strm) {
         device = dev;
         FVM_CUDA_CHECK(cudaSetDevice(dev));
         stream = (cudaStream_t)strm;
         FVM_CUDA_CHECK(cudaMalloc(&partial, kRedMaxBlocks * sizeof(double)));
+        timing = new Timing();
     }
     void* stream_handle() const { return (void*)stream; }
     void* alloc(size_t bytes) { void* p = nullptr; FVM_CUDA_CHECK(cudaMalloc(&p, bytes ? bytes : 1)); return p; }
@@ -73,18 +103,24 @@ struct CudaExec {
     void sync() { FVM_CUDA_CHECK(cudaStreamSynchronize(stream)); }
 
     template <class Body> void run(int n, const Body& b) {
+        tic(Body::kName);
         k_run<Body><<<(n + kBlock - 1) / kBlock, kBlock, 0, stream>>>(b, n);
+        toc();
         FVM_CUDA_CHECK(cudaPeekAtLastError());
     }
     template <class Body> void run_discard(int n, const Body& b) {
+        tic(Body::kName);
         k_run_discard<Body><<<(n + kBlock - 1) / kBlock, kBlock, 0, stream>>>(b, n);
+        toc();
         FVM_CUDA_CHECK(cudaPeekAtLastError());
     }
     template <typename R, class Op, class Body> void reduce(int n, const Body& b, R* out) {
         int nb = (n + kRedBlock - 1) / kRedBlock;
         if (nb > kRedMaxBlocks) nb = kRedMaxBlocks;
         if (nb < 1) nb = 1;
+        tic(Body::kName);
         k_reduce1<R, Op, Body><<<nb, kRedBlock, 0, stream>>>(b, n, (R*)partial);
+        toc();
         k_reduce2<R, Op><<<1, kRedBlock, 0, stream>>>((const R*)partial, nb, out);
         FVM_CUDA_CHECK(cudaPeekAtLastError());
     }

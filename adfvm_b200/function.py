@@ -261,6 +261,20 @@ class PrimalFunction:
     def sync(self):
         self.c.lib.check(self.c.lib.dll.adfvm_sync(self.c.ctx))
 
+    def kernel_timing(self, enable):
+        self.c.lib.check(self.c.lib.dll.adfvm_kernel_timing(self.c.ctx, int(bool(enable))))
+
+    def kernel_report(self):
+        """{kernel: (launches, total_ms)} accumulated since kernel_timing(True)"""
+        buf = C.create_string_buffer(8192)
+        self.c.lib.check(self.c.lib.dll.adfvm_kernel_report(self.c.ctx, buf, 8192))
+        out = {}
+        for line in buf.value.decode().strip().split("\n"):
+            if line:
+                k, n, ms = line.split()
+                out[k] = (int(n), float(ms))
+        return out
+
     @property
     def launches(self):
         return int(self.c.lib.dll.adfvm_launch_count(self.c.ctx))

@@ -108,6 +108,12 @@ int64_t adfvm_launch_count(adfvm_ctx* ctx);
 /* bytes of device memory held by the context */
 int64_t adfvm_device_bytes(adfvm_ctx* ctx);
 
+/* per-kernel device timing (CUDA events on the launching stream around every launch while enabled).
+ * adfvm_kernel_report writes lines "<kernel> <launches> <total_ms>\n" into buf. Counterpart of the reference's
+ * `-o/--profile` per-kernel prints (adpy/adpy/variable.py:437-467). */
+int adfvm_kernel_timing(adfvm_ctx* ctx, int32_t enable);
+int adfvm_kernel_report(adfvm_ctx* ctx, char* buf, int32_t buflen);
+
 /* multi-GPU halo: replaces Function_mpi_init / Function_mpi / Function_mpi_end and their _grad twins
  * (adFVM/cpp/parallel.cpp:31-209) and Function_mpi_allreduce (:214-232) with NCCL point-to-point over NVLink.
  * id: 128-byte ncclUniqueId produced on rank 0 and distributed by the host layer (torch.distributed). */

@@ -44,3 +44,17 @@ def available():
 def relerr(a, b):
     a = np.asarray(a, np.float64); b = np.asarray(b, np.float64)
     return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-300))
+
+
+def group_relerr(arrs, refs, scales=None):
+    """Largest error over a group of arrays that share one physical unit after scaling
+    (e.g. adjoints of rho, rhoU, rhoE scaled by typical rho, rhoU, rhoE), relative to the group's max."""
+    scales = scales or [1.0] * len(arrs)
+    num = max(float(np.abs(np.asarray(a, np.float64) - np.asarray(r, np.float64)).max()) * s
+              for a, r, s in zip(arrs, refs, scales))
+    den = max(float(np.abs(np.asarray(r, np.float64)).max()) * s for r, s in zip(refs, scales))
+    return num / max(den, 1e-300)
+
+
+def state_scales(inputs):
+    return [float(np.abs(inputs[i]).max()) for i in range(3)]

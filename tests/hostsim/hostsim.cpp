@@ -24,6 +24,8 @@ struct HostExec {
     void upload(void* d, const void* s, size_t b) { std::memcpy(d, s, b); }
     void download(void* d, const void* s, size_t b) { std::memcpy(d, s, b); }
     void sync() {}
+    void timing_enable(bool) {}
+    std::string timing_report() { return ""; }
     template <class B> void run(int n, const B& b) {
         #pragma omp parallel for schedule(static)
         for (int i = 0; i < n; i++) b(i);

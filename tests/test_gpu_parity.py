@@ -1,0 +1,126 @@
+"""Parity tests proper: the CUDA library (sm_100a kernels) through the C ABI and the Python host layer,
+against (1) the reference's recorded outputs, (2) the oracle on larger / richer synthetic cases,
+(3) size-independent properties at benchmark-like sizes. fp64 tolerance 1e-10 relative (north star);
+fp32 tolerance 1e-5 relative against the fp64 oracle (the reference's own fp32-vs-fp64
+gap is ~1e-6)."""
+import numpy as np
+import pytest
+
+from golden_util import Golden, available, relerr, group_relerr, state_scales
+from adfvm_b200 import function, cases
+from oracle import adfvm_oracle as O
+
+pytestmark = pytest.mark.gpu
+CASES = [c for c in available() if not c.endswith("_fp32")]
+TOL64, TOL32 = 1e-10, 1e-5
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_golden_primal(name, cudalib):
+    g = Golden(name)
+    for run in ("orig", "perturb"):
+        f = function.PrimalFunction(g.spec, np.float64)
+        for ci, nm, inp, opt, out in g.calls(run, "primal"):
+            r = f(*inp, **opt)
+            for a, b in zip(r, out):
+                assert relerr(a, b) < TOL64
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_golden_adjoint(name, cudalib):
+    g = Golden(name)
+    f = function.PrimalFunction(g.spec, np.float64).grad()
+    for ci, nm, inp, opt, out in g.calls("adjoint", "primal_grad"):
+        r = f(*inp, **opt)
+        sc = state_scales(inp)
+        assert group_relerr(r[:3], out[:3], sc) < TOL64
+        assert group_relerr(r[3:6], out[3:6], sc) < TOL64
+
+
+def _adj_seed(case):
+    rng = np.random.RandomState(3)
+    return [np.ascontiguousarray(rng.randn(*s.shape) * w, case.dtype) for s, w in zip(case.state, (1.0, 1e-2, 1e-5))]
+
+
+@pytest.mark.parametrize("make", [lambda dt: cases.periodic_box((16, 14, 12), dt, warp=0.03),
+                                  lambda dt: cases.walled_box((12, 10, 6), dt)])
+@pytest.mark.parametrize("dtype,tol", [(np.float64, TOL64), (np.float32, TOL32)])
+def test_oracle_parity(make, dtype, tol, cudalib):
+    case = make(dtype)
+    ref_case = make(np.float64)
+    f = function.PrimalFunction(case.spec, dtype)
+    state, ref_state = case.state, ref_case.state
+    for step in range(3):
+        out = f(*case.inputs(state), replace_reusable=(step == 0), return_reusable=True)
+        ref = O.primal(ref_case.spec, ref_case.inputs(ref_state))
+        for a, b in zip(out, ref):
+            assert relerr(a, b) < tol, (step, relerr(a, b))
+        state, ref_state = list(out[:3]), list(ref[:3])
+    adj = _adj_seed(case)
+    g = f.grad()(*case.adjoint_inputs(case.state, adj))
+    gref = O.primal_grad(ref_case.spec, ref_case.adjoint_inputs(ref_case.state, [a.astype(np.float64) for a in adj]))
+    sc = state_scales(ref_case.state)
+    assert group_relerr(g[:3], gref[:3], sc) < tol
+    assert group_relerr(g[3:6], gref[3:6], sc) < tol
+
+
+def test_bitwise_deterministic(cudalib):
+    """no float atomics anywhere: two runs give identical bits, primal and adjoint"""
+    case = cases.periodic_box(24, warp=0.02)
+    res = []
+    for rep in range(2):
+        f = function.PrimalFunction(case.spec, np.float64)
+        out = f(*case.inputs(), replace_reusable=True)
+        g = f.grad()(*case.adjoint_inputs(case.state, _adj_seed(case)))
+        res.append([o.copy() for o in out] + [x.copy() for x in g])
+    for a, b in zip(*res):
+        assert np.array_equal(a, b)
+
+
+def test_resident_equals_host_roundtrip(cudalib):
+    case = cases.periodic_box(20)
+    f1 = function.PrimalFunction(case.spec, np.float64)
+    state = case.state
+    for s in range(3):
+        out = f1(*case.inputs(state), replace_reusable=True, return_reusable=True)
+        state = list(out[:3])
+    f2 = function.PrimalFunction(case.spec, np.float64)
+    f2(*case.inputs(), replace_reusable=True, return_reusable=False)
+    f2.step_resident(case.dt)
+    out2 = f2(*case.inputs(), replace_reusable=False, return_reusable=True)
+    for a, b in zip(out2, out):
+        assert np.array_equal(a, b)
+
+
+def test_adjoint_vs_finite_difference(cudalib):
+    """dJ/dS from one adjoint step against a central finite difference of the primal step (objective on the
+    stage-1 state + a linear functional of the output), the reference's end-to-end criterion
+    (tests/test_adjoint.py:33) applied to a single step where FD noise is small."""
+    case = cases.walled_box((10, 8, 4))
+    f = function.PrimalFunction(case.spec, np.float64)
+    adj = _adj_seed(case)
+    g = f.grad()(*case.adjoint_inputs(case.state, adj))
+    rng = np.random.RandomState(5)
+    pert = [rng.randn(*s.shape) * w for s, w in zip(case.source, (1e1, 1e3, 1e6))]
+    def J(sign, eps=1e-3):
+        c2 = cases.walled_box((10, 8, 4))
+        c2.source = [s + sign * eps * d for s, d in zip(c2.source, pert)]
+        out = function.PrimalFunction(c2.spec, np.float64)(*c2.inputs(), replace_reusable=True)
+        return sum(float((o * a).sum()) for o, a in zip(out[:3], adj)) + float(out[4][0, 0])
+    fd = (J(+1) - J(-1)) / 2e-3
+    ad = sum(float((a * d).sum()) for a, d in zip(g[3:6], pert))
+    assert abs(fd - ad) / abs(fd) < 1e-6, (fd, ad)
+
+
+def test_large_periodic_properties(cudalib):
+    """64^3 periodic box: exact discrete conservation of mass/momentum/energy with zero source (every internal
+    and cyclic face flux enters two cells with opposite sign), checked through the volume-weighted sums."""
+    case = cases.periodic_box(64)
+    case.source = [np.zeros_like(s) for s in case.source]
+    f = function.PrimalFunction(case.spec, np.float64)
+    out = f(*case.inputs(), replace_reusable=True)
+    V = case.mesh.volumes
+    for a, b in zip(out[:3], case.state):
+        s0, s1 = (b * V).sum(axis=0), (a * V).sum(axis=0)
+        assert np.all(np.abs(s1 - s0) <= 1e-12 * np.abs(b * V).sum(axis=0))
+    assert np.isfinite(out[3]).all() and out[3][0, 0] > 0
