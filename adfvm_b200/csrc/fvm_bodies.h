@@ -39,6 +39,10 @@ template <typename R> struct MeshDev {
     const unsigned char *bpatch;         // [nGhostCells] patch index of each boundary face
     const PatchDev<R>* patches;
     int nPatches;
+    // tiles (fvm_tiles.h): tile t owns cells [t*T, min(C,(t+1)*T)) and entries [tile_start[t], tile_start[t+1])
+    int T, nTiles;
+    const int* tile_start; const int* ent_face; const unsigned* ent_loc;
+    const int* cell_perm;                // [C] device cell -> reference (host) cell
 };
 
 template <typename R> struct ObjDev { int kind, patch, dir; };
@@ -494,15 +498,16 @@ template <typename R> struct PrimAdjUpdateBody {
 
 // ------------------------------------------------------------------------------------------ layout helpers
 // AoS host layout ([n][d] row-major, what the reference passes) <-> SoA device layout
+// perm (may be NULL = identity): device row i holds host row perm[i] (tile renumbering of cells / internal faces)
 template <typename R> struct AosToSoaBody {
     static constexpr const char* kName = "aos_to_soa";
-    const R* src; R* dst; int d, stride;
-    FVM_HD void operator()(int i) const { for (int k = 0; k < d; k++) dst[k * stride + i] = src[i * d + k]; }
+    const R* src; R* dst; int d, stride; const int* perm;
+    FVM_HD void operator()(int i) const { const long o = perm ? perm[i] : i; for (int k = 0; k < d; k++) dst[(long)k * stride + i] = src[o * d + k]; }
 };
 template <typename R> struct SoaToAosBody {
     static constexpr const char* kName = "soa_to_aos";
-    const R* src; R* dst; int d, stride;
-    FVM_HD void operator()(int i) const { for (int k = 0; k < d; k++) dst[i * d + k] = src[k * stride + i]; }
+    const R* src; R* dst; int d, stride; const int* perm;
+    FVM_HD void operator()(int i) const { const long o = perm ? perm[i] : i; for (int k = 0; k < d; k++) dst[o * d + k] = src[(long)k * stride + i]; }
 };
 // processor-patch halo: pack owner rows of the remote faces / unpack into ghost rows (adFVM/cpp/parallel.cpp:116-133)
 template <typename R> struct HaloPackBody {

@@ -25,6 +25,16 @@ template <class Body> __global__ void __launch_bounds__(kBlock) k_run_discard(co
     if (i < n) (void)b(i);
 }
 
+template <class Body> __global__ void __launch_bounds__(kBlock) k_tile(const Body b) {
+    extern __shared__ __align__(16) unsigned char tile_smem[];
+    b.device_tile(blockIdx.x, tile_smem);
+}
+template <typename R> struct BufferBody {      // reduce an array already in device memory
+    static constexpr const char* kName = "reduce_buffer";
+    const R* p;
+    __device__ R operator()(int i) const { return p[i]; }
+};
+
 struct OpSum { template <typename R> __device__ static R id() { return R(0); } template <typename R> __device__ static R op(R a, R b) { return a + b; } };
 struct OpMax { template <typename R> __device__ static R id() { return R(-1e30); } template <typename R> __device__ static R op(R a, R b) { return a > b ? a : b; } };
 
@@ -114,6 +124,20 @@ struct CudaExec {
         toc();
         FVM_CUDA_CHECK(cudaPeekAtLastError());
     }
+    // one CTA of kBlock threads per tile, dynamic shared memory sized by the body
+    template <class Body> void run_tiles(int nTiles, int T, const Body& b) {
+        const size_t smem = Body::smem_bytes(T);
+        static size_t configured = 0;
+        if (smem > 48 * 1024 && smem > configured) {
+            FVM_CUDA_CHECK(cudaFuncSetAttribute(k_tile<Body>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            configured = smem;
+        }
+        tic(Body::kName);
+        k_tile<Body><<<nTiles, kBlock, smem, stream>>>(b);
+        toc();
+        FVM_CUDA_CHECK(cudaPeekAtLastError());
+    }
+    template <typename R> void reduce_max_buffer(const R* in, int n, R* out) { reduce<R, OpMax, BufferBody<R>>(n, BufferBody<R>{in}, out); }
     template <typename R, class Op, class Body> void reduce(int n, const Body& b, R* out) {
         int nb = (n + kRedBlock - 1) / kRedBlock;
         if (nb > kRedMaxBlocks) nb = kRedMaxBlocks;

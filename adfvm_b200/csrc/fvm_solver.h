@@ -12,6 +12,8 @@
 #include <vector>
 #include <cstring>
 #include "fvm_bodies.h"
+#include "fvm_tile_bodies.h"
+#include "fvm_tiles.h"
 
 namespace fvm {
 
@@ -56,6 +58,7 @@ public:
     R *A[4] = {0, 0, 0, 0}, *Qb = 0, *Gb = 0, *Sb = 0;
     R *sendbuf = 0, *recvbuf = 0, *stage_aos = 0;
     int *bcells = 0; int nBcells = 0;
+    TilePlan plan; int tile_cells = 128; R* tile_partial = 0; double tile_evals_per_cell = 0; int tile_colours = 0;
     bool have_mesh = false, have_state = false, adjoint_ready = false;
     std::vector<void*> owned;                 // everything to free
 
@@ -70,26 +73,17 @@ public:
     }
     template <class B> void run(int n, const B& b) { if (n > 0) { ex.run(n, b); launches++; } }
 
-    // ---- host AoS [n][d] -> device SoA [d][stride]
-    R* upload_aos(const R* host, long n, int d, int stride, R* dst = nullptr) {
+    // ---- host AoS [n][d] (reference numbering) -> device SoA [d][stride] (tile numbering: device row i = host row perm[i])
+    R* upload_aos(const R* host, long n, int d, int stride, R* dst = nullptr, const int* perm = nullptr) {
         if (!dst) dst = dalloc<R>((size_t)d * stride);
         if (n == 0) return dst;
-        if (d == 1) { ex.upload(dst, host, n * sizeof(R)); return dst; }
+        if (d == 1 && !perm) { ex.upload(dst, host, n * sizeof(R)); return dst; }
         R* tmp = (R*)ex.alloc((size_t)n * d * sizeof(R));
         ex.upload(tmp, host, (size_t)n * d * sizeof(R));
-        run((int)n, AosToSoaBody<R>{tmp, dst, d, stride});
+        run((int)n, AosToSoaBody<R>{tmp, dst, d, stride, perm});
         ex.sync(); ex.free(tmp);
         return dst;
     }
-    void download_aos(R* host, const R* src, long n, int d, int stride) {
-        if (n == 0) return;
-        if (d == 1) { ex.download(host, src, n * sizeof(R)); return; }
-        R* tmp = (R*)ex.alloc((size_t)n * d * sizeof(R));
-        run((int)n, SoaToAosBody<R>{src, tmp, d, stride});
-        ex.download(host, tmp, (size_t)n * d * sizeof(R));
-        ex.sync(); ex.free(tmp);
-    }
-
     void set_physics(double gamma, double Cp, double Pr, int mu_law, double mu_value, int riemann, int briemann) {
         ph.gamma = (R)gamma; ph.Cp = (R)Cp; ph.Pr = (R)Pr; ph.Cv = (R)(Cp / gamma);
         ph.small = sizeof(R) == 8 ? (R)1e-30 : (R)1e-9;
@@ -108,27 +102,46 @@ public:
         if (N != C + (F - Fi) || m.nGhostCells != F - Fi || m.nRemoteCells != N - m.nLocalCells ||
             m.nLocalFaces != m.nLocalCells - C + Fi)
             throw std::runtime_error("inconsistent mesh size constants");
+        for (long f = 0; f < F; f++) if (owner[f] < 0 || owner[f] >= C || neighbour[f] < 0 || neighbour[f] >= N || (f < Fi && neighbour[f] >= C))
+            throw std::runtime_error("owner/neighbour out of range");
         // the kernels use V[owner]/V[neighbour] for volumesL/volumesR; reject inputs where they differ
         for (long f = 0; f < F; f++) if (volumesL[f] != volumes[owner[f]]) throw std::runtime_error("volumesL != volumes[owner] (perturbed volume arrays are not supported)");
         for (long f = 0; f < Fi; f++) if (volumesR[f] != volumes[neighbour[f]]) throw std::runtime_error("volumesR != volumes[neighbour]");
         m.sC = pad32(C); m.sN = pad32(N); m.sF = pad32(F);
-        m.area = upload_aos(areas, F, 1, m.sF); m.weight = upload_aos(weights, F, 1, m.sF);
-        m.delta = upload_aos(deltas, F, 1, m.sF); m.normal = upload_aos(normals, F, 3, m.sF);
-        m.dunit = upload_aos(deltasUnit, F, 3, m.sF); m.linw = upload_aos(linearWeights, F, 2, m.sF);
-        m.quadw = upload_aos(quadraticWeights, F, 6, m.sF); m.vol = upload_aos(volumes, C, 1, m.sC);
-        int* d_owner = dalloc<int>(m.sF); ex.upload(d_owner, owner, (size_t)F * 4); m.owner = d_owner;
-        int* d_neigh = dalloc<int>(m.sF); ex.upload(d_neigh, neighbour, (size_t)F * 4); m.neigh = d_neigh;
-        // connectivity: transpose on the host (ints, one-off)
+        // ---- tile plan: renumber internal cells and internal faces (fvm_tiles.h); ghosts and boundary faces keep their ids
+        plan = build_tile_plan<R>(C, Fi, F, owner, neighbour, cellFaces, deltas, deltasUnit, tile_cells);
+        m.T = plan.T; m.nTiles = plan.nTiles;
+        int* d_cperm = dalloc<int>(m.sC); ex.upload(d_cperm, plan.cell_new2old.data(), (size_t)C * 4); m.cell_perm = d_cperm;
+        int* d_fperm = (int*)ex.alloc((size_t)(F + 1) * 4); ex.upload(d_fperm, plan.face_new2old.data(), (size_t)F * 4);
+        m.area = upload_aos(areas, F, 1, m.sF, nullptr, d_fperm); m.weight = upload_aos(weights, F, 1, m.sF, nullptr, d_fperm);
+        m.delta = upload_aos(deltas, F, 1, m.sF, nullptr, d_fperm); m.normal = upload_aos(normals, F, 3, m.sF, nullptr, d_fperm);
+        m.dunit = upload_aos(deltasUnit, F, 3, m.sF, nullptr, d_fperm); m.linw = upload_aos(linearWeights, F, 2, m.sF, nullptr, d_fperm);
+        m.quadw = upload_aos(quadraticWeights, F, 6, m.sF, nullptr, d_fperm); m.vol = upload_aos(volumes, C, 1, m.sC, nullptr, d_cperm);
+        ex.sync(); ex.free(d_fperm);
+        auto newcell = [&](int c) { return c < C ? plan.cell_old2new[c] : c; };
+        {
+            std::vector<int> ow(m.sF, 0), nb(m.sF, 0);
+            for (long f = 0; f < F; f++) {
+                const int of = plan.face_new2old[f];
+                if (owner[of] < 0 || owner[of] >= C || neighbour[of] < 0 || neighbour[of] >= N) throw std::runtime_error("owner/neighbour out of range");
+                ow[f] = newcell(owner[of]); nb[f] = newcell(neighbour[of]);
+            }
+            int* d_owner = dalloc<int>(m.sF); ex.upload(d_owner, ow.data(), (size_t)F * 4); m.owner = d_owner;
+            int* d_neigh = dalloc<int>(m.sF); ex.upload(d_neigh, nb.data(), (size_t)F * 4); m.neigh = d_neigh;
+            ex.sync();
+        }
+        // connectivity: transpose + renumber on the host (ints, one-off)
         std::vector<int> cf((size_t)6 * m.sC, 0), cn((size_t)6 * m.sC, 0);
         std::vector<unsigned char> co(m.sC, 0);
         std::vector<int> bc_list;
         for (long c = 0; c < C; c++) {
+            const long oc = plan.cell_new2old[c];
             bool b = false; unsigned bits = 0;
             for (int j = 0; j < 6; j++) {
-                int f = cellFaces[c * 6 + j], nb = cellNeighbours[c * 6 + j];
+                int f = cellFaces[oc * 6 + j], nb = cellNeighbours[oc * 6 + j];
                 if (f < 0 || f >= F || nb < 0 || nb >= N) throw std::runtime_error("cellFaces/cellNeighbours out of range");
-                cf[(size_t)j * m.sC + c] = f; cn[(size_t)j * m.sC + c] = nb;
-                if (cellOwner[c * 6 + j]) bits |= 1u << j;
+                cf[(size_t)j * m.sC + c] = plan.face_old2new[f]; cn[(size_t)j * m.sC + c] = newcell(nb);
+                if (cellOwner[oc * 6 + j]) bits |= 1u << j;
                 if (nb >= C) b = true;
             }
             co[c] = (unsigned char)bits;
@@ -139,6 +152,16 @@ public:
         unsigned char* d_co = dalloc<unsigned char>(co.size()); ex.upload(d_co, co.data(), co.size()); m.cellOwner = d_co;
         nBcells = (int)bc_list.size();
         bcells = dalloc<int>(nBcells + 1); ex.upload(bcells, bc_list.data(), (size_t)nBcells * 4);
+        {
+            int* d_ts = dalloc<int>(plan.tile_start.size()); ex.upload(d_ts, plan.tile_start.data(), plan.tile_start.size() * 4); m.tile_start = d_ts;
+            int* d_ef = dalloc<int>(plan.ent_face.size() + 1); ex.upload(d_ef, plan.ent_face.data(), plan.ent_face.size() * 4); m.ent_face = d_ef;
+            unsigned* d_el = dalloc<unsigned>(plan.ent_loc.size() + 1); ex.upload(d_el, plan.ent_loc.data(), plan.ent_loc.size() * 4); m.ent_loc = d_el;
+            tile_partial = dalloc<R>(plan.nTiles + 1);
+            ex.sync();
+        }
+        tile_evals_per_cell = plan.evals_per_cell(); tile_colours = plan.maxColours;
+        // the plan's host vectors are only needed for the I/O permutation, which lives on the device: release them
+        plan = TilePlan(); plan.T = m.T; plan.nTiles = m.nTiles;
         // patches
         patches = patches_in;
         if ((int)patches.size() > MAX_PATCHES) throw std::runtime_error("too many patches");
@@ -215,23 +238,29 @@ public:
     }
     void set_source(const R* s_rho, const R* s_rhoU, const R* s_rhoE) {
         const int C = m.nInternalCells;
-        upload_aos(s_rho, C, 1, m.sC, S); upload_aos(s_rhoU, C, 3, m.sC, S + m.sC); upload_aos(s_rhoE, C, 1, m.sC, S + 4 * (size_t)m.sC);
+        upload_aos(s_rho, C, 1, m.sC, S, m.cell_perm); upload_aos(s_rhoU, C, 3, m.sC, S + m.sC, m.cell_perm);
+        upload_aos(s_rhoE, C, 1, m.sC, S + 4 * (size_t)m.sC, m.cell_perm);
     }
     void set_state(const R* rho, const R* rhoU, const R* rhoE) { put5(W[0], rho, rhoU, rhoE); have_state = true; }
     void get_state(R* rho, R* rhoU, R* rhoE) { get5(W[0], rho, rhoU, rhoE); }
+    // host (rho[C][1], rhoU[C][3], rhoE[C][1]) in reference cell order <-> device [5][sC] in tile order
     void put5(R* dst, const R* a, const R* b, const R* c) {
         const int C = m.nInternalCells;
-        ex.upload(dst, a, (size_t)C * sizeof(R));
-        ex.upload(stage_aos, b, (size_t)3 * C * sizeof(R));
-        run(C, AosToSoaBody<R>{stage_aos, dst + m.sC, 3, m.sC});
-        ex.upload(dst + 4 * (size_t)m.sC, c, (size_t)C * sizeof(R));
+        ex.upload(stage_aos, a, (size_t)C * sizeof(R));
+        ex.upload(stage_aos + C, b, (size_t)3 * C * sizeof(R));
+        ex.upload(stage_aos + 4 * (size_t)C, c, (size_t)C * sizeof(R));
+        run(C, AosToSoaBody<R>{stage_aos, dst, 1, m.sC, m.cell_perm});
+        run(C, AosToSoaBody<R>{stage_aos + C, dst + m.sC, 3, m.sC, m.cell_perm});
+        run(C, AosToSoaBody<R>{stage_aos + 4 * (size_t)C, dst + 4 * (size_t)m.sC, 1, m.sC, m.cell_perm});
     }
     void get5(const R* src, R* a, R* b, R* c) {
         const int C = m.nInternalCells;
-        ex.download(a, src, (size_t)C * sizeof(R));
-        run(C, SoaToAosBody<R>{src + m.sC, stage_aos, 3, m.sC});
-        ex.download(b, stage_aos, (size_t)3 * C * sizeof(R));
-        ex.download(c, src + 4 * (size_t)m.sC, (size_t)C * sizeof(R));
+        run(C, SoaToAosBody<R>{src, stage_aos, 1, m.sC, m.cell_perm});
+        run(C, SoaToAosBody<R>{src + m.sC, stage_aos + C, 3, m.sC, m.cell_perm});
+        run(C, SoaToAosBody<R>{src + 4 * (size_t)m.sC, stage_aos + 4 * (size_t)C, 1, m.sC, m.cell_perm});
+        ex.download(a, stage_aos, (size_t)C * sizeof(R));
+        ex.download(b, stage_aos + C, (size_t)3 * C * sizeof(R));
+        ex.download(c, stage_aos + 4 * (size_t)C, (size_t)C * sizeof(R));
         ex.sync();
     }
 
@@ -272,13 +301,14 @@ public:
         run(C, GradCellBody<R>{m, Qs, Gs});
         run(nLB, GhostGradBody<R>{m, Gs});
         halo(Gs, 15);
-        FluxUpdateBody<R> fb;
+        FluxTileBody<R> fb;
         fb.ph = ph; fb.m = m; fb.Q = Qs; fb.G = Gs;
         fb.W0 = W[0]; fb.W1 = RK_ALPHA[s][1] != 0. ? W[1] : nullptr; fb.W2 = RK_ALPHA[s][2] != 0. ? W[2] : nullptr;
         fb.a0 = (R)RK_ALPHA[s][0]; fb.a1 = (R)RK_ALPHA[s][1]; fb.a2 = (R)RK_ALPHA[s][2];
         fb.beta = (R)RK_BETA[s]; fb.dt = dt; fb.S = S; fb.Wn = W[s + 1]; fb.Qn = Qnext;
-        if (want_dtc_obj) { ex.reduce_max(C, fb, red); launches += 2; }
-        else { ex.run_discard(C, fb); launches++; }
+        fb.dtc_partial = want_dtc_obj ? tile_partial : nullptr;
+        ex.run_tiles(m.nTiles, m.T, fb); launches++;
+        if (want_dtc_obj) { ex.reduce_max_buffer(tile_partial, m.nTiles, red); launches += 2; }
     }
 
     // primal step; state W[0] -> W[0]. keep=true keeps every stage (Q[s], G[s], W[s]) for the reverse sweep.
@@ -328,7 +358,7 @@ public:
         const int C = m.nInternalCells;
         for (int s = 2; s >= 0; s--) {
             const R coef = (R)(-RK_BETA[s]) * dt;
-            run(C, FluxGradBody<R>{ph, m, Q[s], G[s], A[s + 1], coef, Qb, Gb});
+            ex.run_tiles(m.nTiles, m.T, FluxGradTileBody<R>{ph, m, Q[s], G[s], A[s + 1], coef, Qb, Gb}); launches++;
             const R* rG = halo_reverse(Gb, 15);
             run(nBcells, GhostGradAdjBody<R>{m, bcells, Gb, rG});
             run(C, GradCellAdjBody<R>{m, Gb, Qb});

@@ -54,7 +54,7 @@ def _ptr(a):
 class _Context:
     """Owns one adfvm_ctx: device-resident mesh, BC, source and state of one rank."""
 
-    def __init__(self, spec, precision, device, stream, lib):
+    def __init__(self, spec, precision, device, stream, lib, tile_cells=None):
         self.spec = spec
         self.lib = lib or L.default_lib()
         self.dtype = np.dtype(precision)
@@ -71,6 +71,8 @@ class _Context:
         self.lib.check(self.lib.dll.adfvm_set_physics(
             self.ctx, float(spec["gamma"]), float(spec["Cp"]), float(spec["Pr"]), law, float(mu.get("value", 0.)),
             L.RIEMANN[spec["riemannSolver"]], L.RIEMANN[spec["boundaryRiemannSolver"]]))
+        if tile_cells:
+            self.lib.check(self.lib.dll.adfvm_set_tile_cells(self.ctx, int(tile_cells)))
         self.sorted = list(spec["sortedPatches"])
         byname = {p["name"]: p for p in spec["patches"]}
         remote = [p["name"] for p in spec["patches"] if p["type"] in ("processor", "processorCyclic")]
@@ -208,8 +210,14 @@ class PrimalFunction:
     defaultOptions = {"return_static": True, "zero_static": False, "replace_static": False,
                       "return_reusable": True, "replace_reusable": False}   # adpy/adpy/variable.py:282-287
 
-    def __init__(self, spec, precision=np.float64, device=0, stream=None, lib=None):
-        self.c = _Context(spec, precision, device, stream, lib)
+    def __init__(self, spec, precision=np.float64, device=0, stream=None, lib=None, tile_cells=None):
+        self.c = _Context(spec, precision, device, stream, lib, tile_cells)
+
+    def tile_stats(self):
+        """(flux evaluations per cell, max colours per tile, tiles, cells per tile) of the device layout"""
+        a, b, c_, d = C.c_double(), C.c_int32(), C.c_int32(), C.c_int32()
+        self.c.lib.check(self.c.lib.dll.adfvm_tile_stats(self.c.ctx, C.byref(a), C.byref(b), C.byref(c_), C.byref(d)))
+        return a.value, b.value, c_.value, d.value
 
     def _prepare(self, inputs, options):
         opts = dict(self.defaultOptions)

@@ -38,9 +38,9 @@ def algorithmic_bytes(s):
     B_p = per_stage_primal * s + 96
     B_a = (per_stage_primal + per_stage_reverse) * s + 192
     # dominant kernels, rows of BASELINE.md §3 they cover (per cell per launch):
-    #  flux_update = flux (20 + 51 + 3 + 6 scalars, 2F ints) + RK update (23 1/3) + primitive of next stage (10)
-    #  flux_grad   = flux_grad row: 5 + 40 + (51 + 3) + 40 scalars, 2F ints
-    k = {"flux_update": (80 + 23 + 1.0 / 3 + 10) * s + 24, "flux_grad": (5 + 40 + 54 + 40) * s + 24,
+    #  flux_tile   = flux (20 + 51 + 3 + 6 scalars, 2F ints) + RK update (23 1/3) + primitive of next stage (10)
+    #  flux_grad_tile = flux_grad row: 5 + 40 + (51 + 3) + 40 scalars, 2F ints
+    k = {"flux_tile": (80 + 23 + 1.0 / 3 + 10) * s + 24, "flux_grad_tile": (5 + 40 + 54 + 40) * s + 24,
          "grad_cell": (5 + 15 + 1 + 15) * s + 72, "grad_cell_adj": (15 + 15 + 1 + 10) * s + 72}
     return B_p, B_a, k
 

@@ -108,6 +108,13 @@ int64_t adfvm_launch_count(adfvm_ctx* ctx);
 /* bytes of device memory held by the context */
 int64_t adfvm_device_bytes(adfvm_ctx* ctx);
 
+/* Tiling of the flux kernels (internal data layout): cells are regrouped into tiles of `cells`
+ * consecutive cells, one CTA per tile. adfvm_set_tile_cells must precede adfvm_set_mesh (default 128, 32..512).
+ * adfvm_tile_stats reports flux evaluations per cell (3 = every face once, 6 = cell-centred gather), the largest
+ * number of colours of a tile, the number of tiles and the tile size. */
+int adfvm_set_tile_cells(adfvm_ctx* ctx, int32_t cells);
+int adfvm_tile_stats(adfvm_ctx* ctx, double* evals_per_cell, int32_t* max_colours, int32_t* n_tiles, int32_t* tile_cells);
+
 /* per-kernel device timing (CUDA events on the launching stream around every launch while enabled).
  * adfvm_kernel_report writes lines "<kernel> <launches> <total_ms>\n" into buf. Counterpart of the reference's
  * `-o/--profile` per-kernel prints (adpy/adpy/variable.py:437-467). */

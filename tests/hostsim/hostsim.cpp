@@ -34,6 +34,11 @@ struct HostExec {
         #pragma omp parallel for schedule(static)
         for (int i = 0; i < n; i++) (void)b(i);
     }
+    template <class B> void run_tiles(int nTiles, int, const B& b) {
+        #pragma omp parallel for schedule(static)
+        for (int t = 0; t < nTiles; t++) b.host_tile(t);
+    }
+    template <typename R> void reduce_max_buffer(const R* in, int n, R* out) { R a = (R)-1e30; for (int i = 0; i < n; i++) if (in[i] > a) a = in[i]; *out = a; }
     template <class B, typename R> void reduce_sum(int n, const B& b, R* out) { R a = 0; for (int i = 0; i < n; i++) a += b(i); *out = a; }
     template <class B, typename R> void reduce_max(int n, const B& b, R* out) { R a = (R)-1e30; for (int i = 0; i < n; i++) { R v = b(i); if (v > a) a = v; } *out = a; }
 };
