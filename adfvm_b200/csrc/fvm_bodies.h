@@ -7,9 +7,10 @@
 //   Q  [5][sN]   primitive state (U_x, U_y, U_z, T, p), internal + ghost cells
 //   G  [15][sN]  gradients: dU_i/dx_j at 3*i+j, dT/dx_j at 9+j, dp/dx_j at 12+j
 //   face metrics [k][sF]; cell connectivity [6][sC]
-// Every scatter of the reference (Tensor.collate -> atomicAdd, adpy/adpy/tensor.py:393-394) is turned
-// into a cell-centred gather over the six faces of the hexahedron, so all sums have a fixed order:
-// results are bitwise reproducible run to run, primal and adjoint.
+// No scatter of the reference (Tensor.collate -> atomicAdd, adpy/adpy/tensor.py:393-394) is an atomic here: the
+// flux kernels (fvm_tile_bodies.h) sum face contributions per tile in shared memory in colour order, the gradient
+// kernels are cell-centred gathers over the six faces of the hexahedron. All sums have a fixed order: results are
+// bitwise reproducible run to run, primal and adjoint.
 #pragma once
 #include "fvm_math.h"
 
@@ -42,6 +43,7 @@ template <typename R> struct MeshDev {
     // tiles (fvm_tiles.h): tile t owns cells [t*T, min(C,(t+1)*T)) and entries [tile_start[t], tile_start[t+1])
     int T, nTiles;
     const int* tile_start; const int* ent_face; const unsigned* ent_loc;
+    const int* halo_start; const int* halo_cell;    // tile t's halo slots T.. hold cells halo_cell[halo_start[t]..halo_start[t+1])
     const int* cell_perm;                // [C] device cell -> reference (host) cell
 };
 
@@ -195,57 +197,6 @@ template <typename R> struct GradCellBody {
     }
 };
 
-// ------------------------------------------------------------------------------------------ a8-a12
-// Residual of one cell (gather over its 6 faces: internal, coupled, characteristic, boundary) fused with the
-// RK stage update (adFVM/timestep.py:35-45) and with the primitive conversion of the NEW state for the
-// next stage. Returns the cell's dtc (sum_f wave*A/V) for the max-reduction (adFVM/density.py:405-413).
-template <typename R> struct FluxUpdateBody {
-    static constexpr const char* kName = "flux_update";
-    Phys<R> ph; MeshDev<R> m;
-    const R *Q, *G;            // this stage's primitives / gradients (ghosts filled)
-    const R *W0, *W1, *W2;     // previous stage states (W1/W2 may be NULL when their alpha is 0)
-    R a0, a1, a2, beta, dt;
-    const R* S;                // source terms [5][sC]
-    R* Wn;                     // new state
-    R* Qn;                     // primitives of the new state (may be NULL)
-    FVM_HD R operator()(int c) const {
-        Prim<R> qc; Grad<R> gc;
-        load_prim(Q, m.sN, c, qc); load_grad(G, m.sN, c, gc);
-        R res[5] = {0, 0, 0, 0, 0}, dtc = 0;
-        const unsigned ob = m.cellOwner[c];
-        const R iv = R(1) / m.vol[c];
-        for (int j = 0; j < 6; j++) {
-            const int f = m.cellFaces[j * m.sC + c], nb = m.cellNbr[j * m.sC + c];
-            const bool own = (ob >> j) & 1u;
-            Geom<R> gm; load_geom(m, f, gm);
-            Prim<R> qn; Grad<R> gn;
-            load_prim(Q, m.sN, nb, qn); load_grad(G, m.sN, nb, gn);
-            Flux5<R> F; R wave;
-            R s = gm.area * iv;
-            if (own) {
-                face_flux(ph, face_kind(m, f), gm, qc, gc, qn, gn, F, wave);
-            } else {
-                face_flux(ph, (int)FACE_COUPLED, gm, qn, gn, qc, gc, F, wave);
-                s = -s;
-            }
-            res[0] += F.rho * s; res[1] += F.rhoU[0] * s; res[2] += F.rhoU[1] * s; res[3] += F.rhoU[2] * s;
-            res[4] += F.rhoE * s;
-            dtc += wave * (gm.area * iv);
-        }
-        R wn[5];
-        for (int k = 0; k < 5; k++) {
-            R v = a0 * W0[k * m.sC + c];
-            if (W1) v += a1 * W1[k * m.sC + c];
-            if (W2) v += a2 * W2[k * m.sC + c];
-            v += -beta * (res[k] - S[k * m.sC + c]) * dt;
-            wn[k] = v;
-            Wn[k * m.sC + c] = v;
-        }
-        if (Qn) { Prim<R> q; primitive(ph, wn[0], wn + 1, wn[4], q); store_prim(Qn, m.sN, c, q); }
-        return dtc;
-    }
-};
-
 // ------------------------------------------------------------------------------------------ a13
 // objective contributions; reduced with a fixed-order tree
 template <typename R> struct ObjectiveBody {
@@ -291,52 +242,7 @@ template <typename R> FVM_HD void objective_owner_adj(const Phys<R>& ph, const M
 }
 
 // ========================================================================================== reverse
-// A. adjoint of the flux+scatter (+ RK residual weight): for each cell, the part of every adjacent face's VJP
-// that lands on this cell; for boundary faces also the ghost row's part (exclusive writer = the owner).
-//   abar   = adjoint of the stage OUTPUT state, [5][sC]
-//   coef   = -beta_ii * dt   (d W_new / d residual)
-template <typename R> struct FluxGradBody {
-    static constexpr const char* kName = "flux_grad";
-    Phys<R> ph; MeshDev<R> m;
-    const R *Q, *G; const R* abar; R coef;
-    R *Qb, *Gb;                // outputs [5][sN], [15][sN] (overwritten)
-    FVM_HD void operator()(int c) const {
-        Prim<R> qc; Grad<R> gc;
-        load_prim(Q, m.sN, c, qc); load_grad(G, m.sN, c, gc);
-        const R iv = coef / m.vol[c];
-        R rc[5];
-        for (int k = 0; k < 5; k++) rc[k] = abar[k * m.sC + c] * iv;
-        Prim<R> qb; Grad<R> gb; zero(qb); zero(gb);
-        const unsigned ob = m.cellOwner[c];
-        for (int j = 0; j < 6; j++) {
-            const int f = m.cellFaces[j * m.sC + c], nb = m.cellNbr[j * m.sC + c];
-            const bool own = (ob >> j) & 1u;
-            Geom<R> gm; load_geom(m, f, gm);
-            Prim<R> qn; Grad<R> gn;
-            load_prim(Q, m.sN, nb, qn); load_grad(G, m.sN, nb, gn);
-            Flux5<R> Fb;
-            if (f < m.nInternalFaces) {
-                const R ivn = coef / m.vol[nb];
-                R d[5];
-                for (int k = 0; k < 5; k++) {
-                    R rn = abar[k * m.sC + nb] * ivn;
-                    d[k] = gm.area * (own ? rc[k] - rn : rn - rc[k]);
-                }
-                Fb.rho = d[0]; Fb.rhoU[0] = d[1]; Fb.rhoU[1] = d[2]; Fb.rhoU[2] = d[3]; Fb.rhoE = d[4];
-                Prim<R> qx; Grad<R> gx; zero(qx); zero(gx);     // other side's share: discarded
-                if (own) face_flux_vjp(ph, (int)FACE_COUPLED, gm, qc, gc, qn, gn, Fb, qb, gb, qx, gx);
-                else     face_flux_vjp(ph, (int)FACE_COUPLED, gm, qn, gn, qc, gc, Fb, qx, gx, qb, gb);
-            } else {
-                Fb.rho = gm.area * rc[0]; Fb.rhoU[0] = gm.area * rc[1]; Fb.rhoU[1] = gm.area * rc[2];
-                Fb.rhoU[2] = gm.area * rc[3]; Fb.rhoE = gm.area * rc[4];
-                Prim<R> qg; Grad<R> gg; zero(qg); zero(gg);
-                face_flux_vjp(ph, face_kind(m, f), gm, qc, gc, qn, gn, Fb, qb, gb, qg, gg);
-                store_prim(Qb, m.sN, nb, qg); store_grad(Gb, m.sN, nb, gg);
-            }
-        }
-        store_prim(Qb, m.sN, c, qb); store_grad(Gb, m.sN, c, gb);
-    }
-};
+// A. adjoint of the flux + scatter (+ RK residual weight): FluxGradTileBody in fvm_tile_bodies.h
 
 // B. adjoint of the gradient ghost fill, gathered per boundary-adjacent cell (list bcells):
 // Gb[c] += Gb[ghost rows that copied from c]. Processor faces add the rows received from the peer.

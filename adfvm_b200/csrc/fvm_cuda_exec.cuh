@@ -125,8 +125,8 @@ struct CudaExec {
         FVM_CUDA_CHECK(cudaPeekAtLastError());
     }
     // one CTA of kBlock threads per tile, dynamic shared memory sized by the body
-    template <class Body> void run_tiles(int nTiles, int T, const Body& b) {
-        const size_t smem = Body::smem_bytes(T);
+    template <class Body> void run_tiles(int nTiles, const Body& b) {
+        const size_t smem = Body::smem_bytes();
         static size_t configured = 0;
         if (smem > 48 * 1024 && smem > configured) {
             FVM_CUDA_CHECK(cudaFuncSetAttribute(k_tile<Body>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

@@ -58,7 +58,8 @@ public:
     R *A[4] = {0, 0, 0, 0}, *Qb = 0, *Gb = 0, *Sb = 0;
     R *sendbuf = 0, *recvbuf = 0, *stage_aos = 0;
     int *bcells = 0; int nBcells = 0;
-    TilePlan plan; int tile_cells = 128; R* tile_partial = 0; double tile_evals_per_cell = 0; int tile_colours = 0;
+    TilePlan plan; int tile_cells = 128; R* tile_partial = 0; double tile_evals_per_cell = 0; int tile_colours = 0, tile_max_halo = 0;
+    enum { kHalo128 = 256, kHalo64 = 384 };   // halo slots of the two tile-kernel instantiations (T=128: TS=384, T=64: TS=448)
     bool have_mesh = false, have_state = false, adjoint_ready = false;
     std::vector<void*> owned;                 // everything to free
 
@@ -109,7 +110,11 @@ public:
         for (long f = 0; f < Fi; f++) if (volumesR[f] != volumes[neighbour[f]]) throw std::runtime_error("volumesR != volumes[neighbour]");
         m.sC = pad32(C); m.sN = pad32(N); m.sF = pad32(F);
         // ---- tile plan: renumber internal cells and internal faces (fvm_tiles.h); ghosts and boundary faces keep their ids
+        // 128-cell tiles with room for 256 halo slots; meshes with many ghost cells per cell (1-D / 2-D cases, whose
+        // "empty" patches give every cell 2-4 boundary faces) fall back to 64-cell tiles, whose halo always fits
         plan = build_tile_plan<R>(C, Fi, F, owner, neighbour, cellFaces, deltas, deltasUnit, tile_cells);
+        if (tile_cells == 128 && plan.maxHalo > kHalo128) plan = build_tile_plan<R>(C, Fi, F, owner, neighbour, cellFaces, deltas, deltasUnit, 64);
+        if (plan.T == 64 && plan.maxHalo > kHalo64) throw std::runtime_error("tile halo exceeds the kernel's capacity");
         m.T = plan.T; m.nTiles = plan.nTiles;
         int* d_cperm = dalloc<int>(m.sC); ex.upload(d_cperm, plan.cell_new2old.data(), (size_t)C * 4); m.cell_perm = d_cperm;
         int* d_fperm = (int*)ex.alloc((size_t)(F + 1) * 4); ex.upload(d_fperm, plan.face_new2old.data(), (size_t)F * 4);
@@ -156,10 +161,12 @@ public:
             int* d_ts = dalloc<int>(plan.tile_start.size()); ex.upload(d_ts, plan.tile_start.data(), plan.tile_start.size() * 4); m.tile_start = d_ts;
             int* d_ef = dalloc<int>(plan.ent_face.size() + 1); ex.upload(d_ef, plan.ent_face.data(), plan.ent_face.size() * 4); m.ent_face = d_ef;
             unsigned* d_el = dalloc<unsigned>(plan.ent_loc.size() + 1); ex.upload(d_el, plan.ent_loc.data(), plan.ent_loc.size() * 4); m.ent_loc = d_el;
+            int* d_hs = dalloc<int>(plan.halo_start.size()); ex.upload(d_hs, plan.halo_start.data(), plan.halo_start.size() * 4); m.halo_start = d_hs;
+            int* d_hc = dalloc<int>(plan.halo_cell.size() + 1); ex.upload(d_hc, plan.halo_cell.data(), plan.halo_cell.size() * 4); m.halo_cell = d_hc;
             tile_partial = dalloc<R>(plan.nTiles + 1);
             ex.sync();
         }
-        tile_evals_per_cell = plan.evals_per_cell(); tile_colours = plan.maxColours;
+        tile_evals_per_cell = plan.evals_per_cell(); tile_colours = plan.maxColours; tile_max_halo = plan.maxHalo;
         // the plan's host vectors are only needed for the I/O permutation, which lives on the device: release them
         plan = TilePlan(); plan.T = m.T; plan.nTiles = m.nTiles;
         // patches
@@ -301,14 +308,20 @@ public:
         run(C, GradCellBody<R>{m, Qs, Gs});
         run(nLB, GhostGradBody<R>{m, Gs});
         halo(Gs, 15);
-        FluxTileBody<R> fb;
+        if (m.T == 128) run_flux_tile<128, 128 + kHalo128>(s, dt, Qs, Gs, Qnext, want_dtc_obj);
+        else run_flux_tile<64, 64 + kHalo64>(s, dt, Qs, Gs, Qnext, want_dtc_obj);
+        launches++;
+        if (want_dtc_obj) { ex.reduce_max_buffer(tile_partial, m.nTiles, red); launches += 2; }
+    }
+
+    template <int T, int TS> void run_flux_tile(int s, R dt, R* Qs, R* Gs, R* Qnext, bool want_dtc_obj) {
+        FluxTileBody<R, T, TS> fb;
         fb.ph = ph; fb.m = m; fb.Q = Qs; fb.G = Gs;
         fb.W0 = W[0]; fb.W1 = RK_ALPHA[s][1] != 0. ? W[1] : nullptr; fb.W2 = RK_ALPHA[s][2] != 0. ? W[2] : nullptr;
         fb.a0 = (R)RK_ALPHA[s][0]; fb.a1 = (R)RK_ALPHA[s][1]; fb.a2 = (R)RK_ALPHA[s][2];
         fb.beta = (R)RK_BETA[s]; fb.dt = dt; fb.S = S; fb.Wn = W[s + 1]; fb.Qn = Qnext;
         fb.dtc_partial = want_dtc_obj ? tile_partial : nullptr;
-        ex.run_tiles(m.nTiles, m.T, fb); launches++;
-        if (want_dtc_obj) { ex.reduce_max_buffer(tile_partial, m.nTiles, red); launches += 2; }
+        ex.run_tiles(m.nTiles, fb);
     }
 
     // primal step; state W[0] -> W[0]. keep=true keeps every stage (Q[s], G[s], W[s]) for the reverse sweep.
@@ -358,7 +371,9 @@ public:
         const int C = m.nInternalCells;
         for (int s = 2; s >= 0; s--) {
             const R coef = (R)(-RK_BETA[s]) * dt;
-            ex.run_tiles(m.nTiles, m.T, FluxGradTileBody<R>{ph, m, Q[s], G[s], A[s + 1], coef, Qb, Gb}); launches++;
+            if (m.T == 128) ex.run_tiles(m.nTiles, FluxGradTileBody<R, 128, 128 + kHalo128>{ph, m, Q[s], G[s], A[s + 1], coef, Qb, Gb});
+            else ex.run_tiles(m.nTiles, FluxGradTileBody<R, 64, 64 + kHalo64>{ph, m, Q[s], G[s], A[s + 1], coef, Qb, Gb});
+            launches++;
             const R* rG = halo_reverse(Gb, 15);
             run(nBcells, GhostGradAdjBody<R>{m, bcells, Gb, rG});
             run(C, GradCellAdjBody<R>{m, Gb, Qb});

@@ -23,9 +23,8 @@
 
 namespace fvm {
 
-enum { TILE_NONE = 0x3FF };     // "cell not in this tile" marker of the packed entry word
-
-// packed entry word: bits 0-9 owner's local index (TILE_NONE: not in tile), 10-19 neighbour's local index, 20-27 colour
+// packed entry word: bits 0-9 owner's slot, 10-19 neighbour's slot, 20-27 colour. Slots [0,T) are the tile's own
+// cells, slots [T, T+nHalo) the tile's halo: cells of other tiles and ghost cells touched by the tile's faces.
 static inline uint32_t tile_pack(int lo, int ln, int colour) { return (uint32_t)lo | ((uint32_t)ln << 10) | ((uint32_t)colour << 20); }
 
 struct TilePlan {
@@ -36,6 +35,9 @@ struct TilePlan {
     std::vector<int> tile_start;                     // [nTiles+1] offsets into the entry arrays
     std::vector<int> ent_face;                       // NEW face index of each entry
     std::vector<uint32_t> ent_loc;                   // tile_pack(...)
+    std::vector<int> halo_start;                     // [nTiles+1] offsets into halo_cell
+    std::vector<int> halo_cell;                      // NEW cell index (ghost cells: >= C) of each halo slot
+    int maxHalo = 0;
     double evals_per_cell() const { return cell_new2old.empty() ? 0. : (double)nEntries / (double)cell_new2old.size(); }
 };
 
@@ -104,7 +106,7 @@ inline void rcb(std::vector<int>& idx, const std::vector<float>& pos, long lo, l
 template <typename R>
 TilePlan build_tile_plan(int C, int Fi, int F, const int* owner, const int* neigh, const int* cellFaces,
                          const R* deltas, const R* deltasUnit, int T) {
-    if (T <= 0 || T >= TILE_NONE) throw std::runtime_error("tile size out of range");
+    if (T <= 0 || T > 512) throw std::runtime_error("tile size out of range");
     TilePlan P; P.T = T;
     P.nTiles = (C + T - 1) / T;
     // ---- cell order
@@ -126,6 +128,9 @@ TilePlan build_tile_plan(int C, int Fi, int F, const int* owner, const int* neig
     int nextFace = 0;
     std::vector<int> faces; std::vector<int> colour; std::vector<uint32_t> used(T);
     std::vector<int> order;
+    const int N = C + (F - Fi);
+    std::vector<int> slot_of(N, -1), slot_tile(N, -1);
+    P.halo_start.assign(P.nTiles + 1, 0);
     for (int t = 0; t < P.nTiles; t++) {
         const int c0 = t * T, c1 = std::min(C, c0 + T);
         faces.clear();
@@ -163,15 +168,25 @@ TilePlan build_tile_plan(int C, int Fi, int F, const int* owner, const int* neig
         order.resize(faces.size());
         std::iota(order.begin(), order.end(), 0);
         std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return colour[x] < colour[y]; });
+        int nHalo = 0;
+        auto slot = [&](int cell) {           // cell: NEW index (ghosts >= C)
+            if (cell >= c0 && cell < c1) return cell - c0;
+            if (slot_tile[cell] != t) { slot_tile[cell] = t; slot_of[cell] = T + nHalo++; P.halo_cell.push_back(cell); }
+            return slot_of[cell];
+        };
         for (int i : order) {
             const int f = faces[i];
             if (f < Fi && P.face_old2new[f] < 0) { P.face_old2new[f] = nextFace; P.face_new2old[nextFace] = f; nextFace++; }
             const int a = P.cell_old2new[owner[f]];
-            const int b = f < Fi ? P.cell_old2new[neigh[f]] : -1;
-            const int la = (a >= c0 && a < c1) ? a - c0 : TILE_NONE, lb = (b >= c0 && b < c1) ? b - c0 : TILE_NONE;
+            const int b = f < Fi ? P.cell_old2new[neigh[f]] : neigh[f];
+            if (b < 0 || b >= N) throw std::runtime_error("neighbour out of range");
+            const int la = slot(a), lb = slot(b);
+            if (la >= 1024 || lb >= 1024) throw std::runtime_error("tile halo too large");
             P.ent_face.push_back(P.face_old2new[f]);
             P.ent_loc.push_back(tile_pack(la, lb, colour[i]));
         }
+        P.maxHalo = std::max(P.maxHalo, nHalo);
+        P.halo_start[t + 1] = (int)P.halo_cell.size();
         P.tile_start[t + 1] = (int)P.ent_face.size();
     }
     if (nextFace != Fi) throw std::runtime_error("internal face not reachable from any cell (broken cellFaces)");

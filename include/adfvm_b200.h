@@ -109,7 +109,7 @@ int64_t adfvm_launch_count(adfvm_ctx* ctx);
 int64_t adfvm_device_bytes(adfvm_ctx* ctx);
 
 /* Tiling of the flux kernels (internal data layout): cells are regrouped into tiles of `cells`
- * consecutive cells, one CTA per tile. adfvm_set_tile_cells must precede adfvm_set_mesh (default 128, 32..512).
+ * consecutive cells, one CTA per tile. adfvm_set_tile_cells (64 or 128; default 128, with automatic fallback to 64 on 1-D/2-D meshes) must precede adfvm_set_mesh.
  * adfvm_tile_stats reports flux evaluations per cell (3 = every face once, 6 = cell-centred gather), the largest
  * number of colours of a tile, the number of tiles and the tile size. */
 int adfvm_set_tile_cells(adfvm_ctx* ctx, int32_t cells);

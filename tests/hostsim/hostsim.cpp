@@ -34,7 +34,7 @@ struct HostExec {
         #pragma omp parallel for schedule(static)
         for (int i = 0; i < n; i++) (void)b(i);
     }
-    template <class B> void run_tiles(int nTiles, int, const B& b) {
+    template <class B> void run_tiles(int nTiles, const B& b) {
         #pragma omp parallel for schedule(static)
         for (int t = 0; t < nTiles; t++) b.host_tile(t);
     }
