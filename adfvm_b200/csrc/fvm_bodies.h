@@ -34,7 +34,7 @@ template <typename R> struct PatchDev {
 template <typename R> struct MeshDev {
     int nCells, nFaces, nInternalCells, nInternalFaces, nLocalCells, nRemoteCells, nLocalFaces, nGhostCells;
     int sC, sN, sF;
-    const R *area, *normal, *weight, *delta, *dunit, *linw, *quadw, *vol;
+    const R *area, *normal, *weight, *idelta, *dunit, *linw, *quadw, *vol;   // idelta = 1/deltas
     const int *owner, *neigh, *cellFaces, *cellNbr;
     const unsigned char *cellOwner;      // bit j set: the cell owns its j-th face
     const unsigned char *bpatch;         // [nGhostCells] patch index of each boundary face
@@ -69,7 +69,7 @@ template <typename R> FVM_HD void store_grad(R* G, int sN, int c, const Grad<R>&
 }
 template <typename R> FVM_HD void load_geom(const MeshDev<R>& m, int f, Geom<R>& g) {
     const int s = m.sF;
-    g.area = m.area[f]; g.delta = m.delta[f];
+    g.area = m.area[f]; g.idelta = m.idelta[f];
     for (int k = 0; k < 3; k++) { g.n[k] = m.normal[k * s + f]; g.d[k] = m.dunit[k * s + f]; }
     g.lw[0] = m.linw[f]; g.lw[1] = m.linw[s + f];
     for (int k = 0; k < 3; k++) { g.qw[0][k] = m.quadw[k * s + f]; g.qw[1][k] = m.quadw[(3 + k) * s + f]; }
@@ -210,7 +210,7 @@ template <typename R> struct ObjectiveBody {
         // drag (reference templates/cylinder_test.py:9-19)
         const int own = m.owner[f];
         R mu = viscosity(ph, Q[3 * m.sN + g]);
-        R mung = mu * (Q[o.dir * m.sN + g] - Q[o.dir * m.sN + own]) / m.delta[f];
+        R mung = mu * (Q[o.dir * m.sN + g] - Q[o.dir * m.sN + own]) * m.idelta[f];
         return (Q[4 * m.sN + g] * m.normal[o.dir * m.sF + f] - mung) * m.area[f];
     }
 };
@@ -226,7 +226,7 @@ template <typename R> FVM_HD void objective_ghost_adj(const Phys<R>& ph, const M
     R Tg = Q[3 * m.sN + g];
     R mu = viscosity(ph, Tg);
     R du = Q[o.dir * m.sN + g] - Q[o.dir * m.sN + own];
-    R A = m.area[f], idel = R(1) / m.delta[f];
+    R A = m.area[f], idel = m.idelta[f];
     qb.p += obja * m.normal[o.dir * m.sF + f] * A;
     qb.U[o.dir] += -obja * mu * idel * A;
     qb.T += -obja * viscosity_dT(ph, Tg, mu) * du * idel * A;
@@ -238,7 +238,7 @@ template <typename R> FVM_HD void objective_owner_adj(const Phys<R>& ph, const M
     const PatchDev<R>& P = m.patches[o.patch];
     if (f < P.startFace || f >= P.startFace + P.nFaces) return;
     R mu = viscosity(ph, Q[3 * m.sN + m.neigh[f]]);
-    qb.U[o.dir] += obja * mu * m.area[f] / m.delta[f];
+    qb.U[o.dir] += obja * mu * m.area[f] * m.idelta[f];
 }
 
 // ========================================================================================== reverse
@@ -403,6 +403,11 @@ template <typename R> struct PrimAdjUpdateBody {
 };
 
 // ------------------------------------------------------------------------------------------ layout helpers
+template <typename R> struct ReciprocalBody {      // x <- 1/x (deltas -> idelta at mesh upload)
+    static constexpr const char* kName = "reciprocal";
+    R* x;
+    FVM_HD void operator()(int i) const { x[i] = R(1) / x[i]; }
+};
 // AoS host layout ([n][d] row-major, what the reference passes) <-> SoA device layout
 // perm (may be NULL = identity): device row i holds host row perm[i] (tile renumbering of cells / internal faces)
 template <typename R> struct AosToSoaBody {

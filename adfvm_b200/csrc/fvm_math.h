@@ -33,12 +33,54 @@ enum FaceKind { FACE_COUPLED = 0,        // internal, cyclic, processor: reconst
 template <typename R> struct Phys {
     R gamma, Cp, Pr, Cv, small;   // small = config.SMALL (1e-30 fp64 / 1e-9 fp32, adFVM/config.py:171-178)
     R mu_value;
+    R gm1, iCv, iCvgm1, g_gm1, CpPr;   // gamma-1, 1/Cv, 1/(Cv (gamma-1)), gamma/(gamma-1), Cp/Pr (set_physics)
     int mu_law, riemann, boundary_riemann;
 };
 
+// Reciprocal and reciprocal square root without the IEEE-division slow path. The flux kernels are bound by
+// instruction issue, and an fp64 `a/b` costs ~18 SASS instructions + a divergent fix-up branch; MUFU.RCP64H /
+// MUFU.RSQ64H seeds (rel. error 1e-6, measured) + two Newton steps reach 1.1e-16 / 3.7e-16 (tools/rcp_test.cu),
+// i.e. the last bit or two, in 5 / 9 instructions. fp32 uses the MUFU result directly (1e-7, within the stated
+// fp32 tolerance). Arguments on this path are physical quantities (rho, T, p, a^2, V, ...): positive, normal.
+// The CPU build (tests/hostsim) uses plain division.
+FVM_HD double rcp(double x) {
+#if defined(__CUDA_ARCH__)
+    double y; asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    double e = fma(-x, y, 1.0); y = fma(y, e, y);
+    e = fma(-x, y, 1.0); y = fma(y, e, y);
+    return y;
+#else
+    return 1.0 / x;
+#endif
+}
+FVM_HD float rcp(float x) {
+#if defined(__CUDA_ARCH__)
+    float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y;
+#else
+    return 1.0f / x;
+#endif
+}
+FVM_HD double rsqrt_fast(double x) {
+#if defined(__CUDA_ARCH__)
+    double y; asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    double e = fma(-x * y, y, 1.0); y = fma(0.5 * y, e, y);
+    e = fma(-x * y, y, 1.0); y = fma(0.5 * y, e, y);
+    return y;
+#else
+    return 1.0 / sqrt(x);
+#endif
+}
+FVM_HD float rsqrt_fast(float x) {
+#if defined(__CUDA_ARCH__)
+    float y; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y;
+#else
+    return 1.0f / sqrtf(x);
+#endif
+}
+
 template <typename R> struct Prim  { R U[3], T, p; };
 template <typename R> struct Grad  { R U[9], T[3], p[3]; };   // U[3*i+j] = dU_i/dx_j
-template <typename R> struct Geom  { R area, n[3], delta, d[3], lw[2], qw[2][3]; };
+template <typename R> struct Geom  { R area, n[3], idelta, d[3], lw[2], qw[2][3]; };   // idelta = 1/deltas
 template <typename R> struct Flux5 { R rho, rhoU[3], rhoE; };
 
 template <typename R> FVM_HD R sgn_ref(R x) { return x < R(0) ? R(-1) : R(1); }   // scalar.py:209-212
@@ -50,31 +92,31 @@ template <typename R> FVM_HD void zero(Grad<R>& g) {
 }
 
 template <typename R> FVM_HD R viscosity(const Phys<R>& ph, R T) {
-    if (ph.mu_law == MU_SUTHERLAND) return R(1.4792e-06) * T * sqrt(T) / (T + R(116.));   // density.py:27
+    if (ph.mu_law == MU_SUTHERLAND) return R(1.4792e-06) * T * (T * rsqrt_fast(T)) * rcp(T + R(116.));   // density.py:27
     return ph.mu_value;
 }
 template <typename R> FVM_HD R viscosity_dT(const Phys<R>& ph, R T, R mu) {
-    if (ph.mu_law == MU_SUTHERLAND) return mu * (R(1.5) / T - R(1) / (T + R(116.)));
+    if (ph.mu_law == MU_SUTHERLAND) return mu * (R(1.5) * rcp(T) - rcp(T + R(116.)));
     return R(0);
 }
 
 // ---------------------------------------------------------------- cell: conservative -> primitive
 template <typename R> FVM_HD void primitive(const Phys<R>& ph, R rho, const R* rhoU, R rhoE, Prim<R>& q) {
-    R ir = R(1) / rho;
+    R ir = rcp(rho);
     q.U[0] = rhoU[0] * ir; q.U[1] = rhoU[1] * ir; q.U[2] = rhoU[2] * ir;
     R e = rhoE * ir - R(0.5) * dot3(q.U, q.U);
-    q.p = (ph.gamma - R(1)) * rho * e;
-    q.T = e * (R(1) / ph.Cv);
+    q.p = ph.gm1 * rho * e;
+    q.T = e * ph.iCv;
 }
 // reverse: given qb (adjoint of U,T,p) accumulate into (rhob, rhoUb, rhoEb)
 template <typename R> FVM_HD void primitive_vjp(const Phys<R>& ph, R rho, const R* rhoU, R rhoE, const Prim<R>& qb,
                                                 R& rhob, R* rhoUb, R& rhoEb) {
-    R ir = R(1) / rho;
+    R ir = rcp(rho);
     R U[3] = {rhoU[0] * ir, rhoU[1] * ir, rhoU[2] * ir};
     R E = rhoE * ir;
     R e = E - R(0.5) * dot3(U, U);
-    R eb = qb.p * (ph.gamma - R(1)) * rho + qb.T / ph.Cv;
-    R rb = qb.p * (ph.gamma - R(1)) * e;
+    R eb = qb.p * ph.gm1 * rho + qb.T * ph.iCv;
+    R rb = qb.p * ph.gm1 * e;
     R Eb = eb;
     R Ub[3];
     for (int i = 0; i < 3; i++) Ub[i] = qb.U[i] - eb * U[i];
@@ -85,10 +127,12 @@ template <typename R> FVM_HD void primitive_vjp(const Phys<R>& ph, R rho, const 
 }
 
 // ---------------------------------------------------------------- face: primitive -> conservative
-template <typename R> struct Cons { R rho, rhoU[3], rhoE; };
+template <typename R> struct Cons { R rho, rhoU[3], rhoE, iT, irho; };   // iT = 1/T, irho = 1/rho (shared reciprocals)
 template <typename R> FVM_HD void conservative(const Phys<R>& ph, const Prim<R>& q, Cons<R>& w) {
     R e = ph.Cv * q.T;
-    w.rho = q.p / (e * (ph.gamma - R(1)));
+    w.iT = rcp(q.T);
+    w.rho = q.p * w.iT * ph.iCvgm1;                  // p / (Cv T (gamma-1))
+    w.irho = rcp(w.rho);
     w.rhoE = w.rho * (e + R(0.5) * dot3(q.U, q.U));
     for (int i = 0; i < 3; i++) w.rhoU[i] = q.U[i] * w.rho;
 }
@@ -99,8 +143,8 @@ template <typename R> FVM_HD void conservative_vjp(const Phys<R>& ph, const Prim
     R eb = wb.rhoE * w.rho;
     for (int i = 0; i < 3; i++) qb.U[i] += wb.rhoE * w.rho * q.U[i] + wb.rhoU[i] * w.rho;
     // rho = p/(e (g-1))
-    qb.p += rb / (e * (ph.gamma - R(1)));
-    eb += -rb * w.rho / e;
+    qb.p += rb * w.iT * ph.iCvgm1;
+    eb += -rb * w.rho * w.iT * ph.iCv;
     qb.T += eb * ph.Cv;
 }
 
@@ -125,50 +169,56 @@ template <typename R> FVM_HD void reconstruct_vjp(const Prim<R>& Fb, R lw, const
 // ---------------------------------------------------------------- Roe flux (riemann.py:21-70)
 // Forward intermediates needed by the reverse sweep are kept in this struct.
 template <typename R> struct RoeTmp {
-    R unL, unR, mL, mR, hL, hR, sL, sR, dv, Ut[3], ht, qt, a2, a, unt, dr, dU[3], dE;
-    R l1, l2, l3, e1, e2, cL, cR, eps, l1p, l2p, l3p; bool c1, c2, c3;
+    R unL, unR, mL, mR, hL, hR, sL, sR, rsL, rsR, idv, Ut[3], ht, qt, a2, a, ia, unt, dr, dU[3], dE;
+    R l1, l2, l3, e1, e2, cL, cR, icL, icR, eps, ie, l1p, l2p, l3p; bool c1, c2, c3;
     R b1, b2, b3, b4, b5, b6, b7;
 };
 
 template <typename R>
 FVM_HD void roe_forward(const Phys<R>& ph, const Prim<R>& L, const Prim<R>& Rr, const Cons<R>& wL, const Cons<R>& wR,
                         const R* N, Flux5<R>& F, RoeTmp<R>& t) {
-    const R g = ph.gamma, gm1 = ph.gamma - R(1);
-    const R rL = wL.rho, rR = wR.rho;
+    const R g = ph.gamma, gm1 = ph.gm1;
+    const R rL = wL.rho, rR = wR.rho, irL = wL.irho, irR = wR.irho;
     t.unL = dot3(L.U, N); t.unR = dot3(Rr.U, N);
     t.mL = rL * t.unL; t.mR = rR * t.unR;
-    t.hL = g * L.p / (gm1 * rL) + R(0.5) * dot3(L.U, L.U);
-    t.hR = g * Rr.p / (gm1 * rR) + R(0.5) * dot3(Rr.U, Rr.U);
+    t.hL = ph.g_gm1 * L.p * irL + R(0.5) * dot3(L.U, L.U);
+    t.hR = ph.g_gm1 * Rr.p * irR + R(0.5) * dot3(Rr.U, Rr.U);
     F.rho = R(0.5) * (t.mL + t.mR);
     for (int i = 0; i < 3; i++) F.rhoU[i] = R(0.5) * (t.mL * L.U[i] + t.mR * Rr.U[i] + (L.p + Rr.p) * N[i]);
     F.rhoE = R(0.5) * (t.mL * t.hL + t.mR * t.hR);
-    t.sL = sqrt(rL); t.sR = sqrt(rR); t.dv = t.sL + t.sR;
-    for (int i = 0; i < 3; i++) t.Ut[i] = (L.U[i] * t.sL + Rr.U[i] * t.sR) / t.dv;
-    t.ht = (t.hL * t.sL + t.hR * t.sR) / t.dv;
+    t.rsL = rsqrt_fast(rL); t.rsR = rsqrt_fast(rR);
+    t.sL = rL * t.rsL; t.sR = rR * t.rsR;
+    t.idv = rcp(t.sL + t.sR);
+    for (int i = 0; i < 3; i++) t.Ut[i] = (L.U[i] * t.sL + Rr.U[i] * t.sR) * t.idv;
+    t.ht = (t.hL * t.sL + t.hR * t.sR) * t.idv;
     t.qt = R(0.5) * dot3(t.Ut, t.Ut);
     t.a2 = gm1 * (t.ht - t.qt);
-    t.a = sqrt(t.a2);
+    t.ia = rsqrt_fast(t.a2);
+    t.a = t.a2 * t.ia;
     t.unt = dot3(t.Ut, N);
     t.dr = rR - rL;
     for (int i = 0; i < 3; i++) t.dU[i] = rR * Rr.U[i] - rL * L.U[i];
     t.dE = (t.hR * rR - Rr.p) - (t.hL * rL - L.p);
     t.l1 = fabs(t.unt); t.l2 = fabs(t.unt + t.a); t.l3 = fabs(t.unt - t.a);
-    t.e1 = t.mL / rL - t.mR / rR;
-    t.cL = sqrt(g * L.p / rL); t.cR = sqrt(g * Rr.p / rR);
+    t.e1 = t.mL * irL - t.mR * irR;
+    const R xL = g * L.p * irL, xR = g * Rr.p * irR;
+    t.icL = rsqrt_fast(xL); t.icR = rsqrt_fast(xR);
+    t.cL = xL * t.icL; t.cR = xR * t.icR;
     t.e2 = t.cL - t.cR;
     R eps = R(0.5) * fabs(t.e1) + R(0.5) * fabs(t.e2);
     t.eps = (eps < R(0)) ? eps - ph.small : eps + ph.small;            // Tensor.stabilise
     t.c1 = t.l1 < R(2) * t.eps; t.c2 = t.l2 < R(2) * t.eps; t.c3 = t.l3 < R(2) * t.eps;
-    t.l1p = t.c1 ? R(.25) * t.l1 * t.l1 / t.eps + t.eps : t.l1;
-    t.l2p = t.c2 ? R(.25) * t.l2 * t.l2 / t.eps + t.eps : t.l2;
-    t.l3p = t.c3 ? R(.25) * t.l3 * t.l3 / t.eps + t.eps : t.l3;
+    t.ie = (t.c1 || t.c2 || t.c3) ? rcp(t.eps) : R(0);                 // Harten fix is rarely active
+    t.l1p = t.c1 ? R(.25) * t.l1 * t.l1 * t.ie + t.eps : t.l1;
+    t.l2p = t.c2 ? R(.25) * t.l2 * t.l2 * t.ie + t.eps : t.l2;
+    t.l3p = t.c3 ? R(.25) * t.l3 * t.l3 * t.ie + t.eps : t.l3;
     t.b1 = R(0.5) * (t.l2p + t.l3p);
     t.b2 = R(0.5) * (t.l2p - t.l3p);
     t.b3 = t.b1 - t.l1p;
     t.b4 = gm1 * (t.qt * t.dr - dot3(t.Ut, t.dU) + t.dE);
     t.b5 = t.unt * t.dr - dot3(t.dU, N);
-    t.b6 = t.b3 * t.b4 / t.a2 - t.b2 * t.b5 / t.a;
-    t.b7 = t.b3 * t.b5 - t.b2 * t.b4 / t.a;
+    t.b6 = t.b3 * t.b4 * (t.ia * t.ia) - t.b2 * t.b5 * t.ia;
+    t.b7 = t.b3 * t.b5 - t.b2 * t.b4 * t.ia;
     F.rho -= R(0.5) * (t.l1p * t.dr + t.b6);
     for (int i = 0; i < 3; i++) F.rhoU[i] -= R(0.5) * (t.l1p * t.dU[i] + t.Ut[i] * t.b6 - t.b7 * N[i]);
     F.rhoE -= R(0.5) * (t.l1p * t.dE + t.ht * t.b6 - t.unt * t.b7);
@@ -178,8 +228,8 @@ FVM_HD void roe_forward(const Phys<R>& ph, const Prim<R>& L, const Prim<R>& Rr, 
 template <typename R>
 FVM_HD void roe_reverse(const Phys<R>& ph, const Prim<R>& L, const Prim<R>& Rr, const Cons<R>& wL, const Cons<R>& wR,
                         const R* N, const RoeTmp<R>& t, const Flux5<R>& Fb, Prim<R>& Lb, Prim<R>& Rb, R& rLb_out, R& rRb_out) {
-    const R g = ph.gamma, gm1 = ph.gamma - R(1);
-    const R rL = wL.rho, rR = wR.rho;
+    const R g = ph.gamma, gm1 = ph.gm1;
+    const R rL = wL.rho, rR = wR.rho, irL = wL.irho, irR = wR.irho;
     const R h = R(0.5);
     R rLb = R(0), rRb = R(0), pLb = R(0), pRb = R(0), ULb[3] = {0, 0, 0}, URb[3] = {0, 0, 0};
     // ---- dissipation
@@ -194,7 +244,7 @@ FVM_HD void roe_reverse(const Phys<R>& ph, const Prim<R>& L, const Prim<R>& Rr, 
     R htb = -h * Fb.rhoE * t.b6;
     R untb = h * Fb.rhoE * t.b7;
     // b7 = b3*b5 - b2*b4/a ; b6 = b3*b4/a2 - b2*b5/a
-    R ia = R(1) / t.a, ia2 = R(1) / t.a2;
+    R ia = t.ia, ia2 = t.ia * t.ia;
     R b3b = b7b * t.b5 + b6b * t.b4 * ia2;
     R b5b = b7b * t.b3 - b6b * t.b2 * ia;
     R b2b = -b7b * t.b4 * ia - b6b * t.b5 * ia;
@@ -213,18 +263,18 @@ FVM_HD void roe_reverse(const Phys<R>& ph, const Prim<R>& L, const Prim<R>& Rr, 
     R l2pb = h * (b3b + b2b), l3pb = h * (b3b - b2b);
     // entropy fix
     R epsb = R(0), l1b, l2b, l3b;
-    R ie = R(1) / t.eps;
+    const R ie = t.ie;
     if (t.c1) { l1b = l1pb * h * t.l1 * ie; epsb += l1pb * (R(1) - R(.25) * t.l1 * t.l1 * ie * ie); } else l1b = l1pb;
     if (t.c2) { l2b = l2pb * h * t.l2 * ie; epsb += l2pb * (R(1) - R(.25) * t.l2 * t.l2 * ie * ie); } else l2b = l2pb;
     if (t.c3) { l3b = l3pb * h * t.l3 * ie; epsb += l3pb * (R(1) - R(.25) * t.l3 * t.l3 * ie * ie); } else l3b = l3pb;
     // eps = .5|e1| + .5|e2| (+- small)
     R e1b = h * epsb * sgn_ref(t.e1), e2b = h * epsb * sgn_ref(t.e2);
     // cL = sqrt(g pL/rL)
-    pLb += e2b * g / (R(2) * t.cL * rL); rLb += -e2b * t.cL / (R(2) * rL);
-    pRb += -e2b * g / (R(2) * t.cR * rR); rRb += e2b * t.cR / (R(2) * rR);
+    pLb += e2b * g * h * t.icL * irL; rLb += -e2b * t.cL * h * irL;
+    pRb += -e2b * g * h * t.icR * irR; rRb += e2b * t.cR * h * irR;
     // e1 = mL/rL - mR/rR
-    R mLb = e1b / rL, mRb = -e1b / rR;
-    rLb += -e1b * t.mL / (rL * rL); rRb += e1b * t.mR / (rR * rR);
+    R mLb = e1b * irL, mRb = -e1b * irR;
+    rLb += -e1b * t.mL * irL * irL; rRb += e1b * t.mR * irR * irR;
     // l1 = |unt|, l2 = |unt+a|, l3 = |unt-a|
     R s1 = sgn_ref(t.unt), s2 = sgn_ref(t.unt + t.a), s3 = sgn_ref(t.unt - t.a);
     untb += l1b * s1 + l2b * s2 + l3b * s3;
@@ -240,14 +290,14 @@ FVM_HD void roe_reverse(const Phys<R>& ph, const Prim<R>& L, const Prim<R>& Rr, 
     htb += gm1 * a2b; qtb += -gm1 * a2b;
     for (int i = 0; i < 3; i++) Utb[i] += untb * N[i] + qtb * t.Ut[i];
     // ht = (hL sL + hR sR)/dv ; Ut = (UL sL + UR sR)/dv
-    R idv = R(1) / t.dv;
+    R idv = t.idv;
     hLb += htb * t.sL * idv; hRb += htb * t.sR * idv;
     R sLb = htb * t.hL * idv + dot3(Utb, L.U) * idv;
     R sRb = htb * t.hR * idv + dot3(Utb, Rr.U) * idv;
     R dvb = -(htb * t.ht + dot3(Utb, t.Ut)) * idv;
     for (int i = 0; i < 3; i++) { ULb[i] += Utb[i] * t.sL * idv; URb[i] += Utb[i] * t.sR * idv; }
     sLb += dvb; sRb += dvb;
-    rLb += sLb * h / t.sL; rRb += sRb * h / t.sR;
+    rLb += sLb * h * t.rsL; rRb += sRb * h * t.rsR;
     // ---- central part
     mLb += h * Fb.rhoE * t.hL + h * dot3(Fb.rhoU, L.U) + h * Fb.rho;
     mRb += h * Fb.rhoE * t.hR + h * dot3(Fb.rhoU, Rr.U) + h * Fb.rho;
@@ -255,8 +305,8 @@ FVM_HD void roe_reverse(const Phys<R>& ph, const Prim<R>& L, const Prim<R>& Rr, 
     for (int i = 0; i < 3; i++) { ULb[i] += h * t.mL * Fb.rhoU[i]; URb[i] += h * t.mR * Fb.rhoU[i]; }
     pLb += h * FUbN; pRb += h * FUbN;
     // hL = g pL/(gm1 rL) + .5 UL.UL
-    pLb += hLb * g / (gm1 * rL); rLb += -hLb * g * L.p / (gm1 * rL * rL);
-    pRb += hRb * g / (gm1 * rR); rRb += -hRb * g * Rr.p / (gm1 * rR * rR);
+    pLb += hLb * ph.g_gm1 * irL; rLb += -hLb * ph.g_gm1 * L.p * irL * irL;
+    pRb += hRb * ph.g_gm1 * irR; rRb += -hRb * ph.g_gm1 * Rr.p * irR * irR;
     for (int i = 0; i < 3; i++) { ULb[i] += hLb * L.U[i]; URb[i] += hRb * Rr.U[i]; }
     // mL = rL*unL ; unL = UL.N
     rLb += mLb * t.unL; rRb += mRb * t.unR;
@@ -272,7 +322,8 @@ FVM_HD void lf_forward(const Phys<R>& ph, const Prim<R>& L, const Prim<R>& Rr, c
                        const R* N, Flux5<R>& F) {
     const R g = ph.gamma, h = R(0.5);
     R unL = dot3(L.U, N), unR = dot3(Rr.U, N);
-    R cL = sqrt(g * L.p / wL.rho), cR = sqrt(g * Rr.p / wR.rho);
+    const R xL = g * L.p * wL.irho, xR = g * Rr.p * wR.irho;
+    R cL = xL * rsqrt_fast(xL), cR = xR * rsqrt_fast(xR);
     R x1 = fabs(unL) + cL, x2 = fabs(unR) + cR;
     R aF = (x1 > x2) ? x1 : x2;
     F.rho = h * (wL.rho * unL + wR.rho * unR) - h * aF * (wR.rho - wL.rho);
@@ -286,7 +337,9 @@ FVM_HD void lf_reverse(const Phys<R>& ph, const Prim<R>& L, const Prim<R>& Rr, c
                        const R* N, const Flux5<R>& Fb, Prim<R>& Lb, Prim<R>& Rb, Cons<R>& wLb, Cons<R>& wRb) {
     const R g = ph.gamma, h = R(0.5);
     R unL = dot3(L.U, N), unR = dot3(Rr.U, N);
-    R cL = sqrt(g * L.p / wL.rho), cR = sqrt(g * Rr.p / wR.rho);
+    const R xL = g * L.p * wL.irho, xR = g * Rr.p * wR.irho;
+    const R icL = rsqrt_fast(xL), icR = rsqrt_fast(xR);
+    R cL = xL * icL, cR = xR * icR;
     R x1 = fabs(unL) + cL, x2 = fabs(unR) + cR;
     bool first = x1 > x2;
     R aF = first ? x1 : x2;
@@ -301,10 +354,10 @@ FVM_HD void lf_reverse(const Phys<R>& ph, const Prim<R>& L, const Prim<R>& Rr, c
     Lb.p += h * FUbN + h * Fb.rhoE * unL; Rb.p += h * FUbN + h * Fb.rhoE * unR;
     if (first) {
         unLb += aFb * sgn_ref(unL);
-        Lb.p += aFb * g / (R(2) * cL * wL.rho); wLb.rho += -aFb * cL / (R(2) * wL.rho);
+        Lb.p += aFb * g * h * icL * wL.irho; wLb.rho += -aFb * cL * h * wL.irho;
     } else {
         unRb += aFb * sgn_ref(unR);
-        Rb.p += aFb * g / (R(2) * cR * wR.rho); wRb.rho += -aFb * cR / (R(2) * wR.rho);
+        Rb.p += aFb * g * h * icR * wR.irho; wRb.rho += -aFb * cR * h * wR.irho;
     }
     for (int i = 0; i < 3; i++) { Lb.U[i] += unLb * N[i]; Rb.U[i] += unRb * N[i]; }
 }
@@ -316,9 +369,9 @@ template <typename R>
 FVM_HD void viscous_forward(const Phys<R>& ph, const Geom<R>& gm, R TL, R TR, const R* UL, const R* UR, R TF, const R* UF,
                             const R* gTF, const R* gUF, Flux5<R>& F) {
     R mu = viscosity(ph, TF);
-    R kappa = mu * (ph.Cp / ph.Pr);
+    R kappa = mu * ph.CpPr;
     const R* D = gm.d; const R* N = gm.n;
-    R idel = R(1) / gm.delta;
+    R idel = gm.idelta;
     R gT[3], gU[9];
     R snT = (TR - TL) * idel, gTD = dot3(gTF, D);
     for (int j = 0; j < 3; j++) gT[j] = gTF[j] + snT * D[j] - gTD * D[j];
@@ -343,10 +396,10 @@ FVM_HD void viscous_reverse(const Phys<R>& ph, const Geom<R>& gm, R TL, R TR, co
                             const R* gTF, const R* gUF, const Flux5<R>& Fb,
                             R& TLb, R& TRb, R* ULb, R* URb, R& TFb, R* UFb, R* gTFb, R* gUFb) {
     R mu = viscosity(ph, TF);
-    R CpPr = ph.Cp / ph.Pr;
+    R CpPr = ph.CpPr;
     R kappa = mu * CpPr;
     const R* D = gm.d; const R* N = gm.n;
-    R idel = R(1) / gm.delta;
+    R idel = gm.idelta;
     // recompute forward
     R gT[3], gU[9];
     R snT = (TR - TL) * idel, gTD = dot3(gTF, D);
@@ -404,7 +457,7 @@ FVM_HD void face_flux(const Phys<R>& ph, int kind, const Geom<R>& gm, const Prim
         for (int i = 0; i < 3; i++) F.rhoU[i] = w.rhoU[i] * un + qR.p * gm.n[i];
         F.rhoE = (w.rhoE + qR.p) * un;
         viscous_forward(ph, gm, qL.T, qR.T, qL.U, qR.U, qR.T, qR.U, gR.T, gR.U, F);
-        wave = fabs(un) + sqrt(ph.Cp * qR.T * (ph.gamma - R(1)));
+        { const R x = ph.Cp * qR.T * ph.gm1; wave = fabs(un) + x * rsqrt_fast(x); }
         return;
     }
     Prim<R> LF, RF;
@@ -430,7 +483,7 @@ FVM_HD void face_flux(const Phys<R>& ph, int kind, const Geom<R>& gm, const Prim
     if (solver == RIEMANN_ROE) { RoeTmp<R> t; roe_forward(ph, LF, RF, wL, wR, gm.n, F, t); }
     else lf_forward(ph, LF, RF, wL, wR, gm.n, F);
     viscous_forward(ph, gm, qL.T, qR.T, qL.U, qR.U, TF, UF, gTF, gUF, F);
-    wave = fabs(dot3(UF, gm.n)) + sqrt(ph.Cp * TF * (ph.gamma - R(1)));
+    { const R x = ph.Cp * TF * ph.gm1; wave = fabs(dot3(UF, gm.n)) + x * rsqrt_fast(x); }
 }
 
 // Reverse of face_flux w.r.t. (qL, gL, qR, gR) for a given flux adjoint Fb (the wave speed only feeds a

@@ -87,6 +87,8 @@ public:
     }
     void set_physics(double gamma, double Cp, double Pr, int mu_law, double mu_value, int riemann, int briemann) {
         ph.gamma = (R)gamma; ph.Cp = (R)Cp; ph.Pr = (R)Pr; ph.Cv = (R)(Cp / gamma);
+        ph.gm1 = (R)(gamma - 1.); ph.iCv = (R)(gamma / Cp); ph.iCvgm1 = (R)(gamma / (Cp * (gamma - 1.)));
+        ph.g_gm1 = (R)(gamma / (gamma - 1.)); ph.CpPr = (R)(Cp / Pr);
         ph.small = sizeof(R) == 8 ? (R)1e-30 : (R)1e-9;
         ph.mu_law = mu_law; ph.mu_value = (R)mu_value; ph.riemann = riemann; ph.boundary_riemann = briemann;
     }
@@ -119,7 +121,7 @@ public:
         int* d_cperm = dalloc<int>(m.sC); ex.upload(d_cperm, plan.cell_new2old.data(), (size_t)C * 4); m.cell_perm = d_cperm;
         int* d_fperm = (int*)ex.alloc((size_t)(F + 1) * 4); ex.upload(d_fperm, plan.face_new2old.data(), (size_t)F * 4);
         m.area = upload_aos(areas, F, 1, m.sF, nullptr, d_fperm); m.weight = upload_aos(weights, F, 1, m.sF, nullptr, d_fperm);
-        m.delta = upload_aos(deltas, F, 1, m.sF, nullptr, d_fperm); m.normal = upload_aos(normals, F, 3, m.sF, nullptr, d_fperm);
+        { R* idel = upload_aos(deltas, F, 1, m.sF, nullptr, d_fperm); run(F, ReciprocalBody<R>{idel}); m.idelta = idel; } m.normal = upload_aos(normals, F, 3, m.sF, nullptr, d_fperm);
         m.dunit = upload_aos(deltasUnit, F, 3, m.sF, nullptr, d_fperm); m.linw = upload_aos(linearWeights, F, 2, m.sF, nullptr, d_fperm);
         m.quadw = upload_aos(quadraticWeights, F, 6, m.sF, nullptr, d_fperm); m.vol = upload_aos(volumes, C, 1, m.sC, nullptr, d_cperm);
         ex.sync(); ex.free(d_fperm);
