@@ -34,15 +34,15 @@ template <typename R> struct PatchDev {
 template <typename R> struct MeshDev {
     int nCells, nFaces, nInternalCells, nInternalFaces, nLocalCells, nRemoteCells, nLocalFaces, nGhostCells;
     int sC, sN, sF;
-    const R *area, *normal, *weight, *idelta, *dunit, *linw, *quadw, *vol;   // idelta = 1/deltas
+    const R *area, *normal, *weight, *idelta, *vol;   // face-indexed SoA (idelta = 1/deltas); the other flux metrics live in the chunks
     const int *owner, *neigh, *cellFaces, *cellNbr;
     const unsigned char *cellOwner;      // bit j set: the cell owns its j-th face
     const unsigned char *bpatch;         // [nGhostCells] patch index of each boundary face
     const PatchDev<R>* patches;
     int nPatches;
-    // tiles (fvm_tiles.h): tile t owns cells [t*T, min(C,(t+1)*T)) and entries [tile_start[t], tile_start[t+1])
+    // tiles (fvm_tiles.h): tile t owns cells [t*T, min(C,(t+1)*T)) and the per-pass chunks [pass_start[t], pass_start[t+1])
     int T, nTiles;
-    const int* tile_start; const int* ent_face; const unsigned* ent_loc;
+    const int* pass_start; const R* chunks;
     const int* halo_start; const int* halo_cell;    // tile t's halo slots T.. hold cells halo_cell[halo_start[t]..halo_start[t+1])
     const int* cell_perm;                // [C] device cell -> reference (host) cell
 };
@@ -66,13 +66,6 @@ template <typename R> FVM_HD void load_grad(const R* G, int sN, int c, Grad<R>& 
 template <typename R> FVM_HD void store_grad(R* G, int sN, int c, const Grad<R>& g) {
     for (int k = 0; k < 9; k++) G[k * sN + c] = g.U[k];
     for (int k = 0; k < 3; k++) { G[(9 + k) * sN + c] = g.T[k]; G[(12 + k) * sN + c] = g.p[k]; }
-}
-template <typename R> FVM_HD void load_geom(const MeshDev<R>& m, int f, Geom<R>& g) {
-    const int s = m.sF;
-    g.area = m.area[f]; g.idelta = m.idelta[f];
-    for (int k = 0; k < 3; k++) { g.n[k] = m.normal[k * s + f]; g.d[k] = m.dunit[k * s + f]; }
-    g.lw[0] = m.linw[f]; g.lw[1] = m.linw[s + f];
-    for (int k = 0; k < 3; k++) { g.qw[0][k] = m.quadw[k * s + f]; g.qw[1][k] = m.quadw[(3 + k) * s + f]; }
 }
 template <typename R> FVM_HD int face_kind(const MeshDev<R>& m, int f) {
     return f < m.nInternalFaces ? (int)FACE_COUPLED : m.patches[m.bpatch[f - m.nInternalFaces]].kind;

@@ -25,7 +25,7 @@ template <class Body> __global__ void __launch_bounds__(kBlock) k_run_discard(co
     if (i < n) (void)b(i);
 }
 
-template <class Body> __global__ void __launch_bounds__(kBlock) k_tile(const Body b) {
+template <class Body> __global__ void __launch_bounds__(Body::kThreads) k_tile(const Body b) {
     extern __shared__ __align__(16) unsigned char tile_smem[];
     b.device_tile(blockIdx.x, tile_smem);
 }
@@ -133,7 +133,7 @@ struct CudaExec {
             configured = smem;
         }
         tic(Body::kName);
-        k_tile<Body><<<nTiles, kBlock, smem, stream>>>(b);
+        k_tile<Body><<<nTiles, Body::kThreads, smem, stream>>>(b);
         toc();
         FVM_CUDA_CHECK(cudaPeekAtLastError());
     }

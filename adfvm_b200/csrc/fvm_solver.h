@@ -59,7 +59,8 @@ public:
     R *sendbuf = 0, *recvbuf = 0, *stage_aos = 0;
     int *bcells = 0; int nBcells = 0;
     TilePlan plan; int tile_cells = 128; R* tile_partial = 0; double tile_evals_per_cell = 0; int tile_colours = 0, tile_max_halo = 0;
-    enum { kHalo128 = 256, kHalo64 = 384 };   // halo slots of the two tile-kernel instantiations (T=128: TS=384, T=64: TS=448)
+    enum { kHalo128 = 256, kHalo64 = 384, kTileThreads = 128,
+           kRowSlack = 128 };   // the tile kernels bulk-copy whole T-cell rows: the last tile may read past the last row   // halo slots of the two tile-kernel instantiations (T=128: TS=384, T=64: TS=448)
     bool have_mesh = false, have_state = false, adjoint_ready = false;
     std::vector<void*> owned;                 // everything to free
 
@@ -114,16 +115,35 @@ public:
         // ---- tile plan: renumber internal cells and internal faces (fvm_tiles.h); ghosts and boundary faces keep their ids
         // 128-cell tiles with room for 256 halo slots; meshes with many ghost cells per cell (1-D / 2-D cases, whose
         // "empty" patches give every cell 2-4 boundary faces) fall back to 64-cell tiles, whose halo always fits
-        plan = build_tile_plan<R>(C, Fi, F, owner, neighbour, cellFaces, deltas, deltasUnit, tile_cells);
-        if (tile_cells == 128 && plan.maxHalo > kHalo128) plan = build_tile_plan<R>(C, Fi, F, owner, neighbour, cellFaces, deltas, deltasUnit, 64);
+        std::vector<unsigned char> bkind(F - Fi + 1, (unsigned char)FACE_BOUNDARY);
+        for (const PatchHost& h : patches_in) {
+            if (h.nFaces && (h.startFace < Fi || h.startFace + h.nFaces > F)) throw std::runtime_error("patch face range out of bounds");
+            const bool coupled = (h.meshType == 1 || h.meshType == 5 || h.meshType == 6);
+            const unsigned char k = coupled ? FACE_COUPLED : (h.meshType == 4 ? FACE_CHARACTERISTIC : FACE_BOUNDARY);
+            for (int i = 0; i < h.nFaces; i++) bkind[h.startFace - Fi + i] = k;
+        }
+        plan = build_tile_plan<R>(C, Fi, F, owner, neighbour, cellFaces, deltas, deltasUnit, bkind.data(), tile_cells, kTileThreads);
+        if (tile_cells == 128 && plan.maxHalo > kHalo128)
+            plan = build_tile_plan<R>(C, Fi, F, owner, neighbour, cellFaces, deltas, deltasUnit, bkind.data(), 64, kTileThreads);
         if (plan.T == 64 && plan.maxHalo > kHalo64) throw std::runtime_error("tile halo exceeds the kernel's capacity");
         m.T = plan.T; m.nTiles = plan.nTiles;
         int* d_cperm = dalloc<int>(m.sC); ex.upload(d_cperm, plan.cell_new2old.data(), (size_t)C * 4); m.cell_perm = d_cperm;
         int* d_fperm = (int*)ex.alloc((size_t)(F + 1) * 4); ex.upload(d_fperm, plan.face_new2old.data(), (size_t)F * 4);
         m.area = upload_aos(areas, F, 1, m.sF, nullptr, d_fperm); m.weight = upload_aos(weights, F, 1, m.sF, nullptr, d_fperm);
         { R* idel = upload_aos(deltas, F, 1, m.sF, nullptr, d_fperm); run(F, ReciprocalBody<R>{idel}); m.idelta = idel; } m.normal = upload_aos(normals, F, 3, m.sF, nullptr, d_fperm);
-        m.dunit = upload_aos(deltasUnit, F, 3, m.sF, nullptr, d_fperm); m.linw = upload_aos(linearWeights, F, 2, m.sF, nullptr, d_fperm);
-        m.quadw = upload_aos(quadraticWeights, F, 6, m.sF, nullptr, d_fperm); m.vol = upload_aos(volumes, C, 1, m.sC, nullptr, d_cperm);
+        m.vol = upload_aos(volumes, C, 1, m.sC, nullptr, d_cperm);
+        {   // per-pass metric chunks of the flux kernels, gathered on the device from temporary face-indexed arrays
+            R* t_dunit = (R*)ex.alloc((size_t)3 * m.sF * sizeof(R)); upload_aos(deltasUnit, F, 3, m.sF, t_dunit, d_fperm);
+            R* t_linw = (R*)ex.alloc((size_t)2 * m.sF * sizeof(R)); upload_aos(linearWeights, F, 2, m.sF, t_linw, d_fperm);
+            R* t_quadw = (R*)ex.alloc((size_t)6 * m.sF * sizeof(R)); upload_aos(quadraticWeights, F, 6, m.sF, t_quadw, d_fperm);
+            const size_t nslots = plan.ent_face.size();
+            int* t_face = (int*)ex.alloc((nslots + 1) * 4); ex.upload(t_face, plan.ent_face.data(), nslots * 4);
+            unsigned* t_word = (unsigned*)ex.alloc((nslots + 1) * 4); ex.upload(t_word, plan.ent_loc.data(), nslots * 4);
+            R* d_chunks = dalloc<R>((nslots / kTileThreads) * (size_t)Chunk<R, kTileThreads>::kScalars + 16);
+            run((int)nslots, FillChunksBody<R, kTileThreads>{t_face, t_word, m.sF, m.area, m.normal, m.idelta, t_dunit, t_linw, t_quadw, d_chunks});
+            m.chunks = d_chunks;
+            ex.sync(); ex.free(t_dunit); ex.free(t_linw); ex.free(t_quadw); ex.free(t_face); ex.free(t_word);
+        }
         ex.sync(); ex.free(d_fperm);
         auto newcell = [&](int c) { return c < C ? plan.cell_old2new[c] : c; };
         {
@@ -160,9 +180,7 @@ public:
         nBcells = (int)bc_list.size();
         bcells = dalloc<int>(nBcells + 1); ex.upload(bcells, bc_list.data(), (size_t)nBcells * 4);
         {
-            int* d_ts = dalloc<int>(plan.tile_start.size()); ex.upload(d_ts, plan.tile_start.data(), plan.tile_start.size() * 4); m.tile_start = d_ts;
-            int* d_ef = dalloc<int>(plan.ent_face.size() + 1); ex.upload(d_ef, plan.ent_face.data(), plan.ent_face.size() * 4); m.ent_face = d_ef;
-            unsigned* d_el = dalloc<unsigned>(plan.ent_loc.size() + 1); ex.upload(d_el, plan.ent_loc.data(), plan.ent_loc.size() * 4); m.ent_loc = d_el;
+            int* d_ps = dalloc<int>(plan.pass_start.size()); ex.upload(d_ps, plan.pass_start.data(), plan.pass_start.size() * 4); m.pass_start = d_ps;
             int* d_hs = dalloc<int>(plan.halo_start.size()); ex.upload(d_hs, plan.halo_start.data(), plan.halo_start.size() * 4); m.halo_start = d_hs;
             int* d_hc = dalloc<int>(plan.halo_cell.size() + 1); ex.upload(d_hc, plan.halo_cell.data(), plan.halo_cell.size() * 4); m.halo_cell = d_hc;
             tile_partial = dalloc<R>(plan.nTiles + 1);
@@ -201,8 +219,8 @@ public:
         push_patches();
         // state + work buffers
         for (int k = 0; k < 4; k++) W[k] = dalloc<R>((size_t)5 * m.sC);
-        for (int k = 0; k < 2; k++) Q[k] = dalloc<R>((size_t)5 * m.sN);
-        G[0] = dalloc<R>((size_t)15 * m.sN);
+        for (int k = 0; k < 2; k++) Q[k] = dalloc<R>((size_t)5 * m.sN + kRowSlack);
+        G[0] = dalloc<R>((size_t)15 * m.sN + kRowSlack);
         S = dalloc<R>((size_t)5 * m.sC);
         red = dalloc<R>(8);
         stage_aos = dalloc<R>((size_t)5 * m.sC);
@@ -317,7 +335,7 @@ public:
     }
 
     template <int T, int TS> void run_flux_tile(int s, R dt, R* Qs, R* Gs, R* Qnext, bool want_dtc_obj) {
-        FluxTileBody<R, T, TS> fb;
+        FluxTileBody<R, T, TS, kTileThreads> fb;
         fb.ph = ph; fb.m = m; fb.Q = Qs; fb.G = Gs;
         fb.W0 = W[0]; fb.W1 = RK_ALPHA[s][1] != 0. ? W[1] : nullptr; fb.W2 = RK_ALPHA[s][2] != 0. ? W[2] : nullptr;
         fb.a0 = (R)RK_ALPHA[s][0]; fb.a1 = (R)RK_ALPHA[s][1]; fb.a2 = (R)RK_ALPHA[s][2];
@@ -349,8 +367,8 @@ public:
 
     void ensure_adjoint_buffers() {
         if (adjoint_ready) return;
-        Q[2] = dalloc<R>((size_t)5 * m.sN);
-        G[1] = dalloc<R>((size_t)15 * m.sN); G[2] = dalloc<R>((size_t)15 * m.sN);
+        Q[2] = dalloc<R>((size_t)5 * m.sN + kRowSlack);
+        G[1] = dalloc<R>((size_t)15 * m.sN + kRowSlack); G[2] = dalloc<R>((size_t)15 * m.sN + kRowSlack);
         for (int k = 0; k < 4; k++) A[k] = dalloc<R>((size_t)5 * m.sC);
         Qb = dalloc<R>((size_t)5 * m.sN); Gb = dalloc<R>((size_t)15 * m.sN);
         Sb = dalloc<R>((size_t)5 * m.sC);
@@ -373,8 +391,8 @@ public:
         const int C = m.nInternalCells;
         for (int s = 2; s >= 0; s--) {
             const R coef = (R)(-RK_BETA[s]) * dt;
-            if (m.T == 128) ex.run_tiles(m.nTiles, FluxGradTileBody<R, 128, 128 + kHalo128>{ph, m, Q[s], G[s], A[s + 1], coef, Qb, Gb});
-            else ex.run_tiles(m.nTiles, FluxGradTileBody<R, 64, 64 + kHalo64>{ph, m, Q[s], G[s], A[s + 1], coef, Qb, Gb});
+            if (m.T == 128) ex.run_tiles(m.nTiles, FluxGradTileBody<R, 128, 128 + kHalo128, kTileThreads>{ph, m, Q[s], G[s], A[s + 1], coef, Qb, Gb});
+            else ex.run_tiles(m.nTiles, FluxGradTileBody<R, 64, 64 + kHalo64, kTileThreads>{ph, m, Q[s], G[s], A[s + 1], coef, Qb, Gb});
             launches++;
             const R* rG = halo_reverse(Gb, 15);
             run(nBcells, GhostGradAdjBody<R>{m, bcells, Gb, rG});

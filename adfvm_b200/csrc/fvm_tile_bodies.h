@@ -7,15 +7,18 @@
 //   flux_grad_tile  reverse of the flux + scatter: VJP of every face once, both sides' shares summed into
 //                   shared-memory accumulators; ghost rows of boundary faces written directly (exclusive writer).
 //
-// Shared memory of a CTA (R = scalar):
-//   qg  [20][TS]  U(3),T,p and the 15 gradient components of the tile's own cells (slots [0,T), coalesced rows of the
-//                 SoA arrays) and of its halo (slots [T, T+nHalo): cells of other tiles / ghost cells, gathered once)
-//   forward:  ivol [T] 1/V, acc [6][T] residual(5) + dtc          reverse:  r [5][TS] = abar*coef/V, acc [20][T]
-// so the per-face code reads both of its cells from shared memory with compile-time strides and no branches.
+// Data movement of one CTA (R = scalar, W = threads = face entries per pass):
+//   * face metrics live in HBM as per-pass CHUNKS [16][W] R + [W] u32 (area, n, 1/delta, dUnit, linW, quadW and the
+//     packed entry word), laid out in the order the tile consumes them; one cp.async.bulk (TMA engine, SASS UBLKCP)
+//     per pass streams a chunk into shared memory, completion on an mbarrier, issued one pass ahead of its use;
+//   * qg [20][TS]: U(3),T,p and the 15 gradient components of the tile's own cells (slots [0,T): 20 bulk row copies of
+//     the SoA arrays) and of its halo (slots [T,T+nHalo): cells of other tiles / ghost cells, gathered once);
+//   * forward:  ivol [T] 1/V, acc [6][T] residual(5) + dtc          reverse:  r [5][TS] = abar*coef/V, acc [20][T].
+// The per-face code therefore touches shared memory only, with compile-time strides and no branches on residency.
 //
 // Scatter order: entries are sorted by colour, faces of one colour never share an in-tile cell, and colours are
 // applied one after the other (barrier in between) -> every cell receives its contributions in entry order.
-// The CPU simulator (tests/hostsim) runs the same stage/face/scatter/finish functions over the entries sequentially,
+// The CPU simulator (tests/hostsim) runs the same face/scatter/finish functions over the entries sequentially,
 // which is the same order.
 #pragma once
 #include "fvm_bodies.h"
@@ -25,12 +28,25 @@
 
 namespace fvm {
 
-template <typename R> FVM_HD void tile_entry(const MeshDev<R>& m, int e, int& f, int& lo, int& ln, int& col) {
-    f = m.ent_face[e];
-    const unsigned w = m.ent_loc[e];
-    lo = (int)(w & 0x3FFu); ln = (int)((w >> 10) & 0x3FFu); col = (int)(w >> 20);
-}
+// scalars per chunk: 16 metric rows of W + W packed u32 words
+template <typename R, int W> struct Chunk {
+    static constexpr int kScalars = 16 * W + (W * 4) / (int)sizeof(R);
+    static constexpr int kBytes = kScalars * (int)sizeof(R);
+    FVM_HD static const unsigned* words(const R* chunk) { return reinterpret_cast<const unsigned*>(chunk + 16 * W); }
+    FVM_HD static unsigned* words(R* chunk) { return reinterpret_cast<unsigned*>(chunk + 16 * W); }
+};
 
+struct TileEntry { int lo, ln, col, kind; bool valid; };
+FVM_HD void tile_decode(unsigned w, TileEntry& e) {
+    e.lo = (int)(w & 0x3FFu); e.ln = (int)((w >> 10) & 0x3FFu); e.col = (int)((w >> 20) & 0x1Fu);
+    e.kind = (int)((w >> 25) & 3u); e.valid = ((w >> 27) & 1u) != 0;
+}
+template <typename R, int W> FVM_HD void tile_load_geom(const R* chunk, int i, Geom<R>& g) {
+    const R* p = chunk + i;
+    g.area = p[0]; g.n[0] = p[W]; g.n[1] = p[2 * W]; g.n[2] = p[3 * W]; g.idelta = p[4 * W];
+    g.d[0] = p[5 * W]; g.d[1] = p[6 * W]; g.d[2] = p[7 * W]; g.lw[0] = p[8 * W]; g.lw[1] = p[9 * W];
+    for (int k = 0; k < 3; k++) { g.qw[0][k] = p[(10 + k) * W]; g.qw[1][k] = p[(13 + k) * W]; }
+}
 template <typename R, int TS> FVM_HD void tile_load_cell(const R* qg, int l, Prim<R>& q, Grad<R>& g) {
     const R* p = qg + l;
     q.U[0] = p[0]; q.U[1] = p[TS]; q.U[2] = p[2 * TS]; q.T = p[3 * TS]; q.p = p[4 * TS];
@@ -42,7 +58,55 @@ template <typename R, int TS> FVM_HD void tile_stage_cell(R* qg, int slot, const
     for (int k = 0; k < 15; k++) qg[(5 + k) * TS + slot] = G[(long)k * sN + cell];
 }
 
+// fills the chunks from the face-indexed metric arrays (mesh upload, one-off): slot i of the global slot list
+template <typename R, int W> struct FillChunksBody {
+    static constexpr const char* kName = "fill_chunks";
+    const int* slot_face; const unsigned* slot_word; int sF;
+    const R *area, *normal, *idelta, *dunit, *linw, *quadw;
+    R* chunks;
+    FVM_HD void operator()(int i) const {
+        R* c = chunks + (long)(i / W) * Chunk<R, W>::kScalars;
+        const int l = i % W, f = slot_face[i];
+        Chunk<R, W>::words(c)[l] = slot_word[i];
+        R v[16];
+        if (f >= 0) {
+            v[0] = area[f]; v[4] = idelta[f];
+            for (int k = 0; k < 3; k++) { v[1 + k] = normal[(long)k * sF + f]; v[5 + k] = dunit[(long)k * sF + f]; }
+            v[8] = linw[f]; v[9] = linw[(long)sF + f];
+            for (int k = 0; k < 6; k++) v[10 + k] = quadw[(long)k * sF + f];
+        } else {
+            for (int k = 0; k < 16; k++) v[k] = R(0);
+        }
+        for (int k = 0; k < 16; k++) c[k * W + l] = v[k];
+    }
+};
+
 #if defined(__CUDACC__)
+// ---- mbarrier / bulk-copy primitives (PTX; SASS: SYNCS.*, UBLKCP)
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, unsigned bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+    unsigned ok;
+    do {
+        asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
 template <typename R> __device__ __forceinline__ R block_max(R v, R* scratch /* >= 32 */) {
     for (int o = 16; o > 0; o >>= 1) { R x = __shfl_down_sync(0xffffffffu, v, o); v = x > v ? x : v; }
     const int w = threadIdx.x >> 5, l = threadIdx.x & 31, nw = (blockDim.x + 31) >> 5;
@@ -55,20 +119,41 @@ template <typename R> __device__ __forceinline__ R block_max(R v, R* scratch /* 
     }
     return v;   // valid in thread 0
 }
-// rows of the tile's own cells (coalesced) and of its halo (gathered) -> qg
-template <typename R, int T, int TS>
-__device__ __forceinline__ void tile_stage_device(const MeshDev<R>& m, int t, const R* Q, const R* G, R* qg) {
-    const int c0 = t * T, nc = min(T, m.nInternalCells - c0);
+
+// shared-memory carve-up common to both kernels: [qg 20*TS][extra ...][chunk][2 mbarriers]
+template <typename R, int T, int TS, int W, int EXTRA> struct TileSmem {
+    static constexpr size_t kChunkOff = ((size_t)(20 * TS + EXTRA) * sizeof(R) + 127) / 128 * 128;
+    static constexpr size_t kBarOff = kChunkOff + Chunk<R, W>::kBytes;
+    static constexpr size_t kBytes = kBarOff + 16;
+};
+
+// prologue: arm the barriers, start the bulk copies of the tile's own rows and of the first chunk, gather the halo rows
+template <typename R, int T, int TS, int W>
+__device__ __forceinline__ void tile_prologue(const MeshDev<R>& m, int t, const R* Q, const R* G, R* qg, R* chunk,
+                                              unsigned long long* bars, int p0, int np) {
+    const int c0 = t * T;
     const int tid = threadIdx.x, nthr = blockDim.x;
-    for (int l = tid; l < nc; l += nthr) tile_stage_cell<R, TS>(qg, l, Q, G, m.sN, c0 + l);
+    if (tid == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); mbar_fence_init(); }
+    __syncthreads();
+    if (tid == 0) {
+        // rows may run past the last internal cell into ghost rows / padding (allocated, finite, unused)
+        mbar_expect_tx(&bars[0], 20u * T * (unsigned)sizeof(R));
+        for (int k = 0; k < 5; k++) bulk_g2s(qg + k * TS, Q + (long)k * m.sN + c0, T * (unsigned)sizeof(R), &bars[0]);
+        for (int k = 0; k < 15; k++) bulk_g2s(qg + (5 + k) * TS, G + (long)k * m.sN + c0, T * (unsigned)sizeof(R), &bars[0]);
+        if (np > 0) {
+            mbar_expect_tx(&bars[1], (unsigned)Chunk<R, W>::kBytes);
+            bulk_g2s(chunk, m.chunks + (long)p0 * Chunk<R, W>::kScalars, (unsigned)Chunk<R, W>::kBytes, &bars[1]);
+        }
+    }
     const int h0 = m.halo_start[t], nh = m.halo_start[t + 1] - h0;
     for (int h = tid; h < nh; h += nthr) tile_stage_cell<R, TS>(qg, T + h, Q, G, m.sN, m.halo_cell[h0 + h]);
 }
 #endif
 
 // ------------------------------------------------------------------------------------------ forward
-template <typename R, int T, int TS> struct FluxTileBody {
+template <typename R, int T, int TS, int W> struct FluxTileBody {
     static constexpr const char* kName = "flux_tile";
+    static constexpr int kThreads = W;
     Phys<R> ph; MeshDev<R> m;
     const R *Q, *G;            // this stage's primitives / gradients (ghosts filled)
     const R *W0, *W1, *W2;     // previous stage states (W1/W2 NULL when their alpha is 0)
@@ -77,16 +162,18 @@ template <typename R, int T, int TS> struct FluxTileBody {
     R* Wn;                     // new state
     R* Qn;                     // primitives of the new state (may be NULL)
     R* dtc_partial;            // [nTiles] per-tile max of dtc (may be NULL)
-    static size_t smem_bytes() { return (size_t)(20 * TS + T + 6 * T) * sizeof(R); }
+#if defined(__CUDACC__)
+    typedef TileSmem<R, T, TS, W, 7 * T> Smem;
+    static size_t smem_bytes() { return Smem::kBytes; }
+#endif
 
     // flux per unit area of one entry + the scatter weights A/V of its in-tile sides
-    FVM_HD void face(int f, int lo, int ln, const R* qg, const R* ivol, Flux5<R>& F, R& wave, R& sO, R& sNb) const {
-        Geom<R> gm; load_geom(m, f, gm);
+    FVM_HD void face(const Geom<R>& gm, const TileEntry& e, const R* qg, const R* ivol, Flux5<R>& F, R& wave, R& sO, R& sNb) const {
         Prim<R> qL, qR; Grad<R> gL, gR;
-        tile_load_cell<R, TS>(qg, lo, qL, gL); tile_load_cell<R, TS>(qg, ln, qR, gR);
-        face_flux(ph, face_kind(m, f), gm, qL, gL, qR, gR, F, wave);
-        sO = lo < T ? gm.area * ivol[lo] : R(0);
-        sNb = ln < T ? gm.area * ivol[ln] : R(0);
+        tile_load_cell<R, TS>(qg, e.lo, qL, gL); tile_load_cell<R, TS>(qg, e.ln, qR, gR);
+        face_flux(ph, e.kind, gm, qL, gL, qR, gR, F, wave);
+        sO = e.lo < T ? gm.area * ivol[e.lo] : R(0);
+        sNb = e.ln < T ? gm.area * ivol[e.ln] : R(0);
     }
     FVM_HD static void scatter(R* acc, int lo, int ln, const Flux5<R>& F, R wave, R sO, R sNb) {
         if (lo < T) {
@@ -121,11 +208,16 @@ template <typename R, int T, int TS> struct FluxTileBody {
         std::vector<R> qg((size_t)20 * TS, R(0)), ivol(T, R(0)), acc((size_t)6 * T, R(0));
         for (int l = 0; l < nc; l++) { tile_stage_cell<R, TS>(qg.data(), l, Q, G, m.sN, c0 + l); ivol[l] = R(1) / m.vol[c0 + l]; }
         for (int h = m.halo_start[t]; h < m.halo_start[t + 1]; h++) tile_stage_cell<R, TS>(qg.data(), T + h - m.halo_start[t], Q, G, m.sN, m.halo_cell[h]);
-        for (int e = m.tile_start[t]; e < m.tile_start[t + 1]; e++) {
-            int f, lo, ln, col; tile_entry(m, e, f, lo, ln, col);
-            Flux5<R> F; R wave, sO, sNb;
-            face(f, lo, ln, qg.data(), ivol.data(), F, wave, sO, sNb);
-            scatter(acc.data(), lo, ln, F, wave, sO, sNb);
+        for (int p = m.pass_start[t]; p < m.pass_start[t + 1]; p++) {
+            const R* chunk = m.chunks + (long)p * Chunk<R, W>::kScalars;
+            for (int i = 0; i < W; i++) {
+                TileEntry e; tile_decode(Chunk<R, W>::words(chunk)[i], e);
+                if (!e.valid) continue;
+                Geom<R> gm; tile_load_geom<R, W>(chunk, i, gm);
+                Flux5<R> F; R wave, sO, sNb;
+                face(gm, e, qg.data(), ivol.data(), F, wave, sO, sNb);
+                scatter(acc.data(), e.lo, e.ln, F, wave, sO, sNb);
+            }
         }
         R mx = R(-1e30);
         for (int l = 0; l < nc; l++) { R d = finish(c0 + l, &acc[l]); mx = d > mx ? d : mx; }
@@ -134,28 +226,39 @@ template <typename R, int T, int TS> struct FluxTileBody {
 #else
     __device__ __forceinline__ void device_tile(int t, unsigned char* smem) const {
         const int c0 = t * T, nc = min(T, m.nInternalCells - c0);
-        const int tid = threadIdx.x, nthr = blockDim.x;
+        const int tid = threadIdx.x;
         R* qg = reinterpret_cast<R*>(smem);
         R* ivol = qg + 20 * TS;
         R* acc = ivol + T;
-        tile_stage_device<R, T, TS>(m, t, Q, G, qg);
-        for (int l = tid; l < T; l += nthr) ivol[l] = l < nc ? R(1) / m.vol[c0 + l] : R(0);
-        for (int i = tid; i < 6 * T; i += nthr) acc[i] = R(0);
+        R* chunk = reinterpret_cast<R*>(smem + Smem::kChunkOff);
+        unsigned long long* bars = reinterpret_cast<unsigned long long*>(smem + Smem::kBarOff);
+        const int p0 = m.pass_start[t], np = m.pass_start[t + 1] - p0;
+        tile_prologue<R, T, TS, W>(m, t, Q, G, qg, chunk, bars, p0, np);
+        for (int l = tid; l < T; l += W) ivol[l] = l < nc ? rcp(m.vol[c0 + l]) : R(0);
+        for (int i = tid; i < 6 * T; i += W) acc[i] = R(0);
+        mbar_wait(&bars[0], 0);
         __syncthreads();
-        const int e0 = m.tile_start[t], e1 = m.tile_start[t + 1];
-        for (int base = e0; base < e1; base += nthr) {
-            const int e = base + tid;
-            int f = 0, lo = T, ln = T, col = -1;
+        for (int p = 0; p < np; p++) {
+            mbar_wait(&bars[1], (unsigned)(p & 1));
+            TileEntry e; tile_decode(Chunk<R, W>::words(chunk)[tid], e);
+            Geom<R> gm; tile_load_geom<R, W>(chunk, tid, gm);
+            const int cfirst = (int)((Chunk<R, W>::words(chunk)[0] >> 20) & 0x1Fu), clast = (int)((Chunk<R, W>::words(chunk)[W - 1] >> 20) & 0x1Fu);
+            __syncthreads();                       // every thread holds its metrics in registers: the chunk buffer is free
+            if (tid == 0 && p + 1 < np) {
+                fence_proxy_async();
+                mbar_expect_tx(&bars[1], (unsigned)Chunk<R, W>::kBytes);
+                bulk_g2s(chunk, m.chunks + (long)(p0 + p + 1) * Chunk<R, W>::kScalars, (unsigned)Chunk<R, W>::kBytes, &bars[1]);
+            }
             Flux5<R> F; R wave = R(0), sO = R(0), sNb = R(0);
-            if (e < e1) { tile_entry(m, e, f, lo, ln, col); face(f, lo, ln, qg, ivol, F, wave, sO, sNb); }
-            const int cfirst = (int)(m.ent_loc[base] >> 20), clast = (int)(m.ent_loc[min(base + nthr, e1) - 1] >> 20);
+            if (e.valid) face(gm, e, qg, ivol, F, wave, sO, sNb);
+            const int col = e.valid ? e.col : -1;
             for (int c = cfirst; c <= clast; c++) {
-                if (col == c) scatter(acc, lo, ln, F, wave, sO, sNb);
+                if (col == c) scatter(acc, e.lo, e.ln, F, wave, sO, sNb);
                 __syncthreads();
             }
         }
         R mx = R(-1e30);
-        for (int l = tid; l < nc; l += nthr) { R d = finish(c0 + l, acc + l); mx = d > mx ? d : mx; }
+        for (int l = tid; l < nc; l += W) { R d = finish(c0 + l, acc + l); mx = d > mx ? d : mx; }
         if (dtc_partial) {
             mx = block_max(mx, qg);
             if (tid == 0) dtc_partial[t] = mx;
@@ -167,37 +270,46 @@ template <typename R, int T, int TS> struct FluxTileBody {
 // ------------------------------------------------------------------------------------------ reverse
 //   abar = adjoint of the stage OUTPUT state [5][sC]; coef = -beta_ii*dt (d W_new / d residual)
 //   outputs Qb [5][sN], Gb [15][sN]: rows of internal cells and of the ghost cells of ALL boundary faces
-template <typename R, int T, int TS> struct FluxGradTileBody {
+template <typename R, int T, int TS, int W> struct FluxGradTileBody {
     static constexpr const char* kName = "flux_grad_tile";
+    static constexpr int kThreads = W;
     Phys<R> ph; MeshDev<R> m;
     const R *Q, *G; const R* abar; R coef;
     R *Qb, *Gb;
-    static size_t smem_bytes() { return (size_t)(20 * TS + 5 * TS + 20 * T) * sizeof(R); }
+#if defined(__CUDACC__)
+    typedef TileSmem<R, T, TS, W, 5 * TS + 20 * T> Smem;
+    static size_t smem_bytes() { return Smem::kBytes; }
+#endif
 
     // r = abar*coef/V of an internal cell, 0 for ghost cells (boundary faces scatter to their owner only)
     FVM_HD void stage_r(R* r, int slot, int cell) const {
-        if (cell < m.nInternalCells) { const R iv = coef / m.vol[cell]; for (int k = 0; k < 5; k++) r[k * TS + slot] = abar[(long)k * m.sC + cell] * iv; }
+        if (cell < m.nInternalCells) { const R iv = coef * rcp(m.vol[cell]); for (int k = 0; k < 5; k++) r[k * TS + slot] = abar[(long)k * m.sC + cell] * iv; }
         else for (int k = 0; k < 5; k++) r[k * TS + slot] = R(0);
     }
-    FVM_HD void face(int f, int lo, int ln, const R* qg, const R* r, Prim<R>& qLb, Grad<R>& gLb, Prim<R>& qRb, Grad<R>& gRb) const {
-        Geom<R> gm; load_geom(m, f, gm);
+    FVM_HD void face(const Geom<R>& gm, const TileEntry& e, const R* qg, const R* r, Prim<R>& qLb, Grad<R>& gLb, Prim<R>& qRb, Grad<R>& gRb) const {
         Prim<R> qL, qR; Grad<R> gL, gR;
-        tile_load_cell<R, TS>(qg, lo, qL, gL); tile_load_cell<R, TS>(qg, ln, qR, gR);
+        tile_load_cell<R, TS>(qg, e.lo, qL, gL); tile_load_cell<R, TS>(qg, e.ln, qR, gR);
         R d[5];
-        for (int k = 0; k < 5; k++) d[k] = gm.area * (r[k * TS + lo] - r[k * TS + ln]);
+        for (int k = 0; k < 5; k++) d[k] = gm.area * (r[k * TS + e.lo] - r[k * TS + e.ln]);
         Flux5<R> Fb; Fb.rho = d[0]; Fb.rhoU[0] = d[1]; Fb.rhoU[1] = d[2]; Fb.rhoU[2] = d[3]; Fb.rhoE = d[4];
         zero(qLb); zero(gLb); zero(qRb); zero(gRb);
-        face_flux_vjp(ph, face_kind(m, f), gm, qL, gL, qR, gR, Fb, qLb, gLb, qRb, gRb);
+        face_flux_vjp(ph, e.kind, gm, qL, gL, qR, gR, Fb, qLb, gLb, qRb, gRb);
     }
     FVM_HD static void add20(R* a, const Prim<R>& q, const Grad<R>& g) {
         a[0] += q.U[0]; a[T] += q.U[1]; a[2 * T] += q.U[2]; a[3 * T] += q.T; a[4 * T] += q.p;
         for (int k = 0; k < 9; k++) a[(5 + k) * T] += g.U[k];
         for (int k = 0; k < 3; k++) { a[(14 + k) * T] += g.T[k]; a[(17 + k) * T] += g.p[k]; }
     }
-    FVM_HD void scatter(R* acc, int f, int lo, int ln, const Prim<R>& qLb, const Grad<R>& gLb, const Prim<R>& qRb, const Grad<R>& gRb) const {
-        if (lo < T) add20(acc + lo, qLb, gLb);
-        if (f >= m.nInternalFaces) { const int g = m.nInternalCells + (f - m.nInternalFaces); store_prim(Qb, m.sN, g, qRb); store_grad(Gb, m.sN, g, gRb); }
-        else if (ln < T) add20(acc + ln, qRb, gRb);
+    // ghost: global row of the ghost cell of a boundary face (its halo slot's cell), -1 for internal faces
+    FVM_HD void scatter(R* acc, const TileEntry& e, int ghost, const Prim<R>& qLb, const Grad<R>& gLb, const Prim<R>& qRb, const Grad<R>& gRb) const {
+        if (e.lo < T) add20(acc + e.lo, qLb, gLb);
+        if (ghost >= 0) { store_prim(Qb, m.sN, ghost, qRb); store_grad(Gb, m.sN, ghost, gRb); }
+        else if (e.ln < T) add20(acc + e.ln, qRb, gRb);
+    }
+    FVM_HD int ghost_of(int t, const TileEntry& e) const {
+        if (e.ln < T) return -1;
+        const int cell = m.halo_cell[m.halo_start[t] + e.ln - T];
+        return cell >= m.nInternalCells ? cell : -1;
     }
     FVM_HD void finish(int c, const R* a) const {
         for (int k = 0; k < 5; k++) Qb[(long)k * m.sN + c] = a[k * T];
@@ -213,40 +325,57 @@ template <typename R, int T, int TS> struct FluxGradTileBody {
             const int slot = T + h - m.halo_start[t];
             tile_stage_cell<R, TS>(qg.data(), slot, Q, G, m.sN, m.halo_cell[h]); stage_r(r.data(), slot, m.halo_cell[h]);
         }
-        for (int e = m.tile_start[t]; e < m.tile_start[t + 1]; e++) {
-            int f, lo, ln, col; tile_entry(m, e, f, lo, ln, col);
-            Prim<R> qLb, qRb; Grad<R> gLb, gRb;
-            face(f, lo, ln, qg.data(), r.data(), qLb, gLb, qRb, gRb);
-            scatter(acc.data(), f, lo, ln, qLb, gLb, qRb, gRb);
+        for (int p = m.pass_start[t]; p < m.pass_start[t + 1]; p++) {
+            const R* chunk = m.chunks + (long)p * Chunk<R, W>::kScalars;
+            for (int i = 0; i < W; i++) {
+                TileEntry e; tile_decode(Chunk<R, W>::words(chunk)[i], e);
+                if (!e.valid) continue;
+                Geom<R> gm; tile_load_geom<R, W>(chunk, i, gm);
+                Prim<R> qLb, qRb; Grad<R> gLb, gRb;
+                face(gm, e, qg.data(), r.data(), qLb, gLb, qRb, gRb);
+                scatter(acc.data(), e, ghost_of(t, e), qLb, gLb, qRb, gRb);
+            }
         }
         for (int l = 0; l < nc; l++) finish(c0 + l, &acc[l]);
     }
 #else
     __device__ __forceinline__ void device_tile(int t, unsigned char* smem) const {
         const int c0 = t * T, nc = min(T, m.nInternalCells - c0);
-        const int tid = threadIdx.x, nthr = blockDim.x;
+        const int tid = threadIdx.x;
         R* qg = reinterpret_cast<R*>(smem);
         R* r = qg + 20 * TS;
         R* acc = r + 5 * TS;
-        tile_stage_device<R, T, TS>(m, t, Q, G, qg);
-        for (int l = tid; l < nc; l += nthr) stage_r(r, l, c0 + l);
+        R* chunk = reinterpret_cast<R*>(smem + Smem::kChunkOff);
+        unsigned long long* bars = reinterpret_cast<unsigned long long*>(smem + Smem::kBarOff);
+        const int p0 = m.pass_start[t], np = m.pass_start[t + 1] - p0;
+        tile_prologue<R, T, TS, W>(m, t, Q, G, qg, chunk, bars, p0, np);
+        for (int l = tid; l < T; l += W) { if (l < nc) stage_r(r, l, c0 + l); else for (int k = 0; k < 5; k++) r[k * TS + l] = R(0); }
         const int h0 = m.halo_start[t], nh = m.halo_start[t + 1] - h0;
-        for (int h = tid; h < nh; h += nthr) stage_r(r, T + h, m.halo_cell[h0 + h]);
-        for (int i = tid; i < 20 * T; i += nthr) acc[i] = R(0);
+        for (int h = tid; h < nh; h += W) stage_r(r, T + h, m.halo_cell[h0 + h]);
+        for (int i = tid; i < 20 * T; i += W) acc[i] = R(0);
+        mbar_wait(&bars[0], 0);
         __syncthreads();
-        const int e0 = m.tile_start[t], e1 = m.tile_start[t + 1];
-        for (int base = e0; base < e1; base += nthr) {
-            const int e = base + tid;
-            int f = 0, lo = T, ln = T, col = -1;
+        for (int p = 0; p < np; p++) {
+            mbar_wait(&bars[1], (unsigned)(p & 1));
+            TileEntry e; tile_decode(Chunk<R, W>::words(chunk)[tid], e);
+            Geom<R> gm; tile_load_geom<R, W>(chunk, tid, gm);
+            const int cfirst = (int)((Chunk<R, W>::words(chunk)[0] >> 20) & 0x1Fu), clast = (int)((Chunk<R, W>::words(chunk)[W - 1] >> 20) & 0x1Fu);
+            __syncthreads();
+            if (tid == 0 && p + 1 < np) {
+                fence_proxy_async();
+                mbar_expect_tx(&bars[1], (unsigned)Chunk<R, W>::kBytes);
+                bulk_g2s(chunk, m.chunks + (long)(p0 + p + 1) * Chunk<R, W>::kScalars, (unsigned)Chunk<R, W>::kBytes, &bars[1]);
+            }
             Prim<R> qLb, qRb; Grad<R> gLb, gRb;
-            if (e < e1) { tile_entry(m, e, f, lo, ln, col); face(f, lo, ln, qg, r, qLb, gLb, qRb, gRb); }
-            const int cfirst = (int)(m.ent_loc[base] >> 20), clast = (int)(m.ent_loc[min(base + nthr, e1) - 1] >> 20);
+            int ghost = -1;
+            if (e.valid) { face(gm, e, qg, r, qLb, gLb, qRb, gRb); if (e.kind != (int)FACE_COUPLED || e.ln >= T) ghost = ghost_of(t, e); }
+            const int col = e.valid ? e.col : -1;
             for (int c = cfirst; c <= clast; c++) {
-                if (col == c) scatter(acc, f, lo, ln, qLb, gLb, qRb, gRb);
+                if (col == c) scatter(acc, e, ghost, qLb, gLb, qRb, gRb);
                 __syncthreads();
             }
         }
-        for (int l = tid; l < nc; l += nthr) finish(c0 + l, acc + l);
+        for (int l = tid; l < nc; l += W) finish(c0 + l, acc + l);
     }
 #endif
 };

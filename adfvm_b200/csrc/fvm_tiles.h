@@ -23,18 +23,22 @@
 
 namespace fvm {
 
-// packed entry word: bits 0-9 owner's slot, 10-19 neighbour's slot, 20-27 colour. Slots [0,T) are the tile's own
-// cells, slots [T, T+nHalo) the tile's halo: cells of other tiles and ghost cells touched by the tile's faces.
-static inline uint32_t tile_pack(int lo, int ln, int colour) { return (uint32_t)lo | ((uint32_t)ln << 10) | ((uint32_t)colour << 20); }
+// packed entry word: bits 0-9 owner's slot, 10-19 neighbour's slot, 20-24 colour, 25-26 face kind (FaceKind of
+// fvm_math.h), 27 valid. Slots [0,T) are the tile's own cells, slots [T, T+nHalo) the tile's halo: cells of other
+// tiles and ghost cells touched by the tile's faces.
+static inline uint32_t tile_pack(int lo, int ln, int colour, int kind, int valid) {
+    return (uint32_t)lo | ((uint32_t)ln << 10) | ((uint32_t)colour << 20) | ((uint32_t)kind << 25) | ((uint32_t)valid << 27);
+}
 
 struct TilePlan {
     int T = 0, nTiles = 0, maxColours = 0;
     long nEntries = 0;
     std::vector<int> cell_new2old, cell_old2new;     // internal cells
     std::vector<int> face_new2old, face_old2new;     // all faces (identity for boundary faces)
-    std::vector<int> tile_start;                     // [nTiles+1] offsets into the entry arrays
-    std::vector<int> ent_face;                       // NEW face index of each entry
-    std::vector<uint32_t> ent_loc;                   // tile_pack(...)
+    int W = 0;                                       // entries per pass (= threads per CTA)
+    std::vector<int> pass_start;                     // [nTiles+1] first pass of each tile; pass p covers slots [p*W, (p+1)*W)
+    std::vector<int> ent_face;                       // NEW face index of each slot, -1 for padding
+    std::vector<uint32_t> ent_loc;                   // tile_pack(...) of each slot
     std::vector<int> halo_start;                     // [nTiles+1] offsets into halo_cell
     std::vector<int> halo_cell;                      // NEW cell index (ghost cells: >= C) of each halo slot
     int maxHalo = 0;
@@ -103,11 +107,12 @@ inline void rcb(std::vector<int>& idx, const std::vector<float>& pos, long lo, l
 }  // namespace detail
 
 // owner/neigh/cellFaces: the reference's arrays (old numbering). T <= 512.
+// bkind[f - Fi]: FaceKind of each boundary face. W: slots per pass.
 template <typename R>
 TilePlan build_tile_plan(int C, int Fi, int F, const int* owner, const int* neigh, const int* cellFaces,
-                         const R* deltas, const R* deltasUnit, int T) {
+                         const R* deltas, const R* deltasUnit, const unsigned char* bkind, int T, int W) {
     if (T <= 0 || T > 512) throw std::runtime_error("tile size out of range");
-    TilePlan P; P.T = T;
+    TilePlan P; P.T = T; P.W = W;
     P.nTiles = (C + T - 1) / T;
     // ---- cell order
     std::vector<float> pos;
@@ -121,7 +126,7 @@ TilePlan build_tile_plan(int C, int Fi, int F, const int* owner, const int* neig
     P.cell_old2new.assign(C, -1);
     for (int i = 0; i < C; i++) P.cell_old2new[P.cell_new2old[i]] = i;
     // ---- per tile: faces touching it, coloured
-    P.tile_start.assign(P.nTiles + 1, 0);
+    P.pass_start.assign(P.nTiles + 1, 0);
     P.face_old2new.assign(F, -1);
     P.face_new2old.assign(F, -1);
     for (int f = Fi; f < F; f++) { P.face_old2new[f] = f; P.face_new2old[f] = f; }
@@ -183,14 +188,16 @@ TilePlan build_tile_plan(int C, int Fi, int F, const int* owner, const int* neig
             const int la = slot(a), lb = slot(b);
             if (la >= 1024 || lb >= 1024) throw std::runtime_error("tile halo too large");
             P.ent_face.push_back(P.face_old2new[f]);
-            P.ent_loc.push_back(tile_pack(la, lb, colour[i]));
+            P.ent_loc.push_back(tile_pack(la, lb, colour[i], f < Fi ? 0 : (int)bkind[f - Fi], 1));
+            P.nEntries++;
         }
+        // pad the last pass; padding repeats the last colour so that a pass's colour range is [first slot, last slot]
+        while (P.ent_face.size() % (size_t)W) { P.ent_face.push_back(-1); P.ent_loc.push_back(tile_pack(0, 0, ncol ? ncol - 1 : 0, 0, 0)); }
         P.maxHalo = std::max(P.maxHalo, nHalo);
         P.halo_start[t + 1] = (int)P.halo_cell.size();
-        P.tile_start[t + 1] = (int)P.ent_face.size();
+        P.pass_start[t + 1] = (int)(P.ent_face.size() / (size_t)W);
     }
     if (nextFace != Fi) throw std::runtime_error("internal face not reachable from any cell (broken cellFaces)");
-    P.nEntries = (long)P.ent_face.size();
     return P;
 }
 
