@@ -59,7 +59,8 @@ public:
     R *sendbuf = 0, *recvbuf = 0, *stage_aos = 0;
     int *bcells = 0; int nBcells = 0;
     TilePlan plan; int tile_cells = 128; R* tile_partial = 0; double tile_evals_per_cell = 0; int tile_colours = 0, tile_max_halo = 0;
-    enum { kHalo128 = 256, kHalo64 = 384, kTileThreads = 128,
+    int tile_variant = 0;
+    enum { kHalo128s = 160, kHalo128 = 256, kHalo64 = 384, kTileThreads = 128,
            kRowSlack = 128 };   // the tile kernels bulk-copy whole T-cell rows: the last tile may read past the last row   // halo slots of the two tile-kernel instantiations (T=128: TS=384, T=64: TS=448)
     bool have_mesh = false, have_state = false, adjoint_ready = false;
     std::vector<void*> owned;                 // everything to free
@@ -126,6 +127,8 @@ public:
         if (tile_cells == 128 && plan.maxHalo > kHalo128)
             plan = build_tile_plan<R>(C, Fi, F, owner, neighbour, cellFaces, deltas, deltasUnit, bkind.data(), 64, kTileThreads);
         if (plan.T == 64 && plan.maxHalo > kHalo64) throw std::runtime_error("tile halo exceeds the kernel's capacity");
+        // kernel variant: (T, TS) = (128, 288) for compact 3-D tiles (halo <= 160: three fp64 CTAs per SM), (128, 384), (64, 448)
+        tile_variant = plan.T == 64 ? 2 : (plan.maxHalo <= kHalo128s ? 0 : 1);
         m.T = plan.T; m.nTiles = plan.nTiles;
         int* d_cperm = dalloc<int>(m.sC); ex.upload(d_cperm, plan.cell_new2old.data(), (size_t)C * 4); m.cell_perm = d_cperm;
         int* d_fperm = (int*)ex.alloc((size_t)(F + 1) * 4); ex.upload(d_fperm, plan.face_new2old.data(), (size_t)F * 4);
@@ -328,7 +331,8 @@ public:
         run(C, GradCellBody<R>{m, Qs, Gs});
         run(nLB, GhostGradBody<R>{m, Gs});
         halo(Gs, 15);
-        if (m.T == 128) run_flux_tile<128, 128 + kHalo128>(s, dt, Qs, Gs, Qnext, want_dtc_obj);
+        if (tile_variant == 0) run_flux_tile<128, 128 + kHalo128s>(s, dt, Qs, Gs, Qnext, want_dtc_obj);
+        else if (tile_variant == 1) run_flux_tile<128, 128 + kHalo128>(s, dt, Qs, Gs, Qnext, want_dtc_obj);
         else run_flux_tile<64, 64 + kHalo64>(s, dt, Qs, Gs, Qnext, want_dtc_obj);
         launches++;
         if (want_dtc_obj) { ex.reduce_max_buffer(tile_partial, m.nTiles, red); launches += 2; }
@@ -391,7 +395,8 @@ public:
         const int C = m.nInternalCells;
         for (int s = 2; s >= 0; s--) {
             const R coef = (R)(-RK_BETA[s]) * dt;
-            if (m.T == 128) ex.run_tiles(m.nTiles, FluxGradTileBody<R, 128, 128 + kHalo128, kTileThreads>{ph, m, Q[s], G[s], A[s + 1], coef, Qb, Gb});
+            if (tile_variant == 0) ex.run_tiles(m.nTiles, FluxGradTileBody<R, 128, 128 + kHalo128s, kTileThreads>{ph, m, Q[s], G[s], A[s + 1], coef, Qb, Gb});
+            else if (tile_variant == 1) ex.run_tiles(m.nTiles, FluxGradTileBody<R, 128, 128 + kHalo128, kTileThreads>{ph, m, Q[s], G[s], A[s + 1], coef, Qb, Gb});
             else ex.run_tiles(m.nTiles, FluxGradTileBody<R, 64, 64 + kHalo64, kTileThreads>{ph, m, Q[s], G[s], A[s + 1], coef, Qb, Gb});
             launches++;
             const R* rG = halo_reverse(Gb, 15);

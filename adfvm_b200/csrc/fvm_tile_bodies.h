@@ -105,6 +105,10 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned pari
                      : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
     } while (!ok);
 }
+// L2 prefetch of a row that a later phase of the CTA reads with ordinary loads (bytes: multiple of 16)
+__device__ __forceinline__ void bulk_prefetch_l2(const void* src, unsigned bytes) {
+    if (bytes) asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 template <typename R> __device__ __forceinline__ R block_max(R v, R* scratch /* >= 32 */) {
@@ -234,6 +238,14 @@ template <typename R, int T, int TS, int W> struct FluxTileBody {
         unsigned long long* bars = reinterpret_cast<unsigned long long*>(smem + Smem::kBarOff);
         const int p0 = m.pass_start[t], np = m.pass_start[t + 1] - p0;
         tile_prologue<R, T, TS, W>(m, t, Q, G, qg, chunk, bars, p0, np);
+        if (tid == 32) {      // the epilogue's inputs: bring them into L2 while the faces are computed
+            const unsigned bytes = (unsigned)(nc * sizeof(R)) & ~15u;
+            for (int k = 0; k < 5; k++) {
+                bulk_prefetch_l2(W0 + (long)k * m.sC + c0, bytes); bulk_prefetch_l2(S + (long)k * m.sC + c0, bytes);
+                if (W1) bulk_prefetch_l2(W1 + (long)k * m.sC + c0, bytes);
+                if (W2) bulk_prefetch_l2(W2 + (long)k * m.sC + c0, bytes);
+            }
+        }
         for (int l = tid; l < T; l += W) ivol[l] = l < nc ? rcp(m.vol[c0 + l]) : R(0);
         for (int i = tid; i < 6 * T; i += W) acc[i] = R(0);
         mbar_wait(&bars[0], 0);

@@ -113,3 +113,31 @@ static int comm_unique_id(void* id128) {
 #include <unistd.h>
 #include <algorithm>
 #include "../../adfvm_b200/csrc/fvm_capi.inc"
+
+
+// ---- test-only: halo through host callbacks, so that a world_size-2 `gloo` test can drive the rank-local step
+// logic (patch order, tags, reverse halo) from two real processes. Not part of the product ABI.
+namespace {
+typedef void (*exchange_fn)(const void* send, void* recv, int ncomp, int npatches, const int* peer, const int* tag,
+                            const long* offset, const long* count, int scalar_bytes);
+typedef double (*allreduce_fn)(double v, int is_max);
+template <typename R> struct CallbackHalo : fvm::HaloComm<R> {
+    exchange_fn ex; allreduce_fn ar;
+    CallbackHalo(exchange_fn e, allreduce_fn a) : ex(e), ar(a) {}
+    void exchange(const R* send, R* recv, int ncomp, const std::vector<fvm::PatchHost>& remote, void*) override {
+        int first = remote.empty() ? 0 : remote[0].startFace;
+        for (const auto& p : remote) first = std::min(first, p.startFace);
+        std::vector<int> peer, tag; std::vector<long> off, cnt;
+        for (const auto& p : remote) { peer.push_back(p.peer); tag.push_back(p.tag); off.push_back((long)(p.startFace - first) * ncomp); cnt.push_back((long)p.nFaces * ncomp); }
+        ex(send, recv, ncomp, (int)remote.size(), peer.data(), tag.data(), off.data(), cnt.data(), (int)sizeof(R));
+    }
+    double allreduce_sum(double v) override { return ar(v, 0); }
+    double allreduce_max(double v) override { return ar(v, 1); }
+};
+}  // namespace
+extern "C" int adfvm_hostsim_comm_callback(adfvm_ctx* c, exchange_fn e, allreduce_fn a) {
+    if (!c) return 1;
+    if (c->bytes == 8) { delete c->cd; c->cd = new CallbackHalo<double>(e, a); c->sd->comm = c->cd; }
+    else { delete c->cf; c->cf = new CallbackHalo<float>(e, a); c->sf->comm = c->cf; }
+    return 0;
+}

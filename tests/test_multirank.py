@@ -1,0 +1,149 @@
+"""Multi-rank path on CPU: the rank-local step logic (processor patches, halo pack/unpack order, tags, reverse halo
+with add, objective all-reduce) of the device code compiled for the CPU (tests/hostsim), checked for
+decomposition invariance against the single-rank run on the undecomposed mesh — the reference's own criterion
+(tests/test_parallel.py:32-41, 63-81: rel < 1e-9 after 10 steps; here 1e-10 after 2 primal steps + 1 adjoint step).
+  * ranks as threads of one process (in-process rendezvous), 2 / 4 / 8 ranks;
+  * ranks as 2 real processes over torch.distributed `gloo` (halo through host callbacks)."""
+import ctypes as C
+import os
+import sys
+import threading
+
+import numpy as np
+import pytest
+
+from adfvm_b200 import decompose, function
+from golden_util import relerr
+
+TOL = 1e-10
+N = (6, 5, 4)
+
+
+def _seed(state):
+    rng = np.random.RandomState(7)
+    return [np.ascontiguousarray(rng.randn(*s.shape) * w) for s, w in zip(state, (1.0, 1e-2, 1e-5))]
+
+
+def _single(world, lib):
+    g = decompose.global_box(N, world)
+    f = function.PrimalFunction(g.spec, np.float64, lib=lib)
+    out = f(*g.inputs(), replace_reusable=True)
+    out2 = f(*g.inputs(list(out[:3])), replace_reusable=True)
+    adj = _seed(g.state)
+    grad = f.grad()(*g.adjoint_inputs(g.state, adj))
+    return g, out, out2, adj, grad
+
+
+def _rank_run(rank, world, lib, uid, adj_global, results, attach):
+    case = decompose.periodic_box_rank(N, rank, world)
+    f = function.PrimalFunction(case.spec, np.float64, lib=lib)
+    attach(f, rank, world, uid)
+    out = f(*case.inputs(), replace_reusable=True)
+    out2 = f(*case.inputs(list(out[:3])), replace_reusable=True)
+    ids = decompose.global_cell_ids(N, rank, world)
+    adj = [np.ascontiguousarray(a[ids]) for a in adj_global]
+    grad = f.grad()(*case.adjoint_inputs(case.state, adj))
+    results[rank] = (ids, out, out2, grad)
+
+
+def _check(world, single, results):
+    g, out, out2, adj, grad = single
+    for rank in range(world):
+        ids, o, o2, gr = results[rank]
+        for a, b in zip(o[:3], out[:3]):
+            assert relerr(a, b[ids]) < TOL
+        for a, b in zip(o2[:3], out2[:3]):
+            assert relerr(a, b[ids]) < TOL
+        assert relerr(o[4], out[4]) < TOL                     # objective: summed over ranks
+        sc = [float(np.abs(s).max()) for s in g.state]
+        for grp in (slice(0, 3), slice(3, 6)):
+            num = max(np.abs(a - b[ids]).max() * s for a, b, s in zip(gr[grp], grad[grp], sc))
+            den = max(np.abs(b).max() * s for b, s in zip(grad[grp], sc))
+            assert num / den < TOL
+    # dtc: the global max is the max over ranks of the rank-local maxima (adFVM/solver.py:365 parallel.min)
+    assert relerr(max(results[r][1][3][0, 0] for r in range(world)), out[3][0, 0]) < TOL
+
+
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_threads(world, hostsim):
+    single = _single(world, hostsim)
+    uid = C.create_string_buffer(128)
+    hostsim.check(hostsim.dll.adfvm_comm_unique_id(uid))
+    results, errors = {}, []
+
+    def attach(f, rank, world_, uid_):
+        f.c.attach_comm(uid_.raw, rank, world_)
+
+    def run(rank):
+        try:
+            _rank_run(rank, world, hostsim, uid, single[3], results, attach)
+        except Exception as e:      # pragma: no cover
+            errors.append(e)
+    ts = [threading.Thread(target=run, args=(r,)) for r in range(world)]
+    [t.start() for t in ts]
+    [t.join(timeout=300) for t in ts]
+    assert not errors, errors
+    _check(world, single, results)
+
+
+def _gloo_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    import torch
+    import torch.distributed as dist
+    from conftest import build_hostsim
+    from adfvm_b200 import _lib
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    lib = _lib.Lib(build_hostsim())
+    EX = C.CFUNCTYPE(None, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int),
+                     C.POINTER(C.c_long), C.POINTER(C.c_long), C.c_int)
+    AR = C.CFUNCTYPE(C.c_double, C.c_double, C.c_int)
+
+    def exchange(send, recv, ncomp, npatch, peer, tag, off, cnt, sbytes):
+        dt = np.float64 if sbytes == 8 else np.float32
+        order = sorted(range(npatch), key=lambda i: (peer[i], tag[i]))      # both ends post shared patches in tag order
+        reqs, bufs = [], []
+        for i in order:
+            n = cnt[i]
+            s = np.ctypeslib.as_array(C.cast(send + off[i] * sbytes, C.POINTER(C.c_double if sbytes == 8 else C.c_float)), (n,))
+            reqs.append(dist.isend(torch.from_numpy(s.astype(dt)), peer[i], tag=tag[i]))
+            b = torch.empty(n, dtype=torch.float64 if sbytes == 8 else torch.float32)
+            reqs.append(dist.irecv(b, peer[i], tag=tag[i])); bufs.append((i, b))
+        for r in reqs:
+            r.wait()
+        for i, b in bufs:
+            C.memmove(recv + off[i] * sbytes, b.numpy().ctypes.data, cnt[i] * sbytes)
+
+    def allreduce(v, is_max):
+        t = torch.tensor([v], dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX if is_max else dist.ReduceOp.SUM)
+        return float(t[0])
+    ex, ar = EX(exchange), AR(allreduce)
+
+    def attach(f, rank_, world_, uid_):
+        assert lib.dll.adfvm_hostsim_comm_callback(f.c.ctx, ex, ar) == 0
+    single = _single(world, lib)
+    results = {}
+    _rank_run(rank, world, lib, None, single[3], results, attach)
+    _check_one = {rank: results[rank]}
+    try:
+        g, out, out2, adj, grad = single
+        ids, o, o2, gr = results[rank]
+        errs = [relerr(a, b[ids]) for a, b in zip(o2[:3], out2[:3])] + [relerr(o[4], out[4])]
+        errs += [relerr(a, b[ids]) for a, b in zip(gr[:3], grad[:3])]
+        q.put((rank, max(errs)))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_gloo_two_processes():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 2000)
+    ps = [ctx.Process(target=_gloo_worker, args=(r, 2, port, q)) for r in range(2)]
+    [p.start() for p in ps]
+    got = [q.get(timeout=300) for _ in ps]
+    [p.join(timeout=60) for p in ps]
+    assert sorted(r for r, _ in got) == [0, 1]
+    for _, e in got:
+        assert e < 1e-9
