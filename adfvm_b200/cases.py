@@ -10,7 +10,7 @@ from __future__ import annotations
 import numpy as np
 
 from . import hexmesh
-from .metrics import build_mesh, GRAD_FIELDS, INT_FIELDS
+from .metrics import build_mesh, uniform_box, GRAD_FIELDS, INT_FIELDS
 
 
 class Case:
@@ -95,8 +95,7 @@ def periodic_box(n, dtype=np.float64, warp=0.0, dt=None, mesh=None):
     if isinstance(n, int):
         n = (n, n, n)
     if mesh is None:
-        poly = hexmesh.box_mesh(n, warp=hexmesh.sine_warp(warp) if warp else None)
-        mesh = build_mesh(poly)
+        mesh = build_mesh(hexmesh.box_mesh(n, warp=hexmesh.sine_warp(warp))) if warp else uniform_box(n)
     C = mesh.nInternalCells
     cc = mesh.cellCentres[:C]
     U, T, p = smooth_state(cc)

@@ -16,8 +16,8 @@ from __future__ import annotations
 
 import numpy as np
 
-from . import cases, hexmesh
-from .metrics import build_mesh
+from . import cases
+from .metrics import uniform_box
 
 
 def factor3(world):
@@ -80,18 +80,7 @@ def periodic_box_rank(n, rank, world, dtype=np.float64, p=None, dt=None):
                 extra["referPatch"] = c2 if plus else c1
                 name += "through" + extra["referPatch"]
             proc.append((name, ptype, [names[d] + ("+" if plus else "-")], extra))
-    poly = hexmesh.box_mesh(n, lo, hi, patches=phys + proc)
-    # ghost cell centres of processor faces: the peer's owner cell = my own opposite-side owner cell shifted by one block
-    tmp = build_mesh(poly, remote_centres={name: np.zeros((poly.boundary[name]["nFaces"], 3)) for name, _, _, _ in proc})
-    remote = {}
-    for name, _, sides, _ in proc:
-        d = names.index(sides[0][0]); plus = sides[0][1] == "+"
-        opp = [q for q in proc if q[2][0] == names[d] + ("-" if plus else "+")][0][0]
-        bo = tmp.boundary[opp]
-        own = tmp.owner[bo["startFace"]:bo["startFace"] + bo["nFaces"]]
-        shift = np.zeros(3); shift[d] = L[d] if plus else -L[d]
-        remote[name] = tmp.cellCentres[own] + shift
-    mesh = build_mesh(poly, remote_centres=remote)
+    mesh = uniform_box(n, lo, hi, phys + proc)            # ghost centres of processor faces = the peer block's cells
     C = mesh.nInternalCells
     cc = mesh.cellCentres[:C]
     U, T, pr = cases.smooth_state(cc)                     # period 1 in every direction: periodic on the global box too
@@ -111,7 +100,7 @@ def global_box(n, world, dtype=np.float64, p=None, dt=None):
     p = p or factor3(world)
     N = tuple(n[d] * p[d] for d in range(3))
     hi = tuple(float(p[d]) for d in range(3))
-    mesh = build_mesh(hexmesh.box_mesh(N, (0., 0., 0.), hi))
+    mesh = uniform_box(N, (0., 0., 0.), hi)
     C = mesh.nInternalCells
     cc = mesh.cellCentres[:C]
     U, T, pr = cases.smooth_state(cc)

@@ -228,7 +228,7 @@ class PrimalFunction:
         P = self.c.parse(inputs)
         if not self.c.static_loaded:
             self.c.load_static(P)
-        elif opts["replace_static"] or opts["replace_reusable"]:
+        elif opts["replace_static"]:
             self.c.load_replaceable(P)
         if P["sizes"] != self.c.sizes:
             raise ValueError("mesh size constants changed between calls")

@@ -207,3 +207,124 @@ def build_mesh(poly, remote_centres=None):
     m.linearWeights = np.ascontiguousarray(linW)
     m.quadraticWeights = np.ascontiguousarray(quadW)
     return m
+
+
+def uniform_box(n, lo=(0., 0., 0.), hi=(1., 1., 1.), patches=None):
+    """Closed-form MeshData of an undeformed nx*ny*nz box — the same arrays `build_mesh(hexmesh.box_mesh(...))`
+    produces (checked to round-off in tests/test_metrics.py), without building points/faces or sorting: the
+    benchmark sizes of BASELINE.json (up to 368^3 cells per GPU) are generated in seconds instead of minutes.
+    patches: as hexmesh.box_mesh (default: six cyclic patches). Processor patches get the periodic-image / next-block
+    cell centre as ghost centre (what the reference exchanges in createGhostCells, adFVM/mesh.py:784-805)."""
+    from .hexmesh import SIDES
+    nx, ny, nz = [int(v) for v in n]
+    if patches is None:
+        patches = [("x1", "cyclic", ["x-"], {"neighbourPatch": "x2"}), ("x2", "cyclic", ["x+"], {"neighbourPatch": "x1"}),
+                   ("y1", "cyclic", ["y-"], {"neighbourPatch": "y2"}), ("y2", "cyclic", ["y+"], {"neighbourPatch": "y1"}),
+                   ("z1", "cyclic", ["z-"], {"neighbourPatch": "z2"}), ("z2", "cyclic", ["z+"], {"neighbourPatch": "z1"})]
+    lo = np.asarray(lo, np.float64); hi = np.asarray(hi, np.float64)
+    h = (hi - lo) / np.array([nx, ny, nz], np.float64)
+    C = nx * ny * nz
+    stride = np.array([1, nx, nx * ny], np.int64)
+    c = np.arange(C, dtype=np.int64)
+    I, J, K = c % nx, (c // nx) % ny, c // (nx * ny)
+    idx = (I, J, K); dims = (nx, ny, nz)
+    has = [idx[d] < dims[d] - 1 for d in range(3)]
+    cnt = has[0].astype(np.int64) + has[1] + has[2]
+    start = np.cumsum(cnt) - cnt
+    fid = [start, start + has[0], start + has[0] + has[1]]           # id of the cell's +x/+y/+z internal face
+    Fi = int(cnt.sum())
+    # boundary faces, patch by patch, side by side
+    def side_cells(side):
+        d = "xyz".index(side[0]); a, b = [q for q in range(3) if q != d]
+        Bb, Aa = np.meshgrid(np.arange(dims[b]), np.arange(dims[a]), indexing="ij")
+        ijk = [None, None, None]
+        ijk[a], ijk[b] = Aa.ravel(), Bb.ravel()
+        ijk[d] = np.zeros_like(ijk[a]) if side[1] == "-" else np.full_like(ijk[a], dims[d] - 1)
+        return d, ijk[0] + nx * (ijk[1] + ny * ijk[2])
+    boundary = OrderedDict()
+    b_owner, b_dim, b_sign, b_coupled = [], [], [], []
+    used = set(); startFace = Fi
+    side_list = []
+    for name, ptype, sides, extra in patches:
+        n_p = 0
+        for s in sides:
+            assert s in SIDES and s not in used, s
+            used.add(s)
+            d, cells = side_cells(s)
+            side_list.append((startFace + n_p, cells))
+            b_owner.append(cells); b_dim.append(np.full(len(cells), d)); b_sign.append(np.full(len(cells), -1. if s[1] == "-" else 1.))
+            b_coupled.append(np.full(len(cells), ptype in COUPLED_PATCHES))
+            n_p += len(cells)
+        dct = OrderedDict(type=ptype, nFaces=int(n_p), startFace=int(startFace)); dct.update(extra or {})
+        boundary[name] = dct
+        startFace += n_p
+    assert used == set(SIDES)
+    b_owner = np.concatenate(b_owner); b_dim = np.concatenate(b_dim); b_sign = np.concatenate(b_sign); b_coupled = np.concatenate(b_coupled)
+    G = len(b_owner); F = Fi + G
+    m = MeshData()
+    m.boundary = boundary
+    m.nFaces, m.nInternalFaces, m.nInternalCells, m.nGhostCells, m.nCells, m.nBoundaryFaces = F, Fi, C, G, C + G, G
+    owner = np.empty(F, np.int64); neigh = np.empty(F, np.int64); fdim = np.empty(F, np.int8)
+    for d in range(3):
+        sel = has[d]
+        owner[fid[d][sel]] = c[sel]; neigh[fid[d][sel]] = c[sel] + stride[d]; fdim[fid[d][sel]] = d
+    owner[Fi:] = b_owner; neigh[Fi:] = C + np.arange(G); fdim[Fi:] = b_dim
+    sign = np.ones(F); sign[Fi:] = b_sign
+    coupled = np.ones(F, bool); coupled[Fi:] = b_coupled
+    # patches: local / remote split, cellStartFace
+    delta_cf = C - Fi
+    local, remote = [], []
+    nLocalCells = C
+    for pid, patch in boundary.items():
+        patch["cellStartFace"] = patch["startFace"] + delta_cf
+        (remote if patch["type"] in PROCESSOR_PATCHES else local).append(pid)
+        if patch["type"] not in PROCESSOR_PATCHES:
+            nLocalCells += patch["nFaces"]
+    if remote:
+        assert min(boundary[p]["startFace"] for p in remote) >= max([boundary[p]["startFace"] + boundary[p]["nFaces"] for p in local] + [Fi])
+    m.localPatches, m.remotePatches, m.sortedPatches = local, remote, sorted(local)
+    m.nLocalCells, m.nRemoteCells, m.nLocalFaces = nLocalCells, C + G - nLocalCells, nLocalCells - C + Fi
+    # geometry
+    hf = h[fdim]                                                  # spacing normal to the face
+    area = (h[0] * h[1] * h[2]) / hf
+    normals = np.zeros((F, 3)); normals[np.arange(F), fdim] = sign
+    cc = np.empty((C + G, 3))
+    cc[:C, 0] = lo[0] + (I + 0.5) * h[0]; cc[:C, 1] = lo[1] + (J + 0.5) * h[1]; cc[:C, 2] = lo[2] + (K + 0.5) * h[2]
+    fc = cc[owner].copy(); fc[np.arange(F), fdim] += 0.5 * hf * sign
+    gh = fc[Fi:].copy()
+    bc = coupled[Fi:]
+    gh[bc, b_dim[bc]] += 0.5 * hf[Fi:][bc] * b_sign[bc]           # coupled: the image cell's centre; else the face centre
+    cc[C:] = gh
+    dist = np.where(coupled, hf, 0.5 * hf)
+    w1 = np.where(coupled, 0.5, 1.0); w2 = np.where(coupled, 0.5, 0.0)
+    pFv = 0.5 * hf[:, None] * normals
+    nFv = np.where(coupled[:, None], -pFv, 0.0)
+    dvec = -dist[:, None] * normals                               # P - N
+    m.owner = np.ascontiguousarray(owner, np.int32); m.neighbour = np.ascontiguousarray(neigh, np.int32)
+    m.normals = normals; m.faceCentres = fc; m.cellCentres = cc
+    m.areas = area.reshape(-1, 1)
+    m.volumes = np.full((C, 1), h[0] * h[1] * h[2])
+    m.volumesL = m.volumes[m.owner]; m.volumesR = m.volumes[m.neighbour[:Fi]]
+    m.deltas = dist.reshape(-1, 1); m.deltasUnit = normals.copy()
+    m.weights = np.where(coupled, 0.5, 0.0).reshape(-1, 1)
+    m.linearWeights = np.stack([w1 / 3, w2 / 3], axis=1)
+    m.quadraticWeights = np.ascontiguousarray(np.stack([2. / 3 * pFv + 1. / 3 * (pFv + w1[:, None] * dvec),
+                                                        2. / 3 * nFv + 1. / 3 * (nFv - w2[:, None] * dvec)], axis=1))
+    # cellFaces: owned faces ascending (internal +x,+y,+z, then boundary in face order), then neighbour-side faces ascending
+    cellFaces = np.full((C, 6), -1, np.int64); fill = np.zeros(C, np.int64)
+    def put(cells, faces):
+        cellFaces[cells, fill[cells]] = faces; fill[cells] += 1
+    for d in range(3):
+        put(c[has[d]], fid[d][has[d]])
+    for s0, cells in side_list:
+        put(cells, s0 + np.arange(len(cells)))
+    for d in (2, 1, 0):
+        sel = idx[d] > 0
+        put(c[sel], fid[d][c[sel] - stride[d]])
+    assert np.all(fill == 6)
+    fo = owner[cellFaces]; fn = neigh[cellFaces]
+    own_flag = fo == c[:, None]
+    m.cellFaces = np.ascontiguousarray(cellFaces, np.int32)
+    m.cellNeighbours = np.ascontiguousarray(np.where(own_flag, fn, fo), np.int32)
+    m.cellOwner = np.ascontiguousarray(own_flag, np.int32)
+    return m

@@ -231,7 +231,7 @@ def main():
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_s = te.item()
-    h2d = (5 * C * s + s) + (10 * C * s + 4 * s) + 5 * C * s      # primal: state+dt (+source re-upload); adjoint: state+adjoint+scalars
+    h2d = (5 * C * s + s) + (10 * C * s + 4 * s)                  # primal: state + dt; adjoint: state + adjoint + 4 scalars
     d2h = (5 * C * s + 2 * s) + (10 * C * s)                        # primal: state+dtc+obj; adjoint: adjoint fields + source gradients
 
     if rank != 0:

@@ -40,3 +40,21 @@ def test_metrics_match_reference(name):
         assert np.array_equal(getattr(m, a), inp[14 + k]), a
     assert m.getScalar() == [int(x) for x in inp[19:19 + 8 + 3 * len(m.sortedPatches)]]
     np.testing.assert_allclose(m.cellCentres, g.mesh_array("orig", "cellCentres"), rtol=1e-12, atol=1e-14)
+
+
+def test_uniform_box_matches_general_builder():
+    """the closed-form box generator used for benchmark-size meshes == the general metric builder"""
+    import numpy as np
+    from adfvm_b200 import hexmesh, metrics
+    walls = [("inlet", "patch", ["x-"], {}), ("outlet", "patch", ["x+"], {}), ("floor", "symmetryPlane", ["y-"], {}),
+             ("lid", "patch", ["y+"], {}), ("z1", "cyclic", ["z-"], {"neighbourPatch": "z2"}),
+             ("z2", "cyclic", ["z+"], {"neighbourPatch": "z1"})]
+    for n, lo, hi, patches in (((5, 4, 3), (0, 0, 0), (1, 2, 0.5), None), ((4, 3, 5), (0.5, 0, 0), (2, 1, 0.5), walls)):
+        a = metrics.build_mesh(hexmesh.box_mesh(n, lo, hi, patches=patches))
+        b = metrics.uniform_box(n, lo, hi, patches)
+        for k in metrics.GRAD_FIELDS + ["cellCentres"]:
+            x, y = getattr(a, k), getattr(b, k)
+            assert x.shape == y.shape and np.abs(x - y).max() <= 1e-12 * max(1, np.abs(x).max()), k
+        for k in metrics.INT_FIELDS:
+            assert np.array_equal(getattr(a, k), getattr(b, k)), k
+        assert a.getScalar() == b.getScalar() and a.sortedPatches == b.sortedPatches

@@ -23,12 +23,13 @@ def main(path):
     out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(out)))
     hdr = rows[0]
+    units = dict(zip(hdr, rows[1]))
     for r in rows[2:]:
         d = dict(zip(hdr, r))
         print("==", d.get("Kernel Name", "")[:110], "grid", d.get("Grid Size"), "block", d.get("Block Size"))
         for k in KEYS:
             if k in d:
-                print("  %-70s %s" % (k, d[k]))
+                print("  %-70s %s %s" % (k, d[k], units.get(k, "")))
         stalls = [(k, float(v.replace(",", ""))) for k, v in d.items()
                   if k.startswith("smsp__average_warps_issue_stalled") and k.endswith("_per_issue_active.ratio") and v not in ("", "n/a")]
         stalls.sort(key=lambda kv: -kv[1])
