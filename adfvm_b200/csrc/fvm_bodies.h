@@ -43,6 +43,7 @@ template <typename R> struct MeshDev {
     // tiles (fvm_tiles.h): tile t owns cells [t*T, min(C,(t+1)*T)) and the per-pass chunks [pass_start[t], pass_start[t+1])
     int T, nTiles;
     const int* pass_start; const R* chunks;
+    const int* halo_pass;                // [nTiles] first pass (relative to pass_start) whose entries read halo slots
     const int* halo_start; const int* halo_cell;    // tile t's halo slots T.. hold cells halo_cell[halo_start[t]..halo_start[t+1])
     const int* cell_perm;                // [C] device cell -> reference (host) cell
 };

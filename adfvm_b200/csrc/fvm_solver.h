@@ -134,7 +134,7 @@ public:
         int* d_fperm = (int*)ex.alloc((size_t)(F + 1) * 4); ex.upload(d_fperm, plan.face_new2old.data(), (size_t)F * 4);
         m.area = upload_aos(areas, F, 1, m.sF, nullptr, d_fperm); m.weight = upload_aos(weights, F, 1, m.sF, nullptr, d_fperm);
         { R* idel = upload_aos(deltas, F, 1, m.sF, nullptr, d_fperm); run(F, ReciprocalBody<R>{idel}); m.idelta = idel; } m.normal = upload_aos(normals, F, 3, m.sF, nullptr, d_fperm);
-        m.vol = upload_aos(volumes, C, 1, m.sC, nullptr, d_cperm);
+        { R* d_vol = dalloc<R>((size_t)m.sC + kRowSlack); m.vol = upload_aos(volumes, C, 1, m.sC, d_vol, d_cperm); }
         {   // per-pass metric chunks of the flux kernels, gathered on the device from temporary face-indexed arrays
             R* t_dunit = (R*)ex.alloc((size_t)3 * m.sF * sizeof(R)); upload_aos(deltasUnit, F, 3, m.sF, t_dunit, d_fperm);
             R* t_linw = (R*)ex.alloc((size_t)2 * m.sF * sizeof(R)); upload_aos(linearWeights, F, 2, m.sF, t_linw, d_fperm);
@@ -184,6 +184,7 @@ public:
         bcells = dalloc<int>(nBcells + 1); ex.upload(bcells, bc_list.data(), (size_t)nBcells * 4);
         {
             int* d_ps = dalloc<int>(plan.pass_start.size()); ex.upload(d_ps, plan.pass_start.data(), plan.pass_start.size() * 4); m.pass_start = d_ps;
+            int* d_hp = dalloc<int>(plan.halo_pass.size() + 1); ex.upload(d_hp, plan.halo_pass.data(), plan.halo_pass.size() * 4); m.halo_pass = d_hp;
             int* d_hs = dalloc<int>(plan.halo_start.size()); ex.upload(d_hs, plan.halo_start.data(), plan.halo_start.size() * 4); m.halo_start = d_hs;
             int* d_hc = dalloc<int>(plan.halo_cell.size() + 1); ex.upload(d_hc, plan.halo_cell.data(), plan.halo_cell.size() * 4); m.halo_cell = d_hc;
             tile_partial = dalloc<R>(plan.nTiles + 1);
@@ -221,10 +222,10 @@ public:
         m.patches = patches_dev;
         push_patches();
         // state + work buffers
-        for (int k = 0; k < 4; k++) W[k] = dalloc<R>((size_t)5 * m.sC);
+        for (int k = 0; k < 4; k++) W[k] = dalloc<R>((size_t)5 * m.sC + kRowSlack);
         for (int k = 0; k < 2; k++) Q[k] = dalloc<R>((size_t)5 * m.sN + kRowSlack);
         G[0] = dalloc<R>((size_t)15 * m.sN + kRowSlack);
-        S = dalloc<R>((size_t)5 * m.sC);
+        S = dalloc<R>((size_t)5 * m.sC + kRowSlack);
         red = dalloc<R>(8);
         stage_aos = dalloc<R>((size_t)5 * m.sC);
         if (m.nRemoteCells > 0) { sendbuf = dalloc<R>((size_t)15 * m.nRemoteCells); recvbuf = dalloc<R>((size_t)15 * m.nRemoteCells); }
@@ -316,7 +317,8 @@ public:
     }
 
     // ---- one residual stage + RK update
-    void stage(int s, R dt, R* Qs, R* Gs, R* Qnext, bool want_dtc_obj) {
+    // flux=false: stop after the gradients (the adjoint's forward sweep needs Q,G of the last stage, not its output state)
+    void stage(int s, R dt, R* Qs, R* Gs, R* Qnext, bool want_dtc_obj, bool flux = true) {
         const int C = m.nInternalCells, nLB = m.nLocalFaces - m.nInternalFaces;
         if (s == 0) run(C, PrimitiveBody<R>{ph, m.sC, m.sN, W[0], Qs});
         run(nLB, GhostPrimBody<R>{ph, m, Qs});
@@ -331,6 +333,7 @@ public:
         run(C, GradCellBody<R>{m, Qs, Gs});
         run(nLB, GhostGradBody<R>{m, Gs});
         halo(Gs, 15);
+        if (!flux) return;
         if (tile_variant == 0) run_flux_tile<128, 128 + kHalo128s>(s, dt, Qs, Gs, Qnext, want_dtc_obj);
         else if (tile_variant == 1) run_flux_tile<128, 128 + kHalo128>(s, dt, Qs, Gs, Qnext, want_dtc_obj);
         else run_flux_tile<64, 64 + kHalo64>(s, dt, Qs, Gs, Qnext, want_dtc_obj);
@@ -357,7 +360,7 @@ public:
             R* Qs = keep ? Q[s] : Q[s % 2];
             R* Gs = keep ? G[s] : G[0];
             R* Qn = (s < 2) ? (keep ? Q[s + 1] : Q[(s + 1) % 2]) : nullptr;
-            stage(s, dt, Qs, Gs, Qn, s == 1);
+            stage(s, dt, Qs, Gs, Qn, s == 1 && !keep, !(keep && s == 2));
         }
         if (!keep) { R* t = W[0]; W[0] = W[3]; W[3] = t; }
     }
@@ -373,7 +376,7 @@ public:
         if (adjoint_ready) return;
         Q[2] = dalloc<R>((size_t)5 * m.sN + kRowSlack);
         G[1] = dalloc<R>((size_t)15 * m.sN + kRowSlack); G[2] = dalloc<R>((size_t)15 * m.sN + kRowSlack);
-        for (int k = 0; k < 4; k++) A[k] = dalloc<R>((size_t)5 * m.sC);
+        for (int k = 0; k < 4; k++) A[k] = dalloc<R>((size_t)5 * m.sC + kRowSlack);
         Qb = dalloc<R>((size_t)5 * m.sN); Gb = dalloc<R>((size_t)15 * m.sN);
         Sb = dalloc<R>((size_t)5 * m.sC);
         adjoint_ready = true;

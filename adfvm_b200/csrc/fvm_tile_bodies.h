@@ -124,34 +124,19 @@ template <typename R> __device__ __forceinline__ R block_max(R v, R* scratch /* 
     return v;   // valid in thread 0
 }
 
-// shared-memory carve-up common to both kernels: [qg 20*TS][extra ...][chunk][2 mbarriers]
+// Ampere-style asynchronous element copies (SASS LDGSTS) for the halo gather: no registers, no stall at issue
+template <int BYTES> __device__ __forceinline__ void cp_async_elem(void* dst, const void* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" ::"r"(smem_u32(dst)), "l"(src), "n"(BYTES) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+// shared-memory carve-up common to both kernels: [qg 20*TS][extra ...][chunk][3 mbarriers]
 template <typename R, int T, int TS, int W, int EXTRA> struct TileSmem {
     static constexpr size_t kChunkOff = ((size_t)(20 * TS + EXTRA) * sizeof(R) + 127) / 128 * 128;
     static constexpr size_t kBarOff = kChunkOff + Chunk<R, W>::kBytes;
-    static constexpr size_t kBytes = kBarOff + 16;
+    static constexpr size_t kBytes = kBarOff + 32;
 };
-
-// prologue: arm the barriers, start the bulk copies of the tile's own rows and of the first chunk, gather the halo rows
-template <typename R, int T, int TS, int W>
-__device__ __forceinline__ void tile_prologue(const MeshDev<R>& m, int t, const R* Q, const R* G, R* qg, R* chunk,
-                                              unsigned long long* bars, int p0, int np) {
-    const int c0 = t * T;
-    const int tid = threadIdx.x, nthr = blockDim.x;
-    if (tid == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); mbar_fence_init(); }
-    __syncthreads();
-    if (tid == 0) {
-        // rows may run past the last internal cell into ghost rows / padding (allocated, finite, unused)
-        mbar_expect_tx(&bars[0], 20u * T * (unsigned)sizeof(R));
-        for (int k = 0; k < 5; k++) bulk_g2s(qg + k * TS, Q + (long)k * m.sN + c0, T * (unsigned)sizeof(R), &bars[0]);
-        for (int k = 0; k < 15; k++) bulk_g2s(qg + (5 + k) * TS, G + (long)k * m.sN + c0, T * (unsigned)sizeof(R), &bars[0]);
-        if (np > 0) {
-            mbar_expect_tx(&bars[1], (unsigned)Chunk<R, W>::kBytes);
-            bulk_g2s(chunk, m.chunks + (long)p0 * Chunk<R, W>::kScalars, (unsigned)Chunk<R, W>::kBytes, &bars[1]);
-        }
-    }
-    const int h0 = m.halo_start[t], nh = m.halo_start[t + 1] - h0;
-    for (int h = tid; h < nh; h += nthr) tile_stage_cell<R, TS>(qg, T + h, Q, G, m.sN, m.halo_cell[h0 + h]);
-}
 #endif
 
 // ------------------------------------------------------------------------------------------ forward
@@ -160,7 +145,7 @@ template <typename R, int T, int TS, int W> struct FluxTileBody {
     static constexpr int kThreads = W;
     Phys<R> ph; MeshDev<R> m;
     const R *Q, *G;            // this stage's primitives / gradients (ghosts filled)
-    const R *W0, *W1, *W2;     // previous stage states (W1/W2 NULL when their alpha is 0)
+    const R *W0, *W1, *W2;     // previous stage states (W1/W2 NULL when their alpha is 0; never both set in SSPRK3)
     R a0, a1, a2, beta, dt;
     const R* S;                // source terms [5][sC]
     R* Wn;                     // new state
@@ -171,13 +156,13 @@ template <typename R, int T, int TS, int W> struct FluxTileBody {
     static size_t smem_bytes() { return Smem::kBytes; }
 #endif
 
-    // flux per unit area of one entry + the scatter weights A/V of its in-tile sides
-    FVM_HD void face(const Geom<R>& gm, const TileEntry& e, const R* qg, const R* ivol, Flux5<R>& F, R& wave, R& sO, R& sNb) const {
+    // flux per unit area of one entry + the scatter weights A/V of its in-tile sides (vol: the tile's own volumes [T])
+    FVM_HD void face(const Geom<R>& gm, const TileEntry& e, const R* qg, const R* vol, Flux5<R>& F, R& wave, R& sO, R& sNb) const {
         Prim<R> qL, qR; Grad<R> gL, gR;
         tile_load_cell<R, TS>(qg, e.lo, qL, gL); tile_load_cell<R, TS>(qg, e.ln, qR, gR);
         face_flux(ph, e.kind, gm, qL, gL, qR, gR, F, wave);
-        sO = e.lo < T ? gm.area * ivol[e.lo] : R(0);
-        sNb = e.ln < T ? gm.area * ivol[e.ln] : R(0);
+        sO = e.lo < T ? gm.area * rcp(vol[e.lo]) : R(0);
+        sNb = e.ln < T ? gm.area * rcp(vol[e.ln]) : R(0);
     }
     FVM_HD static void scatter(R* acc, int lo, int ln, const Flux5<R>& F, R wave, R sO, R sNb) {
         if (lo < T) {
@@ -191,14 +176,14 @@ template <typename R, int T, int TS, int W> struct FluxTileBody {
             a[4 * T] += F.rhoE * s; a[5 * T] += wave * sNb;
         }
     }
-    // RK stage update + primitives of the new state for cell c; res[k*T] = residual component k, res[5*T] = dtc
-    FVM_HD R finish(int c, const R* res) const {
+    // RK stage update + primitives of the new state for cell c; res[k*T] = residual component k, res[5*T] = dtc;
+    // w0/wx/src: this cell's previous-stage states and source, component stride ws (wx = W1 or W2, coefficient ax)
+    FVM_HD R finish(int c, const R* res, const R* w0, const R* wx, R ax, const R* src, int ws) const {
         R wn[5];
         for (int k = 0; k < 5; k++) {
-            R v = a0 * W0[(long)k * m.sC + c];
-            if (W1) v += a1 * W1[(long)k * m.sC + c];
-            if (W2) v += a2 * W2[(long)k * m.sC + c];
-            v += -beta * (res[k * T] - S[(long)k * m.sC + c]) * dt;
+            R v = a0 * w0[(long)k * ws];
+            if (wx) v += ax * wx[(long)k * ws];
+            v += -beta * (res[k * T] - src[(long)k * ws]) * dt;
             wn[k] = v;
             Wn[(long)k * m.sC + c] = v;
         }
@@ -209,22 +194,24 @@ template <typename R, int T, int TS, int W> struct FluxTileBody {
 #if !defined(__CUDACC__)
     void host_tile(int t) const {
         const int c0 = t * T, nc = (m.nInternalCells - c0 < T) ? m.nInternalCells - c0 : T;
-        std::vector<R> qg((size_t)20 * TS, R(0)), ivol(T, R(0)), acc((size_t)6 * T, R(0));
-        for (int l = 0; l < nc; l++) { tile_stage_cell<R, TS>(qg.data(), l, Q, G, m.sN, c0 + l); ivol[l] = R(1) / m.vol[c0 + l]; }
+        std::vector<R> qg((size_t)20 * TS, R(0)), vol(T, R(1)), acc((size_t)6 * T, R(0));
+        for (int l = 0; l < nc; l++) { tile_stage_cell<R, TS>(qg.data(), l, Q, G, m.sN, c0 + l); vol[l] = m.vol[c0 + l]; }
         for (int h = m.halo_start[t]; h < m.halo_start[t + 1]; h++) tile_stage_cell<R, TS>(qg.data(), T + h - m.halo_start[t], Q, G, m.sN, m.halo_cell[h]);
         for (int p = m.pass_start[t]; p < m.pass_start[t + 1]; p++) {
             const R* chunk = m.chunks + (long)p * Chunk<R, W>::kScalars;
             for (int i = 0; i < W; i++) {
                 TileEntry e; tile_decode(Chunk<R, W>::words(chunk)[i], e);
                 if (!e.valid) continue;
+                if ((e.lo >= T || e.ln >= T) && p - m.pass_start[t] < m.halo_pass[t]) throw std::runtime_error("halo_pass inconsistent");
                 Geom<R> gm; tile_load_geom<R, W>(chunk, i, gm);
                 Flux5<R> F; R wave, sO, sNb;
-                face(gm, e, qg.data(), ivol.data(), F, wave, sO, sNb);
+                face(gm, e, qg.data(), vol.data(), F, wave, sO, sNb);
                 scatter(acc.data(), e.lo, e.ln, F, wave, sO, sNb);
             }
         }
+        const R* wx = W1 ? W1 : W2; const R ax = W1 ? a1 : a2;
         R mx = R(-1e30);
-        for (int l = 0; l < nc; l++) { R d = finish(c0 + l, &acc[l]); mx = d > mx ? d : mx; }
+        for (int l = 0; l < nc; l++) { const int c = c0 + l; R d = finish(c, &acc[l], W0 + c, wx ? wx + c : nullptr, ax, S + c, m.sC); mx = d > mx ? d : mx; }
         if (dtc_partial) dtc_partial[t] = mx;
     }
 #else
@@ -232,45 +219,67 @@ template <typename R, int T, int TS, int W> struct FluxTileBody {
         const int c0 = t * T, nc = min(T, m.nInternalCells - c0);
         const int tid = threadIdx.x;
         R* qg = reinterpret_cast<R*>(smem);
-        R* ivol = qg + 20 * TS;
-        R* acc = ivol + T;
+        R* vol = qg + 20 * TS;
+        R* acc = vol + T;
         R* chunk = reinterpret_cast<R*>(smem + Smem::kChunkOff);
         unsigned long long* bars = reinterpret_cast<unsigned long long*>(smem + Smem::kBarOff);
         const int p0 = m.pass_start[t], np = m.pass_start[t + 1] - p0;
-        tile_prologue<R, T, TS, W>(m, t, Q, G, qg, chunk, bars, p0, np);
-        if (tid == 32) {      // the epilogue's inputs: bring them into L2 while the faces are computed
-            const unsigned bytes = (unsigned)(nc * sizeof(R)) & ~15u;
-            for (int k = 0; k < 5; k++) {
-                bulk_prefetch_l2(W0 + (long)k * m.sC + c0, bytes); bulk_prefetch_l2(S + (long)k * m.sC + c0, bytes);
-                if (W1) bulk_prefetch_l2(W1 + (long)k * m.sC + c0, bytes);
-                if (W2) bulk_prefetch_l2(W2 + (long)k * m.sC + c0, bytes);
-            }
+        const int h0 = m.halo_start[t], nh = m.halo_start[t + 1] - h0, hp = m.halo_pass[t];
+        const R* wx = W1 ? W1 : W2; const R ax = W1 ? a1 : a2;
+        constexpr unsigned kRow = T * (unsigned)sizeof(R);
+        if (tid == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); mbar_init(&bars[2], 1); mbar_fence_init(); }
+        __syncthreads();
+        if (tid == 0) {
+            // the tile's own rows (may run past the last internal cell into ghost rows / slack: allocated, unused) + first chunk
+            mbar_expect_tx(&bars[0], 21u * kRow);
+            for (int k = 0; k < 5; k++) bulk_g2s(qg + k * TS, Q + (long)k * m.sN + c0, kRow, &bars[0]);
+            for (int k = 0; k < 15; k++) bulk_g2s(qg + (5 + k) * TS, G + (long)k * m.sN + c0, kRow, &bars[0]);
+            bulk_g2s(vol, m.vol + c0, kRow, &bars[0]);
+            mbar_expect_tx(&bars[1], (unsigned)Chunk<R, W>::kBytes);
+            bulk_g2s(chunk, m.chunks + (long)p0 * Chunk<R, W>::kScalars, (unsigned)Chunk<R, W>::kBytes, &bars[1]);
         }
-        for (int l = tid; l < T; l += W) ivol[l] = l < nc ? rcp(m.vol[c0 + l]) : R(0);
+        // halo rows: asynchronous gather, consumed from pass `hp` on (the passes before it only touch the tile's own cells)
+        for (int h = tid; h < nh; h += W) {
+            const int cell = m.halo_cell[h0 + h];
+            for (int k = 0; k < 5; k++) cp_async_elem<sizeof(R)>(qg + k * TS + T + h, Q + (long)k * m.sN + cell);
+            for (int k = 0; k < 15; k++) cp_async_elem<sizeof(R)>(qg + (5 + k) * TS + T + h, G + (long)k * m.sN + cell);
+        }
+        cp_async_commit();
         for (int i = tid; i < 6 * T; i += W) acc[i] = R(0);
         mbar_wait(&bars[0], 0);
-        __syncthreads();
         for (int p = 0; p < np; p++) {
             mbar_wait(&bars[1], (unsigned)(p & 1));
             TileEntry e; tile_decode(Chunk<R, W>::words(chunk)[tid], e);
             Geom<R> gm; tile_load_geom<R, W>(chunk, tid, gm);
             const int cfirst = (int)((Chunk<R, W>::words(chunk)[0] >> 20) & 0x1Fu), clast = (int)((Chunk<R, W>::words(chunk)[W - 1] >> 20) & 0x1Fu);
-            __syncthreads();                       // every thread holds its metrics in registers: the chunk buffer is free
-            if (tid == 0 && p + 1 < np) {
+            if (p == hp) cp_async_wait_all();
+            __syncthreads();                       // metrics are in registers: the chunk buffer is free; halo rows visible from pass hp on
+            if (tid == 0) {
                 fence_proxy_async();
-                mbar_expect_tx(&bars[1], (unsigned)Chunk<R, W>::kBytes);
-                bulk_g2s(chunk, m.chunks + (long)(p0 + p + 1) * Chunk<R, W>::kScalars, (unsigned)Chunk<R, W>::kBytes, &bars[1]);
+                if (p + 1 < np) {
+                    mbar_expect_tx(&bars[1], (unsigned)Chunk<R, W>::kBytes);
+                    bulk_g2s(chunk, m.chunks + (long)(p0 + p + 1) * Chunk<R, W>::kScalars, (unsigned)Chunk<R, W>::kBytes, &bars[1]);
+                } else {
+                    // last pass: the chunk buffer now receives the RK update's inputs (W0, S, W1|W2 rows of the tile)
+                    mbar_expect_tx(&bars[2], (wx ? 15u : 10u) * kRow);
+                    for (int k = 0; k < 5; k++) {
+                        bulk_g2s(chunk + k * T, W0 + (long)k * m.sC + c0, kRow, &bars[2]);
+                        bulk_g2s(chunk + (5 + k) * T, S + (long)k * m.sC + c0, kRow, &bars[2]);
+                        if (wx) bulk_g2s(chunk + (10 + k) * T, wx + (long)k * m.sC + c0, kRow, &bars[2]);
+                    }
+                }
             }
             Flux5<R> F; R wave = R(0), sO = R(0), sNb = R(0);
-            if (e.valid) face(gm, e, qg, ivol, F, wave, sO, sNb);
+            if (e.valid) face(gm, e, qg, vol, F, wave, sO, sNb);
             const int col = e.valid ? e.col : -1;
             for (int c = cfirst; c <= clast; c++) {
                 if (col == c) scatter(acc, e.lo, e.ln, F, wave, sO, sNb);
                 __syncthreads();
             }
         }
+        mbar_wait(&bars[2], 0);
         R mx = R(-1e30);
-        for (int l = tid; l < nc; l += W) { R d = finish(c0 + l, acc + l); mx = d > mx ? d : mx; }
+        for (int l = tid; l < nc; l += W) { R d = finish(c0 + l, acc + l, chunk + l, wx ? chunk + 10 * T + l : nullptr, ax, chunk + 5 * T + l, T); mx = d > mx ? d : mx; }
         if (dtc_partial) {
             mx = block_max(mx, qg);
             if (tid == 0) dtc_partial[t] = mx;
@@ -289,20 +298,21 @@ template <typename R, int T, int TS, int W> struct FluxGradTileBody {
     const R *Q, *G; const R* abar; R coef;
     R *Qb, *Gb;
 #if defined(__CUDACC__)
-    typedef TileSmem<R, T, TS, W, 5 * TS + 20 * T> Smem;
+    typedef TileSmem<R, T, TS, W, 6 * TS + 20 * T> Smem;
     static size_t smem_bytes() { return Smem::kBytes; }
 #endif
 
-    // r = abar*coef/V of an internal cell, 0 for ghost cells (boundary faces scatter to their owner only)
-    FVM_HD void stage_r(R* r, int slot, int cell) const {
-        if (cell < m.nInternalCells) { const R iv = coef * rcp(m.vol[cell]); for (int k = 0; k < 5; k++) r[k * TS + slot] = abar[(long)k * m.sC + cell] * iv; }
-        else for (int k = 0; k < 5; k++) r[k * TS + slot] = R(0);
+    // ab [5][TS]: abar of the slot's cell (0 for ghost cells: boundary faces scatter to their owner only), vol [TS]
+    FVM_HD void stage_ab(R* ab, R* vol, int slot, int cell) const {
+        if (cell < m.nInternalCells) { for (int k = 0; k < 5; k++) ab[k * TS + slot] = abar[(long)k * m.sC + cell]; vol[slot] = m.vol[cell]; }
+        else { for (int k = 0; k < 5; k++) ab[k * TS + slot] = R(0); vol[slot] = R(1); }
     }
-    FVM_HD void face(const Geom<R>& gm, const TileEntry& e, const R* qg, const R* r, Prim<R>& qLb, Grad<R>& gLb, Prim<R>& qRb, Grad<R>& gRb) const {
+    FVM_HD void face(const Geom<R>& gm, const TileEntry& e, const R* qg, const R* ab, const R* vol, Prim<R>& qLb, Grad<R>& gLb, Prim<R>& qRb, Grad<R>& gRb) const {
         Prim<R> qL, qR; Grad<R> gL, gR;
         tile_load_cell<R, TS>(qg, e.lo, qL, gL); tile_load_cell<R, TS>(qg, e.ln, qR, gR);
+        const R sO = gm.area * coef * rcp(vol[e.lo]), sN_ = gm.area * coef * rcp(vol[e.ln]);
         R d[5];
-        for (int k = 0; k < 5; k++) d[k] = gm.area * (r[k * TS + e.lo] - r[k * TS + e.ln]);
+        for (int k = 0; k < 5; k++) d[k] = ab[k * TS + e.lo] * sO - ab[k * TS + e.ln] * sN_;
         Flux5<R> Fb; Fb.rho = d[0]; Fb.rhoU[0] = d[1]; Fb.rhoU[1] = d[2]; Fb.rhoU[2] = d[3]; Fb.rhoE = d[4];
         zero(qLb); zero(gLb); zero(qRb); zero(gRb);
         face_flux_vjp(ph, e.kind, gm, qL, gL, qR, gR, Fb, qLb, gLb, qRb, gRb);
@@ -331,11 +341,11 @@ template <typename R, int T, int TS, int W> struct FluxGradTileBody {
 #if !defined(__CUDACC__)
     void host_tile(int t) const {
         const int c0 = t * T, nc = (m.nInternalCells - c0 < T) ? m.nInternalCells - c0 : T;
-        std::vector<R> qg((size_t)20 * TS, R(0)), r((size_t)5 * TS, R(0)), acc((size_t)20 * T, R(0));
-        for (int l = 0; l < nc; l++) { tile_stage_cell<R, TS>(qg.data(), l, Q, G, m.sN, c0 + l); stage_r(r.data(), l, c0 + l); }
+        std::vector<R> qg((size_t)20 * TS, R(0)), ab((size_t)5 * TS, R(0)), vol(TS, R(1)), acc((size_t)20 * T, R(0));
+        for (int l = 0; l < nc; l++) { tile_stage_cell<R, TS>(qg.data(), l, Q, G, m.sN, c0 + l); stage_ab(ab.data(), vol.data(), l, c0 + l); }
         for (int h = m.halo_start[t]; h < m.halo_start[t + 1]; h++) {
             const int slot = T + h - m.halo_start[t];
-            tile_stage_cell<R, TS>(qg.data(), slot, Q, G, m.sN, m.halo_cell[h]); stage_r(r.data(), slot, m.halo_cell[h]);
+            tile_stage_cell<R, TS>(qg.data(), slot, Q, G, m.sN, m.halo_cell[h]); stage_ab(ab.data(), vol.data(), slot, m.halo_cell[h]);
         }
         for (int p = m.pass_start[t]; p < m.pass_start[t + 1]; p++) {
             const R* chunk = m.chunks + (long)p * Chunk<R, W>::kScalars;
@@ -344,7 +354,7 @@ template <typename R, int T, int TS, int W> struct FluxGradTileBody {
                 if (!e.valid) continue;
                 Geom<R> gm; tile_load_geom<R, W>(chunk, i, gm);
                 Prim<R> qLb, qRb; Grad<R> gLb, gRb;
-                face(gm, e, qg.data(), r.data(), qLb, gLb, qRb, gRb);
+                face(gm, e, qg.data(), ab.data(), vol.data(), qLb, gLb, qRb, gRb);
                 scatter(acc.data(), e, ghost_of(t, e), qLb, gLb, qRb, gRb);
             }
         }
@@ -355,23 +365,46 @@ template <typename R, int T, int TS, int W> struct FluxGradTileBody {
         const int c0 = t * T, nc = min(T, m.nInternalCells - c0);
         const int tid = threadIdx.x;
         R* qg = reinterpret_cast<R*>(smem);
-        R* r = qg + 20 * TS;
-        R* acc = r + 5 * TS;
+        R* ab = qg + 20 * TS;
+        R* vol = ab + 5 * TS;
+        R* acc = vol + TS;
         R* chunk = reinterpret_cast<R*>(smem + Smem::kChunkOff);
         unsigned long long* bars = reinterpret_cast<unsigned long long*>(smem + Smem::kBarOff);
         const int p0 = m.pass_start[t], np = m.pass_start[t + 1] - p0;
-        tile_prologue<R, T, TS, W>(m, t, Q, G, qg, chunk, bars, p0, np);
-        for (int l = tid; l < T; l += W) { if (l < nc) stage_r(r, l, c0 + l); else for (int k = 0; k < 5; k++) r[k * TS + l] = R(0); }
-        const int h0 = m.halo_start[t], nh = m.halo_start[t + 1] - h0;
-        for (int h = tid; h < nh; h += W) stage_r(r, T + h, m.halo_cell[h0 + h]);
+        const int h0 = m.halo_start[t], nh = m.halo_start[t + 1] - h0, hp = m.halo_pass[t];
+        constexpr unsigned kRow = T * (unsigned)sizeof(R);
+        if (tid == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); mbar_fence_init(); }
+        __syncthreads();
+        if (tid == 0) {
+            mbar_expect_tx(&bars[0], 26u * kRow);
+            for (int k = 0; k < 5; k++) bulk_g2s(qg + k * TS, Q + (long)k * m.sN + c0, kRow, &bars[0]);
+            for (int k = 0; k < 15; k++) bulk_g2s(qg + (5 + k) * TS, G + (long)k * m.sN + c0, kRow, &bars[0]);
+            for (int k = 0; k < 5; k++) bulk_g2s(ab + k * TS, abar + (long)k * m.sC + c0, kRow, &bars[0]);
+            bulk_g2s(vol, m.vol + c0, kRow, &bars[0]);
+            mbar_expect_tx(&bars[1], (unsigned)Chunk<R, W>::kBytes);
+            bulk_g2s(chunk, m.chunks + (long)p0 * Chunk<R, W>::kScalars, (unsigned)Chunk<R, W>::kBytes, &bars[1]);
+        }
+        for (int h = tid; h < nh; h += W) {
+            const int cell = m.halo_cell[h0 + h], slot = T + h;
+            for (int k = 0; k < 5; k++) cp_async_elem<sizeof(R)>(qg + k * TS + slot, Q + (long)k * m.sN + cell);
+            for (int k = 0; k < 15; k++) cp_async_elem<sizeof(R)>(qg + (5 + k) * TS + slot, G + (long)k * m.sN + cell);
+            if (cell < m.nInternalCells) {
+                for (int k = 0; k < 5; k++) cp_async_elem<sizeof(R)>(ab + k * TS + slot, abar + (long)k * m.sC + cell);
+                cp_async_elem<sizeof(R)>(vol + slot, m.vol + cell);
+            } else {
+                for (int k = 0; k < 5; k++) ab[k * TS + slot] = R(0);
+                vol[slot] = R(1);
+            }
+        }
+        cp_async_commit();
         for (int i = tid; i < 20 * T; i += W) acc[i] = R(0);
         mbar_wait(&bars[0], 0);
-        __syncthreads();
         for (int p = 0; p < np; p++) {
             mbar_wait(&bars[1], (unsigned)(p & 1));
             TileEntry e; tile_decode(Chunk<R, W>::words(chunk)[tid], e);
             Geom<R> gm; tile_load_geom<R, W>(chunk, tid, gm);
             const int cfirst = (int)((Chunk<R, W>::words(chunk)[0] >> 20) & 0x1Fu), clast = (int)((Chunk<R, W>::words(chunk)[W - 1] >> 20) & 0x1Fu);
+            if (p == hp) cp_async_wait_all();
             __syncthreads();
             if (tid == 0 && p + 1 < np) {
                 fence_proxy_async();
@@ -380,7 +413,7 @@ template <typename R, int T, int TS, int W> struct FluxGradTileBody {
             }
             Prim<R> qLb, qRb; Grad<R> gLb, gRb;
             int ghost = -1;
-            if (e.valid) { face(gm, e, qg, r, qLb, gLb, qRb, gRb); if (e.kind != (int)FACE_COUPLED || e.ln >= T) ghost = ghost_of(t, e); }
+            if (e.valid) { face(gm, e, qg, ab, vol, qLb, gLb, qRb, gRb); ghost = ghost_of(t, e); }
             const int col = e.valid ? e.col : -1;
             for (int c = cfirst; c <= clast; c++) {
                 if (col == c) scatter(acc, e, ghost, qLb, gLb, qRb, gRb);

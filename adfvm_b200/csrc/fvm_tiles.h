@@ -42,6 +42,7 @@ struct TilePlan {
     std::vector<int> halo_start;                     // [nTiles+1] offsets into halo_cell
     std::vector<int> halo_cell;                      // NEW cell index (ghost cells: >= C) of each halo slot
     int maxHalo = 0;
+    std::vector<int> halo_pass;                      // [nTiles] first pass of the tile (relative) that reads a halo slot
     double evals_per_cell() const { return cell_new2old.empty() ? 0. : (double)nEntries / (double)cell_new2old.size(); }
 };
 
@@ -133,6 +134,7 @@ TilePlan build_tile_plan(int C, int Fi, int F, const int* owner, const int* neig
     int nextFace = 0;
     std::vector<int> faces; std::vector<int> colour; std::vector<uint32_t> used(T);
     std::vector<int> order;
+    int nInteriorColours = 0;
     const int N = C + (F - Fi);
     std::vector<int> slot_of(N, -1), slot_tile(N, -1);
     P.halo_start.assign(P.nTiles + 1, 0);
@@ -152,28 +154,35 @@ TilePlan build_tile_plan(int C, int Fi, int F, const int* owner, const int* neig
                 else faces.push_back(f);
             }
         }
-        // greedy colouring: no two faces of one colour share an in-tile cell
-        std::fill(used.begin(), used.end(), 0u);
+        // greedy colouring: no two faces of one colour share an in-tile cell. Faces with both cells in the tile are
+        // coloured first, faces that need a halo cell (cut by the tile boundary, or boundary faces) get colours above
+        // them: sorted by colour, the passes that only need the tile's own rows come first and overlap the halo gather.
         colour.assign(faces.size(), 0);
         int ncol = 0;
-        for (size_t i = 0; i < faces.size(); i++) {
-            const int f = faces[i];
-            const int a = P.cell_old2new[owner[f]];
-            const int b = f < Fi ? P.cell_old2new[neigh[f]] : -1;
-            const int la = (a >= c0 && a < c1) ? a - c0 : -1, lb = (b >= c0 && b < c1) ? b - c0 : -1;
-            uint32_t m = (la >= 0 ? used[la] : 0u) | (lb >= 0 ? used[lb] : 0u);
-            int col = 0;
-            while (m & (1u << col)) col++;
-            if (col >= 32) throw std::runtime_error("face colouring needs more than 32 colours");
-            colour[i] = col; ncol = std::max(ncol, col + 1);
-            if (la >= 0) used[la] |= 1u << col;
-            if (lb >= 0) used[lb] |= 1u << col;
+        for (int group = 0; group < 2; group++) {
+            std::fill(used.begin(), used.end(), 0u);
+            const int base = ncol;
+            for (size_t i = 0; i < faces.size(); i++) {
+                const int f = faces[i];
+                const int a = P.cell_old2new[owner[f]];
+                const int b = f < Fi ? P.cell_old2new[neigh[f]] : -1;
+                const int la = (a >= c0 && a < c1) ? a - c0 : -1, lb = (b >= c0 && b < c1) ? b - c0 : -1;
+                if (((la >= 0 && lb >= 0) ? 0 : 1) != group) continue;
+                uint32_t m = (la >= 0 ? used[la] : 0u) | (lb >= 0 ? used[lb] : 0u);
+                int col = 0;
+                while (m & (1u << col)) col++;
+                if (base + col >= 32) throw std::runtime_error("face colouring needs more than 32 colours");
+                colour[i] = base + col; ncol = std::max(ncol, base + col + 1);
+                if (la >= 0) used[la] |= 1u << col;
+                if (lb >= 0) used[lb] |= 1u << col;
+            }
+            if (group == 0) nInteriorColours = ncol;
         }
         P.maxColours = std::max(P.maxColours, ncol);
         order.resize(faces.size());
         std::iota(order.begin(), order.end(), 0);
         std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return colour[x] < colour[y]; });
-        int nHalo = 0;
+        int nHalo = 0, firstHaloEntry = -1, nEnt = 0;
         auto slot = [&](int cell) {           // cell: NEW index (ghosts >= C)
             if (cell >= c0 && cell < c1) return cell - c0;
             if (slot_tile[cell] != t) { slot_tile[cell] = t; slot_of[cell] = T + nHalo++; P.halo_cell.push_back(cell); }
@@ -187,10 +196,12 @@ TilePlan build_tile_plan(int C, int Fi, int F, const int* owner, const int* neig
             if (b < 0 || b >= N) throw std::runtime_error("neighbour out of range");
             const int la = slot(a), lb = slot(b);
             if (la >= 1024 || lb >= 1024) throw std::runtime_error("tile halo too large");
+            if ((la >= T || lb >= T) && firstHaloEntry < 0) firstHaloEntry = nEnt;
             P.ent_face.push_back(P.face_old2new[f]);
             P.ent_loc.push_back(tile_pack(la, lb, colour[i], f < Fi ? 0 : (int)bkind[f - Fi], 1));
-            P.nEntries++;
+            P.nEntries++; nEnt++;
         }
+        P.halo_pass.push_back(firstHaloEntry < 0 ? (nEnt + W - 1) / W : firstHaloEntry / W);
         // pad the last pass; padding repeats the last colour so that a pass's colour range is [first slot, last slot]
         while (P.ent_face.size() % (size_t)W) { P.ent_face.push_back(-1); P.ent_loc.push_back(tile_pack(0, 0, ncol ? ncol - 1 : 0, 0, 0)); }
         P.maxHalo = std::max(P.maxHalo, nHalo);

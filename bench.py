@@ -127,7 +127,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--n", type=int, default=int(os.environ.get("ADFVM_BENCH_N", "128")), help="cells per side per GPU")
+    ap.add_argument("--size", dest="n", type=int, default=int(os.environ.get("ADFVM_BENCH_N", "128")), help="cells per side per GPU")
     ap.add_argument("--dtype", default="f64", choices=["f64", "f32"])
     ap.add_argument("--cpu-n", type=int, default=40, help="box size of the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
