@@ -25,7 +25,7 @@ template <class Body> __global__ void __launch_bounds__(kBlock) k_run_discard(co
     if (i < n) (void)b(i);
 }
 
-template <class Body> __global__ void __launch_bounds__(Body::kThreads) k_tile(const Body b) {
+template <class Body> __global__ void __launch_bounds__(Body::kThreads, Body::kMinBlocks) k_tile(const Body b) {
     extern __shared__ __align__(16) unsigned char tile_smem[];
     b.device_tile(blockIdx.x, tile_smem);
 }

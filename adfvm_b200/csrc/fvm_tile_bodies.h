@@ -143,6 +143,7 @@ template <typename R, int T, int TS, int W, int EXTRA> struct TileSmem {
 template <typename R, int T, int TS, int W> struct FluxTileBody {
     static constexpr const char* kName = "flux_tile";
     static constexpr int kThreads = W;
+    static constexpr int kMinBlocks = (sizeof(R) == 8 && W == 160) ? 3 : 1;
     Phys<R> ph; MeshDev<R> m;
     const R *Q, *G;            // this stage's primitives / gradients (ghosts filled)
     const R *W0, *W1, *W2;     // previous stage states (W1/W2 NULL when their alpha is 0; never both set in SSPRK3)
@@ -294,6 +295,7 @@ template <typename R, int T, int TS, int W> struct FluxTileBody {
 template <typename R, int T, int TS, int W> struct FluxGradTileBody {
     static constexpr const char* kName = "flux_grad_tile";
     static constexpr int kThreads = W;
+    static constexpr int kMinBlocks = 1;
     Phys<R> ph; MeshDev<R> m;
     const R *Q, *G; const R* abar; R coef;
     R *Qb, *Gb;
