@@ -35,7 +35,7 @@ EXPORTS = ["adfvm_last_error", "adfvm_version", "adfvm_is_cuda", "adfvm_create",
            "adfvm_set_mesh", "adfvm_set_bc_value", "adfvm_set_objective", "adfvm_set_source", "adfvm_primal",
            "adfvm_primal_grad", "adfvm_primal_step_resident", "adfvm_adjoint_step_resident", "adfvm_get_dtc_obj",
            "adfvm_get_state", "adfvm_sync", "adfvm_launch_count", "adfvm_device_bytes", "adfvm_comm_unique_id",
-           "adfvm_comm_init", "adfvm_kernel_timing", "adfvm_kernel_report", "adfvm_set_tile_cells", "adfvm_tile_stats"]
+           "adfvm_comm_init", "adfvm_kernel_timing", "adfvm_kernel_report", "adfvm_set_tile_cells", "adfvm_tile_stats", "adfvm_tile_halo_stats"]
 
 
 class Lib:
@@ -69,6 +69,7 @@ class Lib:
         d.adfvm_kernel_report.argtypes = [vp, C.c_char_p, i32]
         d.adfvm_set_tile_cells.argtypes = [vp, i32]
         d.adfvm_tile_stats.argtypes = [vp, C.POINTER(f64), C.POINTER(i32), C.POINTER(i32), C.POINTER(i32)]
+        d.adfvm_tile_halo_stats.argtypes = [vp, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32), i32]
         d.adfvm_comm_unique_id.argtypes = [vp]
         d.adfvm_comm_init.argtypes = [vp, vp, i32, i32]
 

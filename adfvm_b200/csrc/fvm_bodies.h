@@ -40,10 +40,11 @@ template <typename R> struct MeshDev {
     const unsigned char *bpatch;         // [nGhostCells] patch index of each boundary face
     const PatchDev<R>* patches;
     int nPatches;
-    // tiles (fvm_tiles.h): tile t owns cells [t*T, min(C,(t+1)*T)) and the per-pass chunks [pass_start[t], pass_start[t+1])
+    // tiles (fvm_tiles.h): tile t owns cells [t*T, min(C,(t+1)*T)); its sub-tile w (32 cells, one warp) owns the per-round
+    // chunks [round_start[t*T/32+w], round_start[t*T/32+w+1])
     int T, nTiles;
-    const int* pass_start; const R* chunks;
-    const int* halo_pass;                // [nTiles] first pass (relative to pass_start) whose entries read halo slots
+    const int* round_start; const R* chunks;
+    const int* halo_round;               // [nTiles*T/32] first round (relative to round_start) whose entries read halo slots
     const int* halo_start; const int* halo_cell;    // tile t's halo slots T.. hold cells halo_cell[halo_start[t]..halo_start[t+1])
     const int* cell_perm;                // [C] device cell -> reference (host) cell
 };

@@ -60,7 +60,8 @@ public:
     int *bcells = 0; int nBcells = 0;
     TilePlan plan; int tile_cells = 128; R* tile_partial = 0; double tile_evals_per_cell = 0; int tile_colours = 0, tile_max_halo = 0;
     int tile_variant = 0;
-    enum { kHalo128s = 160, kHalo128 = 256, kHalo64 = 384, kTileThreads = 128,
+    std::vector<int> tile_halo_hist;          // tiles per halo-size bin of 32 slots (introspection)
+    enum { kHalo128s = 192, kHalo128 = 256, kHalo64 = 384,
            kRowSlack = 128 };   // the tile kernels bulk-copy whole T-cell rows: the last tile may read past the last row   // halo slots of the two tile-kernel instantiations (T=128: TS=384, T=64: TS=448)
     bool have_mesh = false, have_state = false, adjoint_ready = false;
     std::vector<void*> owned;                 // everything to free
@@ -123,11 +124,11 @@ public:
             const unsigned char k = coupled ? FACE_COUPLED : (h.meshType == 4 ? FACE_CHARACTERISTIC : FACE_BOUNDARY);
             for (int i = 0; i < h.nFaces; i++) bkind[h.startFace - Fi + i] = k;
         }
-        plan = build_tile_plan<R>(C, Fi, F, owner, neighbour, cellFaces, deltas, deltasUnit, bkind.data(), tile_cells, kTileThreads);
+        plan = build_tile_plan<R>(C, Fi, F, owner, neighbour, cellFaces, deltas, deltasUnit, bkind.data(), tile_cells);
         if (tile_cells == 128 && plan.maxHalo > kHalo128)
-            plan = build_tile_plan<R>(C, Fi, F, owner, neighbour, cellFaces, deltas, deltasUnit, bkind.data(), 64, kTileThreads);
+            plan = build_tile_plan<R>(C, Fi, F, owner, neighbour, cellFaces, deltas, deltasUnit, bkind.data(), 64);
         if (plan.T == 64 && plan.maxHalo > kHalo64) throw std::runtime_error("tile halo exceeds the kernel's capacity");
-        // kernel variant: (T, TS) = (128, 288) for compact 3-D tiles (halo <= 160: three fp64 CTAs per SM), (128, 384), (64, 448)
+        // kernel variant: (T, TS) = (128, 320) for compact 3-D tiles (halo <= 192; ragged box sizes reach 170: three fp64 forward CTAs and two reverse CTAs per SM), (128, 384), (64, 448)
         tile_variant = plan.T == 64 ? 2 : (plan.maxHalo <= kHalo128s ? 0 : 1);
         m.T = plan.T; m.nTiles = plan.nTiles;
         int* d_cperm = dalloc<int>(m.sC); ex.upload(d_cperm, plan.cell_new2old.data(), (size_t)C * 4); m.cell_perm = d_cperm;
@@ -142,8 +143,8 @@ public:
             const size_t nslots = plan.ent_face.size();
             int* t_face = (int*)ex.alloc((nslots + 1) * 4); ex.upload(t_face, plan.ent_face.data(), nslots * 4);
             unsigned* t_word = (unsigned*)ex.alloc((nslots + 1) * 4); ex.upload(t_word, plan.ent_loc.data(), nslots * 4);
-            R* d_chunks = dalloc<R>((nslots / kTileThreads) * (size_t)Chunk<R, kTileThreads>::kScalars + 16);
-            run((int)nslots, FillChunksBody<R, kTileThreads>{t_face, t_word, m.sF, m.area, m.normal, m.idelta, t_dunit, t_linw, t_quadw, d_chunks});
+            R* d_chunks = dalloc<R>((nslots / kRound) * (size_t)Chunk<R, kRound>::kScalars + 16);
+            run((int)nslots, FillChunksBody<R, kRound>{t_face, t_word, m.sF, m.area, m.normal, m.idelta, t_dunit, t_linw, t_quadw, d_chunks});
             m.chunks = d_chunks;
             ex.sync(); ex.free(t_dunit); ex.free(t_linw); ex.free(t_quadw); ex.free(t_face); ex.free(t_word);
         }
@@ -183,14 +184,16 @@ public:
         nBcells = (int)bc_list.size();
         bcells = dalloc<int>(nBcells + 1); ex.upload(bcells, bc_list.data(), (size_t)nBcells * 4);
         {
-            int* d_ps = dalloc<int>(plan.pass_start.size()); ex.upload(d_ps, plan.pass_start.data(), plan.pass_start.size() * 4); m.pass_start = d_ps;
-            int* d_hp = dalloc<int>(plan.halo_pass.size() + 1); ex.upload(d_hp, plan.halo_pass.data(), plan.halo_pass.size() * 4); m.halo_pass = d_hp;
+            int* d_ps = dalloc<int>(plan.round_start.size()); ex.upload(d_ps, plan.round_start.data(), plan.round_start.size() * 4); m.round_start = d_ps;
+            int* d_hp = dalloc<int>(plan.halo_round.size() + 1); ex.upload(d_hp, plan.halo_round.data(), plan.halo_round.size() * 4); m.halo_round = d_hp;
             int* d_hs = dalloc<int>(plan.halo_start.size()); ex.upload(d_hs, plan.halo_start.data(), plan.halo_start.size() * 4); m.halo_start = d_hs;
             int* d_hc = dalloc<int>(plan.halo_cell.size() + 1); ex.upload(d_hc, plan.halo_cell.data(), plan.halo_cell.size() * 4); m.halo_cell = d_hc;
-            tile_partial = dalloc<R>(plan.nTiles + 1);
+            tile_partial = dalloc<R>((size_t)plan.nTiles * plan.NW + 1);
             ex.sync();
         }
         tile_evals_per_cell = plan.evals_per_cell(); tile_colours = plan.maxColours; tile_max_halo = plan.maxHalo;
+        tile_halo_hist.assign(32, 0);
+        for (int t = 0; t < plan.nTiles; t++) tile_halo_hist[std::min(31, (plan.halo_start[t + 1] - plan.halo_start[t]) / 32)]++;
         // the plan's host vectors are only needed for the I/O permutation, which lives on the device: release them
         plan = TilePlan(); plan.T = m.T; plan.nTiles = m.nTiles;
         // patches
@@ -338,11 +341,11 @@ public:
         else if (tile_variant == 1) run_flux_tile<128, 128 + kHalo128>(s, dt, Qs, Gs, Qnext, want_dtc_obj);
         else run_flux_tile<64, 64 + kHalo64>(s, dt, Qs, Gs, Qnext, want_dtc_obj);
         launches++;
-        if (want_dtc_obj) { ex.reduce_max_buffer(tile_partial, m.nTiles, red); launches += 2; }
+        if (want_dtc_obj) { ex.reduce_max_buffer(tile_partial, m.nTiles * (m.T / kRound), red); launches += 2; }
     }
 
     template <int T, int TS> void run_flux_tile(int s, R dt, R* Qs, R* Gs, R* Qnext, bool want_dtc_obj) {
-        FluxTileBody<R, T, TS, kTileThreads> fb;
+        FluxTileBody<R, T, TS> fb;
         fb.ph = ph; fb.m = m; fb.Q = Qs; fb.G = Gs;
         fb.W0 = W[0]; fb.W1 = RK_ALPHA[s][1] != 0. ? W[1] : nullptr; fb.W2 = RK_ALPHA[s][2] != 0. ? W[2] : nullptr;
         fb.a0 = (R)RK_ALPHA[s][0]; fb.a1 = (R)RK_ALPHA[s][1]; fb.a2 = (R)RK_ALPHA[s][2];
@@ -398,9 +401,9 @@ public:
         const int C = m.nInternalCells;
         for (int s = 2; s >= 0; s--) {
             const R coef = (R)(-RK_BETA[s]) * dt;
-            if (tile_variant == 0) ex.run_tiles(m.nTiles, FluxGradTileBody<R, 128, 128 + kHalo128s, kTileThreads>{ph, m, Q[s], G[s], A[s + 1], coef, Qb, Gb});
-            else if (tile_variant == 1) ex.run_tiles(m.nTiles, FluxGradTileBody<R, 128, 128 + kHalo128, kTileThreads>{ph, m, Q[s], G[s], A[s + 1], coef, Qb, Gb});
-            else ex.run_tiles(m.nTiles, FluxGradTileBody<R, 64, 64 + kHalo64, kTileThreads>{ph, m, Q[s], G[s], A[s + 1], coef, Qb, Gb});
+            if (tile_variant == 0) ex.run_tiles(m.nTiles, FluxGradTileBody<R, 128, 128 + kHalo128s>{ph, m, Q[s], G[s], A[s + 1], coef, Qb, Gb});
+            else if (tile_variant == 1) ex.run_tiles(m.nTiles, FluxGradTileBody<R, 128, 128 + kHalo128>{ph, m, Q[s], G[s], A[s + 1], coef, Qb, Gb});
+            else ex.run_tiles(m.nTiles, FluxGradTileBody<R, 64, 64 + kHalo64>{ph, m, Q[s], G[s], A[s + 1], coef, Qb, Gb});
             launches++;
             const R* rG = halo_reverse(Gb, 15);
             run(nBcells, GhostGradAdjBody<R>{m, bcells, Gb, rG});

@@ -1,28 +1,31 @@
-// Tiled flux kernels: one CTA per tile of T consecutive cells (fvm_tiles.h), one thread per face entry.
+// Tiled flux kernels: one CTA per tile of T consecutive cells (fvm_tiles.h), one WARP per sub-tile of 32 cells,
+// one thread per face entry of the warp's current round.
 //
 //   flux_tile       a8-a12: face flux (reconstruction + Riemann + viscous, adFVM/density.py:253-331) of every face
-//                   touching the tile, scatter +F*A/V_owner / -F*A/V_neighbour (adFVM/op.py:12-29) into
-//                   shared-memory accumulators, then RK stage update (adFVM/timestep.py:35-45) and the primitive
-//                   conversion of the new state (adFVM/density.py:162-171) for the tile's cells.
-//   flux_grad_tile  reverse of the flux + scatter: VJP of every face once, both sides' shares summed into
-//                   shared-memory accumulators; ghost rows of boundary faces written directly (exclusive writer).
+//                   touching the sub-tile, scatter +F*A/V_owner / -F*A/V_neighbour (adFVM/op.py:12-29) into the
+//                   sub-tile's shared-memory accumulators, then RK stage update (adFVM/timestep.py:35-45) and the
+//                   primitive conversion of the new state (adFVM/density.py:162-171) for the sub-tile's cells.
+//   flux_grad_tile  reverse of the flux + scatter: VJP of every face of the sub-tile, the shares of the sub-tile's
+//                   own cells summed into shared-memory accumulators; ghost rows of boundary faces written directly
+//                   (exclusive writer).
 //
-// Data movement of one CTA (R = scalar, W = threads = face entries per pass):
-//   * face metrics live in HBM as per-pass CHUNKS [16][W] R + [W] u32 (area, n, 1/delta, dUnit, linW, quadW and the
-//     packed entry word), laid out in the order the tile consumes them; one cp.async.bulk (TMA engine, SASS UBLKCP)
-//     per pass streams a chunk into shared memory, completion on an mbarrier, issued one pass ahead of its use;
+// Data movement of one CTA (R = scalar):
 //   * qg [20][TS]: U(3),T,p and the 15 gradient components of the tile's own cells (slots [0,T): 20 bulk row copies of
-//     the SoA arrays) and of its halo (slots [T,T+nHalo): cells of other tiles / ghost cells, gathered once);
-//   * forward:  ivol [T] 1/V, acc [6][T] residual(5) + dtc          reverse:  r [5][TS] = abar*coef/V, acc [20][T].
-// The per-face code therefore touches shared memory only, with compile-time strides and no branches on residency.
-//
-// Scatter order: entries are sorted by colour, faces of one colour never share an in-tile cell, and colours are
-// applied one after the other (barrier in between) -> every cell receives its contributions in entry order.
+//     the SoA arrays, cp.async.bulk / SASS UBLKCP, completion on an mbarrier) and of its halo (slots [T,T+nHalo): cells
+//     of other tiles / ghost cells, gathered once with LDGSTS, completion on a second mbarrier);
+//   * face metrics live in HBM as per-round CHUNKS [16][32] R + [32] u32 (area, n, 1/delta, dUnit, linW, quadW and the
+//     packed entry word) in the order the warp consumes them; one bulk copy per warp and round streams a chunk into the
+//     warp's own buffer, issued one round ahead of its use, completion on the warp's own mbarrier;
+//   * forward:  vol [T], acc [6][T] residual(5) + dtc          reverse:  ab [5][TS] = abar, vol [TS], acc [20][T].
+// After the staging the warps of a CTA never synchronise with each other: a warp only writes the accumulator columns
+// of its own 32 cells, and the order inside a warp is fixed by the colouring (__syncwarp between colours).
 // The CPU simulator (tests/hostsim) runs the same face/scatter/finish functions over the entries sequentially,
 // which is the same order.
 #pragma once
 #include "fvm_bodies.h"
 #if !defined(__CUDACC__)
+#include <limits>
+#include <stdexcept>
 #include <vector>
 #endif
 
@@ -36,10 +39,11 @@ template <typename R, int W> struct Chunk {
     FVM_HD static unsigned* words(R* chunk) { return reinterpret_cast<unsigned*>(chunk + 16 * W); }
 };
 
-struct TileEntry { int lo, ln, col, kind; bool valid; };
+struct TileEntry { int lo, ln, col, kind; bool valid, so, sn, ghost; };   // so/sn: scatter to the owner / neighbour side
 FVM_HD void tile_decode(unsigned w, TileEntry& e) {
     e.lo = (int)(w & 0x3FFu); e.ln = (int)((w >> 10) & 0x3FFu); e.col = (int)((w >> 20) & 0x1Fu);
     e.kind = (int)((w >> 25) & 3u); e.valid = ((w >> 27) & 1u) != 0;
+    e.so = ((w >> 28) & 1u) != 0; e.sn = ((w >> 29) & 1u) != 0; e.ghost = ((w >> 30) & 1u) != 0;
 }
 template <typename R, int W> FVM_HD void tile_load_geom(const R* chunk, int i, Geom<R>& g) {
     const R* p = chunk + i;
@@ -111,39 +115,36 @@ __device__ __forceinline__ void bulk_prefetch_l2(const void* src, unsigned bytes
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-template <typename R> __device__ __forceinline__ R block_max(R v, R* scratch /* >= 32 */) {
+template <typename R> __device__ __forceinline__ R warp_max(R v) {
     for (int o = 16; o > 0; o >>= 1) { R x = __shfl_down_sync(0xffffffffu, v, o); v = x > v ? x : v; }
-    const int w = threadIdx.x >> 5, l = threadIdx.x & 31, nw = (blockDim.x + 31) >> 5;
-    __syncthreads();
-    if (l == 0) scratch[w] = v;
-    __syncthreads();
-    if (w == 0) {
-        v = l < nw ? scratch[l] : R(-1e30);
-        for (int o = 16; o > 0; o >>= 1) { R x = __shfl_down_sync(0xffffffffu, v, o); v = x > v ? x : v; }
-    }
-    return v;   // valid in thread 0
+    return v;   // valid in lane 0
 }
 
 // Ampere-style asynchronous element copies (SASS LDGSTS) for the halo gather: no registers, no stall at issue
 template <int BYTES> __device__ __forceinline__ void cp_async_elem(void* dst, const void* src) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" ::"r"(smem_u32(dst)), "l"(src), "n"(BYTES) : "memory");
 }
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+// the mbarrier (initialised with one pending arrival per thread) receives this thread's arrival once all its earlier
+// cp.async copies have landed
+__device__ __forceinline__ void cp_async_arrive(unsigned long long* bar) {
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 
-// shared-memory carve-up common to both kernels: [qg 20*TS][extra ...][chunk][3 mbarriers]
-template <typename R, int T, int TS, int W, int EXTRA> struct TileSmem {
+// shared-memory carve-up common to both kernels: [qg 20*TS][extra ...][one chunk per warp][2 + T/32 mbarriers]
+template <typename R, int T, int TS, int EXTRA> struct TileSmem {
+    static constexpr int NW = T / 32;
     static constexpr size_t kChunkOff = ((size_t)(20 * TS + EXTRA) * sizeof(R) + 127) / 128 * 128;
-    static constexpr size_t kBarOff = kChunkOff + Chunk<R, W>::kBytes;
-    static constexpr size_t kBytes = kBarOff + 32;
+    static constexpr size_t kBarOff = kChunkOff + (size_t)NW * Chunk<R, 32>::kBytes;
+    static constexpr size_t kBytes = kBarOff + 8 * (2 + NW);
 };
 #endif
 
 // ------------------------------------------------------------------------------------------ forward
-template <typename R, int T, int TS, int W> struct FluxTileBody {
+template <typename R, int T, int TS> struct FluxTileBody {
     static constexpr const char* kName = "flux_tile";
-    static constexpr int kThreads = W;
-    static constexpr int kMinBlocks = (sizeof(R) == 8 && W == 160) ? 3 : 1;
+    static constexpr int kThreads = T, NW = T / 32;
+    static constexpr int kMinBlocks = 1;
+    typedef Chunk<R, 32> Ch;
     Phys<R> ph; MeshDev<R> m;
     const R *Q, *G;            // this stage's primitives / gradients (ghosts filled)
     const R *W0, *W1, *W2;     // previous stage states (W1/W2 NULL when their alpha is 0; never both set in SSPRK3)
@@ -151,28 +152,28 @@ template <typename R, int T, int TS, int W> struct FluxTileBody {
     const R* S;                // source terms [5][sC]
     R* Wn;                     // new state
     R* Qn;                     // primitives of the new state (may be NULL)
-    R* dtc_partial;            // [nTiles] per-tile max of dtc (may be NULL)
+    R* dtc_partial;            // [nTiles*NW] per-sub-tile max of dtc (may be NULL)
 #if defined(__CUDACC__)
-    typedef TileSmem<R, T, TS, W, 7 * T> Smem;
+    typedef TileSmem<R, T, TS, 7 * T> Smem;
     static size_t smem_bytes() { return Smem::kBytes; }
 #endif
 
-    // flux per unit area of one entry + the scatter weights A/V of its in-tile sides (vol: the tile's own volumes [T])
+    // flux per unit area of one entry + the scatter weights A/V of its sub-tile sides (vol: the tile's own volumes [T])
     FVM_HD void face(const Geom<R>& gm, const TileEntry& e, const R* qg, const R* vol, Flux5<R>& F, R& wave, R& sO, R& sNb) const {
         Prim<R> qL, qR; Grad<R> gL, gR;
         tile_load_cell<R, TS>(qg, e.lo, qL, gL); tile_load_cell<R, TS>(qg, e.ln, qR, gR);
         face_flux(ph, e.kind, gm, qL, gL, qR, gR, F, wave);
-        sO = e.lo < T ? gm.area * rcp(vol[e.lo]) : R(0);
-        sNb = e.ln < T ? gm.area * rcp(vol[e.ln]) : R(0);
+        sO = e.so ? gm.area * rcp(vol[e.lo]) : R(0);
+        sNb = e.sn ? gm.area * rcp(vol[e.ln]) : R(0);
     }
-    FVM_HD static void scatter(R* acc, int lo, int ln, const Flux5<R>& F, R wave, R sO, R sNb) {
-        if (lo < T) {
-            R* a = acc + lo;
+    FVM_HD static void scatter(R* acc, const TileEntry& e, const Flux5<R>& F, R wave, R sO, R sNb) {
+        if (e.so) {
+            R* a = acc + e.lo;
             a[0] += F.rho * sO; a[T] += F.rhoU[0] * sO; a[2 * T] += F.rhoU[1] * sO; a[3 * T] += F.rhoU[2] * sO;
             a[4 * T] += F.rhoE * sO; a[5 * T] += wave * sO;
         }
-        if (ln < T) {
-            R* a = acc + ln; const R s = -sNb;
+        if (e.sn) {
+            R* a = acc + e.ln; const R s = -sNb;
             a[0] += F.rho * s; a[T] += F.rhoU[0] * s; a[2 * T] += F.rhoU[1] * s; a[3 * T] += F.rhoU[2] * s;
             a[4 * T] += F.rhoE * s; a[5 * T] += wave * sNb;
         }
@@ -198,75 +199,91 @@ template <typename R, int T, int TS, int W> struct FluxTileBody {
         std::vector<R> qg((size_t)20 * TS, R(0)), vol(T, R(1)), acc((size_t)6 * T, R(0));
         for (int l = 0; l < nc; l++) { tile_stage_cell<R, TS>(qg.data(), l, Q, G, m.sN, c0 + l); vol[l] = m.vol[c0 + l]; }
         for (int h = m.halo_start[t]; h < m.halo_start[t + 1]; h++) tile_stage_cell<R, TS>(qg.data(), T + h - m.halo_start[t], Q, G, m.sN, m.halo_cell[h]);
-        for (int p = m.pass_start[t]; p < m.pass_start[t + 1]; p++) {
-            const R* chunk = m.chunks + (long)p * Chunk<R, W>::kScalars;
-            for (int i = 0; i < W; i++) {
-                TileEntry e; tile_decode(Chunk<R, W>::words(chunk)[i], e);
-                if (!e.valid) continue;
-                if ((e.lo >= T || e.ln >= T) && p - m.pass_start[t] < m.halo_pass[t]) throw std::runtime_error("halo_pass inconsistent");
-                Geom<R> gm; tile_load_geom<R, W>(chunk, i, gm);
-                Flux5<R> F; R wave, sO, sNb;
-                face(gm, e, qg.data(), vol.data(), F, wave, sO, sNb);
-                scatter(acc.data(), e.lo, e.ln, F, wave, sO, sNb);
-            }
-        }
         const R* wx = W1 ? W1 : W2; const R ax = W1 ? a1 : a2;
-        R mx = R(-1e30);
-        for (int l = 0; l < nc; l++) { const int c = c0 + l; R d = finish(c, &acc[l], W0 + c, wx ? wx + c : nullptr, ax, S + c, m.sC); mx = d > mx ? d : mx; }
-        if (dtc_partial) dtc_partial[t] = mx;
+        for (int w = 0; w < NW; w++) {
+            const int r0 = m.round_start[t * NW + w], r1 = m.round_start[t * NW + w + 1];
+            for (int r = r0; r < r1; r++) {
+                const R* chunk = m.chunks + (long)r * Ch::kScalars;
+                for (int i = 0; i < 32; i++) {
+                    TileEntry e; tile_decode(Ch::words(chunk)[i], e);
+                    if (!e.valid) continue;
+                    if ((e.lo >= T || e.ln >= T) && r - r0 < m.halo_round[t * NW + w]) throw std::runtime_error("halo_round inconsistent");
+                    if ((e.so && (e.lo >> 5) != w) || (e.sn && (e.ln >> 5) != w)) throw std::runtime_error("scatter outside the sub-tile");
+                    Geom<R> gm; tile_load_geom<R, 32>(chunk, i, gm);
+                    Flux5<R> F; R wave, sO, sNb;
+                    face(gm, e, qg.data(), vol.data(), F, wave, sO, sNb);
+                    scatter(acc.data(), e, F, wave, sO, sNb);
+                }
+            }
+            R mx = R(-1e30);
+            for (int l = w * 32; l < nc && l < w * 32 + 32; l++) {
+                const int c = c0 + l;
+                R d = finish(c, &acc[l], W0 + c, wx ? wx + c : nullptr, ax, S + c, m.sC); mx = d > mx ? d : mx;
+            }
+            if (dtc_partial) dtc_partial[t * NW + w] = mx;
+        }
     }
 #else
     __device__ __forceinline__ void device_tile(int t, unsigned char* smem) const {
         const int c0 = t * T, nc = min(T, m.nInternalCells - c0);
-        const int tid = threadIdx.x;
+        const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
         R* qg = reinterpret_cast<R*>(smem);
         R* vol = qg + 20 * TS;
         R* acc = vol + T;
-        R* chunk = reinterpret_cast<R*>(smem + Smem::kChunkOff);
+        R* chunk = reinterpret_cast<R*>(smem + Smem::kChunkOff) + w * Ch::kScalars;
         unsigned long long* bars = reinterpret_cast<unsigned long long*>(smem + Smem::kBarOff);
-        const int p0 = m.pass_start[t], np = m.pass_start[t + 1] - p0;
-        const int h0 = m.halo_start[t], nh = m.halo_start[t + 1] - h0, hp = m.halo_pass[t];
+        unsigned long long *bar_rows = &bars[0], *bar_halo = &bars[1], *bar_chunk = &bars[2 + w];
+        const int r0 = m.round_start[t * NW + w], nr = m.round_start[t * NW + w + 1] - r0;
+        const int h0 = m.halo_start[t], nh = m.halo_start[t + 1] - h0, hr = m.halo_round[t * NW + w];
         const R* wx = W1 ? W1 : W2; const R ax = W1 ? a1 : a2;
-        constexpr unsigned kRow = T * (unsigned)sizeof(R);
-        if (tid == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); mbar_init(&bars[2], 1); mbar_fence_init(); }
+        constexpr unsigned kRow = T * (unsigned)sizeof(R), kSub = 32u * (unsigned)sizeof(R);
+        if (tid == 0) {
+            mbar_init(bar_rows, 1); mbar_init(bar_halo, T);
+            for (int i = 0; i < NW; i++) mbar_init(&bars[2 + i], 1);
+            mbar_fence_init();
+        }
         __syncthreads();
         if (tid == 0) {
-            // the tile's own rows (may run past the last internal cell into ghost rows / slack: allocated, unused) + first chunk
-            mbar_expect_tx(&bars[0], 21u * kRow);
-            for (int k = 0; k < 5; k++) bulk_g2s(qg + k * TS, Q + (long)k * m.sN + c0, kRow, &bars[0]);
-            for (int k = 0; k < 15; k++) bulk_g2s(qg + (5 + k) * TS, G + (long)k * m.sN + c0, kRow, &bars[0]);
-            bulk_g2s(vol, m.vol + c0, kRow, &bars[0]);
-            mbar_expect_tx(&bars[1], (unsigned)Chunk<R, W>::kBytes);
-            bulk_g2s(chunk, m.chunks + (long)p0 * Chunk<R, W>::kScalars, (unsigned)Chunk<R, W>::kBytes, &bars[1]);
+            // the tile's own rows (may run past the last internal cell into ghost rows / slack: allocated, unused)
+            mbar_expect_tx(bar_rows, 21u * kRow);
+            for (int k = 0; k < 5; k++) bulk_g2s(qg + k * TS, Q + (long)k * m.sN + c0, kRow, bar_rows);
+            for (int k = 0; k < 15; k++) bulk_g2s(qg + (5 + k) * TS, G + (long)k * m.sN + c0, kRow, bar_rows);
+            bulk_g2s(vol, m.vol + c0, kRow, bar_rows);
         }
-        // halo rows: asynchronous gather, consumed from pass `hp` on (the passes before it only touch the tile's own cells)
-        for (int h = tid; h < nh; h += W) {
+        if (lane == 0 && nr > 0) {
+            mbar_expect_tx(bar_chunk, (unsigned)Ch::kBytes);
+            bulk_g2s(chunk, m.chunks + (long)r0 * Ch::kScalars, (unsigned)Ch::kBytes, bar_chunk);
+        }
+        // halo rows: asynchronous gather, consumed from round `hr` on (the rounds before it only touch the tile's own cells)
+        for (int h = tid; h < nh; h += T) {
             const int cell = m.halo_cell[h0 + h];
             for (int k = 0; k < 5; k++) cp_async_elem<sizeof(R)>(qg + k * TS + T + h, Q + (long)k * m.sN + cell);
             for (int k = 0; k < 15; k++) cp_async_elem<sizeof(R)>(qg + (5 + k) * TS + T + h, G + (long)k * m.sN + cell);
         }
-        cp_async_commit();
-        for (int i = tid; i < 6 * T; i += W) acc[i] = R(0);
-        mbar_wait(&bars[0], 0);
-        for (int p = 0; p < np; p++) {
-            mbar_wait(&bars[1], (unsigned)(p & 1));
-            TileEntry e; tile_decode(Chunk<R, W>::words(chunk)[tid], e);
-            Geom<R> gm; tile_load_geom<R, W>(chunk, tid, gm);
-            const int cfirst = (int)((Chunk<R, W>::words(chunk)[0] >> 20) & 0x1Fu), clast = (int)((Chunk<R, W>::words(chunk)[W - 1] >> 20) & 0x1Fu);
-            if (p == hp) cp_async_wait_all();
-            __syncthreads();                       // metrics are in registers: the chunk buffer is free; halo rows visible from pass hp on
-            if (tid == 0) {
+        cp_async_arrive(bar_halo);
+        if (nr == 0) return;                       // sub-tile beyond the last internal cell
+        for (int k = 0; k < 6; k++) acc[k * T + tid] = R(0);
+        mbar_wait(bar_rows, 0);
+        for (int r = 0; r < nr; r++) {
+            mbar_wait(bar_chunk, (unsigned)(r & 1));
+            TileEntry e; tile_decode(Ch::words(chunk)[lane], e);
+            Geom<R> gm; tile_load_geom<R, 32>(chunk, lane, gm);
+            const int cfirst = __shfl_sync(0xffffffffu, e.col, 0), clast = __shfl_sync(0xffffffffu, e.col, 31);
+            if (r == hr) mbar_wait(bar_halo, 0);
+            __syncwarp();                          // metrics are in registers: the warp's chunk buffer is free
+            if (lane == 0) {
                 fence_proxy_async();
-                if (p + 1 < np) {
-                    mbar_expect_tx(&bars[1], (unsigned)Chunk<R, W>::kBytes);
-                    bulk_g2s(chunk, m.chunks + (long)(p0 + p + 1) * Chunk<R, W>::kScalars, (unsigned)Chunk<R, W>::kBytes, &bars[1]);
+                if (r + 1 < nr) {
+                    mbar_expect_tx(bar_chunk, (unsigned)Ch::kBytes);
+                    bulk_g2s(chunk, m.chunks + (long)(r0 + r + 1) * Ch::kScalars, (unsigned)Ch::kBytes, bar_chunk);
                 } else {
-                    // last pass: the chunk buffer now receives the RK update's inputs (W0, S, W1|W2 rows of the tile)
-                    mbar_expect_tx(&bars[2], (wx ? 15u : 10u) * kRow);
+                    // last round: the chunk buffer now receives the RK update's inputs (W0, S, W1|W2 of the sub-tile's cells)
+                    const long cw = c0 + w * 32;
+                    mbar_expect_tx(bar_chunk, (wx ? 15u : 10u) * kSub);
                     for (int k = 0; k < 5; k++) {
-                        bulk_g2s(chunk + k * T, W0 + (long)k * m.sC + c0, kRow, &bars[2]);
-                        bulk_g2s(chunk + (5 + k) * T, S + (long)k * m.sC + c0, kRow, &bars[2]);
-                        if (wx) bulk_g2s(chunk + (10 + k) * T, wx + (long)k * m.sC + c0, kRow, &bars[2]);
+                        bulk_g2s(chunk + k * 32, W0 + (long)k * m.sC + cw, kSub, bar_chunk);
+                        bulk_g2s(chunk + (5 + k) * 32, S + (long)k * m.sC + cw, kSub, bar_chunk);
+                        if (wx) bulk_g2s(chunk + (10 + k) * 32, wx + (long)k * m.sC + cw, kSub, bar_chunk);
                     }
                 }
             }
@@ -274,16 +291,16 @@ template <typename R, int T, int TS, int W> struct FluxTileBody {
             if (e.valid) face(gm, e, qg, vol, F, wave, sO, sNb);
             const int col = e.valid ? e.col : -1;
             for (int c = cfirst; c <= clast; c++) {
-                if (col == c) scatter(acc, e.lo, e.ln, F, wave, sO, sNb);
-                __syncthreads();
+                if (col == c) scatter(acc, e, F, wave, sO, sNb);
+                __syncwarp();
             }
         }
-        mbar_wait(&bars[2], 0);
+        mbar_wait(bar_chunk, (unsigned)(nr & 1));
         R mx = R(-1e30);
-        for (int l = tid; l < nc; l += W) { R d = finish(c0 + l, acc + l, chunk + l, wx ? chunk + 10 * T + l : nullptr, ax, chunk + 5 * T + l, T); mx = d > mx ? d : mx; }
+        if (tid < nc) mx = finish(c0 + tid, acc + tid, chunk + lane, wx ? chunk + 10 * 32 + lane : nullptr, ax, chunk + 5 * 32 + lane, 32);
         if (dtc_partial) {
-            mx = block_max(mx, qg);
-            if (tid == 0) dtc_partial[t] = mx;
+            mx = warp_max(mx);
+            if (lane == 0) dtc_partial[t * NW + w] = mx;
         }
     }
 #endif
@@ -292,29 +309,33 @@ template <typename R, int T, int TS, int W> struct FluxTileBody {
 // ------------------------------------------------------------------------------------------ reverse
 //   abar = adjoint of the stage OUTPUT state [5][sC]; coef = -beta_ii*dt (d W_new / d residual)
 //   outputs Qb [5][sN], Gb [15][sN]: rows of internal cells and of the ghost cells of ALL boundary faces
-template <typename R, int T, int TS, int W> struct FluxGradTileBody {
+template <typename R, int T, int TS> struct FluxGradTileBody {
     static constexpr const char* kName = "flux_grad_tile";
-    static constexpr int kThreads = W;
+    static constexpr int kThreads = T, NW = T / 32;
     static constexpr int kMinBlocks = 1;
+    typedef Chunk<R, 32> Ch;
     Phys<R> ph; MeshDev<R> m;
     const R *Q, *G; const R* abar; R coef;
     R *Qb, *Gb;
 #if defined(__CUDACC__)
-    typedef TileSmem<R, T, TS, W, 6 * TS + 20 * T> Smem;
+    typedef TileSmem<R, T, TS, 6 * TS + 20 * T> Smem;
     static size_t smem_bytes() { return Smem::kBytes; }
 #endif
 
-    // ab [5][TS]: abar of the slot's cell (0 for ghost cells: boundary faces scatter to their owner only), vol [TS]
+    // ab [5][TS]: abar of the slot's cell, vol [TS]; ghost slots are never read (boundary faces scatter to their owner only)
     FVM_HD void stage_ab(R* ab, R* vol, int slot, int cell) const {
         if (cell < m.nInternalCells) { for (int k = 0; k < 5; k++) ab[k * TS + slot] = abar[(long)k * m.sC + cell]; vol[slot] = m.vol[cell]; }
-        else { for (int k = 0; k < 5; k++) ab[k * TS + slot] = R(0); vol[slot] = R(1); }
     }
     FVM_HD void face(const Geom<R>& gm, const TileEntry& e, const R* qg, const R* ab, const R* vol, Prim<R>& qLb, Grad<R>& gLb, Prim<R>& qRb, Grad<R>& gRb) const {
         Prim<R> qL, qR; Grad<R> gL, gR;
         tile_load_cell<R, TS>(qg, e.lo, qL, gL); tile_load_cell<R, TS>(qg, e.ln, qR, gR);
-        const R sO = gm.area * coef * rcp(vol[e.lo]), sN_ = gm.area * coef * rcp(vol[e.ln]);
+        const R sO = gm.area * coef * rcp(vol[e.lo]);
         R d[5];
-        for (int k = 0; k < 5; k++) d[k] = ab[k * TS + e.lo] * sO - ab[k * TS + e.ln] * sN_;
+        for (int k = 0; k < 5; k++) d[k] = ab[k * TS + e.lo] * sO;
+        if (!e.ghost) {
+            const R sN_ = gm.area * coef * rcp(vol[e.ln]);
+            for (int k = 0; k < 5; k++) d[k] -= ab[k * TS + e.ln] * sN_;
+        }
         Flux5<R> Fb; Fb.rho = d[0]; Fb.rhoU[0] = d[1]; Fb.rhoU[1] = d[2]; Fb.rhoU[2] = d[3]; Fb.rhoE = d[4];
         zero(qLb); zero(gLb); zero(qRb); zero(gRb);
         face_flux_vjp(ph, e.kind, gm, qL, gL, qR, gR, Fb, qLb, gLb, qRb, gRb);
@@ -326,15 +347,11 @@ template <typename R, int T, int TS, int W> struct FluxGradTileBody {
     }
     // ghost: global row of the ghost cell of a boundary face (its halo slot's cell), -1 for internal faces
     FVM_HD void scatter(R* acc, const TileEntry& e, int ghost, const Prim<R>& qLb, const Grad<R>& gLb, const Prim<R>& qRb, const Grad<R>& gRb) const {
-        if (e.lo < T) add20(acc + e.lo, qLb, gLb);
+        if (e.so) add20(acc + e.lo, qLb, gLb);
         if (ghost >= 0) { store_prim(Qb, m.sN, ghost, qRb); store_grad(Gb, m.sN, ghost, gRb); }
-        else if (e.ln < T) add20(acc + e.ln, qRb, gRb);
+        else if (e.sn) add20(acc + e.ln, qRb, gRb);
     }
-    FVM_HD int ghost_of(int t, const TileEntry& e) const {
-        if (e.ln < T) return -1;
-        const int cell = m.halo_cell[m.halo_start[t] + e.ln - T];
-        return cell >= m.nInternalCells ? cell : -1;
-    }
+    FVM_HD int ghost_of(int t, const TileEntry& e) const { return e.ghost ? m.halo_cell[m.halo_start[t] + e.ln - T] : -1; }
     FVM_HD void finish(int c, const R* a) const {
         for (int k = 0; k < 5; k++) Qb[(long)k * m.sN + c] = a[k * T];
         for (int k = 0; k < 15; k++) Gb[(long)k * m.sN + c] = a[(5 + k) * T];
@@ -343,21 +360,25 @@ template <typename R, int T, int TS, int W> struct FluxGradTileBody {
 #if !defined(__CUDACC__)
     void host_tile(int t) const {
         const int c0 = t * T, nc = (m.nInternalCells - c0 < T) ? m.nInternalCells - c0 : T;
-        std::vector<R> qg((size_t)20 * TS, R(0)), ab((size_t)5 * TS, R(0)), vol(TS, R(1)), acc((size_t)20 * T, R(0));
+        const R nan = std::numeric_limits<R>::quiet_NaN();       // ghost slots of ab / vol must never be read
+        std::vector<R> qg((size_t)20 * TS, R(0)), ab((size_t)5 * TS, nan), vol(TS, nan), acc((size_t)20 * T, R(0));
         for (int l = 0; l < nc; l++) { tile_stage_cell<R, TS>(qg.data(), l, Q, G, m.sN, c0 + l); stage_ab(ab.data(), vol.data(), l, c0 + l); }
         for (int h = m.halo_start[t]; h < m.halo_start[t + 1]; h++) {
             const int slot = T + h - m.halo_start[t];
             tile_stage_cell<R, TS>(qg.data(), slot, Q, G, m.sN, m.halo_cell[h]); stage_ab(ab.data(), vol.data(), slot, m.halo_cell[h]);
         }
-        for (int p = m.pass_start[t]; p < m.pass_start[t + 1]; p++) {
-            const R* chunk = m.chunks + (long)p * Chunk<R, W>::kScalars;
-            for (int i = 0; i < W; i++) {
-                TileEntry e; tile_decode(Chunk<R, W>::words(chunk)[i], e);
-                if (!e.valid) continue;
-                Geom<R> gm; tile_load_geom<R, W>(chunk, i, gm);
-                Prim<R> qLb, qRb; Grad<R> gLb, gRb;
-                face(gm, e, qg.data(), ab.data(), vol.data(), qLb, gLb, qRb, gRb);
-                scatter(acc.data(), e, ghost_of(t, e), qLb, gLb, qRb, gRb);
+        for (int w = 0; w < NW; w++) {
+            for (int r = m.round_start[t * NW + w]; r < m.round_start[t * NW + w + 1]; r++) {
+                const R* chunk = m.chunks + (long)r * Ch::kScalars;
+                for (int i = 0; i < 32; i++) {
+                    TileEntry e; tile_decode(Ch::words(chunk)[i], e);
+                    if (!e.valid) continue;
+                    if (e.ghost != (e.ln >= T && m.halo_cell[m.halo_start[t] + e.ln - T] >= m.nInternalCells)) throw std::runtime_error("ghost flag inconsistent");
+                    Geom<R> gm; tile_load_geom<R, 32>(chunk, i, gm);
+                    Prim<R> qLb, qRb; Grad<R> gLb, gRb;
+                    face(gm, e, qg.data(), ab.data(), vol.data(), qLb, gLb, qRb, gRb);
+                    scatter(acc.data(), e, ghost_of(t, e), qLb, gLb, qRb, gRb);
+                }
             }
         }
         for (int l = 0; l < nc; l++) finish(c0 + l, &acc[l]);
@@ -365,53 +386,58 @@ template <typename R, int T, int TS, int W> struct FluxGradTileBody {
 #else
     __device__ __forceinline__ void device_tile(int t, unsigned char* smem) const {
         const int c0 = t * T, nc = min(T, m.nInternalCells - c0);
-        const int tid = threadIdx.x;
+        const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
         R* qg = reinterpret_cast<R*>(smem);
         R* ab = qg + 20 * TS;
         R* vol = ab + 5 * TS;
         R* acc = vol + TS;
-        R* chunk = reinterpret_cast<R*>(smem + Smem::kChunkOff);
+        R* chunk = reinterpret_cast<R*>(smem + Smem::kChunkOff) + w * Ch::kScalars;
         unsigned long long* bars = reinterpret_cast<unsigned long long*>(smem + Smem::kBarOff);
-        const int p0 = m.pass_start[t], np = m.pass_start[t + 1] - p0;
-        const int h0 = m.halo_start[t], nh = m.halo_start[t + 1] - h0, hp = m.halo_pass[t];
+        unsigned long long *bar_rows = &bars[0], *bar_halo = &bars[1], *bar_chunk = &bars[2 + w];
+        const int r0 = m.round_start[t * NW + w], nr = m.round_start[t * NW + w + 1] - r0;
+        const int h0 = m.halo_start[t], nh = m.halo_start[t + 1] - h0, hr = m.halo_round[t * NW + w];
         constexpr unsigned kRow = T * (unsigned)sizeof(R);
-        if (tid == 0) { mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); mbar_fence_init(); }
+        if (tid == 0) {
+            mbar_init(bar_rows, 1); mbar_init(bar_halo, T);
+            for (int i = 0; i < NW; i++) mbar_init(&bars[2 + i], 1);
+            mbar_fence_init();
+        }
         __syncthreads();
         if (tid == 0) {
-            mbar_expect_tx(&bars[0], 26u * kRow);
-            for (int k = 0; k < 5; k++) bulk_g2s(qg + k * TS, Q + (long)k * m.sN + c0, kRow, &bars[0]);
-            for (int k = 0; k < 15; k++) bulk_g2s(qg + (5 + k) * TS, G + (long)k * m.sN + c0, kRow, &bars[0]);
-            for (int k = 0; k < 5; k++) bulk_g2s(ab + k * TS, abar + (long)k * m.sC + c0, kRow, &bars[0]);
-            bulk_g2s(vol, m.vol + c0, kRow, &bars[0]);
-            mbar_expect_tx(&bars[1], (unsigned)Chunk<R, W>::kBytes);
-            bulk_g2s(chunk, m.chunks + (long)p0 * Chunk<R, W>::kScalars, (unsigned)Chunk<R, W>::kBytes, &bars[1]);
+            mbar_expect_tx(bar_rows, 26u * kRow);
+            for (int k = 0; k < 5; k++) bulk_g2s(qg + k * TS, Q + (long)k * m.sN + c0, kRow, bar_rows);
+            for (int k = 0; k < 15; k++) bulk_g2s(qg + (5 + k) * TS, G + (long)k * m.sN + c0, kRow, bar_rows);
+            for (int k = 0; k < 5; k++) bulk_g2s(ab + k * TS, abar + (long)k * m.sC + c0, kRow, bar_rows);
+            bulk_g2s(vol, m.vol + c0, kRow, bar_rows);
         }
-        for (int h = tid; h < nh; h += W) {
+        if (lane == 0 && nr > 0) {
+            mbar_expect_tx(bar_chunk, (unsigned)Ch::kBytes);
+            bulk_g2s(chunk, m.chunks + (long)r0 * Ch::kScalars, (unsigned)Ch::kBytes, bar_chunk);
+        }
+        for (int h = tid; h < nh; h += T) {
             const int cell = m.halo_cell[h0 + h], slot = T + h;
             for (int k = 0; k < 5; k++) cp_async_elem<sizeof(R)>(qg + k * TS + slot, Q + (long)k * m.sN + cell);
             for (int k = 0; k < 15; k++) cp_async_elem<sizeof(R)>(qg + (5 + k) * TS + slot, G + (long)k * m.sN + cell);
             if (cell < m.nInternalCells) {
                 for (int k = 0; k < 5; k++) cp_async_elem<sizeof(R)>(ab + k * TS + slot, abar + (long)k * m.sC + cell);
                 cp_async_elem<sizeof(R)>(vol + slot, m.vol + cell);
-            } else {
-                for (int k = 0; k < 5; k++) ab[k * TS + slot] = R(0);
-                vol[slot] = R(1);
             }
         }
-        cp_async_commit();
-        for (int i = tid; i < 20 * T; i += W) acc[i] = R(0);
-        mbar_wait(&bars[0], 0);
-        for (int p = 0; p < np; p++) {
-            mbar_wait(&bars[1], (unsigned)(p & 1));
-            TileEntry e; tile_decode(Chunk<R, W>::words(chunk)[tid], e);
-            Geom<R> gm; tile_load_geom<R, W>(chunk, tid, gm);
-            const int cfirst = (int)((Chunk<R, W>::words(chunk)[0] >> 20) & 0x1Fu), clast = (int)((Chunk<R, W>::words(chunk)[W - 1] >> 20) & 0x1Fu);
-            if (p == hp) cp_async_wait_all();
-            __syncthreads();
-            if (tid == 0 && p + 1 < np) {
+        cp_async_arrive(bar_halo);
+        if (nr == 0) return;
+        for (int k = 0; k < 20; k++) acc[k * T + tid] = R(0);
+        mbar_wait(bar_rows, 0);
+        for (int r = 0; r < nr; r++) {
+            mbar_wait(bar_chunk, (unsigned)(r & 1));
+            TileEntry e; tile_decode(Ch::words(chunk)[lane], e);
+            Geom<R> gm; tile_load_geom<R, 32>(chunk, lane, gm);
+            const int cfirst = __shfl_sync(0xffffffffu, e.col, 0), clast = __shfl_sync(0xffffffffu, e.col, 31);
+            if (r == hr) mbar_wait(bar_halo, 0);
+            __syncwarp();
+            if (lane == 0 && r + 1 < nr) {
                 fence_proxy_async();
-                mbar_expect_tx(&bars[1], (unsigned)Chunk<R, W>::kBytes);
-                bulk_g2s(chunk, m.chunks + (long)(p0 + p + 1) * Chunk<R, W>::kScalars, (unsigned)Chunk<R, W>::kBytes, &bars[1]);
+                mbar_expect_tx(bar_chunk, (unsigned)Ch::kBytes);
+                bulk_g2s(chunk, m.chunks + (long)(r0 + r + 1) * Ch::kScalars, (unsigned)Ch::kBytes, bar_chunk);
             }
             Prim<R> qLb, qRb; Grad<R> gLb, gRb;
             int ghost = -1;
@@ -419,10 +445,10 @@ template <typename R, int T, int TS, int W> struct FluxGradTileBody {
             const int col = e.valid ? e.col : -1;
             for (int c = cfirst; c <= clast; c++) {
                 if (col == c) scatter(acc, e, ghost, qLb, gLb, qRb, gRb);
-                __syncthreads();
+                __syncwarp();
             }
         }
-        for (int l = tid; l < nc; l += W) finish(c0 + l, acc + l);
+        if (tid < nc) finish(c0 + tid, acc + tid);
     }
 #endif
 };

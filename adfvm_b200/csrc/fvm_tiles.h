@@ -2,18 +2,20 @@
 //
 // The reference scatters face fluxes into cells with one atomicAdd per scalar (adpy/adpy/tensor.py:393-394) and
 // visits faces in file order. Here the internal cells are regrouped into spatially compact TILES of `T`
-// consecutive (renumbered) cells; one CTA owns one tile, stages the tile's cell rows in shared memory, evaluates
-// every face touching the tile exactly once (faces cut by a tile boundary are evaluated by both tiles) and sums
-// the contributions into per-tile shared-memory accumulators in a FIXED order given by a face colouring:
-// faces of one colour never share an in-tile cell, colours are applied one after the other. No float atomics,
-// bitwise reproducible, and 3.4-3.7 flux evaluations per hex cell instead of the 6 of a cell-centred gather.
+// consecutive (renumbered) cells, each made of T/32 compact SUB-TILES of 32 consecutive cells. One CTA owns one
+// tile and stages the tile's cell rows (+ halo) in shared memory once; one WARP owns one sub-tile: it evaluates
+// every face touching its 32 cells (faces cut by a sub-tile boundary are evaluated by both sides, each side adds
+// only its own share) and sums the contributions into shared-memory accumulators that no other warp touches, in a
+// FIXED order given by a face colouring: faces of one colour never share a cell of the sub-tile, colours are
+// applied one after the other. No float atomics, no block-wide barriers in the face loop, bitwise reproducible,
+// and 4.0 flux evaluations per hex cell (4x4x2 sub-tiles) instead of the 6 of a cell-centred gather.
 //
 //   * tiles: recursive coordinate bisection of the cell centres (recovered up to a translation by walking the
 //     internal faces and adding deltas*deltasUnit = N-P, reference adFVM/cpp/cmesh.cpp:184-193), always splitting
-//     at a multiple of T so that every tile but the last is full;
-//   * internal faces are renumbered so that the faces first listed by a tile are consecutive in colour order
-//     (coalesced metric loads); boundary faces and ghost cells keep the reference's numbering
-//     (ghost(f) = C + f - Fi, adFVM/mesh.py:244), so patch ranges and the halo layout are untouched.
+//     at a multiple of T (then of 32 inside a tile) so that every tile / sub-tile but the last is full;
+//   * internal faces are renumbered in the order the sub-tiles first list them (coalesced metric loads);
+//     boundary faces and ghost cells keep the reference's numbering (ghost(f) = C + f - Fi, adFVM/mesh.py:244),
+//     so patch ranges and the halo layout are untouched.
 #pragma once
 #include <algorithm>
 #include <cstdint>
@@ -24,25 +26,27 @@
 namespace fvm {
 
 // packed entry word: bits 0-9 owner's slot, 10-19 neighbour's slot, 20-24 colour, 25-26 face kind (FaceKind of
-// fvm_math.h), 27 valid. Slots [0,T) are the tile's own cells, slots [T, T+nHalo) the tile's halo: cells of other
-// tiles and ghost cells touched by the tile's faces.
-static inline uint32_t tile_pack(int lo, int ln, int colour, int kind, int valid) {
-    return (uint32_t)lo | ((uint32_t)ln << 10) | ((uint32_t)colour << 20) | ((uint32_t)kind << 25) | ((uint32_t)valid << 27);
+// fvm_math.h), 27 valid, 28 owner is a cell of this sub-tile (scatter to it), 29 neighbour is a cell of this
+// sub-tile, 30 neighbour is a ghost cell (boundary face). Slots [0,T) are the tile's own cells, slots
+// [T, T+nHalo) the tile's halo: cells of other tiles and ghost cells touched by the tile's faces.
+enum { kRound = 32 };   // entries per warp round
+static inline uint32_t tile_pack(int lo, int ln, int colour, int kind, int valid, int so = 0, int sn = 0, int ghost = 0) {
+    return (uint32_t)lo | ((uint32_t)ln << 10) | ((uint32_t)colour << 20) | ((uint32_t)kind << 25) | ((uint32_t)valid << 27) |
+           ((uint32_t)so << 28) | ((uint32_t)sn << 29) | ((uint32_t)ghost << 30);
 }
 
 struct TilePlan {
-    int T = 0, nTiles = 0, maxColours = 0;
+    int T = 0, nTiles = 0, NW = 0, maxColours = 0;   // NW = T/32 sub-tiles (warps) per tile
     long nEntries = 0;
     std::vector<int> cell_new2old, cell_old2new;     // internal cells
     std::vector<int> face_new2old, face_old2new;     // all faces (identity for boundary faces)
-    int W = 0;                                       // entries per pass (= threads per CTA)
-    std::vector<int> pass_start;                     // [nTiles+1] first pass of each tile; pass p covers slots [p*W, (p+1)*W)
-    std::vector<int> ent_face;                       // NEW face index of each slot, -1 for padding
-    std::vector<uint32_t> ent_loc;                   // tile_pack(...) of each slot
+    std::vector<int> round_start;                    // [nTiles*NW+1] first round of each sub-tile; round r covers entry slots [32r, 32r+32)
+    std::vector<int> ent_face;                       // NEW face index of each entry slot, -1 for padding
+    std::vector<uint32_t> ent_loc;                   // tile_pack(...) of each entry slot
     std::vector<int> halo_start;                     // [nTiles+1] offsets into halo_cell
     std::vector<int> halo_cell;                      // NEW cell index (ghost cells: >= C) of each halo slot
     int maxHalo = 0;
-    std::vector<int> halo_pass;                      // [nTiles] first pass of the tile (relative) that reads a halo slot
+    std::vector<int> halo_round;                     // [nTiles*NW] first round of the sub-tile (relative) that reads a halo slot
     double evals_per_cell() const { return cell_new2old.empty() ? 0. : (double)nEntries / (double)cell_new2old.size(); }
 };
 
@@ -107,106 +111,120 @@ inline void rcb(std::vector<int>& idx, const std::vector<float>& pos, long lo, l
 
 }  // namespace detail
 
-// owner/neigh/cellFaces: the reference's arrays (old numbering). T <= 512.
-// bkind[f - Fi]: FaceKind of each boundary face. W: slots per pass.
+// owner/neigh/cellFaces: the reference's arrays (old numbering). T: multiple of 32, <= 512.
+// bkind[f - Fi]: FaceKind of each boundary face.
 template <typename R>
 TilePlan build_tile_plan(int C, int Fi, int F, const int* owner, const int* neigh, const int* cellFaces,
-                         const R* deltas, const R* deltasUnit, const unsigned char* bkind, int T, int W) {
-    if (T <= 0 || T > 512) throw std::runtime_error("tile size out of range");
-    TilePlan P; P.T = T; P.W = W;
+                         const R* deltas, const R* deltasUnit, const unsigned char* bkind, int T) {
+    if (T <= 0 || T > 512 || T % kRound) throw std::runtime_error("tile size out of range");
+    TilePlan P; P.T = T; P.NW = T / kRound;
     P.nTiles = (C + T - 1) / T;
-    // ---- cell order
+    const int NW = P.NW;
+    // ---- cell order: tiles of T cells, inside a tile sub-tiles of 32 cells, inside a sub-tile ascending old ids
     std::vector<float> pos;
     detail::integrate_centres(C, Fi, owner, neigh, cellFaces, deltas, deltasUnit, pos);
     P.cell_new2old.resize(C);
     std::iota(P.cell_new2old.begin(), P.cell_new2old.end(), 0);
     detail::rcb(P.cell_new2old, pos, 0, C, T);
-    // inside a tile keep ascending old ids (stable, cache-friendly for the host I/O permutation)
-    for (int t = 0; t < P.nTiles; t++)
-        std::sort(P.cell_new2old.begin() + (size_t)t * T, P.cell_new2old.begin() + std::min<size_t>((size_t)(t + 1) * T, C));
+    for (int t = 0; t < P.nTiles; t++) detail::rcb(P.cell_new2old, pos, (long)t * T, std::min<long>((long)(t + 1) * T, C), kRound);
+    for (long b = 0; b < C; b += kRound)
+        std::sort(P.cell_new2old.begin() + b, P.cell_new2old.begin() + std::min<long>(b + kRound, C));
     P.cell_old2new.assign(C, -1);
     for (int i = 0; i < C; i++) P.cell_old2new[P.cell_new2old[i]] = i;
-    // ---- per tile: faces touching it, coloured
-    P.pass_start.assign(P.nTiles + 1, 0);
+    // ---- per sub-tile: faces touching it, coloured
+    P.round_start.assign((size_t)P.nTiles * NW + 1, 0);
+    P.halo_round.assign((size_t)P.nTiles * NW, 0);
     P.face_old2new.assign(F, -1);
     P.face_new2old.assign(F, -1);
     for (int f = Fi; f < F; f++) { P.face_old2new[f] = f; P.face_new2old[f] = f; }
     int nextFace = 0;
-    std::vector<int> faces; std::vector<int> colour; std::vector<uint32_t> used(T);
-    std::vector<int> order;
-    int nInteriorColours = 0;
+    std::vector<int> faces, colour, group, order;
+    std::vector<uint32_t> used(kRound);
     const int N = C + (F - Fi);
     std::vector<int> slot_of(N, -1), slot_tile(N, -1);
     P.halo_start.assign(P.nTiles + 1, 0);
     for (int t = 0; t < P.nTiles; t++) {
         const int c0 = t * T, c1 = std::min(C, c0 + T);
-        faces.clear();
-        for (int c = c0; c < c1; c++) {
-            const int oc = P.cell_new2old[c];
-            for (int j = 0; j < 6; j++) {
-                const int f = cellFaces[(size_t)oc * 6 + j];
-                if (f < 0 || f >= F) throw std::runtime_error("cellFaces out of range");
-                if (f >= Fi) { faces.push_back(f); continue; }
-                // internal face: list once per tile (when reached from its lower in-tile cell)
-                const int a = P.cell_old2new[owner[f]], b = P.cell_old2new[neigh[f]];
-                const bool ain = a >= c0 && a < c1, bin = b >= c0 && b < c1;
-                if (ain && bin) { if (c == std::min(a, b)) faces.push_back(f); }
-                else faces.push_back(f);
-            }
-        }
-        // greedy colouring: no two faces of one colour share an in-tile cell. Faces with both cells in the tile are
-        // coloured first, faces that need a halo cell (cut by the tile boundary, or boundary faces) get colours above
-        // them: sorted by colour, the passes that only need the tile's own rows come first and overlap the halo gather.
-        colour.assign(faces.size(), 0);
-        int ncol = 0;
-        for (int group = 0; group < 2; group++) {
-            std::fill(used.begin(), used.end(), 0u);
-            const int base = ncol;
-            for (size_t i = 0; i < faces.size(); i++) {
-                const int f = faces[i];
-                const int a = P.cell_old2new[owner[f]];
-                const int b = f < Fi ? P.cell_old2new[neigh[f]] : -1;
-                const int la = (a >= c0 && a < c1) ? a - c0 : -1, lb = (b >= c0 && b < c1) ? b - c0 : -1;
-                if (((la >= 0 && lb >= 0) ? 0 : 1) != group) continue;
-                uint32_t m = (la >= 0 ? used[la] : 0u) | (lb >= 0 ? used[lb] : 0u);
-                int col = 0;
-                while (m & (1u << col)) col++;
-                if (base + col >= 32) throw std::runtime_error("face colouring needs more than 32 colours");
-                colour[i] = base + col; ncol = std::max(ncol, base + col + 1);
-                if (la >= 0) used[la] |= 1u << col;
-                if (lb >= 0) used[lb] |= 1u << col;
-            }
-            if (group == 0) nInteriorColours = ncol;
-        }
-        P.maxColours = std::max(P.maxColours, ncol);
-        order.resize(faces.size());
-        std::iota(order.begin(), order.end(), 0);
-        std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return colour[x] < colour[y]; });
-        int nHalo = 0, firstHaloEntry = -1, nEnt = 0;
+        int nHalo = 0;
         auto slot = [&](int cell) {           // cell: NEW index (ghosts >= C)
             if (cell >= c0 && cell < c1) return cell - c0;
             if (slot_tile[cell] != t) { slot_tile[cell] = t; slot_of[cell] = T + nHalo++; P.halo_cell.push_back(cell); }
             return slot_of[cell];
         };
-        for (int i : order) {
-            const int f = faces[i];
-            if (f < Fi && P.face_old2new[f] < 0) { P.face_old2new[f] = nextFace; P.face_new2old[nextFace] = f; nextFace++; }
-            const int a = P.cell_old2new[owner[f]];
-            const int b = f < Fi ? P.cell_old2new[neigh[f]] : neigh[f];
-            if (b < 0 || b >= N) throw std::runtime_error("neighbour out of range");
-            const int la = slot(a), lb = slot(b);
-            if (la >= 1024 || lb >= 1024) throw std::runtime_error("tile halo too large");
-            if ((la >= T || lb >= T) && firstHaloEntry < 0) firstHaloEntry = nEnt;
-            P.ent_face.push_back(P.face_old2new[f]);
-            P.ent_loc.push_back(tile_pack(la, lb, colour[i], f < Fi ? 0 : (int)bkind[f - Fi], 1));
-            P.nEntries++; nEnt++;
+        for (int w = 0; w < NW; w++) {
+            const int s0 = c0 + w * kRound, s1 = std::min(c1, s0 + kRound);
+            faces.clear();
+            for (int c = s0; c < s1; c++) {
+                const int oc = P.cell_new2old[c];
+                for (int j = 0; j < 6; j++) {
+                    const int f = cellFaces[(size_t)oc * 6 + j];
+                    if (f < 0 || f >= F) throw std::runtime_error("cellFaces out of range");
+                    if (f >= Fi) { faces.push_back(f); continue; }
+                    // internal face: list once per sub-tile (when reached from its lower cell of the sub-tile)
+                    const int a = P.cell_old2new[owner[f]], b = P.cell_old2new[neigh[f]];
+                    const bool ain = a >= s0 && a < s1, bin = b >= s0 && b < s1;
+                    if (ain && bin) { if (c == std::min(a, b)) faces.push_back(f); }
+                    else faces.push_back(f);
+                }
+            }
+            // greedy colouring: no two faces of one colour share a cell of the sub-tile. Faces inside the sub-tile are
+            // coloured first, then faces whose other cell is elsewhere in the tile, then faces that need a halo slot (cut
+            // by the tile boundary, or boundary faces): sorted by colour, the rounds that only need the tile's own rows
+            // come first and overlap the halo gather.
+            colour.assign(faces.size(), 0); group.assign(faces.size(), 0);
+            for (size_t i = 0; i < faces.size(); i++) {
+                const int f = faces[i];
+                const int a = P.cell_old2new[owner[f]];
+                const int b = f < Fi ? P.cell_old2new[neigh[f]] : -1;
+                const bool ain = a >= s0 && a < s1, bin = b >= s0 && b < s1;
+                const bool atile = a >= c0 && a < c1, btile = b >= c0 && b < c1;
+                group[i] = (ain && bin) ? 0 : ((atile && btile) ? 1 : 2);
+            }
+            int ncol = 0;
+            for (int grp = 0; grp < 3; grp++) {
+                std::fill(used.begin(), used.end(), 0u);
+                const int base = ncol;
+                for (size_t i = 0; i < faces.size(); i++) {
+                    if (group[i] != grp) continue;
+                    const int f = faces[i];
+                    const int a = P.cell_old2new[owner[f]];
+                    const int b = f < Fi ? P.cell_old2new[neigh[f]] : -1;
+                    const int la = (a >= s0 && a < s1) ? a - s0 : -1, lb = (b >= s0 && b < s1) ? b - s0 : -1;
+                    uint32_t mk = (la >= 0 ? used[la] : 0u) | (lb >= 0 ? used[lb] : 0u);
+                    int col = 0;
+                    while (mk & (1u << col)) col++;
+                    if (base + col >= 32) throw std::runtime_error("face colouring needs more than 32 colours");
+                    colour[i] = base + col; ncol = std::max(ncol, base + col + 1);
+                    if (la >= 0) used[la] |= 1u << col;
+                    if (lb >= 0) used[lb] |= 1u << col;
+                }
+            }
+            P.maxColours = std::max(P.maxColours, ncol);
+            order.resize(faces.size());
+            std::iota(order.begin(), order.end(), 0);
+            std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return colour[x] < colour[y]; });
+            int firstHaloEntry = -1, nEnt = 0;
+            for (int i : order) {
+                const int f = faces[i];
+                if (f < Fi && P.face_old2new[f] < 0) { P.face_old2new[f] = nextFace; P.face_new2old[nextFace] = f; nextFace++; }
+                const int a = P.cell_old2new[owner[f]];
+                const int b = f < Fi ? P.cell_old2new[neigh[f]] : neigh[f];
+                if (b < 0 || b >= N) throw std::runtime_error("neighbour out of range");
+                const int la = slot(a), lb = slot(b);
+                if (la >= 1024 || lb >= 1024) throw std::runtime_error("tile halo too large");
+                if ((la >= T || lb >= T) && firstHaloEntry < 0) firstHaloEntry = nEnt;
+                P.ent_face.push_back(P.face_old2new[f]);
+                P.ent_loc.push_back(tile_pack(la, lb, colour[i], f < Fi ? 0 : (int)bkind[f - Fi], 1,
+                                              a >= s0 && a < s1, b >= s0 && b < s1, b >= C));
+                P.nEntries++; nEnt++;
+            }
+            P.halo_round[(size_t)t * NW + w] = firstHaloEntry < 0 ? (nEnt + kRound - 1) / kRound : firstHaloEntry / kRound;
+            // pad the last round; padding repeats the last colour so that a round's colour range is [first slot, last slot]
+            while (P.ent_face.size() % (size_t)kRound) { P.ent_face.push_back(-1); P.ent_loc.push_back(tile_pack(0, 0, ncol ? ncol - 1 : 0, 0, 0)); }
+            P.round_start[(size_t)t * NW + w + 1] = (int)(P.ent_face.size() / (size_t)kRound);
         }
-        P.halo_pass.push_back(firstHaloEntry < 0 ? (nEnt + W - 1) / W : firstHaloEntry / W);
-        // pad the last pass; padding repeats the last colour so that a pass's colour range is [first slot, last slot]
-        while (P.ent_face.size() % (size_t)W) { P.ent_face.push_back(-1); P.ent_loc.push_back(tile_pack(0, 0, ncol ? ncol - 1 : 0, 0, 0)); }
         P.maxHalo = std::max(P.maxHalo, nHalo);
         P.halo_start[t + 1] = (int)P.halo_cell.size();
-        P.pass_start[t + 1] = (int)(P.ent_face.size() / (size_t)W);
     }
     if (nextFace != Fi) throw std::runtime_error("internal face not reachable from any cell (broken cellFaces)");
     return P;

@@ -219,6 +219,13 @@ class PrimalFunction:
         self.c.lib.check(self.c.lib.dll.adfvm_tile_stats(self.c.ctx, C.byref(a), C.byref(b), C.byref(c_), C.byref(d)))
         return a.value, b.value, c_.value, d.value
 
+    def tile_halo_stats(self):
+        """(largest tile halo, kernel variant, tiles per halo-size bin of 32 slots)"""
+        a, b = C.c_int32(), C.c_int32()
+        h = (C.c_int32 * 32)()
+        self.c.lib.check(self.c.lib.dll.adfvm_tile_halo_stats(self.c.ctx, C.byref(a), C.byref(b), h, 32))
+        return a.value, b.value, list(h)
+
     def _prepare(self, inputs, options):
         opts = dict(self.defaultOptions)
         for k in options:

@@ -115,6 +115,10 @@ int64_t adfvm_device_bytes(adfvm_ctx* ctx);
 int adfvm_set_tile_cells(adfvm_ctx* ctx, int32_t cells);
 int adfvm_tile_stats(adfvm_ctx* ctx, double* evals_per_cell, int32_t* max_colours, int32_t* n_tiles, int32_t* tile_cells);
 
+/* largest halo (slots beyond the tile's own cells) of any tile, the kernel variant chosen from it and a
+ * histogram of tiles per halo size in bins of 32 slots */
+int adfvm_tile_halo_stats(adfvm_ctx* ctx, int32_t* max_halo, int32_t* variant, int32_t* hist, int32_t nbins);
+
 /* per-kernel device timing (CUDA events on the launching stream around every launch while enabled).
  * adfvm_kernel_report writes lines "<kernel> <launches> <total_ms>\n" into buf. Counterpart of the reference's
  * `-o/--profile` per-kernel prints (adpy/adpy/variable.py:437-467). */
