@@ -35,6 +35,7 @@ template <typename R> struct MeshDev {
     int nCells, nFaces, nInternalCells, nInternalFaces, nLocalCells, nRemoteCells, nLocalFaces, nGhostCells;
     int sC, sN, sF;
     const R *area, *normal, *weight, *idelta, *vol;   // face-indexed SoA (idelta = 1/deltas); the other flux metrics live in the chunks
+    const R *cfm;                        // cell-face metrics of the Green-Gauss gradient [24][sC] (CellFaceMetricBody)
     const int *owner, *neigh, *cellFaces, *cellNbr;
     const unsigned char *cellOwner;      // bit j set: the cell owns its j-th face
     const unsigned char *bpatch;         // [nGhostCells] patch index of each boundary face
@@ -261,48 +262,92 @@ template <typename R> struct GhostGradAdjBody {
             for (int k = 0; k < 15; k++) acc[k] += Gb[k * m.sN + g];
             any = true;
         }
-        if (any) for (int k = 0; k < 15; k++) Gb[k * m.sN + c] += acc[k];
+        // internal rows of Gb hold the gradient adjoint already divided by the cell volume (FluxGradTileBody::finish)
+        if (any) { const R iv = rcp(m.vol[c]); for (int k = 0; k < 15; k++) Gb[k * m.sN + c] += acc[k] * iv; }
     }
 };
 
-// C. adjoint of gradCell: Qb[c] += sum over faces of (own-gradient share + neighbour-gradient share);
-// ghost rows receive their share from the owning cell.
-template <typename R> struct GradCellAdjBody {
-    static constexpr const char* kName = "grad_cell_adj";
-    MeshDev<R> m; const R* Gb; R* Qb;
+// C + F. adjoint of gradCell fused with the adjoint of primitive() and of the RK combination, one thread per cell.
+//   Green-Gauss (adFVM/op.py:45-63): G_c = 1/V_c sum_j (a_j phi_c + (1-a_j) phi_nb_j) SN_j, with SN_j = +-S_f n_f
+//   outward of c and a_j the weight of the cell's own value (cfm rows 4j..4j+3). With H = Gb/V (internal rows of Gb
+//   are stored that way), the face shared by c and nb appears in G_c with weight a_j, normal SN_j and in G_nb with
+//   weight a_j on phi_c and normal -SN_j:   Qb_c += sum_j a_j SN_j . (H_c - H_nb_j);
+//   a ghost neighbour has no gradient of its own and receives (1-a_j) SN_j . H_c in its Qb row (exclusive writer).
+//   Then a_s = sum_k alpha_k a_k + (dQ/dW)^T Qb_c (+ cell objective seed, + source-gradient accumulation on the last
+//   reverse stage). Cells next to a boundary get the share of their ghost rows later (GhostPrimAdjBody, linear).
+template <typename R> struct GradAdjUpdateBody {
+    static constexpr const char* kName = "grad_adj_update";
+    Phys<R> ph; MeshDev<R> m;
+    const R* Gb; R* Qb;
+    const R* W;                // stage state the residual was evaluated at
+    const R *A1, *A2, *A3;     // adjoints of later stage outputs (NULL when coefficient is 0)
+    R c1, c2, c3;
+    R objT;                    // obja for OBJ_CELL_TV on the objective stage, else 0
+    R* Aout;                   // [5][sC]
+    R* Sb; R s1, s2, s3;       // source gradient accumulation (only when Sb != NULL): Sb += s1*A1 + s2*A2 + s3*A3
     FVM_HD void operator()(int c) const {
-        Grad<R> gc; load_grad(Gb, m.sN, c, gc);
-        const R ivc = R(1) / m.vol[c];
-        Prim<R> acc; zero(acc);
+        const int sC = m.sC, sN = m.sN, C = m.nInternalCells;
+        const R* FVM_RESTRICT gb = Gb; const R* FVM_RESTRICT cfm = m.cfm; const int* FVM_RESTRICT cn = m.cellNbr;
+        R H[15];
+        for (int k = 0; k < 15; k++) H[k] = gb[(long)k * sN + c];
+        Prim<R> acc; load_prim(Qb, sN, c, acc);
+        int nbr[6];
+        for (int j = 0; j < 6; j++) nbr[j] = cn[(long)j * sC + c];
+        unsigned ghosts = 0;
+        for (int j = 0; j < 6; j++) {
+            const int nb = nbr[j];
+            const R SN[3] = {cfm[(long)(4 * j) * sC + c], cfm[(long)(4 * j + 1) * sC + c], cfm[(long)(4 * j + 2) * sC + c]};
+            const R a = cfm[(long)(4 * j + 3) * sC + c];
+            R D[15];
+            if (nb >= C) { ghosts |= 1u << j; for (int k = 0; k < 15; k++) D[k] = H[k]; }
+            else for (int k = 0; k < 15; k++) D[k] = H[k] - gb[(long)k * sN + nb];
+            for (int i = 0; i < 3; i++) acc.U[i] += a * (SN[0] * D[3 * i] + SN[1] * D[3 * i + 1] + SN[2] * D[3 * i + 2]);
+            acc.T += a * (SN[0] * D[9] + SN[1] * D[10] + SN[2] * D[11]);
+            acc.p += a * (SN[0] * D[12] + SN[1] * D[13] + SN[2] * D[14]);
+        }
+        if (ghosts) {
+            for (int j = 0; j < 6; j++) {
+                if (!((ghosts >> j) & 1u)) continue;
+                const R SN[3] = {cfm[(long)(4 * j) * sC + c], cfm[(long)(4 * j + 1) * sC + c], cfm[(long)(4 * j + 2) * sC + c]};
+                const R wp = R(1) - cfm[(long)(4 * j + 3) * sC + c];
+                Prim<R> gq;
+                for (int i = 0; i < 3; i++) gq.U[i] = wp * (SN[0] * H[3 * i] + SN[1] * H[3 * i + 1] + SN[2] * H[3 * i + 2]);
+                gq.T = wp * (SN[0] * H[9] + SN[1] * H[10] + SN[2] * H[11]);
+                gq.p = wp * (SN[0] * H[12] + SN[1] * H[13] + SN[2] * H[14]);
+                add_prim(Qb, sN, nbr[j], gq);
+            }
+        }
+        if (objT != R(0)) acc.T += objT * m.vol[c];
+        R rhoU[3] = {W[sC + c], W[2 * sC + c], W[3 * sC + c]};
+        R out[5] = {0, 0, 0, 0, 0};
+        primitive_vjp(ph, W[c], rhoU, W[4 * sC + c], acc, out[0], out + 1, out[4]);
+        for (int k = 0; k < 5; k++) {
+            R v = out[k];
+            R x1 = A1 ? A1[k * sC + c] : R(0), x2 = A2 ? A2[k * sC + c] : R(0), x3 = A3 ? A3[k * sC + c] : R(0);
+            if (A1) v += c1 * x1;
+            if (A2) v += c2 * x2;
+            if (A3) v += c3 * x3;
+            Aout[k * sC + c] = v;
+            if (Sb) Sb[k * sC + c] += s1 * x1 + s2 * x2 + s3 * x3;
+        }
+    }
+};
+// cell-face metrics (mesh upload, one-off): rows 4j..4j+2 = +-S_f n_f (outward of the cell), row 4j+3 = weight of the
+// cell's own value in the face interpolate (adFVM/op.py:52-58: w' = w + o - 2 w o is the NEIGHBOUR's weight)
+template <typename R> struct CellFaceMetricBody {
+    static constexpr const char* kName = "cell_face_metric";
+    MeshDev<R> m; R* cfm;
+    FVM_HD void operator()(int c) const {
         const unsigned ob = m.cellOwner[c];
         for (int j = 0; j < 6; j++) {
-            const int f = m.cellFaces[j * m.sC + c], nb = m.cellNbr[j * m.sC + c];
+            const int f = m.cellFaces[j * m.sC + c];
             const bool own = (ob >> j) & 1u;
             const R S = m.area[f], w = m.weight[f];
             const R sg = own ? S : -S;
-            const R SN[3] = {sg * m.normal[f], sg * m.normal[m.sF + f], sg * m.normal[2 * m.sF + f]};
+            for (int k = 0; k < 3; k++) cfm[(long)(4 * j + k) * m.sC + c] = sg * m.normal[(long)k * m.sF + f];
             const R wp = own ? R(1) - w : w;
-            const R a = R(1) - wp;
-            // this cell's gradient: phiF = phi_c*a + phi_nb*wp
-            Prim<R> t;
-            for (int i = 0; i < 3; i++) t.U[i] = (SN[0] * gc.U[3 * i] + SN[1] * gc.U[3 * i + 1] + SN[2] * gc.U[3 * i + 2]) * ivc;
-            t.T = dot3(SN, gc.T) * ivc; t.p = dot3(SN, gc.p) * ivc;
-            for (int i = 0; i < 3; i++) acc.U[i] += a * t.U[i];
-            acc.T += a * t.T; acc.p += a * t.p;
-            if (nb >= m.nInternalCells) {
-                Prim<R> gq;
-                for (int i = 0; i < 3; i++) gq.U[i] = wp * t.U[i];
-                gq.T = wp * t.T; gq.p = wp * t.p;
-                add_prim(Qb, m.sN, nb, gq);
-            } else {
-                // neighbour's gradient used phi_c with weight (1 - wp) and normal -SN
-                Grad<R> gn; load_grad(Gb, m.sN, nb, gn);
-                const R ivn = -a / m.vol[nb];
-                for (int i = 0; i < 3; i++) acc.U[i] += (SN[0] * gn.U[3 * i] + SN[1] * gn.U[3 * i + 1] + SN[2] * gn.U[3 * i + 2]) * ivn;
-                acc.T += dot3(SN, gn.T) * ivn; acc.p += dot3(SN, gn.p) * ivn;
-            }
+            cfm[(long)(4 * j + 3) * m.sC + c] = R(1) - wp;
         }
-        add_prim(Qb, m.sN, c, acc);
     }
 };
 
@@ -310,7 +355,8 @@ template <typename R> struct GradCellAdjBody {
 template <typename R> struct GhostPrimAdjBody {
     static constexpr const char* kName = "ghost_prim_adj";
     Phys<R> ph; MeshDev<R> m; ObjDev<R> o; R obja;   // obja == 0 on stages that do not carry the objective
-    const int* bcells; const R* Q; R* Qb; const R* recvQ;   // recvQ: patch-major halo buffer or NULL
+    const int* bcells; const R* Q; const R* Qb; const R* recvQ;   // recvQ: patch-major halo buffer or NULL
+    const R* W; R* Aout;       // the ghost rows' share goes straight into the stage adjoint: Aout[c] += (dQ/dW)^T acc (linear)
     FVM_HD void ghost_total(int f, Prim<R>& q) const {
         load_prim(Qb, m.sN, m.nInternalCells + (f - m.nInternalFaces), q);
         if (obja != R(0)) objective_ghost_adj(ph, m, o, Q, obja, f, q);
@@ -361,39 +407,11 @@ template <typename R> struct GhostPrimAdjBody {
             }
             if (obja != R(0)) objective_owner_adj(ph, m, o, Q, obja, f, acc);
         }
-        add_prim(Qb, m.sN, c, acc);
-    }
-};
-
-// F. adjoint of primitive() + adjoint of the RK combination: a_s = sum_k alpha_k * a_{k} + dQ/dW^T Qb
-// (+ optional cell objective seed, + on the last reverse stage the source-term gradient accumulation).
-template <typename R> struct PrimAdjUpdateBody {
-    static constexpr const char* kName = "prim_adj_update";
-    Phys<R> ph; MeshDev<R> m;
-    const R* W;                // stage state the residual was evaluated at
-    const R* Qb;
-    const R *A1, *A2, *A3;     // adjoints of later stage outputs (NULL when coefficient is 0)
-    R c1, c2, c3;
-    R objT;                    // obja for OBJ_CELL_TV on the objective stage, else 0
-    R* Aout;                   // [5][sC]
-    // source gradient accumulation (only when Sb != NULL): Sb += s1*A1 + s2*A2 + s3*A3
-    R* Sb; R s1, s2, s3;
-    FVM_HD void operator()(int c) const {
         const int sC = m.sC;
-        Prim<R> qb; load_prim(Qb, m.sN, c, qb);
-        if (objT != R(0)) qb.T += objT * m.vol[c];
         R rhoU[3] = {W[sC + c], W[2 * sC + c], W[3 * sC + c]};
         R out[5] = {0, 0, 0, 0, 0};
-        primitive_vjp(ph, W[c], rhoU, W[4 * sC + c], qb, out[0], out + 1, out[4]);
-        for (int k = 0; k < 5; k++) {
-            R v = out[k];
-            R x1 = A1 ? A1[k * sC + c] : R(0), x2 = A2 ? A2[k * sC + c] : R(0), x3 = A3 ? A3[k * sC + c] : R(0);
-            if (A1) v += c1 * x1;
-            if (A2) v += c2 * x2;
-            if (A3) v += c3 * x3;
-            Aout[k * sC + c] = v;
-            if (Sb) Sb[k * sC + c] += s1 * x1 + s2 * x2 + s3 * x3;
-        }
+        primitive_vjp(ph, W[c], rhoU, W[4 * sC + c], acc, out[0], out + 1, out[4]);
+        for (int k = 0; k < 5; k++) Aout[k * sC + c] += out[k];
     }
 };
 

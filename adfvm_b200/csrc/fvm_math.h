@@ -17,8 +17,10 @@
 
 #if defined(__CUDACC__)
 #define FVM_HD __host__ __device__ __forceinline__
+#define FVM_RESTRICT __restrict__
 #else
 #define FVM_HD inline
+#define FVM_RESTRICT __restrict__
 #endif
 
 namespace fvm {

@@ -136,6 +136,7 @@ public:
         m.area = upload_aos(areas, F, 1, m.sF, nullptr, d_fperm); m.weight = upload_aos(weights, F, 1, m.sF, nullptr, d_fperm);
         { R* idel = upload_aos(deltas, F, 1, m.sF, nullptr, d_fperm); run(F, ReciprocalBody<R>{idel}); m.idelta = idel; } m.normal = upload_aos(normals, F, 3, m.sF, nullptr, d_fperm);
         { R* d_vol = dalloc<R>((size_t)m.sC + kRowSlack); m.vol = upload_aos(volumes, C, 1, m.sC, d_vol, d_cperm); }
+        for (long c = 0; c < C; c++) if (!(volumes[c] > R(0))) throw std::runtime_error("non-positive cell volume");
         {   // per-pass metric chunks of the flux kernels, gathered on the device from temporary face-indexed arrays
             R* t_dunit = (R*)ex.alloc((size_t)3 * m.sF * sizeof(R)); upload_aos(deltasUnit, F, 3, m.sF, t_dunit, d_fperm);
             R* t_linw = (R*)ex.alloc((size_t)2 * m.sF * sizeof(R)); upload_aos(linearWeights, F, 2, m.sF, t_linw, d_fperm);
@@ -181,6 +182,7 @@ public:
         int* d_cf = dalloc<int>(cf.size()); ex.upload(d_cf, cf.data(), cf.size() * 4); m.cellFaces = d_cf;
         int* d_cn = dalloc<int>(cn.size()); ex.upload(d_cn, cn.data(), cn.size() * 4); m.cellNbr = d_cn;
         unsigned char* d_co = dalloc<unsigned char>(co.size()); ex.upload(d_co, co.data(), co.size()); m.cellOwner = d_co;
+        { R* d_cfm = dalloc<R>((size_t)24 * m.sC); run(C, CellFaceMetricBody<R>{m, d_cfm}); m.cfm = d_cfm; }
         nBcells = (int)bc_list.size();
         bcells = dalloc<int>(nBcells + 1); ex.upload(bcells, bc_list.data(), (size_t)nBcells * 4);
         {
@@ -407,12 +409,8 @@ public:
             launches++;
             const R* rG = halo_reverse(Gb, 15);
             run(nBcells, GhostGradAdjBody<R>{m, bcells, Gb, rG});
-            run(C, GradCellAdjBody<R>{m, Gb, Qb});
-            const R* rQ = halo_reverse(Qb, 5);
-            const R oa = (s == 1) ? obja : R(0);
-            run(nBcells, GhostPrimAdjBody<R>{ph, m, obj, oa, bcells, Q[s], Qb, rQ});
-            PrimAdjUpdateBody<R> pb;
-            pb.ph = ph; pb.m = m; pb.W = W[s]; pb.Qb = Qb;
+            GradAdjUpdateBody<R> pb;
+            pb.ph = ph; pb.m = m; pb.Gb = Gb; pb.Qb = Qb; pb.W = W[s];
             // a_s = sum_{k>=s} alpha[k][s] * a_{k+1}
             pb.A1 = (s <= 0 && RK_ALPHA[0][s] != 0.) ? A[1] : nullptr; pb.c1 = (R)(s <= 0 ? RK_ALPHA[0][s] : 0.);
             pb.A2 = (s <= 1 && RK_ALPHA[1][s] != 0.) ? A[2] : nullptr; pb.c2 = (R)(s <= 1 ? RK_ALPHA[1][s] : 0.);
@@ -422,6 +420,9 @@ public:
             pb.Sb = (s == 0) ? Sb : nullptr;
             pb.s1 = (R)RK_BETA[0] * dt; pb.s2 = (R)RK_BETA[1] * dt; pb.s3 = (R)RK_BETA[2] * dt;
             run(C, pb);
+            const R* rQ = halo_reverse(Qb, 5);
+            const R oa = (s == 1) ? obja : R(0);
+            run(nBcells, GhostPrimAdjBody<R>{ph, m, obj, oa, bcells, Q[s], Qb, rQ, W[s], A[s]});
         }
     }
     void get_adjoint(R* rhoa, R* rhoUa, R* rhoEa) { get5(A[0], rhoa, rhoUa, rhoEa); }

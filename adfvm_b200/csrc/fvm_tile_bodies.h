@@ -352,9 +352,10 @@ template <typename R, int T, int TS> struct FluxGradTileBody {
         else if (e.sn) add20(acc + e.ln, qRb, gRb);
     }
     FVM_HD int ghost_of(int t, const TileEntry& e) const { return e.ghost ? m.halo_cell[m.halo_start[t] + e.ln - T] : -1; }
-    FVM_HD void finish(int c, const R* a) const {
+    // internal rows of Gb are stored divided by the cell volume (what GradAdjUpdateBody consumes); iv = 1/V_c
+    FVM_HD void finish(int c, const R* a, R iv) const {
         for (int k = 0; k < 5; k++) Qb[(long)k * m.sN + c] = a[k * T];
-        for (int k = 0; k < 15; k++) Gb[(long)k * m.sN + c] = a[(5 + k) * T];
+        for (int k = 0; k < 15; k++) Gb[(long)k * m.sN + c] = a[(5 + k) * T] * iv;
     }
 
 #if !defined(__CUDACC__)
@@ -381,7 +382,7 @@ template <typename R, int T, int TS> struct FluxGradTileBody {
                 }
             }
         }
-        for (int l = 0; l < nc; l++) finish(c0 + l, &acc[l]);
+        for (int l = 0; l < nc; l++) finish(c0 + l, &acc[l], rcp(vol[l]));
     }
 #else
     __device__ __forceinline__ void device_tile(int t, unsigned char* smem) const {
@@ -448,7 +449,7 @@ template <typename R, int T, int TS> struct FluxGradTileBody {
                 __syncwarp();
             }
         }
-        if (tid < nc) finish(c0 + tid, acc + tid);
+        if (tid < nc) finish(c0 + tid, acc + tid, rcp(vol[tid]));
     }
 #endif
 };

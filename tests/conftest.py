@@ -18,7 +18,7 @@ def build_hostsim():
     d = os.path.join(ROOT, "tests", "hostsim")
     so = os.path.join(d, "libadfvm_hostsim.so")
     srcs = [os.path.join(d, "hostsim.cpp")] + [os.path.join(ROOT, "adfvm_b200", "csrc", f) for f in
-                                               ("fvm_math.h", "fvm_bodies.h", "fvm_solver.h", "fvm_capi.inc")]
+                                               ("fvm_math.h", "fvm_bodies.h", "fvm_tile_bodies.h", "fvm_tiles.h", "fvm_solver.h", "fvm_capi.inc")]
     if not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
         subprocess.check_call(["g++", "-std=c++17", "-O2", "-fPIC", "-shared", "-fopenmp", "-o", so, srcs[0]], cwd=d)
     return so
