@@ -268,7 +268,7 @@ template <typename R, int T, int TS> struct FluxTileBody {
             mbar_wait(bar_chunk, (unsigned)(r & 1));
             TileEntry e; tile_decode(Ch::words(chunk)[lane], e);
             Geom<R> gm; tile_load_geom<R, 32>(chunk, lane, gm);
-            const int cfirst = __shfl_sync(0xffffffffu, e.col, 0), clast = __shfl_sync(0xffffffffu, e.col, 31);
+            const int cfirst = (int)__reduce_min_sync(0xffffffffu, (unsigned)e.col), clast = (int)__reduce_max_sync(0xffffffffu, (unsigned)e.col);   // lanes are not colour-sorted (fvm_tiles.h RoundBalancer)
             if (r == hr) mbar_wait(bar_halo, 0);
             __syncwarp();                          // metrics are in registers: the warp's chunk buffer is free
             if (lane == 0) {
@@ -432,7 +432,7 @@ template <typename R, int T, int TS> struct FluxGradTileBody {
             mbar_wait(bar_chunk, (unsigned)(r & 1));
             TileEntry e; tile_decode(Ch::words(chunk)[lane], e);
             Geom<R> gm; tile_load_geom<R, 32>(chunk, lane, gm);
-            const int cfirst = __shfl_sync(0xffffffffu, e.col, 0), clast = __shfl_sync(0xffffffffu, e.col, 31);
+            const int cfirst = (int)__reduce_min_sync(0xffffffffu, (unsigned)e.col), clast = (int)__reduce_max_sync(0xffffffffu, (unsigned)e.col);   // lanes are not colour-sorted (fvm_tiles.h RoundBalancer)
             if (r == hr) mbar_wait(bar_halo, 0);
             __syncwarp();
             if (lane == 0 && r + 1 < nr) {

@@ -19,8 +19,10 @@
 #pragma once
 #include <algorithm>
 #include <cstdint>
+#include <cstring>
 #include <numeric>
 #include <stdexcept>
+#include <unordered_map>
 #include <vector>
 
 namespace fvm {
@@ -109,6 +111,78 @@ inline void rcb(std::vector<int>& idx, const std::vector<float>& pos, long lo, l
     }
 }
 
+
+// Lane assignment inside one round of 32 entries (8-byte scalars). A warp-wide LDS.64 is served half-warp by
+// half-warp; lanes of one half that read DIFFERENT cell slots with the same slot%16 (the same pair of 4-byte banks)
+// serialise. The accumulation order is fixed by the colours, not by the lanes, so the lanes of a round may be
+// permuted freely: pick the split into two halves that minimises, for the owner-side and the neighbour-side loads,
+// the largest number of distinct slots per bank pair (greedy start + pairwise-swap descent; identical rounds of a
+// structured mesh are memoised).
+struct RoundBalancer {
+    std::unordered_map<uint64_t, std::vector<std::pair<std::vector<uint32_t>, std::vector<uint8_t>>>> memo;
+    // per half h, side s (0 owner slot, 1 neighbour slot): refs[h][s][slot] entries reading the slot, distinct[h][s][res]
+    uint8_t refs[2][2][1024]; uint8_t distinct[2][2][16];
+    static int slot_of(uint32_t w, int side) { return side ? (int)((w >> 10) & 0x3FFu) : (int)(w & 0x3FFu); }
+    void add(int h, uint32_t w, int d) {
+        if (!((w >> 27) & 1u)) return;                      // padding entries do not load
+        for (int s = 0; s < 2; s++) {
+            const int sl = slot_of(w, s);
+            if (d > 0) { if (refs[h][s][sl]++ == 0) distinct[h][s][sl & 15]++; }
+            else { if (--refs[h][s][sl] == 0) distinct[h][s][sl & 15]--; }
+        }
+    }
+    int cost() const {
+        int c = 0;
+        for (int h = 0; h < 2; h++) for (int s = 0; s < 2; s++) {
+            int mx = 0, sum = 0;
+            for (int r = 0; r < 16; r++) { const int d = distinct[h][s][r]; mx = std::max(mx, d); sum += d * d; }
+            c += 64 * mx + sum;                             // wavefronts first, spread as the tie-break
+        }
+        return c;
+    }
+    void balance(uint32_t* loc, int* face) {
+        uint64_t key = 1469598103934665603ull;
+        for (int i = 0; i < kRound; i++) { key ^= loc[i] & 0x080FFFFFu; key *= 1099511628211ull; }
+        std::vector<uint32_t> sig(loc, loc + kRound);
+        for (auto& x : sig) x &= 0x080FFFFFu;
+        std::vector<uint8_t> perm;
+        auto& bucket = memo[key];
+        for (auto& kv : bucket) if (kv.first == sig) { perm = kv.second; break; }
+        if (perm.empty()) {
+            std::memset(refs, 0, sizeof(refs)); std::memset(distinct, 0, sizeof(distinct));
+            int half[kRound], n[2] = {0, 0};
+            for (int i = 0; i < kRound; i++) {              // greedy: the half where the entry adds less
+                int best = -1, bc = 0;
+                for (int h = 0; h < 2; h++) {
+                    if (n[h] >= kRound / 2) continue;
+                    add(h, loc[i], +1); const int c = cost() + n[h]; add(h, loc[i], -1);
+                    if (best < 0 || c < bc) { best = h; bc = c; }
+                }
+                half[i] = best; n[best]++; add(best, loc[i], +1);
+            }
+            int cur = cost();
+            for (int sweep = 0; sweep < 4; sweep++) {
+                bool improved = false;
+                for (int i = 0; i < kRound; i++) for (int j = i + 1; j < kRound; j++) {
+                    if (half[i] == half[j]) continue;
+                    add(half[i], loc[i], -1); add(half[j], loc[j], -1); add(half[j], loc[i], +1); add(half[i], loc[j], +1);
+                    const int c = cost();
+                    if (c < cur) { cur = c; std::swap(half[i], half[j]); improved = true; }
+                    else { add(half[j], loc[i], -1); add(half[i], loc[j], -1); add(half[i], loc[i], +1); add(half[j], loc[j], +1); }
+                }
+                if (!improved) break;
+            }
+            perm.resize(kRound);
+            int pos[2] = {0, kRound / 2};
+            for (int i = 0; i < kRound; i++) perm[pos[half[i]]++] = (uint8_t)i;    // new lane -> old lane
+            bucket.push_back({sig, perm});
+        }
+        uint32_t l2[kRound]; int f2[kRound];
+        for (int i = 0; i < kRound; i++) { l2[i] = loc[perm[i]]; f2[i] = face[perm[i]]; }
+        for (int i = 0; i < kRound; i++) { loc[i] = l2[i]; face[i] = f2[i]; }
+    }
+};
+
 }  // namespace detail
 
 // owner/neigh/cellFaces: the reference's arrays (old numbering). T: multiple of 32, <= 512.
@@ -140,6 +214,7 @@ TilePlan build_tile_plan(int C, int Fi, int F, const int* owner, const int* neig
     int nextFace = 0;
     std::vector<int> faces, colour, group, order;
     std::vector<uint32_t> used(kRound);
+    static thread_local detail::RoundBalancer balancer_store; detail::RoundBalancer& balancer = balancer_store; balancer.memo.clear();
     const int N = C + (F - Fi);
     std::vector<int> slot_of(N, -1), slot_tile(N, -1);
     P.halo_start.assign(P.nTiles + 1, 0);
@@ -219,8 +294,11 @@ TilePlan build_tile_plan(int C, int Fi, int F, const int* owner, const int* neig
                 P.nEntries++; nEnt++;
             }
             P.halo_round[(size_t)t * NW + w] = firstHaloEntry < 0 ? (nEnt + kRound - 1) / kRound : firstHaloEntry / kRound;
-            // pad the last round; padding repeats the last colour so that a round's colour range is [first slot, last slot]
+            // pad the last round (padding repeats the last colour: the kernels scan the colours present in a round)
             while (P.ent_face.size() % (size_t)kRound) { P.ent_face.push_back(-1); P.ent_loc.push_back(tile_pack(0, 0, ncol ? ncol - 1 : 0, 0, 0)); }
+            if (sizeof(R) == 8)
+                for (size_t e = (size_t)P.round_start[(size_t)t * NW + w] * kRound; e < P.ent_face.size(); e += kRound)
+                    balancer.balance(&P.ent_loc[e], &P.ent_face[e]);
             P.round_start[(size_t)t * NW + w + 1] = (int)(P.ent_face.size() / (size_t)kRound);
         }
         P.maxHalo = std::max(P.maxHalo, nHalo);
