@@ -488,6 +488,75 @@ FVM_HD void face_flux(const Phys<R>& ph, int kind, const Geom<R>& gm, const Prim
     { const R x = ph.Cp * TF * ph.gm1; wave = fabs(dot3(UF, gm.n)) + x * rsqrt_fast(x); }
 }
 
+// Compact form of the reverse of a COUPLED face (both sides reconstructed): everything the 40 input adjoints are
+// made of. LF/RF: adjoints of the reconstructed states (face means of T,U folded in), dU/dT: the normal-derivative
+// (snGrad) share of the owner-side cell values (the neighbour side gets the opposite), hgU/hgT: half the adjoint
+// of the face gradient (both sides get it).
+template <typename R> struct FaceAdj { Prim<R> LF, RF; R dU[3], dT, hgU[9], hgT[3]; };
+
+template <typename R>
+FVM_HD void face_flux_vjp_coupled(const Phys<R>& ph, const Geom<R>& gm, const Prim<R>& qL, const Grad<R>& gL,
+                                  const Prim<R>& qR, const Grad<R>& gR, const Flux5<R>& Fb, FaceAdj<R>& c) {
+    const R h = R(0.5);
+    // ---- recompute forward
+    Prim<R> LF, RF;
+    reconstruct(qL, qR, gL, gm.lw[0], gm.qw[0], LF);
+    reconstruct(qR, qL, gR, gm.lw[1], gm.qw[1], RF);
+    Cons<R> wL, wR;
+    conservative(ph, LF, wL);
+    conservative(ph, RF, wR);
+    R UF[3], gTF[3], gUF[9];
+    const R TF = h * (LF.T + RF.T);
+    for (int i = 0; i < 3; i++) { UF[i] = h * (LF.U[i] + RF.U[i]); gTF[i] = h * (gL.T[i] + gR.T[i]); }
+    for (int i = 0; i < 9; i++) gUF[i] = h * (gL.U[i] + gR.U[i]);
+    // ---- reverse
+    zero(c.LF); zero(c.RF);
+    Cons<R> wLb, wRb;
+    wLb.rho = wRb.rho = wLb.rhoE = wRb.rhoE = R(0);
+    for (int i = 0; i < 3; i++) wLb.rhoU[i] = wRb.rhoU[i] = R(0);
+    R TFb = R(0), UFb[3] = {0, 0, 0}, gTFb[3] = {0, 0, 0}, gUFb[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    R TLb = R(0), TRb = R(0), ULb[3] = {0, 0, 0}, URb[3] = {0, 0, 0};
+    viscous_reverse(ph, gm, qL.T, qR.T, qL.U, qR.U, TF, UF, gTF, gUF, Fb, TLb, TRb, ULb, URb, TFb, UFb, gTFb, gUFb);
+    if (ph.riemann == RIEMANN_ROE) {
+        Flux5<R> F; RoeTmp<R> t;
+        roe_forward(ph, LF, RF, wL, wR, gm.n, F, t);
+        roe_reverse(ph, LF, RF, wL, wR, gm.n, t, Fb, c.LF, c.RF, wLb.rho, wRb.rho);
+    } else {
+        lf_reverse(ph, LF, RF, wL, wR, gm.n, Fb, c.LF, c.RF, wLb, wRb);
+    }
+    conservative_vjp(ph, LF, wL, wLb, c.LF);
+    conservative_vjp(ph, RF, wR, wRb, c.RF);
+    c.LF.T += h * TFb; c.RF.T += h * TFb;
+    for (int i = 0; i < 3; i++) { c.LF.U[i] += h * UFb[i]; c.RF.U[i] += h * UFb[i]; c.dU[i] = ULb[i]; c.hgT[i] = h * gTFb[i]; }
+    c.dT = TLb;
+    for (int i = 0; i < 9; i++) c.hgU[i] = h * gUFb[i];
+}
+// component k (0-4 U,T,p; 5-13 gradU; 14-16 gradT; 17-19 gradp) of the owner-side / neighbour-side input adjoints
+// (reverse of the two reconstructions, interp.py:20-28, + the shares above)
+template <typename R> FVM_HD R face_adj_owner(const FaceAdj<R>& c, const Geom<R>& gm, int k) {
+    const R a = R(1) - gm.lw[0], b = gm.lw[1];
+    if (k < 3) return c.dU[k] + c.LF.U[k] * a + c.RF.U[k] * b;
+    if (k == 3) return c.dT + c.LF.T * a + c.RF.T * b;
+    if (k == 4) return c.LF.p * a + c.RF.p * b;
+    if (k < 14) return c.hgU[k - 5] + gm.qw[0][(k - 5) % 3] * c.LF.U[(k - 5) / 3];
+    if (k < 17) return c.hgT[k - 14] + gm.qw[0][k - 14] * c.LF.T;
+    return gm.qw[0][k - 17] * c.LF.p;
+}
+template <typename R> FVM_HD R face_adj_neighbour(const FaceAdj<R>& c, const Geom<R>& gm, int k) {
+    const R a = R(1) - gm.lw[1], b = gm.lw[0];
+    if (k < 3) return -c.dU[k] + c.RF.U[k] * a + c.LF.U[k] * b;
+    if (k == 3) return -c.dT + c.RF.T * a + c.LF.T * b;
+    if (k == 4) return c.RF.p * a + c.LF.p * b;
+    if (k < 14) return c.hgU[k - 5] + gm.qw[1][(k - 5) % 3] * c.RF.U[(k - 5) / 3];
+    if (k < 17) return c.hgT[k - 14] + gm.qw[1][k - 14] * c.RF.T;
+    return gm.qw[1][k - 17] * c.RF.p;
+}
+template <typename R> FVM_HD void add20(Prim<R>& q, Grad<R>& g, const R* v) {
+    q.U[0] += v[0]; q.U[1] += v[1]; q.U[2] += v[2]; q.T += v[3]; q.p += v[4];
+    for (int k = 0; k < 9; k++) g.U[k] += v[5 + k];
+    for (int k = 0; k < 3; k++) { g.T[k] += v[14 + k]; g.p[k] += v[17 + k]; }
+}
+
 // Reverse of face_flux w.r.t. (qL, gL, qR, gR) for a given flux adjoint Fb (the wave speed only feeds a
 // max-reduction, which carries no gradient). ACCUMULATES into qLb, gLb, qRb, gRb.
 template <typename R>
@@ -513,55 +582,37 @@ FVM_HD void face_flux_vjp(const Phys<R>& ph, int kind, const Geom<R>& gm, const 
         for (int i = 0; i < 3; i++) qRb.U[i] += UFb[i];
         return;
     }
-    // ---- recompute forward
-    Prim<R> LF, RF;
+    if (kind == FACE_COUPLED) {
+        FaceAdj<R> c; face_flux_vjp_coupled(ph, gm, qL, gL, qR, gR, Fb, c);
+        R vo[20], vn[20];
+        for (int k = 0; k < 20; k++) { vo[k] = face_adj_owner(c, gm, k); vn[k] = face_adj_neighbour(c, gm, k); }
+        add20(qLb, gLb, vo); add20(qRb, gRb, vn);
+        return;
+    }
+    // ---- characteristic face (density.py:266-274): left reconstruction, right = ghost state
+    Prim<R> LF;
     reconstruct(qL, qR, gL, gm.lw[0], gm.qw[0], LF);
     Cons<R> wL, wR;
     conservative(ph, LF, wL);
-    R TF, UF[3], gTF[3], gUF[9];
-    int solver;
-    const bool ch = (kind == FACE_CHARACTERISTIC);
-    if (ch) {
-        RF = qR; solver = ph.boundary_riemann; TF = qR.T;
-        for (int i = 0; i < 3; i++) { UF[i] = qR.U[i]; gTF[i] = gR.T[i]; }
-        for (int i = 0; i < 9; i++) gUF[i] = gR.U[i];
-    } else {
-        reconstruct(qR, qL, gR, gm.lw[1], gm.qw[1], RF);
-        solver = ph.riemann; TF = h * (LF.T + RF.T);
-        for (int i = 0; i < 3; i++) { UF[i] = h * (LF.U[i] + RF.U[i]); gTF[i] = h * (gL.T[i] + gR.T[i]); }
-        for (int i = 0; i < 9; i++) gUF[i] = h * (gL.U[i] + gR.U[i]);
-    }
-    conservative(ph, RF, wR);
-    // ---- reverse
+    conservative(ph, qR, wR);
     Prim<R> LFb, RFb; zero(LFb); zero(RFb);
     Cons<R> wLb, wRb;
     wLb.rho = wRb.rho = wLb.rhoE = wRb.rhoE = R(0);
     for (int i = 0; i < 3; i++) wLb.rhoU[i] = wRb.rhoU[i] = R(0);
-    R TFb = R(0), UFb[3] = {0, 0, 0}, gTFb[3] = {0, 0, 0}, gUFb[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
-    viscous_reverse(ph, gm, qL.T, qR.T, qL.U, qR.U, TF, UF, gTF, gUF, Fb,
-                    qLb.T, qRb.T, qLb.U, qRb.U, TFb, UFb, gTFb, gUFb);
-    if (solver == RIEMANN_ROE) {
+    R TFb = R(0), UFb[3] = {0, 0, 0};
+    viscous_reverse(ph, gm, qL.T, qR.T, qL.U, qR.U, qR.T, qR.U, gR.T, gR.U, Fb,
+                    qLb.T, qRb.T, qLb.U, qRb.U, TFb, UFb, gRb.T, gRb.U);
+    if (ph.boundary_riemann == RIEMANN_ROE) {
         Flux5<R> F; RoeTmp<R> t;
-        roe_forward(ph, LF, RF, wL, wR, gm.n, F, t);
-        roe_reverse(ph, LF, RF, wL, wR, gm.n, t, Fb, LFb, RFb, wLb.rho, wRb.rho);
+        roe_forward(ph, LF, qR, wL, wR, gm.n, F, t);
+        roe_reverse(ph, LF, qR, wL, wR, gm.n, t, Fb, LFb, RFb, wLb.rho, wRb.rho);
     } else {
-        lf_reverse(ph, LF, RF, wL, wR, gm.n, Fb, LFb, RFb, wLb, wRb);
+        lf_reverse(ph, LF, qR, wL, wR, gm.n, Fb, LFb, RFb, wLb, wRb);
     }
     conservative_vjp(ph, LF, wL, wLb, LFb);
-    conservative_vjp(ph, RF, wR, wRb, RFb);
-    if (ch) {
-        RFb.T += TFb;
-        for (int i = 0; i < 3; i++) { RFb.U[i] += UFb[i]; gRb.T[i] += gTFb[i]; }
-        for (int i = 0; i < 9; i++) gRb.U[i] += gUFb[i];
-        qRb.T += RFb.T; qRb.p += RFb.p;
-        for (int i = 0; i < 3; i++) qRb.U[i] += RFb.U[i];
-    } else {
-        LFb.T += h * TFb; RFb.T += h * TFb;
-        for (int i = 0; i < 3; i++) { LFb.U[i] += h * UFb[i]; RFb.U[i] += h * UFb[i];
-                                      gLb.T[i] += h * gTFb[i]; gRb.T[i] += h * gTFb[i]; }
-        for (int i = 0; i < 9; i++) { gLb.U[i] += h * gUFb[i]; gRb.U[i] += h * gUFb[i]; }
-        reconstruct_vjp(RFb, gm.lw[1], gm.qw[1], qRb, qLb, gRb);
-    }
+    conservative_vjp(ph, qR, wR, wRb, RFb);
+    qRb.T += RFb.T + TFb; qRb.p += RFb.p;
+    for (int i = 0; i < 3; i++) qRb.U[i] += RFb.U[i] + UFb[i];
     reconstruct_vjp(LFb, gm.lw[0], gm.qw[0], qLb, qRb, gLb);
 }
 

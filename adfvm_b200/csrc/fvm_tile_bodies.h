@@ -1,13 +1,14 @@
 // Tiled flux kernels: one CTA per tile of T consecutive cells (fvm_tiles.h), one WARP per sub-tile of 32 cells,
-// one thread per face entry of the warp's current round.
+// one LANE per cell: the lane evaluates the entries homed at its cell (one per round, always as the owner side,
+// fvm_tiles.h) and keeps the cell's accumulators in registers.
 //
 //   flux_tile       a8-a12: face flux (reconstruction + Riemann + viscous, adFVM/density.py:253-331) of every face
-//                   touching the sub-tile, scatter +F*A/V_owner / -F*A/V_neighbour (adFVM/op.py:12-29) into the
-//                   sub-tile's shared-memory accumulators, then RK stage update (adFVM/timestep.py:35-45) and the
-//                   primitive conversion of the new state (adFVM/density.py:162-171) for the sub-tile's cells.
-//   flux_grad_tile  reverse of the flux + scatter: VJP of every face of the sub-tile, the shares of the sub-tile's
-//                   own cells summed into shared-memory accumulators; ghost rows of boundary faces written directly
-//                   (exclusive writer).
+//                   touching the sub-tile, +F*A/V to the home cell, -F*A/V_other sent to the other cell's lane by warp
+//                   shuffle (adFVM/op.py:12-29), then RK stage update (adFVM/timestep.py:35-45) and the primitive
+//                   conversion of the new state (adFVM/density.py:162-171) of the lane's cell.
+//   flux_grad_tile  reverse of the flux + scatter: VJP of every face of the sub-tile in compact form (FaceAdj), the home
+//                   cell's 20 input adjoints summed in registers, the other cell's sent by shuffle; ghost rows of
+//                   boundary faces written directly (exclusive writer).
 //
 // Data movement of one CTA (R = scalar):
 //   * qg [20][TS]: U(3),T,p and the 15 gradient components of the tile's own cells (slots [0,T): 20 bulk row copies of
@@ -16,11 +17,9 @@
 //   * face metrics live in HBM as per-round CHUNKS [16][32] R + [32] u32 (area, n, 1/delta, dUnit, linW, quadW and the
 //     packed entry word) in the order the warp consumes them; one bulk copy per warp and round streams a chunk into the
 //     warp's own buffer, issued one round ahead of its use, completion on the warp's own mbarrier;
-//   * forward:  vol [T], acc [6][T] residual(5) + dtc          reverse:  ab [5][TS] = abar, vol [TS], acc [20][T].
-// After the staging the warps of a CTA never synchronise with each other: a warp only writes the accumulator columns
-// of its own 32 cells, and the order inside a warp is fixed by the colouring (__syncwarp between colours).
-// The CPU simulator (tests/hostsim) runs the same face/scatter/finish functions over the entries sequentially,
-// which is the same order.
+//   * forward:  vol [T]          reverse:  ab [5][TS] = abar, vol [TS].
+// After the staging the warps of a CTA never synchronise with each other. The CPU simulator (tests/hostsim) runs the
+// same face / share functions round by round in the same order.
 #pragma once
 #include "fvm_bodies.h"
 #if !defined(__CUDACC__)
@@ -39,11 +38,11 @@ template <typename R, int W> struct Chunk {
     FVM_HD static unsigned* words(R* chunk) { return reinterpret_cast<unsigned*>(chunk + 16 * W); }
 };
 
-struct TileEntry { int lo, ln, col, kind; bool valid, so, sn, ghost; };   // so/sn: scatter to the owner / neighbour side
+struct TileEntry { int ln, kind, src; bool valid, sn, ghost, has_src; };   // sn: the other cell's share is sent to its lane
 FVM_HD void tile_decode(unsigned w, TileEntry& e) {
-    e.lo = (int)(w & 0x3FFu); e.ln = (int)((w >> 10) & 0x3FFu); e.col = (int)((w >> 20) & 0x1Fu);
+    e.src = (int)(w & 0x1Fu); e.has_src = ((w >> 5) & 1u) != 0; e.ln = (int)((w >> 10) & 0x3FFu);
     e.kind = (int)((w >> 25) & 3u); e.valid = ((w >> 27) & 1u) != 0;
-    e.so = ((w >> 28) & 1u) != 0; e.sn = ((w >> 29) & 1u) != 0; e.ghost = ((w >> 30) & 1u) != 0;
+    e.sn = ((w >> 29) & 1u) != 0; e.ghost = ((w >> 30) & 1u) != 0;
 }
 template <typename R, int W> FVM_HD void tile_load_geom(const R* chunk, int i, Geom<R>& g) {
     const R* p = chunk + i;
@@ -78,6 +77,10 @@ template <typename R, int W> struct FillChunksBody {
             for (int k = 0; k < 3; k++) { v[1 + k] = normal[(long)k * sF + f]; v[5 + k] = dunit[(long)k * sF + f]; }
             v[8] = linw[f]; v[9] = linw[(long)sF + f];
             for (int k = 0; k < 6; k++) v[10 + k] = quadw[(long)k * sF + f];
+            if (slot_word[i] >> 31) {        // home cell = the face's neighbour: reverse the face (fvm_tiles.h)
+                for (int k = 0; k < 3; k++) { v[1 + k] = -v[1 + k]; v[5 + k] = -v[5 + k]; const R q = v[10 + k]; v[10 + k] = v[13 + k]; v[13 + k] = q; }
+                const R l = v[8]; v[8] = v[9]; v[9] = l;
+            }
         } else {
             for (int k = 0; k < 16; k++) v[k] = R(0);
         }
@@ -143,7 +146,7 @@ template <typename R, int T, int TS, int EXTRA> struct TileSmem {
 template <typename R, int T, int TS> struct FluxTileBody {
     static constexpr const char* kName = "flux_tile";
     static constexpr int kThreads = T, NW = T / 32;
-    static constexpr int kMinBlocks = 1;
+    static constexpr int kMinBlocks = sizeof(R) == 8 ? 3 : 5;     // register cap: 168 (fp64), 96 (fp32)
     typedef Chunk<R, 32> Ch;
     Phys<R> ph; MeshDev<R> m;
     const R *Q, *G;            // this stage's primitives / gradients (ghosts filled)
@@ -154,71 +157,78 @@ template <typename R, int T, int TS> struct FluxTileBody {
     R* Qn;                     // primitives of the new state (may be NULL)
     R* dtc_partial;            // [nTiles*NW] per-sub-tile max of dtc (may be NULL)
 #if defined(__CUDACC__)
-    typedef TileSmem<R, T, TS, 7 * T> Smem;
+    typedef TileSmem<R, T, TS, T> Smem;
     static size_t smem_bytes() { return Smem::kBytes; }
 #endif
 
-    // flux per unit area of one entry + the scatter weights A/V of its sub-tile sides (vol: the tile's own volumes [T])
-    FVM_HD void face(const Geom<R>& gm, const TileEntry& e, const R* qg, const R* vol, Flux5<R>& F, R& wave, R& sO, R& sNb) const {
+    // one entry of the lane whose cell sits in slot lo: own[6] = the home cell's share of (residual(5), dtc),
+    // snd[6] = the other cell's share (zero unless e.sn). ivh = 1/V_home, vol: the tile's own volumes [T]
+    FVM_HD void face(const Geom<R>& gm, const TileEntry& e, int lo, const R* qg, R ivh, const R* vol, R* own, R* snd) const {
         Prim<R> qL, qR; Grad<R> gL, gR;
-        tile_load_cell<R, TS>(qg, e.lo, qL, gL); tile_load_cell<R, TS>(qg, e.ln, qR, gR);
+        tile_load_cell<R, TS>(qg, lo, qL, gL); tile_load_cell<R, TS>(qg, e.ln, qR, gR);
+        Flux5<R> F; R wave;
         face_flux(ph, e.kind, gm, qL, gL, qR, gR, F, wave);
-        sO = e.so ? gm.area * rcp(vol[e.lo]) : R(0);
-        sNb = e.sn ? gm.area * rcp(vol[e.ln]) : R(0);
+        const R sO = gm.area * ivh;
+        const R sNb = e.sn ? gm.area * rcp(vol[e.ln]) : R(0);
+        own[0] = F.rho * sO; own[1] = F.rhoU[0] * sO; own[2] = F.rhoU[1] * sO; own[3] = F.rhoU[2] * sO; own[4] = F.rhoE * sO; own[5] = wave * sO;
+        const R s = -sNb;
+        snd[0] = F.rho * s; snd[1] = F.rhoU[0] * s; snd[2] = F.rhoU[1] * s; snd[3] = F.rhoU[2] * s; snd[4] = F.rhoE * s; snd[5] = wave * sNb;
     }
-    FVM_HD static void scatter(R* acc, const TileEntry& e, const Flux5<R>& F, R wave, R sO, R sNb) {
-        if (e.so) {
-            R* a = acc + e.lo;
-            a[0] += F.rho * sO; a[T] += F.rhoU[0] * sO; a[2 * T] += F.rhoU[1] * sO; a[3 * T] += F.rhoU[2] * sO;
-            a[4 * T] += F.rhoE * sO; a[5 * T] += wave * sO;
-        }
-        if (e.sn) {
-            R* a = acc + e.ln; const R s = -sNb;
-            a[0] += F.rho * s; a[T] += F.rhoU[0] * s; a[2 * T] += F.rhoU[1] * s; a[3 * T] += F.rhoU[2] * s;
-            a[4 * T] += F.rhoE * s; a[5 * T] += wave * sNb;
-        }
-    }
-    // RK stage update + primitives of the new state for cell c; res[k*T] = residual component k, res[5*T] = dtc;
+    // RK stage update + primitives of the new state for cell c; res[0..4] = residual, res[5] = dtc;
     // w0/wx/src: this cell's previous-stage states and source, component stride ws (wx = W1 or W2, coefficient ax)
     FVM_HD R finish(int c, const R* res, const R* w0, const R* wx, R ax, const R* src, int ws) const {
         R wn[5];
         for (int k = 0; k < 5; k++) {
             R v = a0 * w0[(long)k * ws];
             if (wx) v += ax * wx[(long)k * ws];
-            v += -beta * (res[k * T] - src[(long)k * ws]) * dt;
+            v += -beta * (res[k] - src[(long)k * ws]) * dt;
             wn[k] = v;
             Wn[(long)k * m.sC + c] = v;
         }
         if (Qn) { Prim<R> q; primitive(ph, wn[0], wn + 1, wn[4], q); store_prim(Qn, m.sN, c, q); }
-        return res[5 * T];
+        return res[5];
     }
 
 #if !defined(__CUDACC__)
     void host_tile(int t) const {
         const int c0 = t * T, nc = (m.nInternalCells - c0 < T) ? m.nInternalCells - c0 : T;
-        std::vector<R> qg((size_t)20 * TS, R(0)), vol(T, R(1)), acc((size_t)6 * T, R(0));
+        std::vector<R> qg((size_t)20 * TS, R(0)), vol(T, R(1));
         for (int l = 0; l < nc; l++) { tile_stage_cell<R, TS>(qg.data(), l, Q, G, m.sN, c0 + l); vol[l] = m.vol[c0 + l]; }
         for (int h = m.halo_start[t]; h < m.halo_start[t + 1]; h++) tile_stage_cell<R, TS>(qg.data(), T + h - m.halo_start[t], Q, G, m.sN, m.halo_cell[h]);
         const R* wx = W1 ? W1 : W2; const R ax = W1 ? a1 : a2;
         for (int w = 0; w < NW; w++) {
             const int r0 = m.round_start[t * NW + w], r1 = m.round_start[t * NW + w + 1];
+            R acc[32][6], snd[32][6], own[6];
+            for (int l = 0; l < 32; l++) for (int k = 0; k < 6; k++) acc[l][k] = R(0);
             for (int r = r0; r < r1; r++) {
                 const R* chunk = m.chunks + (long)r * Ch::kScalars;
+                TileEntry e[32];
                 for (int i = 0; i < 32; i++) {
-                    TileEntry e; tile_decode(Ch::words(chunk)[i], e);
-                    if (!e.valid) continue;
-                    if ((e.lo >= T || e.ln >= T) && r - r0 < m.halo_round[t * NW + w]) throw std::runtime_error("halo_round inconsistent");
-                    if ((e.so && (e.lo >> 5) != w) || (e.sn && (e.ln >> 5) != w)) throw std::runtime_error("scatter outside the sub-tile");
+                    tile_decode(Ch::words(chunk)[i], e[i]);
+                    for (int k = 0; k < 6; k++) snd[i][k] = R(0);
+                    if (!e[i].valid) continue;
+                    if (e[i].ln >= T && r - r0 < m.halo_round[t * NW + w]) throw std::runtime_error("halo_round inconsistent");
+                    if (w * 32 + i >= nc) throw std::runtime_error("entry homed at a lane without a cell");
+                    if (e[i].sn && (e[i].ln >> 5) != w) throw std::runtime_error("share sent outside the sub-tile");
                     Geom<R> gm; tile_load_geom<R, 32>(chunk, i, gm);
-                    Flux5<R> F; R wave, sO, sNb;
-                    face(gm, e, qg.data(), vol.data(), F, wave, sO, sNb);
-                    scatter(acc.data(), e, F, wave, sO, sNb);
+                    face(gm, e[i], w * 32 + i, qg.data(), R(1) / vol[w * 32 + i], vol.data(), own, snd[i]);
+                    for (int k = 0; k < 6; k++) acc[i][k] += own[k];
+                }
+                for (int i = 0; i < 32; i++) {
+                    if (!e[i].has_src) continue;
+                    const TileEntry& s = e[e[i].src];
+                    if (!s.valid || !s.sn || s.ln != w * 32 + i) throw std::runtime_error("receive lane inconsistent");
+                    for (int k = 0; k < 6; k++) acc[i][k] += snd[e[i].src][k];
+                }
+                for (int i = 0; i < 32; i++) if (e[i].valid && e[i].sn) {      // every sent share has exactly one receiver
+                    const TileEntry& d = e[e[i].ln - w * 32];
+                    if (!d.has_src || d.src != i) throw std::runtime_error("sent share without receiver");
                 }
             }
             R mx = R(-1e30);
             for (int l = w * 32; l < nc && l < w * 32 + 32; l++) {
                 const int c = c0 + l;
-                R d = finish(c, &acc[l], W0 + c, wx ? wx + c : nullptr, ax, S + c, m.sC); mx = d > mx ? d : mx;
+                R d = finish(c, acc[l - w * 32], W0 + c, wx ? wx + c : nullptr, ax, S + c, m.sC); mx = d > mx ? d : mx;
             }
             if (dtc_partial) dtc_partial[t * NW + w] = mx;
         }
@@ -229,7 +239,6 @@ template <typename R, int T, int TS> struct FluxTileBody {
         const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
         R* qg = reinterpret_cast<R*>(smem);
         R* vol = qg + 20 * TS;
-        R* acc = vol + T;
         R* chunk = reinterpret_cast<R*>(smem + Smem::kChunkOff) + w * Ch::kScalars;
         unsigned long long* bars = reinterpret_cast<unsigned long long*>(smem + Smem::kBarOff);
         unsigned long long *bar_rows = &bars[0], *bar_halo = &bars[1], *bar_chunk = &bars[2 + w];
@@ -262,13 +271,13 @@ template <typename R, int T, int TS> struct FluxTileBody {
         }
         cp_async_arrive(bar_halo);
         if (nr == 0) return;                       // sub-tile beyond the last internal cell
-        for (int k = 0; k < 6; k++) acc[k * T + tid] = R(0);
         mbar_wait(bar_rows, 0);
+        const R ivh = tid < nc ? rcp(vol[tid]) : R(0);
+        R acc[6] = {R(0), R(0), R(0), R(0), R(0), R(0)};
         for (int r = 0; r < nr; r++) {
             mbar_wait(bar_chunk, (unsigned)(r & 1));
             TileEntry e; tile_decode(Ch::words(chunk)[lane], e);
             Geom<R> gm; tile_load_geom<R, 32>(chunk, lane, gm);
-            const int cfirst = (int)__reduce_min_sync(0xffffffffu, (unsigned)e.col), clast = (int)__reduce_max_sync(0xffffffffu, (unsigned)e.col);   // lanes are not colour-sorted (fvm_tiles.h RoundBalancer)
             if (r == hr) mbar_wait(bar_halo, 0);
             __syncwarp();                          // metrics are in registers: the warp's chunk buffer is free
             if (lane == 0) {
@@ -287,17 +296,16 @@ template <typename R, int T, int TS> struct FluxTileBody {
                     }
                 }
             }
-            Flux5<R> F; R wave = R(0), sO = R(0), sNb = R(0);
-            if (e.valid) face(gm, e, qg, vol, F, wave, sO, sNb);
-            const int col = e.valid ? e.col : -1;
-            for (int c = cfirst; c <= clast; c++) {
-                if (col == c) scatter(acc, e, F, wave, sO, sNb);
-                __syncwarp();
+            R own[6] = {R(0), R(0), R(0), R(0), R(0), R(0)}, snd[6] = {R(0), R(0), R(0), R(0), R(0), R(0)};
+            if (e.valid) face(gm, e, tid, qg, ivh, vol, own, snd);
+            for (int k = 0; k < 6; k++) acc[k] += own[k];
+            if (__any_sync(0xffffffffu, e.has_src)) {
+                for (int k = 0; k < 6; k++) { const R v = __shfl_sync(0xffffffffu, snd[k], e.src); if (e.has_src) acc[k] += v; }
             }
         }
         mbar_wait(bar_chunk, (unsigned)(nr & 1));
         R mx = R(-1e30);
-        if (tid < nc) mx = finish(c0 + tid, acc + tid, chunk + lane, wx ? chunk + 10 * 32 + lane : nullptr, ax, chunk + 5 * 32 + lane, 32);
+        if (tid < nc) mx = finish(c0 + tid, acc, chunk + lane, wx ? chunk + 10 * 32 + lane : nullptr, ax, chunk + 5 * 32 + lane, 32);
         if (dtc_partial) {
             mx = warp_max(mx);
             if (lane == 0) dtc_partial[t * NW + w] = mx;
@@ -308,17 +316,18 @@ template <typename R, int T, int TS> struct FluxTileBody {
 
 // ------------------------------------------------------------------------------------------ reverse
 //   abar = adjoint of the stage OUTPUT state [5][sC]; coef = -beta_ii*dt (d W_new / d residual)
-//   outputs Qb [5][sN], Gb [15][sN]: rows of internal cells and of the ghost cells of ALL boundary faces
+//   outputs Qb [5][sN], Gb [15][sN]: rows of internal cells (Gb divided by the cell volume, see GradAdjUpdateBody)
+//   and of the ghost cells of ALL boundary faces
 template <typename R, int T, int TS> struct FluxGradTileBody {
     static constexpr const char* kName = "flux_grad_tile";
     static constexpr int kThreads = T, NW = T / 32;
-    static constexpr int kMinBlocks = 1;
+    static constexpr int kMinBlocks = sizeof(R) == 8 ? 2 : 4;     // register cap: 255 (fp64), 128 (fp32)
     typedef Chunk<R, 32> Ch;
     Phys<R> ph; MeshDev<R> m;
     const R *Q, *G; const R* abar; R coef;
     R *Qb, *Gb;
 #if defined(__CUDACC__)
-    typedef TileSmem<R, T, TS, 6 * TS + 20 * T> Smem;
+    typedef TileSmem<R, T, TS, 6 * TS> Smem;
     static size_t smem_bytes() { return Smem::kBytes; }
 #endif
 
@@ -326,63 +335,71 @@ template <typename R, int T, int TS> struct FluxGradTileBody {
     FVM_HD void stage_ab(R* ab, R* vol, int slot, int cell) const {
         if (cell < m.nInternalCells) { for (int k = 0; k < 5; k++) ab[k * TS + slot] = abar[(long)k * m.sC + cell]; vol[slot] = m.vol[cell]; }
     }
-    FVM_HD void face(const Geom<R>& gm, const TileEntry& e, const R* qg, const R* ab, const R* vol, Prim<R>& qLb, Grad<R>& gLb, Prim<R>& qRb, Grad<R>& gRb) const {
+    // one entry of the lane whose cell sits in slot lo: own[20] += the home cell's input adjoints; snd[20] = the other
+    // cell's (set when e.sn; zero otherwise); ghost >= 0: global row of the other cell when it is a ghost cell, whose
+    // adjoints are stored straight to Qb/Gb
+    FVM_HD void face(const Geom<R>& gm, const TileEntry& e, int lo, int ghost, const R* qg, const R* ab, R ivh, const R* vol, R* own, R* snd) const {
         Prim<R> qL, qR; Grad<R> gL, gR;
-        tile_load_cell<R, TS>(qg, e.lo, qL, gL); tile_load_cell<R, TS>(qg, e.ln, qR, gR);
-        const R sO = gm.area * coef * rcp(vol[e.lo]);
+        tile_load_cell<R, TS>(qg, lo, qL, gL); tile_load_cell<R, TS>(qg, e.ln, qR, gR);
+        const R sO = gm.area * coef * ivh;
         R d[5];
-        for (int k = 0; k < 5; k++) d[k] = ab[k * TS + e.lo] * sO;
+        for (int k = 0; k < 5; k++) d[k] = ab[k * TS + lo] * sO;
         if (!e.ghost) {
             const R sN_ = gm.area * coef * rcp(vol[e.ln]);
             for (int k = 0; k < 5; k++) d[k] -= ab[k * TS + e.ln] * sN_;
         }
         Flux5<R> Fb; Fb.rho = d[0]; Fb.rhoU[0] = d[1]; Fb.rhoU[1] = d[2]; Fb.rhoU[2] = d[3]; Fb.rhoE = d[4];
-        zero(qLb); zero(gLb); zero(qRb); zero(gRb);
-        face_flux_vjp(ph, e.kind, gm, qL, gL, qR, gR, Fb, qLb, gLb, qRb, gRb);
-    }
-    FVM_HD static void add20(R* a, const Prim<R>& q, const Grad<R>& g) {
-        a[0] += q.U[0]; a[T] += q.U[1]; a[2 * T] += q.U[2]; a[3 * T] += q.T; a[4 * T] += q.p;
-        for (int k = 0; k < 9; k++) a[(5 + k) * T] += g.U[k];
-        for (int k = 0; k < 3; k++) { a[(14 + k) * T] += g.T[k]; a[(17 + k) * T] += g.p[k]; }
-    }
-    // ghost: global row of the ghost cell of a boundary face (its halo slot's cell), -1 for internal faces
-    FVM_HD void scatter(R* acc, const TileEntry& e, int ghost, const Prim<R>& qLb, const Grad<R>& gLb, const Prim<R>& qRb, const Grad<R>& gRb) const {
-        if (e.so) add20(acc + e.lo, qLb, gLb);
-        if (ghost >= 0) { store_prim(Qb, m.sN, ghost, qRb); store_grad(Gb, m.sN, ghost, gRb); }
-        else if (e.sn) add20(acc + e.ln, qRb, gRb);
+        if (e.kind == FACE_COUPLED) {
+            FaceAdj<R> c; face_flux_vjp_coupled(ph, gm, qL, gL, qR, gR, Fb, c);
+            for (int k = 0; k < 20; k++) own[k] += face_adj_owner(c, gm, k);
+            if (ghost >= 0) { for (int k = 0; k < 20; k++) (k < 5 ? Qb : Gb)[(long)(k < 5 ? k : k - 5) * m.sN + ghost] = face_adj_neighbour(c, gm, k); }
+            else if (e.sn) for (int k = 0; k < 20; k++) snd[k] = face_adj_neighbour(c, gm, k);
+        } else {
+            Prim<R> qLb, qRb; Grad<R> gLb, gRb;
+            zero(qLb); zero(gLb); zero(qRb); zero(gRb);
+            face_flux_vjp(ph, e.kind, gm, qL, gL, qR, gR, Fb, qLb, gLb, qRb, gRb);
+            own[0] += qLb.U[0]; own[1] += qLb.U[1]; own[2] += qLb.U[2]; own[3] += qLb.T; own[4] += qLb.p;
+            for (int k = 0; k < 9; k++) own[5 + k] += gLb.U[k];
+            for (int k = 0; k < 3; k++) { own[14 + k] += gLb.T[k]; own[17 + k] += gLb.p[k]; }
+            if (ghost >= 0) { store_prim(Qb, m.sN, ghost, qRb); store_grad(Gb, m.sN, ghost, gRb); }
+        }
     }
     FVM_HD int ghost_of(int t, const TileEntry& e) const { return e.ghost ? m.halo_cell[m.halo_start[t] + e.ln - T] : -1; }
     // internal rows of Gb are stored divided by the cell volume (what GradAdjUpdateBody consumes); iv = 1/V_c
     FVM_HD void finish(int c, const R* a, R iv) const {
-        for (int k = 0; k < 5; k++) Qb[(long)k * m.sN + c] = a[k * T];
-        for (int k = 0; k < 15; k++) Gb[(long)k * m.sN + c] = a[(5 + k) * T] * iv;
+        for (int k = 0; k < 5; k++) Qb[(long)k * m.sN + c] = a[k];
+        for (int k = 0; k < 15; k++) Gb[(long)k * m.sN + c] = a[5 + k] * iv;
     }
 
 #if !defined(__CUDACC__)
     void host_tile(int t) const {
         const int c0 = t * T, nc = (m.nInternalCells - c0 < T) ? m.nInternalCells - c0 : T;
         const R nan = std::numeric_limits<R>::quiet_NaN();       // ghost slots of ab / vol must never be read
-        std::vector<R> qg((size_t)20 * TS, R(0)), ab((size_t)5 * TS, nan), vol(TS, nan), acc((size_t)20 * T, R(0));
+        std::vector<R> qg((size_t)20 * TS, R(0)), ab((size_t)5 * TS, nan), vol(TS, nan);
         for (int l = 0; l < nc; l++) { tile_stage_cell<R, TS>(qg.data(), l, Q, G, m.sN, c0 + l); stage_ab(ab.data(), vol.data(), l, c0 + l); }
         for (int h = m.halo_start[t]; h < m.halo_start[t + 1]; h++) {
             const int slot = T + h - m.halo_start[t];
             tile_stage_cell<R, TS>(qg.data(), slot, Q, G, m.sN, m.halo_cell[h]); stage_ab(ab.data(), vol.data(), slot, m.halo_cell[h]);
         }
         for (int w = 0; w < NW; w++) {
+            R acc[32][20], snd[32][20];
+            for (int l = 0; l < 32; l++) for (int k = 0; k < 20; k++) acc[l][k] = R(0);
             for (int r = m.round_start[t * NW + w]; r < m.round_start[t * NW + w + 1]; r++) {
                 const R* chunk = m.chunks + (long)r * Ch::kScalars;
+                TileEntry e[32];
                 for (int i = 0; i < 32; i++) {
-                    TileEntry e; tile_decode(Ch::words(chunk)[i], e);
-                    if (!e.valid) continue;
-                    if (e.ghost != (e.ln >= T && m.halo_cell[m.halo_start[t] + e.ln - T] >= m.nInternalCells)) throw std::runtime_error("ghost flag inconsistent");
+                    tile_decode(Ch::words(chunk)[i], e[i]);
+                    for (int k = 0; k < 20; k++) snd[i][k] = R(0);
+                    if (!e[i].valid) continue;
+                    if (e[i].ghost != (e[i].ln >= T && m.halo_cell[m.halo_start[t] + e[i].ln - T] >= m.nInternalCells)) throw std::runtime_error("ghost flag inconsistent");
+                    if (e[i].kind != FACE_COUPLED && !e[i].ghost) throw std::runtime_error("boundary-kind entry without a ghost cell");
                     Geom<R> gm; tile_load_geom<R, 32>(chunk, i, gm);
-                    Prim<R> qLb, qRb; Grad<R> gLb, gRb;
-                    face(gm, e, qg.data(), ab.data(), vol.data(), qLb, gLb, qRb, gRb);
-                    scatter(acc.data(), e, ghost_of(t, e), qLb, gLb, qRb, gRb);
+                    face(gm, e[i], w * 32 + i, ghost_of(t, e[i]), qg.data(), ab.data(), R(1) / vol[w * 32 + i], vol.data(), acc[i], snd[i]);
                 }
+                for (int i = 0; i < 32; i++) if (e[i].has_src) for (int k = 0; k < 20; k++) acc[i][k] += snd[e[i].src][k];
             }
+            for (int l = w * 32; l < nc && l < w * 32 + 32; l++) finish(c0 + l, acc[l - w * 32], R(1) / vol[l]);
         }
-        for (int l = 0; l < nc; l++) finish(c0 + l, &acc[l], rcp(vol[l]));
     }
 #else
     __device__ __forceinline__ void device_tile(int t, unsigned char* smem) const {
@@ -391,7 +408,6 @@ template <typename R, int T, int TS> struct FluxGradTileBody {
         R* qg = reinterpret_cast<R*>(smem);
         R* ab = qg + 20 * TS;
         R* vol = ab + 5 * TS;
-        R* acc = vol + TS;
         R* chunk = reinterpret_cast<R*>(smem + Smem::kChunkOff) + w * Ch::kScalars;
         unsigned long long* bars = reinterpret_cast<unsigned long long*>(smem + Smem::kBarOff);
         unsigned long long *bar_rows = &bars[0], *bar_halo = &bars[1], *bar_chunk = &bars[2 + w];
@@ -426,13 +442,14 @@ template <typename R, int T, int TS> struct FluxGradTileBody {
         }
         cp_async_arrive(bar_halo);
         if (nr == 0) return;
-        for (int k = 0; k < 20; k++) acc[k * T + tid] = R(0);
         mbar_wait(bar_rows, 0);
+        const R ivh = tid < nc ? rcp(vol[tid]) : R(0);
+        R acc[20];
+        for (int k = 0; k < 20; k++) acc[k] = R(0);
         for (int r = 0; r < nr; r++) {
             mbar_wait(bar_chunk, (unsigned)(r & 1));
             TileEntry e; tile_decode(Ch::words(chunk)[lane], e);
             Geom<R> gm; tile_load_geom<R, 32>(chunk, lane, gm);
-            const int cfirst = (int)__reduce_min_sync(0xffffffffu, (unsigned)e.col), clast = (int)__reduce_max_sync(0xffffffffu, (unsigned)e.col);   // lanes are not colour-sorted (fvm_tiles.h RoundBalancer)
             if (r == hr) mbar_wait(bar_halo, 0);
             __syncwarp();
             if (lane == 0 && r + 1 < nr) {
@@ -440,16 +457,14 @@ template <typename R, int T, int TS> struct FluxGradTileBody {
                 mbar_expect_tx(bar_chunk, (unsigned)Ch::kBytes);
                 bulk_g2s(chunk, m.chunks + (long)(r0 + r + 1) * Ch::kScalars, (unsigned)Ch::kBytes, bar_chunk);
             }
-            Prim<R> qLb, qRb; Grad<R> gLb, gRb;
-            int ghost = -1;
-            if (e.valid) { face(gm, e, qg, ab, vol, qLb, gLb, qRb, gRb); ghost = ghost_of(t, e); }
-            const int col = e.valid ? e.col : -1;
-            for (int c = cfirst; c <= clast; c++) {
-                if (col == c) scatter(acc, e, ghost, qLb, gLb, qRb, gRb);
-                __syncwarp();
+            R snd[20];
+            for (int k = 0; k < 20; k++) snd[k] = R(0);
+            if (e.valid) face(gm, e, tid, ghost_of(t, e), qg, ab, ivh, vol, acc, snd);
+            if (__any_sync(0xffffffffu, e.has_src)) {
+                for (int k = 0; k < 20; k++) { const R v = __shfl_sync(0xffffffffu, snd[k], e.src); if (e.has_src) acc[k] += v; }
             }
         }
-        if (tid < nc) finish(c0 + tid, acc + tid, rcp(vol[tid]));
+        if (tid < nc) finish(c0 + tid, acc, ivh);
     }
 #endif
 };

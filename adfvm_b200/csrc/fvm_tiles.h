@@ -3,12 +3,21 @@
 // The reference scatters face fluxes into cells with one atomicAdd per scalar (adpy/adpy/tensor.py:393-394) and
 // visits faces in file order. Here the internal cells are regrouped into spatially compact TILES of `T`
 // consecutive (renumbered) cells, each made of T/32 compact SUB-TILES of 32 consecutive cells. One CTA owns one
-// tile and stages the tile's cell rows (+ halo) in shared memory once; one WARP owns one sub-tile: it evaluates
-// every face touching its 32 cells (faces cut by a sub-tile boundary are evaluated by both sides, each side adds
-// only its own share) and sums the contributions into shared-memory accumulators that no other warp touches, in a
-// FIXED order given by a face colouring: faces of one colour never share a cell of the sub-tile, colours are
-// applied one after the other. No float atomics, no block-wide barriers in the face loop, bitwise reproducible,
-// and 4.0 flux evaluations per hex cell (4x4x2 sub-tiles) instead of the 6 of a cell-centred gather.
+// tile and stages the tile's cell rows (+ halo) in shared memory once; one WARP owns one sub-tile and LANE l OWNS
+// CELL l of it: the lane keeps that cell's accumulators in registers for the whole kernel.
+//   * every face touching the sub-tile is one ENTRY (faces cut by a sub-tile boundary are evaluated by both sides);
+//     an entry has a HOME cell inside the sub-tile; the lane of the home cell evaluates it, always as the "owner"
+//     side: when the home cell is the face's neighbour the entry's metrics are stored FLIPPED (normal and delta
+//     reversed, the two sides' reconstruction weights swapped), which turns the neighbour's share -F*A/V into the
+//     owner's share +F'*A/V of the flipped face (all fluxes on the path are antisymmetric under the flip);
+//   * if the other cell of an entry is in the sub-tile too, its share travels by a warp shuffle: in each round a lane
+//     evaluates at most one entry and receives at most one share;
+//   * the schedule is an orientation of the sub-tile's inner faces (which end is home) that balances the number of
+//     entries per lane (augmenting paths), followed by a bipartite edge colouring (home lane x receiving lane) with
+//     as many colours = ROUNDS as the largest degree (Koenig). A 4x4x2 hex sub-tile needs exactly 4 full rounds:
+//     4.0 flux evaluations per cell instead of the 6 of a cell-centred gather, no idle lanes.
+// No float atomics, no shared-memory accumulators, no barriers in the face loop; the summation order of a cell
+// (round by round, own share then received share) is fixed: results are bitwise reproducible.
 //
 //   * tiles: recursive coordinate bisection of the cell centres (recovered up to a translation by walking the
 //     internal faces and adding deltas*deltasUnit = N-P, reference adFVM/cpp/cmesh.cpp:184-193), always splitting
@@ -27,18 +36,19 @@
 
 namespace fvm {
 
-// packed entry word: bits 0-9 owner's slot, 10-19 neighbour's slot, 20-24 colour, 25-26 face kind (FaceKind of
-// fvm_math.h), 27 valid, 28 owner is a cell of this sub-tile (scatter to it), 29 neighbour is a cell of this
-// sub-tile, 30 neighbour is a ghost cell (boundary face). Slots [0,T) are the tile's own cells, slots
-// [T, T+nHalo) the tile's halo: cells of other tiles and ghost cells touched by the tile's faces.
-enum { kRound = 32 };   // entries per warp round
-static inline uint32_t tile_pack(int lo, int ln, int colour, int kind, int valid, int so = 0, int sn = 0, int ghost = 0) {
-    return (uint32_t)lo | ((uint32_t)ln << 10) | ((uint32_t)colour << 20) | ((uint32_t)kind << 25) | ((uint32_t)valid << 27) |
-           ((uint32_t)so << 28) | ((uint32_t)sn << 29) | ((uint32_t)ghost << 30);
+// packed entry word of lane l in a round: bits 0-4 lane whose share this lane receives in this round, 5 "receives",
+// 10-19 slot of the entry's OTHER cell (the home cell's slot is implicit: 32*warp + lane), 25-26 face kind (FaceKind
+// of fvm_math.h), 27 valid, 29 the other cell is a cell of this sub-tile (its share is sent by shuffle), 30 the other
+// cell is a ghost cell (boundary face), 31 metrics stored flipped (only read by FillChunksBody). Slots [0,T) are the
+// tile's own cells, slots [T, T+nHalo) the tile's halo: cells of other tiles and ghost cells touched by the tile.
+enum { kRound = 32 };   // lanes per round
+static inline uint32_t tile_pack(int ln, int kind, int valid, int sn, int ghost, int flip, int has_src, int src) {
+    return (uint32_t)src | ((uint32_t)has_src << 5) | ((uint32_t)ln << 10) | ((uint32_t)kind << 25) | ((uint32_t)valid << 27) |
+           ((uint32_t)sn << 29) | ((uint32_t)ghost << 30) | ((uint32_t)flip << 31);
 }
 
 struct TilePlan {
-    int T = 0, nTiles = 0, NW = 0, maxColours = 0;   // NW = T/32 sub-tiles (warps) per tile
+    int T = 0, nTiles = 0, NW = 0, maxColours = 0;   // NW = T/32 sub-tiles (warps) per tile; maxColours = most rounds of a sub-tile
     long nEntries = 0;
     std::vector<int> cell_new2old, cell_old2new;     // internal cells
     std::vector<int> face_new2old, face_old2new;     // all faces (identity for boundary faces)
@@ -112,74 +122,108 @@ inline void rcb(std::vector<int>& idx, const std::vector<float>& pos, long lo, l
 }
 
 
-// Lane assignment inside one round of 32 entries (8-byte scalars). A warp-wide LDS.64 is served half-warp by
-// half-warp; lanes of one half that read DIFFERENT cell slots with the same slot%16 (the same pair of 4-byte banks)
-// serialise. The accumulation order is fixed by the colours, not by the lanes, so the lanes of a round may be
-// permuted freely: pick the split into two halves that minimises, for the owner-side and the neighbour-side loads,
-// the largest number of distinct slots per bank pair (greedy start + pairwise-swap descent; identical rounds of a
-// structured mesh are memoised).
-struct RoundBalancer {
-    std::unordered_map<uint64_t, std::vector<std::pair<std::vector<uint32_t>, std::vector<uint8_t>>>> memo;
-    // per half h, side s (0 owner slot, 1 neighbour slot): refs[h][s][slot] entries reading the slot, distinct[h][s][res]
-    uint8_t refs[2][2][1024]; uint8_t distinct[2][2][16];
-    static int slot_of(uint32_t w, int side) { return side ? (int)((w >> 10) & 0x3FFu) : (int)(w & 0x3FFu); }
-    void add(int h, uint32_t w, int d) {
-        if (!((w >> 27) & 1u)) return;                      // padding entries do not load
-        for (int s = 0; s < 2; s++) {
-            const int sl = slot_of(w, s);
-            if (d > 0) { if (refs[h][s][sl]++ == 0) distinct[h][s][sl & 15]++; }
-            else { if (--refs[h][s][sl] == 0) distinct[h][s][sl & 15]--; }
+// Schedule of one sub-tile: entries -> (round, lane). home[e]/other[e]: local cell (0..31) of the entry's home /
+// of its other cell when that is in the sub-tile too (else -1); both-in entries may be re-oriented (swap).
+struct SubTileSchedule {
+    struct Ent { int a, b; bool both; int pref; };   // a: home candidate, b: other candidate (both-in) or -1; pref: 0 early round, 1 late
+    std::vector<Ent> E;
+    std::vector<int> home, other, round;
+    int R = 0;
+    void solve() {
+        const int n = (int)E.size();
+        home.assign(n, -1); other.assign(n, -1); round.assign(n, -1);
+        int load[kRound], inner[kRound], fixedLoad[kRound];
+        for (int l = 0; l < kRound; l++) load[l] = inner[l] = fixedLoad[l] = 0;
+        for (int e = 0; e < n; e++) {
+            if (E[e].both) { inner[E[e].a]++; inner[E[e].b]++; }
+            else fixedLoad[E[e].a]++;
         }
-    }
-    int cost() const {
-        int c = 0;
-        for (int h = 0; h < 2; h++) for (int s = 0; s < 2; s++) {
-            int mx = 0, sum = 0;
-            for (int r = 0; r < 16; r++) { const int d = distinct[h][s][r]; mx = std::max(mx, d); sum += d * d; }
-            c += 64 * mx + sum;                             // wavefronts first, spread as the tie-break
+        int Rmin = (n + kRound - 1) / kRound;
+        for (int l = 0; l < kRound; l++) Rmin = std::max(Rmin, fixedLoad[l]);
+        if (Rmin < 1) Rmin = 1;
+        // orientation: greedy, then augmenting paths until home loads <= R and received shares <= R
+        for (int l = 0; l < kRound; l++) load[l] = fixedLoad[l];
+        for (int e = 0; e < n; e++) {
+            if (!E[e].both) { home[e] = E[e].a; other[e] = -1; continue; }
+            const int a = E[e].a, b = E[e].b;
+            if (load[a] <= load[b]) { home[e] = a; other[e] = b; load[a]++; } else { home[e] = b; other[e] = a; load[b]++; }
         }
-        return c;
-    }
-    void balance(uint32_t* loc, int* face) {
-        uint64_t key = 1469598103934665603ull;
-        for (int i = 0; i < kRound; i++) { key ^= loc[i] & 0x080FFFFFu; key *= 1099511628211ull; }
-        std::vector<uint32_t> sig(loc, loc + kRound);
-        for (auto& x : sig) x &= 0x080FFFFFu;
-        std::vector<uint8_t> perm;
-        auto& bucket = memo[key];
-        for (auto& kv : bucket) if (kv.first == sig) { perm = kv.second; break; }
-        if (perm.empty()) {
-            std::memset(refs, 0, sizeof(refs)); std::memset(distinct, 0, sizeof(distinct));
-            int half[kRound], n[2] = {0, 0};
-            for (int i = 0; i < kRound; i++) {              // greedy: the half where the entry adds less
-                int best = -1, bc = 0;
-                for (int h = 0; h < 2; h++) {
-                    if (n[h] >= kRound / 2) continue;
-                    add(h, loc[i], +1); const int c = cost() + n[h]; add(h, loc[i], -1);
-                    if (best < 0 || c < bc) { best = h; bc = c; }
+        std::vector<std::vector<int>> inc(kRound);
+        for (int e = 0; e < n; e++) if (E[e].both) { inc[E[e].a].push_back(e); inc[E[e].b].push_back(e); }
+        for (R = Rmin;; R++) {
+            // a cell hands over load along edges homed at it; BFS to a cell with room. Lower bound: received = inner - (load - fixed) <= R
+            bool ok = true;
+            for (int guard = 0; guard < 4096; guard++) {
+                int u = -1; bool over = true;
+                for (int l = 0; l < kRound && u < 0; l++) if (load[l] > R) { u = l; over = true; }
+                for (int l = 0; l < kRound && u < 0; l++) if (inner[l] - (load[l] - fixedLoad[l]) > R) { u = l; over = false; }
+                if (u < 0) break;
+                // over: push one unit from u to some v with load[v] < R (and that still satisfies its own bounds);
+                // under (too many received): pull one unit into u from some v with load[v]-1 still fine
+                int prevE[kRound], seen[kRound]; for (int l = 0; l < kRound; l++) { prevE[l] = -1; seen[l] = 0; }
+                std::vector<int> q; q.push_back(u); seen[u] = 1; int found = -1;
+                for (size_t h = 0; h < q.size() && found < 0; h++) {
+                    const int x = q[h];
+                    for (int e : inc[x]) {
+                        const bool homedAtX = home[e] == x;
+                        if (over != homedAtX) continue;          // push along edges homed at x; pull along edges homed at the other end
+                        const int y = (E[e].a == x) ? E[e].b : E[e].a;
+                        if (seen[y]) continue;
+                        seen[y] = 1; prevE[y] = e; q.push_back(y);
+                        const bool room = over ? (load[y] < R) : (load[y] - 1 >= 0 && inner[y] - (load[y] - 1 - fixedLoad[y]) <= R && load[y] > fixedLoad[y]);
+                        if (room) { found = y; break; }
+                    }
                 }
-                half[i] = best; n[best]++; add(best, loc[i], +1);
-            }
-            int cur = cost();
-            for (int sweep = 0; sweep < 4; sweep++) {
-                bool improved = false;
-                for (int i = 0; i < kRound; i++) for (int j = i + 1; j < kRound; j++) {
-                    if (half[i] == half[j]) continue;
-                    add(half[i], loc[i], -1); add(half[j], loc[j], -1); add(half[j], loc[i], +1); add(half[i], loc[j], +1);
-                    const int c = cost();
-                    if (c < cur) { cur = c; std::swap(half[i], half[j]); improved = true; }
-                    else { add(half[j], loc[i], -1); add(half[i], loc[j], -1); add(half[i], loc[i], +1); add(half[j], loc[j], +1); }
+                if (found < 0) { ok = false; break; }
+                // flip the path found -> ... -> u
+                int y = found;
+                while (y != u) {
+                    const int e = prevE[y];
+                    const int x = (E[e].a == y) ? E[e].b : E[e].a;
+                    if (over) { home[e] = y; other[e] = x; load[y]++; load[x]--; }     // edge was homed at x: moves to y
+                    else { home[e] = x; other[e] = y; load[x]++; load[y]--; }           // edge was homed at y: moves to x
+                    y = x;
                 }
-                if (!improved) break;
             }
-            perm.resize(kRound);
-            int pos[2] = {0, kRound / 2};
-            for (int i = 0; i < kRound; i++) perm[pos[half[i]]++] = (uint8_t)i;    // new lane -> old lane
-            bucket.push_back({sig, perm});
+            if (!ok) continue;
+            bool fine = true;
+            for (int l = 0; l < kRound; l++) if (load[l] > R || inner[l] - (load[l] - fixedLoad[l]) > R) fine = false;
+            if (fine) break;
         }
-        uint32_t l2[kRound]; int f2[kRound];
-        for (int i = 0; i < kRound; i++) { l2[i] = loc[perm[i]]; f2[i] = face[perm[i]]; }
-        for (int i = 0; i < kRound; i++) { loc[i] = l2[i]; face[i] = f2[i]; }
+        // bipartite edge colouring with R colours: left = home lane, right = receiving lane
+        std::vector<int> colL((size_t)kRound * R, -1), colR((size_t)kRound * R, -1);
+        auto freeL = [&](int u, bool late) { if (late) { for (int c = R - 1; c >= 0; c--) if (colL[(size_t)u * R + c] < 0) return c; }
+                                             else for (int c = 0; c < R; c++) if (colL[(size_t)u * R + c] < 0) return c; return -1; };
+        std::vector<int> order(n); std::iota(order.begin(), order.end(), 0);
+        std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return E[x].pref < E[y].pref; });
+        for (int e : order) {
+            const int u = home[e], v = other[e];
+            const bool late = E[e].pref > 0;
+            if (v < 0) { const int c = freeL(u, late); if (c < 0) throw std::runtime_error("tile schedule: no free round"); colL[(size_t)u * R + c] = e; round[e] = c; continue; }
+            int both = -1;
+            for (int c = 0; c < R; c++) if (colL[(size_t)u * R + c] < 0 && colR[(size_t)v * R + c] < 0) { both = c; break; }
+            if (both < 0) {
+                int ca = -1, cb = -1;
+                for (int c = 0; c < R; c++) { if (ca < 0 && colL[(size_t)u * R + c] < 0) ca = c; if (cb < 0 && colR[(size_t)v * R + c] < 0) cb = c; }
+                if (ca < 0 || cb < 0) throw std::runtime_error("tile schedule: degree exceeds the number of rounds");
+                // alternating ca/cb path starting at right vertex v (ca busy there): swap the colours along it
+                std::vector<int> path; int x = v; bool right = true; int want = ca;
+                for (;;) {
+                    const int pe = right ? colR[(size_t)x * R + want] : colL[(size_t)x * R + want];
+                    if (pe < 0) break;
+                    path.push_back(pe);
+                    x = right ? home[pe] : other[pe];
+                    right = !right; want = (want == ca) ? cb : ca;
+                    if (x < 0) break;                             // reached an entry without a receiving end
+                }
+                for (int pe : path) { colL[(size_t)home[pe] * R + round[pe]] = -1; if (other[pe] >= 0) colR[(size_t)other[pe] * R + round[pe]] = -1; }
+                for (int pe : path) { round[pe] = (round[pe] == ca) ? cb : ca; }
+                for (int pe : path) { colL[(size_t)home[pe] * R + round[pe]] = pe; if (other[pe] >= 0) colR[(size_t)other[pe] * R + round[pe]] = pe; }
+                both = ca;
+                if (colL[(size_t)u * R + both] >= 0 || colR[(size_t)v * R + both] >= 0) throw std::runtime_error("tile schedule: alternating path failed");
+            }
+            colL[(size_t)u * R + both] = e; colR[(size_t)v * R + both] = e; round[e] = both;
+        }
     }
 };
 
@@ -205,16 +249,15 @@ TilePlan build_tile_plan(int C, int Fi, int F, const int* owner, const int* neig
         std::sort(P.cell_new2old.begin() + b, P.cell_new2old.begin() + std::min<long>(b + kRound, C));
     P.cell_old2new.assign(C, -1);
     for (int i = 0; i < C; i++) P.cell_old2new[P.cell_new2old[i]] = i;
-    // ---- per sub-tile: faces touching it, coloured
+    // ---- per sub-tile: entries (faces touching it) and their (round, lane) schedule
     P.round_start.assign((size_t)P.nTiles * NW + 1, 0);
     P.halo_round.assign((size_t)P.nTiles * NW, 0);
     P.face_old2new.assign(F, -1);
     P.face_new2old.assign(F, -1);
     for (int f = Fi; f < F; f++) { P.face_old2new[f] = f; P.face_new2old[f] = f; }
     int nextFace = 0;
-    std::vector<int> faces, colour, group, order;
-    std::vector<uint32_t> used(kRound);
-    static thread_local detail::RoundBalancer balancer_store; detail::RoundBalancer& balancer = balancer_store; balancer.memo.clear();
+    std::vector<int> faces;
+    detail::SubTileSchedule sch;
     const int N = C + (F - Fi);
     std::vector<int> slot_of(N, -1), slot_tile(N, -1);
     P.halo_start.assign(P.nTiles + 1, 0);
@@ -228,77 +271,56 @@ TilePlan build_tile_plan(int C, int Fi, int F, const int* owner, const int* neig
         };
         for (int w = 0; w < NW; w++) {
             const int s0 = c0 + w * kRound, s1 = std::min(c1, s0 + kRound);
-            faces.clear();
+            faces.clear(); sch.E.clear();
             for (int c = s0; c < s1; c++) {
                 const int oc = P.cell_new2old[c];
                 for (int j = 0; j < 6; j++) {
                     const int f = cellFaces[(size_t)oc * 6 + j];
                     if (f < 0 || f >= F) throw std::runtime_error("cellFaces out of range");
-                    if (f >= Fi) { faces.push_back(f); continue; }
-                    // internal face: list once per sub-tile (when reached from its lower cell of the sub-tile)
-                    const int a = P.cell_old2new[owner[f]], b = P.cell_old2new[neigh[f]];
+                    int a = P.cell_old2new[owner[f]], b = -1;
+                    if (f < Fi) {
+                        b = P.cell_old2new[neigh[f]];
+                        if (a == b) throw std::runtime_error("face with identical owner and neighbour");
+                    }
                     const bool ain = a >= s0 && a < s1, bin = b >= s0 && b < s1;
-                    if (ain && bin) { if (c == std::min(a, b)) faces.push_back(f); }
-                    else faces.push_back(f);
+                    // inner face of the sub-tile: list once (when reached from its lower cell)
+                    if (ain && bin && c != std::min(a, b)) continue;
+                    const bool atile = a >= c0 && a < c1, btile = b >= c0 && b < c1;
+                    detail::SubTileSchedule::Ent e;
+                    e.both = ain && bin;
+                    e.a = ain ? a - s0 : b - s0; e.b = e.both ? b - s0 : -1;
+                    e.pref = (atile && btile) ? 0 : 1;      // entries that read a halo slot go to the late rounds (overlap of the halo gather)
+                    faces.push_back(f); sch.E.push_back(e);
                 }
             }
-            // greedy colouring: no two faces of one colour share a cell of the sub-tile. Faces inside the sub-tile are
-            // coloured first, then faces whose other cell is elsewhere in the tile, then faces that need a halo slot (cut
-            // by the tile boundary, or boundary faces): sorted by colour, the rounds that only need the tile's own rows
-            // come first and overlap the halo gather.
-            colour.assign(faces.size(), 0); group.assign(faces.size(), 0);
+            sch.solve();
+            const int Rw = faces.empty() ? 0 : sch.R;
+            P.maxColours = std::max(P.maxColours, Rw);
+            std::vector<int> at((size_t)Rw * kRound, -1), from((size_t)Rw * kRound, -1);
             for (size_t i = 0; i < faces.size(); i++) {
-                const int f = faces[i];
-                const int a = P.cell_old2new[owner[f]];
-                const int b = f < Fi ? P.cell_old2new[neigh[f]] : -1;
-                const bool ain = a >= s0 && a < s1, bin = b >= s0 && b < s1;
-                const bool atile = a >= c0 && a < c1, btile = b >= c0 && b < c1;
-                group[i] = (ain && bin) ? 0 : ((atile && btile) ? 1 : 2);
+                at[(size_t)sch.round[i] * kRound + sch.home[i]] = (int)i;
+                if (sch.other[i] >= 0) from[(size_t)sch.round[i] * kRound + sch.other[i]] = sch.home[i];
             }
-            int ncol = 0;
-            for (int grp = 0; grp < 3; grp++) {
-                std::fill(used.begin(), used.end(), 0u);
-                const int base = ncol;
-                for (size_t i = 0; i < faces.size(); i++) {
-                    if (group[i] != grp) continue;
-                    const int f = faces[i];
-                    const int a = P.cell_old2new[owner[f]];
-                    const int b = f < Fi ? P.cell_old2new[neigh[f]] : -1;
-                    const int la = (a >= s0 && a < s1) ? a - s0 : -1, lb = (b >= s0 && b < s1) ? b - s0 : -1;
-                    uint32_t mk = (la >= 0 ? used[la] : 0u) | (lb >= 0 ? used[lb] : 0u);
-                    int col = 0;
-                    while (mk & (1u << col)) col++;
-                    if (base + col >= 32) throw std::runtime_error("face colouring needs more than 32 colours");
-                    colour[i] = base + col; ncol = std::max(ncol, base + col + 1);
-                    if (la >= 0) used[la] |= 1u << col;
-                    if (lb >= 0) used[lb] |= 1u << col;
-                }
-            }
-            P.maxColours = std::max(P.maxColours, ncol);
-            order.resize(faces.size());
-            std::iota(order.begin(), order.end(), 0);
-            std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return colour[x] < colour[y]; });
-            int firstHaloEntry = -1, nEnt = 0;
-            for (int i : order) {
+            int firstHaloRound = -1;
+            for (int r = 0; r < Rw; r++) for (int l = 0; l < kRound; l++) {
+                const int i = at[(size_t)r * kRound + l], src = from[(size_t)r * kRound + l];
+                if (i < 0) { P.ent_face.push_back(-1); P.ent_loc.push_back(tile_pack(0, 0, 0, 0, 0, 0, src >= 0, src >= 0 ? src : 0)); continue; }
                 const int f = faces[i];
                 if (f < Fi && P.face_old2new[f] < 0) { P.face_old2new[f] = nextFace; P.face_new2old[nextFace] = f; nextFace++; }
                 const int a = P.cell_old2new[owner[f]];
                 const int b = f < Fi ? P.cell_old2new[neigh[f]] : neigh[f];
                 if (b < 0 || b >= N) throw std::runtime_error("neighbour out of range");
-                const int la = slot(a), lb = slot(b);
-                if (la >= 1024 || lb >= 1024) throw std::runtime_error("tile halo too large");
-                if ((la >= T || lb >= T) && firstHaloEntry < 0) firstHaloEntry = nEnt;
+                const bool flip = (a - s0) != l;                 // the home cell is the face's neighbour
+                if (flip && (f >= Fi || b - s0 != l)) throw std::runtime_error("tile schedule: home cell is not a cell of the face");
+                const int lo = slot(flip ? b : a), ln = slot(flip ? a : b);
+                if (lo != w * kRound + l) throw std::runtime_error("tile schedule: home slot mismatch");
+                if (ln >= 1024) throw std::runtime_error("tile halo too large");
+                if (ln >= T && firstHaloRound < 0) firstHaloRound = r;
                 P.ent_face.push_back(P.face_old2new[f]);
-                P.ent_loc.push_back(tile_pack(la, lb, colour[i], f < Fi ? 0 : (int)bkind[f - Fi], 1,
-                                              a >= s0 && a < s1, b >= s0 && b < s1, b >= C));
-                P.nEntries++; nEnt++;
+                P.ent_loc.push_back(tile_pack(ln, f < Fi ? 0 : (int)bkind[f - Fi], 1, sch.other[i] >= 0, b >= C, flip, src >= 0, src >= 0 ? src : 0));
+                P.nEntries++;
             }
-            P.halo_round[(size_t)t * NW + w] = firstHaloEntry < 0 ? (nEnt + kRound - 1) / kRound : firstHaloEntry / kRound;
-            // pad the last round (padding repeats the last colour: the kernels scan the colours present in a round)
-            while (P.ent_face.size() % (size_t)kRound) { P.ent_face.push_back(-1); P.ent_loc.push_back(tile_pack(0, 0, ncol ? ncol - 1 : 0, 0, 0)); }
-            if (sizeof(R) == 8)
-                for (size_t e = (size_t)P.round_start[(size_t)t * NW + w] * kRound; e < P.ent_face.size(); e += kRound)
-                    balancer.balance(&P.ent_loc[e], &P.ent_face[e]);
+            P.halo_round[(size_t)t * NW + w] = firstHaloRound < 0 ? Rw : firstHaloRound;
             P.round_start[(size_t)t * NW + w + 1] = (int)(P.ent_face.size() / (size_t)kRound);
         }
         P.maxHalo = std::max(P.maxHalo, nHalo);

@@ -9,7 +9,7 @@ python bench.py --steps 10 --warmup 3 --size 128 --dtype f32 --no-cpu-baseline >
 python bench.py --steps 5 --warmup 3 --size 256 --no-cpu-baseline > gpurun_out/${TAG}_bench256_f64.json 2> gpurun_out/${TAG}_bench256_f64.err
 if [ -z "$NO_NCU" ]; then
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${TAG}_launches_f64.csv python tools/run_step.py --n 128 --steps 2 > gpurun_out/${TAG}_launch.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:'k_tile|GradAdjUpdate' -s 14 -c 5 -o gpurun_out/${TAG}_tiles_f64 python tools/run_step.py --n 128 --steps 2 > gpurun_out/${TAG}_ncu1.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:'k_tile|GradAdjUpdate' -s 14 -c 5 -o gpurun_out/${TAG}_tiles_f32 python tools/run_step.py --n 128 --steps 2 --dtype f32 > gpurun_out/${TAG}_ncu2.log 2>&1
+ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k regex:'FluxTileBody|FluxGradTileBody|GradAdjUpdateBody' -s 6 -c 6 -o gpurun_out/${TAG}_tiles_f64 python tools/run_step.py --n 128 --steps 2 > gpurun_out/${TAG}_ncu1.log 2>&1
+ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k regex:'FluxTileBody|FluxGradTileBody|GradAdjUpdateBody' -s 6 -c 6 -o gpurun_out/${TAG}_tiles_f32 python tools/run_step.py --n 128 --steps 2 --dtype f32 > gpurun_out/${TAG}_ncu2.log 2>&1
 fi
 for f in gpurun_out/${TAG}_bench*.json; do python tools/bench_summary.py $f | head -8; done
