@@ -16,18 +16,18 @@ namespace fvm {
 
 enum { kBlock = 128, kRedBlock = 256, kRedMaxBlocks = 148 * 8 };
 
-template <class Body> __global__ void __launch_bounds__(kBlock) k_run(const Body b, int n) {
+template <class Body> __global__ void __launch_bounds__(kBlock) k_run(const Body b, int first, int n) {
     const int i = blockIdx.x * kBlock + threadIdx.x;
-    if (i < n) b(i);
+    if (i < n) b(first + i);
 }
 template <class Body> __global__ void __launch_bounds__(kBlock) k_run_discard(const Body b, int n) {
     const int i = blockIdx.x * kBlock + threadIdx.x;
     if (i < n) (void)b(i);
 }
 
-template <class Body> __global__ void __launch_bounds__(Body::kThreads, Body::kMinBlocks) k_tile(const Body b) {
+template <class Body> __global__ void __launch_bounds__(Body::kThreads, Body::kMinBlocks) k_tile(const Body b, int first) {
     extern __shared__ __align__(16) unsigned char tile_smem[];
-    b.device_tile(blockIdx.x, tile_smem);
+    b.device_tile(first + blockIdx.x, tile_smem);
 }
 template <typename R> struct BufferBody {      // reduce an array already in device memory
     static constexpr const char* kName = "reduce_buffer";
@@ -112,12 +112,29 @@ struct CudaExec {
     void download(void* dst, const void* src, size_t bytes) { if (bytes) FVM_CUDA_CHECK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, stream)); }
     void sync() { FVM_CUDA_CHECK(cudaStreamSynchronize(stream)); }
 
-    template <class Body> void run(int n, const Body& b) {
+    template <class Body> void run(int n, const Body& b) { run_range(0, n, b); }
+    // elements [first, first+n)
+    template <class Body> void run_range(int first, int n, const Body& b) {
         tic(Body::kName);
-        k_run<Body><<<(n + kBlock - 1) / kBlock, kBlock, 0, stream>>>(b, n);
+        k_run<Body><<<(n + kBlock - 1) / kBlock, kBlock, 0, stream>>>(b, first, n);
         toc();
         FVM_CUDA_CHECK(cudaPeekAtLastError());
     }
+    // ---- side stream for the halo exchange (high priority, so that its small kernels and the NCCL copies are not
+    // queued behind the grid of the compute kernel they overlap with)
+    cudaStream_t side = nullptr; cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    void ensure_side() {
+        if (side) return;
+        int lo = 0, hi = 0; cudaDeviceGetStreamPriorityRange(&lo, &hi);
+        FVM_CUDA_CHECK(cudaStreamCreateWithPriority(&side, cudaStreamNonBlocking, hi));
+        FVM_CUDA_CHECK(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
+        FVM_CUDA_CHECK(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
+    }
+    // fork: work issued between side_begin() and side_end() runs on the side stream, after everything issued on the
+    // main stream so far; join(): the main stream waits for the side stream's work
+    void side_begin() { ensure_side(); FVM_CUDA_CHECK(cudaEventRecord(ev_fork, stream)); FVM_CUDA_CHECK(cudaStreamWaitEvent(side, ev_fork, 0)); std::swap(stream, side); }
+    void side_end() { FVM_CUDA_CHECK(cudaEventRecord(ev_join, stream)); std::swap(stream, side); }
+    void join() { FVM_CUDA_CHECK(cudaStreamWaitEvent(stream, ev_join, 0)); }
     template <class Body> void run_discard(int n, const Body& b) {
         tic(Body::kName);
         k_run_discard<Body><<<(n + kBlock - 1) / kBlock, kBlock, 0, stream>>>(b, n);
@@ -125,7 +142,9 @@ struct CudaExec {
         FVM_CUDA_CHECK(cudaPeekAtLastError());
     }
     // one CTA of kBlock threads per tile, dynamic shared memory sized by the body
-    template <class Body> void run_tiles(int nTiles, const Body& b) {
+    template <class Body> void run_tiles(int nTiles, const Body& b) { run_tiles_range(0, nTiles, b); }
+    template <class Body> void run_tiles_range(int first, int nTiles, const Body& b) {
+        if (nTiles <= 0) return;
         const size_t smem = Body::smem_bytes();
         static size_t configured = 0;
         if (smem > 48 * 1024 && smem > configured) {
@@ -133,7 +152,7 @@ struct CudaExec {
             configured = smem;
         }
         tic(Body::kName);
-        k_tile<Body><<<nTiles, Body::kThreads, smem, stream>>>(b);
+        k_tile<Body><<<nTiles, Body::kThreads, smem, stream>>>(b, first);
         toc();
         FVM_CUDA_CHECK(cudaPeekAtLastError());
     }

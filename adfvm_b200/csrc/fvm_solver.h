@@ -60,6 +60,7 @@ public:
     int *bcells = 0; int nBcells = 0;
     TilePlan plan; int tile_cells = 128; R* tile_partial = 0; double tile_evals_per_cell = 0; int tile_colours = 0, tile_max_halo = 0;
     int tile_variant = 0;
+    int nEarlyTiles = 0;                      // tiles [0,nEarlyTiles) and their cells do not depend on processor-patch data
     std::vector<int> tile_halo_hist;          // tiles per halo-size bin of 32 slots (introspection)
     enum { kHalo128s = 192, kHalo128 = 256, kHalo64 = 384,
            kRowSlack = 128 };   // the tile kernels bulk-copy whole T-cell rows: the last tile may read past the last row   // halo slots of the two tile-kernel instantiations (T=128: TS=384, T=64: TS=448)
@@ -124,13 +125,13 @@ public:
             const unsigned char k = coupled ? FACE_COUPLED : (h.meshType == 4 ? FACE_CHARACTERISTIC : FACE_BOUNDARY);
             for (int i = 0; i < h.nFaces; i++) bkind[h.startFace - Fi + i] = k;
         }
-        plan = build_tile_plan<R>(C, Fi, F, owner, neighbour, cellFaces, deltas, deltasUnit, bkind.data(), tile_cells);
+        plan = build_tile_plan<R>(C, Fi, F, owner, neighbour, cellFaces, deltas, deltasUnit, bkind.data(), tile_cells, m.nLocalFaces);
         if (tile_cells == 128 && plan.maxHalo > kHalo128)
-            plan = build_tile_plan<R>(C, Fi, F, owner, neighbour, cellFaces, deltas, deltasUnit, bkind.data(), 64);
+            plan = build_tile_plan<R>(C, Fi, F, owner, neighbour, cellFaces, deltas, deltasUnit, bkind.data(), 64, m.nLocalFaces);
         if (plan.T == 64 && plan.maxHalo > kHalo64) throw std::runtime_error("tile halo exceeds the kernel's capacity");
         // kernel variant: (T, TS) = (128, 320) for compact 3-D tiles (halo <= 192; ragged box sizes reach 170: three fp64 forward CTAs and two reverse CTAs per SM), (128, 384), (64, 448)
         tile_variant = plan.T == 64 ? 2 : (plan.maxHalo <= kHalo128s ? 0 : 1);
-        m.T = plan.T; m.nTiles = plan.nTiles;
+        m.T = plan.T; m.nTiles = plan.nTiles; nEarlyTiles = plan.nEarly;
         int* d_cperm = dalloc<int>(m.sC); ex.upload(d_cperm, plan.cell_new2old.data(), (size_t)C * 4); m.cell_perm = d_cperm;
         int* d_fperm = (int*)ex.alloc((size_t)(F + 1) * 4); ex.upload(d_fperm, plan.face_new2old.data(), (size_t)F * 4);
         m.area = upload_aos(areas, F, 1, m.sF, nullptr, d_fperm); m.weight = upload_aos(weights, F, 1, m.sF, nullptr, d_fperm);
@@ -306,28 +307,41 @@ public:
         for (const PatchHost& p : patches) if (p.meshType == 5 || p.meshType == 6) r.push_back(p);
         return r;
     }
-    void halo(R* X, int ncomp) {
+    // The exchange runs on the executor's side stream between halo_begin and halo_end; kernels issued on the main
+    // stream in between overlap with it (they must not touch remote ghost rows, sendbuf or recvbuf).
+    void halo_begin(R* X, int ncomp) {
         if (m.nRemoteCells == 0) return;
         if (!comm) throw std::runtime_error("mesh has processor patches but no communicator was attached");
         run(m.nRemoteCells, HaloPackBody<R>{m, X, ncomp, sendbuf});
+        ex.side_begin();
         comm->exchange(sendbuf, recvbuf, ncomp, remote_patches(), ex.stream_handle());
         run(m.nRemoteCells, HaloUnpackBody<R>{m, X, ncomp, recvbuf});
+        ex.side_end();
     }
-    const R* halo_reverse(const R* Xb, int ncomp) {
-        if (m.nRemoteCells == 0) return nullptr;
+    void halo_end() { if (m.nRemoteCells > 0) ex.join(); }
+    void halo_reverse_begin(const R* Xb, int ncomp) {
+        if (m.nRemoteCells == 0) return;
         if (!comm) throw std::runtime_error("mesh has processor patches but no communicator was attached");
         run(m.nRemoteCells, HaloPackGhostBody<R>{m, Xb, ncomp, sendbuf});
+        ex.side_begin();
         comm->exchange(sendbuf, recvbuf, ncomp, remote_patches(), ex.stream_handle());
-        return recvbuf;
+        ex.side_end();
     }
+    const R* halo_reverse_end() { if (m.nRemoteCells == 0) return nullptr; ex.join(); return recvbuf; }
+    // cells / tiles split for the overlap: [0, early) while the halo is in flight, the rest after it
+    int early_tiles() const { return m.nRemoteCells > 0 ? nEarlyTiles : m.nTiles; }
+    int early_cells() const { const long e = (long)early_tiles() * m.T; return (int)(e < m.nInternalCells ? e : m.nInternalCells); }
+    template <class B> void run_range(int first, int n, const B& b) { if (n > 0) { ex.run_range(first, n, b); launches++; } }
+    template <class B> void run_tiles_range(int first, int n, const B& b) { if (n > 0) { ex.run_tiles_range(first, n, b); launches++; } }
 
     // ---- one residual stage + RK update
     // flux=false: stop after the gradients (the adjoint's forward sweep needs Q,G of the last stage, not its output state)
     void stage(int s, R dt, R* Qs, R* Gs, R* Qnext, bool want_dtc_obj, bool flux = true) {
         const int C = m.nInternalCells, nLB = m.nLocalFaces - m.nInternalFaces;
         if (s == 0) run(C, PrimitiveBody<R>{ph, m.sC, m.sN, W[0], Qs});
+        const int Ce = early_cells(), Te = early_tiles();
         run(nLB, GhostPrimBody<R>{ph, m, Qs});
-        halo(Qs, 5);
+        halo_begin(Qs, 5);
         if (want_dtc_obj) {
             if (obj.kind == OBJ_NONE) ex.zero(red + 1, sizeof(R));
             else {
@@ -335,25 +349,30 @@ public:
                 ex.reduce_sum(n, ObjectiveBody<R>{ph, m, obj, Qs}, red + 1); launches += 2;
             }
         }
-        run(C, GradCellBody<R>{m, Qs, Gs});
+        run_range(0, Ce, GradCellBody<R>{m, Qs, Gs});                  // overlaps the exchange of U,T,p
+        halo_end();
+        run_range(Ce, C - Ce, GradCellBody<R>{m, Qs, Gs});
         run(nLB, GhostGradBody<R>{m, Gs});
-        halo(Gs, 15);
-        if (!flux) return;
-        if (tile_variant == 0) run_flux_tile<128, 128 + kHalo128s>(s, dt, Qs, Gs, Qnext, want_dtc_obj);
-        else if (tile_variant == 1) run_flux_tile<128, 128 + kHalo128>(s, dt, Qs, Gs, Qnext, want_dtc_obj);
-        else run_flux_tile<64, 64 + kHalo64>(s, dt, Qs, Gs, Qnext, want_dtc_obj);
-        launches++;
+        halo_begin(Gs, 15);
+        if (!flux) { halo_end(); return; }
+        for (int part = 0; part < 2; part++) {                          // early tiles overlap the exchange of the gradients
+            const int t0 = part ? Te : 0, nt = part ? m.nTiles - Te : Te;
+            if (part) halo_end();
+            if (tile_variant == 0) run_flux_tile<128, 128 + kHalo128s>(s, dt, Qs, Gs, Qnext, want_dtc_obj, t0, nt);
+            else if (tile_variant == 1) run_flux_tile<128, 128 + kHalo128>(s, dt, Qs, Gs, Qnext, want_dtc_obj, t0, nt);
+            else run_flux_tile<64, 64 + kHalo64>(s, dt, Qs, Gs, Qnext, want_dtc_obj, t0, nt);
+        }
         if (want_dtc_obj) { ex.reduce_max_buffer(tile_partial, m.nTiles * (m.T / kRound), red); launches += 2; }
     }
 
-    template <int T, int TS> void run_flux_tile(int s, R dt, R* Qs, R* Gs, R* Qnext, bool want_dtc_obj) {
+    template <int T, int TS> void run_flux_tile(int s, R dt, R* Qs, R* Gs, R* Qnext, bool want_dtc_obj, int t0, int nt) {
         FluxTileBody<R, T, TS> fb;
         fb.ph = ph; fb.m = m; fb.Q = Qs; fb.G = Gs;
         fb.W0 = W[0]; fb.W1 = RK_ALPHA[s][1] != 0. ? W[1] : nullptr; fb.W2 = RK_ALPHA[s][2] != 0. ? W[2] : nullptr;
         fb.a0 = (R)RK_ALPHA[s][0]; fb.a1 = (R)RK_ALPHA[s][1]; fb.a2 = (R)RK_ALPHA[s][2];
         fb.beta = (R)RK_BETA[s]; fb.dt = dt; fb.S = S; fb.Wn = W[s + 1]; fb.Qn = Qnext;
         fb.dtc_partial = want_dtc_obj ? tile_partial : nullptr;
-        ex.run_tiles(m.nTiles, fb);
+        run_tiles_range(t0, nt, fb);
     }
 
     // primal step; state W[0] -> W[0]. keep=true keeps every stage (Q[s], G[s], W[s]) for the reverse sweep.
@@ -403,11 +422,16 @@ public:
         const int C = m.nInternalCells;
         for (int s = 2; s >= 0; s--) {
             const R coef = (R)(-RK_BETA[s]) * dt;
-            if (tile_variant == 0) ex.run_tiles(m.nTiles, FluxGradTileBody<R, 128, 128 + kHalo128s>{ph, m, Q[s], G[s], A[s + 1], coef, Qb, Gb});
-            else if (tile_variant == 1) ex.run_tiles(m.nTiles, FluxGradTileBody<R, 128, 128 + kHalo128>{ph, m, Q[s], G[s], A[s + 1], coef, Qb, Gb});
-            else ex.run_tiles(m.nTiles, FluxGradTileBody<R, 64, 64 + kHalo64>{ph, m, Q[s], G[s], A[s + 1], coef, Qb, Gb});
-            launches++;
-            const R* rG = halo_reverse(Gb, 15);
+            const int Ce = early_cells(), Te = early_tiles();
+            // late tiles first: they produce the ghost-row adjoints that travel; the early tiles overlap the exchange
+            for (int part = 1; part >= 0; part--) {
+                const int t0 = part ? Te : 0, nt = part ? m.nTiles - Te : Te;
+                if (tile_variant == 0) run_tiles_range(t0, nt, FluxGradTileBody<R, 128, 128 + kHalo128s>{ph, m, Q[s], G[s], A[s + 1], coef, Qb, Gb});
+                else if (tile_variant == 1) run_tiles_range(t0, nt, FluxGradTileBody<R, 128, 128 + kHalo128>{ph, m, Q[s], G[s], A[s + 1], coef, Qb, Gb});
+                else run_tiles_range(t0, nt, FluxGradTileBody<R, 64, 64 + kHalo64>{ph, m, Q[s], G[s], A[s + 1], coef, Qb, Gb});
+                if (part) halo_reverse_begin(Gb, 15);
+            }
+            const R* rG = halo_reverse_end();
             run(nBcells, GhostGradAdjBody<R>{m, bcells, Gb, rG});
             GradAdjUpdateBody<R> pb;
             pb.ph = ph; pb.m = m; pb.Gb = Gb; pb.Qb = Qb; pb.W = W[s];
@@ -419,8 +443,10 @@ public:
             pb.Aout = A[s];
             pb.Sb = (s == 0) ? Sb : nullptr;
             pb.s1 = (R)RK_BETA[0] * dt; pb.s2 = (R)RK_BETA[1] * dt; pb.s3 = (R)RK_BETA[2] * dt;
-            run(C, pb);
-            const R* rQ = halo_reverse(Qb, 5);
+            run_range(Ce, C - Ce, pb);               // late cells first: they complete the ghost rows of U,T,p that travel
+            halo_reverse_begin(Qb, 5);
+            run_range(0, Ce, pb);
+            const R* rQ = halo_reverse_end();
             const R oa = (s == 1) ? obja : R(0);
             run(nBcells, GhostPrimAdjBody<R>{ph, m, obj, oa, bcells, Q[s], Qb, rQ, W[s], A[s]});
         }

@@ -48,6 +48,7 @@ static inline uint32_t tile_pack(int ln, int kind, int valid, int sn, int ghost,
 }
 
 struct TilePlan {
+    int nEarly = 0;                                  // tiles [0,nEarly) touch no processor-patch data (see build_tile_plan)
     int T = 0, nTiles = 0, NW = 0, maxColours = 0;   // NW = T/32 sub-tiles (warps) per tile; maxColours = most rounds of a sub-tile
     long nEntries = 0;
     std::vector<int> cell_new2old, cell_old2new;     // internal cells
@@ -230,10 +231,12 @@ struct SubTileSchedule {
 }  // namespace detail
 
 // owner/neigh/cellFaces: the reference's arrays (old numbering). T: multiple of 32, <= 512.
-// bkind[f - Fi]: FaceKind of each boundary face.
+// bkind[f - Fi]: FaceKind of each boundary face. Faces [nLocalFaces, F) belong to processor patches: tiles that hold,
+// as own or halo cell, a cell next to such a face (hence every tile that reads or writes a remote ghost row) are LATE
+// and numbered after the EARLY ones, so that early tiles / their cells can be processed while the halo is in flight.
 template <typename R>
 TilePlan build_tile_plan(int C, int Fi, int F, const int* owner, const int* neigh, const int* cellFaces,
-                         const R* deltas, const R* deltasUnit, const unsigned char* bkind, int T) {
+                         const R* deltas, const R* deltasUnit, const unsigned char* bkind, int T, int nLocalFaces) {
     if (T <= 0 || T > 512 || T % kRound) throw std::runtime_error("tile size out of range");
     TilePlan P; P.T = T; P.NW = T / kRound;
     P.nTiles = (C + T - 1) / T;
@@ -247,6 +250,30 @@ TilePlan build_tile_plan(int C, int Fi, int F, const int* owner, const int* neig
     for (int t = 0; t < P.nTiles; t++) detail::rcb(P.cell_new2old, pos, (long)t * T, std::min<long>((long)(t + 1) * T, C), kRound);
     for (long b = 0; b < C; b += kRound)
         std::sort(P.cell_new2old.begin() + b, P.cell_new2old.begin() + std::min<long>(b + kRound, C));
+    P.nEarly = P.nTiles;
+    if (nLocalFaces < F) {
+        std::vector<char> rb(C, 0), late(P.nTiles, 0);
+        for (int f = nLocalFaces; f < F; f++) rb[owner[f]] = 1;
+        for (int t = 0; t < P.nTiles; t++)
+            for (long c = (long)t * T; c < std::min<long>((long)(t + 1) * T, C) && !late[t]; c++) {
+                const int oc = P.cell_new2old[c];
+                if (rb[oc]) { late[t] = 1; break; }
+                for (int j = 0; j < 6; j++) {
+                    const int f = cellFaces[(size_t)oc * 6 + j];
+                    if (f >= 0 && f < Fi && rb[owner[f] == oc ? neigh[f] : owner[f]]) { late[t] = 1; break; }
+                }
+            }
+        if (C % T) late[P.nTiles - 1] = 1;           // the partial tile stays last
+        std::vector<int> reordered; reordered.reserve(C);
+        P.nEarly = 0;
+        for (int pass = 0; pass < 2; pass++)
+            for (int t = 0; t < P.nTiles; t++) {
+                if (late[t] != pass) continue;
+                if (!pass) P.nEarly++;
+                for (long c = (long)t * T; c < std::min<long>((long)(t + 1) * T, C); c++) reordered.push_back(P.cell_new2old[c]);
+            }
+        P.cell_new2old.swap(reordered);
+    }
     P.cell_old2new.assign(C, -1);
     for (int i = 0; i < C; i++) P.cell_old2new[P.cell_new2old[i]] = i;
     // ---- per sub-tile: entries (faces touching it) and their (round, lane) schedule

@@ -26,17 +26,22 @@ struct HostExec {
     void sync() {}
     void timing_enable(bool) {}
     std::string timing_report() { return ""; }
-    template <class B> void run(int n, const B& b) {
+    template <class B> void run(int n, const B& b) { run_range(0, n, b); }
+    template <class B> void run_range(int first, int n, const B& b) {
         #pragma omp parallel for schedule(static)
-        for (int i = 0; i < n; i++) b(i);
+        for (int i = first; i < first + n; i++) b(i);
     }
+    void side_begin() {}
+    void side_end() {}
+    void join() {}
     template <class B> void run_discard(int n, const B& b) {
         #pragma omp parallel for schedule(static)
         for (int i = 0; i < n; i++) (void)b(i);
     }
-    template <class B> void run_tiles(int nTiles, const B& b) {
+    template <class B> void run_tiles(int nTiles, const B& b) { run_tiles_range(0, nTiles, b); }
+    template <class B> void run_tiles_range(int first, int nTiles, const B& b) {
         #pragma omp parallel for schedule(static)
-        for (int t = 0; t < nTiles; t++) b.host_tile(t);
+        for (int t = first; t < first + nTiles; t++) b.host_tile(t);
     }
     template <typename R> void reduce_max_buffer(const R* in, int n, R* out) { R a = (R)-1e30; for (int i = 0; i < n; i++) if (in[i] > a) a = in[i]; *out = a; }
     template <class B, typename R> void reduce_sum(int n, const B& b, R* out) { R a = 0; for (int i = 0; i < n; i++) a += b(i); *out = a; }
