@@ -277,6 +277,7 @@ template <typename R> struct GhostGradAdjBody {
 //   reverse stage). Cells next to a boundary get the share of their ghost rows later (GhostPrimAdjBody, linear).
 template <typename R> struct GradAdjUpdateBody {
     static constexpr const char* kName = "grad_adj_update";
+    static constexpr int kMinBlocks = sizeof(R) == 8 ? 4 : 6;      // a latency-bound gather: 16 (fp64) / 24 (fp32) warps per SM
     Phys<R> ph; MeshDev<R> m;
     const R* Gb; R* Qb;
     const R* W;                // stage state the residual was evaluated at

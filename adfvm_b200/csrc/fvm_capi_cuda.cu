@@ -88,6 +88,8 @@ static void exec_init(ExecT& ex, int device, void* stream) { ex.init(device, str
 template <typename R> fvm::HaloComm<R>* make_comm(ExecT& ex, const void* id, int rank, int nranks) {
     return new NcclHalo<R>(ex, id, rank, nranks);
 }
+static void* host_alloc_pinned(size_t bytes) { void* p = nullptr; FVM_CUDA_CHECK(cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault)); return p; }
+static void host_free_pinned(void* p) { if (p) cudaFreeHost(p); }
 static int comm_unique_id(void* id128) {
     g_nccl.load();
     ncclUniqueId uid;

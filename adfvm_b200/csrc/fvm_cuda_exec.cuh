@@ -16,7 +16,11 @@ namespace fvm {
 
 enum { kBlock = 128, kRedBlock = 256, kRedMaxBlocks = 148 * 8 };
 
-template <class Body> __global__ void __launch_bounds__(kBlock) k_run(const Body b, int first, int n) {
+// resident CTAs per SM a body asks for (register cap = 64K / (128 * n)); bodies without kMinBlocks get 1
+template <class B, class = void> struct MinBlocksOf { static constexpr int value = 1; };
+template <class B> struct MinBlocksOf<B, decltype((void)B::kMinBlocks)> { static constexpr int value = B::kMinBlocks; };
+
+template <class Body> __global__ void __launch_bounds__(kBlock, MinBlocksOf<Body>::value) k_run(const Body b, int first, int n) {
     const int i = blockIdx.x * kBlock + threadIdx.x;
     if (i < n) b(first + i);
 }

@@ -51,6 +51,61 @@ def _ptr(a):
     return None if a is None else a.ctypes.data_as(C.c_void_p)
 
 
+class _PinnedBlock:
+    """One page-locked host block; numpy arrays made from it keep it alive (array interface base), and the block
+    goes back to its pool when the last of them is released."""
+
+    def __init__(self, pool, ptr, nbytes):
+        self.pool, self.ptr, self.nbytes = pool, ptr, nbytes
+        self.__array_interface__ = {"data": (ptr, False), "shape": (nbytes,), "typestr": "|u1", "version": 3}
+
+    def __del__(self):
+        pool = self.pool
+        if pool is not None:
+            pool._release(self.ptr, self.nbytes)
+
+
+class _PinnedPool:
+    """Result arrays of a call (reference: fresh `new T[]` per output, adpy/adpy/cpp/include/interface.hpp:54-80)
+    are fresh numpy arrays over recycled page-locked blocks: the device-to-host copies run asynchronously at the
+    full PCIe rate instead of staging through pageable memory."""
+
+    def __init__(self, lib, keep=8):
+        self.lib, self.free, self.keep = lib, {}, keep
+
+    def empty(self, shape, dtype):
+        n = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        nbytes = max(64, (n + 63) // 64 * 64)
+        lst = self.free.get(nbytes)
+        if lst:
+            ptr = lst.pop()
+        else:
+            p = C.c_void_p()
+            self.lib.check(self.lib.dll.adfvm_host_alloc(C.byref(p), nbytes))
+            ptr = p.value
+        block = _PinnedBlock(self, ptr, nbytes)
+        return np.asarray(block)[:n].view(dtype).reshape(shape)
+
+    def _release(self, ptr, nbytes):
+        lst = self.free.setdefault(nbytes, [])
+        if len(lst) < self.keep:
+            lst.append(ptr)
+        else:
+            try:
+                self.lib.dll.adfvm_host_free(C.c_void_p(ptr))
+            except Exception:
+                pass
+
+    def close(self):
+        for lst in self.free.values():
+            for ptr in lst:
+                try:
+                    self.lib.dll.adfvm_host_free(C.c_void_p(ptr))
+                except Exception:
+                    pass
+        self.free = {}
+
+
 class _Context:
     """Owns one adfvm_ctx: device-resident mesh, BC, source and state of one rank."""
 
@@ -80,9 +135,11 @@ class _Context:
         self.patch = byname
         self.static_loaded = False
         self.sizes = None
+        self.pool = _PinnedPool(self.lib)
 
     def close(self):
         if self.ctx:
+            self.pool.close()
             self.lib.dll.adfvm_destroy(self.ctx)
             self.ctx = C.c_void_p()
 
@@ -253,7 +310,7 @@ class PrimalFunction:
         flags = (L.RETURN_REUSABLE if opts["return_reusable"] else 0) | (L.REPLACE_REUSABLE if opts["replace_reusable"] else 0)
         outs = [None, None, None]
         if opts["return_reusable"]:
-            outs = [np.empty((C_, 1), c.dtype), np.empty((C_, 3), c.dtype), np.empty((C_, 1), c.dtype)]
+            outs = [c.pool.empty((C_, 1), c.dtype), c.pool.empty((C_, 3), c.dtype), c.pool.empty((C_, 1), c.dtype)]
         dtc, obj = np.zeros((1, 1), c.dtype), np.zeros((1, 1), c.dtype)
         c.lib.check(c.lib.dll.adfvm_primal(c.ctx, _ptr(rho), _ptr(rhoU), _ptr(rhoE), float(dt[0, 0]), flags,
                                            _ptr(outs[0]), _ptr(outs[1]), _ptr(outs[2]), _ptr(dtc), _ptr(obj)))
@@ -325,10 +382,10 @@ class AdjointFunction:
         c._arr(ra, (1,), "rhoa", C_); c._arr(rUa, (3,), "rhoUa", C_); c._arr(rEa, (1,), "rhoEa", C_)
         dtca = float(c._arr(rest[3], (1,), "dtca", 1)[0, 0]); obja = float(c._arr(rest[4], (1,), "obja", 1)[0, 0])
         flags = (L.RETURN_STATIC if opts["return_static"] else 0) | (L.ZERO_STATIC if opts["zero_static"] else 0)
-        outs = [np.empty((C_, 1), c.dtype), np.empty((C_, 3), c.dtype), np.empty((C_, 1), c.dtype)]
+        outs = [c.pool.empty((C_, 1), c.dtype), c.pool.empty((C_, 3), c.dtype), c.pool.empty((C_, 1), c.dtype)]
         grads = [None, None, None]
         if opts["return_static"]:
-            grads = [np.empty((C_, 1), c.dtype), np.empty((C_, 3), c.dtype), np.empty((C_, 1), c.dtype)]
+            grads = [c.pool.empty((C_, 1), c.dtype), c.pool.empty((C_, 3), c.dtype), c.pool.empty((C_, 1), c.dtype)]
         c.lib.check(c.lib.dll.adfvm_primal_grad(
             c.ctx, _ptr(rho), _ptr(rhoU), _ptr(rhoE), float(dt[0, 0]), _ptr(ra), _ptr(rUa), _ptr(rEa), dtca, obja, flags,
             _ptr(outs[0]), _ptr(outs[1]), _ptr(outs[2]), _ptr(grads[0]), _ptr(grads[1]), _ptr(grads[2])))

@@ -40,9 +40,16 @@ def algorithmic_bytes(s):
     # dominant kernels, rows of BASELINE.md §3 they cover (per cell per launch):
     #  flux_tile   = flux (20 + 51 + 3 + 6 scalars, 2F ints) + RK update (23 1/3) + primitive of next stage (10)
     #  flux_grad_tile = flux_grad row: 5 + 40 + (51 + 3) + 40 scalars, 2F ints
+    #  grad_adj_update = gradCell VJP + primitive VJP + RK combination fused: Qb 5, Gb 15, cell-face metrics 24, W 5,
+    #                    later-stage adjoints 5/5/15 (+ source-gradient RMW 10 on the last reverse stage) = 11 2/3 avg, out 5; 6 ints
     k = {"flux_tile": (80 + 23 + 1.0 / 3 + 10) * s + 24, "flux_grad_tile": (5 + 40 + 54 + 40) * s + 24,
-         "grad_cell": (5 + 15 + 1 + 15) * s + 72, "grad_cell_adj": (15 + 15 + 1 + 10) * s + 72}
+         "grad_cell": (5 + 15 + 1 + 15) * s + 72, "grad_adj_update": (5 + 15 + 24 + 5 + 11 + 2.0 / 3 + 5) * s + 24}
     return B_p, B_a, k
+
+
+# full passes over the mesh per (primal + adjoint) step: a kernel may be launched in two parts (tiles / cells that
+# do not depend on halo data first), so rates are computed from its total time per step, not per launch
+PASSES = {"flux_tile": 5, "flux_grad_tile": 3, "grad_cell": 6, "grad_adj_update": 3}
 
 
 class ClockSampler:
@@ -127,9 +134,9 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--size", dest="n", type=int, default=int(os.environ.get("ADFVM_BENCH_N", "128")), help="cells per side per GPU")
+    ap.add_argument("--size", dest="n", type=int, default=int(os.environ.get("ADFVM_BENCH_N", "256")), help="cells per side per GPU")
     ap.add_argument("--dtype", default="f64", choices=["f64", "f32"])
-    ap.add_argument("--cpu-n", type=int, default=40, help="box size of the bounded CPU-baseline sample")
+    ap.add_argument("--cpu-n", type=int, default=64, help="box size of the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -256,7 +263,8 @@ def main():
         per = ms / cnt
         e = {"launches_per_step": cnt / nrep, "ms_per_launch": per, "share": None}
         if name in kb:
-            e["algorithmic_GBs"] = kb[name] * C / (per * 1e-3) / 1e9
+            e["ms_per_pass"] = ms / nrep / PASSES[name]
+            e["algorithmic_GBs"] = kb[name] * C / (e["ms_per_pass"] * 1e-3) / 1e9
             e["frac"] = e["algorithmic_GBs"] / peak
         kernels[name] = e
     tot = sum(ms for _, ms in rep.values())
@@ -266,8 +274,10 @@ def main():
     traffic = None
     try:
         tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
-        key = "%s_%s_n%d" % (dom, args.dtype, args.n)
+        key = "%s_%s_n128" % (dom, args.dtype)      # ncu --set full capture at 128^3; DRAM bytes scale with the cell count
         traffic = tr.get(key)
+        if traffic is not None:
+            traffic = int(traffic * (C / 128.0 ** 3))
     except Exception:
         pass
     roof = {"bound": "hbm", "kernel": dom, "achieved": kernels[dom]["algorithmic_GBs"], "peak": peak, "unit": "GB/s",

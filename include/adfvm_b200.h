@@ -14,6 +14,7 @@
  */
 #ifndef ADFVM_B200_H
 #define ADFVM_B200_H
+#include <stddef.h>
 #include <stdint.h>
 #ifdef __cplusplus
 extern "C" {
@@ -124,6 +125,12 @@ int adfvm_tile_halo_stats(adfvm_ctx* ctx, int32_t* max_halo, int32_t* variant, i
  * `-o/--profile` per-kernel prints (adpy/adpy/variable.py:437-467). */
 int adfvm_kernel_timing(adfvm_ctx* ctx, int32_t enable);
 int adfvm_kernel_report(adfvm_ctx* ctx, char* buf, int32_t buflen);
+
+/* page-locked host memory for the arrays a call returns: replaces putArray's per-call `new T[size]`
+ * (adpy/adpy/cpp/include/interface.hpp:54-80); device-to-host copies into it are asynchronous and run at the full
+ * PCIe rate. The Python host layer recycles the blocks when the numpy arrays that wrap them are released. */
+int adfvm_host_alloc(void** out, size_t bytes);
+int adfvm_host_free(void* p);
 
 /* multi-GPU halo: replaces Function_mpi_init / Function_mpi / Function_mpi_end and their _grad twins
  * (adFVM/cpp/parallel.cpp:31-209) and Function_mpi_allreduce (:214-232) with NCCL point-to-point over NVLink.

@@ -109,6 +109,8 @@ typedef fvm::HostExec ExecT;
 static const int kIsCuda = 0;
 static void exec_init(ExecT&, int, void*) {}
 template <typename R> fvm::HaloComm<R>* make_comm(ExecT&, const void* id, int rank, int nranks) { return new ThreadHalo<R>(id, rank, nranks); }
+static void* host_alloc_pinned(size_t bytes) { return std::malloc(bytes ? bytes : 1); }
+static void host_free_pinned(void* p) { std::free(p); }
 static int comm_unique_id(void* id128) {
     static int counter = 0;
     std::memset(id128, 0, 128);
