@@ -218,7 +218,45 @@ def case_box_upt():
                 mid="[0.5,0.25,0.25]", amp="1e2", width="60", nSteps=4, writeInterval=2, dt=1e-6)
 
 
-CASES = {"box_cyclic": case_box_cyclic, "tube": case_tube, "box_walls": case_box_walls, "box_upt": case_box_upt}
+def case_cyl2d():
+    """2-D laminar cylinder in the spirit of reference templates/cylinder.py (config 2 of BASELINE.json): half
+    annulus around a cylinder of radius 0.5 mm, geometric radial grading, one cell in the span with cyclic z1/z2 (as
+    cases/cylinder/0/U), no-slip wall (fixedValue U, zeroGradient T and p), CBC_UPT far field with the
+    Lax-Friedrichs boundary Riemann solver, symmetry planes on the axis, mu = 2.5e-5, drag objective on the
+    cylinder (templates/cylinder.py:9-19), source perturbation just upstream of the cylinder (:62-73)."""
+    r0, r1, nr, nt = 0.5e-3, 8e-3, 12, 16
+    def warp(p):
+        r = r0 * (r1 / r0) ** p[:, 0]
+        th = np.pi * p[:, 1]
+        return np.stack([r * np.cos(th), r * np.sin(th), p[:, 2]], axis=1)
+    poly = hexmesh.box_mesh((nr, nt, 1), (0., 0., 0.), (1., 1., 2e-4), warp=warp, patches=[
+        ("cylinder", "patch", ["x-"], {}),
+        ("far", "patch", ["x+"], {}),
+        ("axis", "symmetryPlane", ["y-", "y+"], {}),
+        ("z1", "cyclic", ["z-"], {"neighbourPatch": "z2"}),
+        ("z2", "cyclic", ["z+"], {"neighbourPatch": "z1"})])
+    m = build_mesh(poly)
+    cc = m.cellCentres[:m.nInternalCells]
+    r = np.linalg.norm(cc[:, :2], axis=1)
+    # potential-flow-like start: U = U0 (1 - r0^2/r^2) blended to zero at the wall
+    U0 = 33.
+    th = np.arctan2(cc[:, 1], cc[:, 0])
+    f = 1 - (r0 / r) ** 2
+    U = np.stack([U0 * (1 - (r0 / r) ** 2 * np.cos(2 * th)) * f, -U0 * (r0 / r) ** 2 * np.sin(2 * th) * f, 0 * r], axis=1)
+    T = (300 + 2 * np.exp(-((r - r0) / 1e-3) ** 2)).reshape(-1, 1)
+    p = (101325 + 0.5 * 1.17 * (U0 ** 2 - (U ** 2).sum(axis=1))).reshape(-1, 1)
+    cyc = {"z1": {"type": "cyclic"}, "z2": {"type": "cyclic"}}
+    bU = dict(cyc, cylinder={"type": "fixedValue", "value": "uniform (0 0 0)"}, far={"type": "calculated"}, axis={"type": "symmetryPlane"})
+    bT = dict(cyc, cylinder={"type": "zeroGradient"}, far={"type": "calculated"}, axis={"type": "symmetryPlane"})
+    bp = dict(cyc, cylinder={"type": "zeroGradient"}, axis={"type": "symmetryPlane"},
+              far={"type": "CBC_UPT", "U0": "uniform (33 0 0)", "T0": "uniform 300", "p0": "uniform 101325", "value": "uniform 101325"})
+    return dict(poly=poly, fields={"U": (U, bU), "T": (T, bT), "p": (p, bp)},
+                objective=OBJ_DRAG.format(patch="cylinder"), obj_spec={"kind": "drag", "patch": "cylinder", "direction": 0},
+                rcf_extra=", mu=lambda T: 2.5e-5, boundaryRiemannSolver='eulerLaxFriedrichs'",
+                mid="[-0.8e-3,0.1e-3,1e-4]", amp="1e-1", width="2.5e6", nSteps=4, writeInterval=2, dt=2e-9)
+
+
+CASES = {"cyl2d": case_cyl2d, "box_cyclic": case_box_cyclic, "tube": case_tube, "box_walls": case_box_walls, "box_upt": case_box_upt}
 
 
 def run(cmd, cwd):

@@ -10,6 +10,9 @@ from oracle import adfvm_oracle as O
 
 CASES = [c for c in available() if not c.endswith("_fp32")]
 TOL = 1e-12
+# the drag on the half cylinder of `cyl2d` is a sum of pressure forces that cancel to 1e-4 of their size: the objective
+# is compared at the north-star tolerance there
+OBJ_TOL = {"cyl2d": 1e-10}
 
 
 @pytest.mark.parametrize("name", CASES)
@@ -21,7 +24,7 @@ def test_oracle_primal_matches_reference(name):
             r = O.primal(g.spec, inp)
             for a, b in zip(r[:3], out[:3]):
                 assert relerr(a, b) < TOL
-            assert relerr(r[3], out[3]) < TOL and relerr(r[4], out[4]) < TOL
+            assert relerr(r[3], out[3]) < TOL and relerr(r[4], out[4]) < OBJ_TOL.get(name, TOL)
             n += 1
     assert n >= 4
 
