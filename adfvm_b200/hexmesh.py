@@ -183,3 +183,71 @@ def sine_warp(amp=0.03, lo=(0.0, 0.0, 0.0), hi=(1.0, 1.0, 1.0)):
         return lo + q * (hi - lo)
 
     return f
+
+
+def masked_box_mesh(n, lo, hi, keep, patches, hole=("obstacle", "patch", {}), grading=None):
+    """Structured nx*ny*nz box with the cells where `keep[k, j, i]` is False removed (e.g. the forward-facing step
+    of reference cases/forwardStep/constant/polyMesh/blockMeshDict, whose three blocks are a box minus the step).
+    patches: as in box_mesh, for the faces on the six box sides; faces between a kept and a removed cell go to the
+    patch `hole` = (name, type, extra), placed after them. Unused points are kept (harmless to the readers)."""
+    nx, ny, nz = [int(v) for v in n]
+    keep = np.asarray(keep, bool).reshape(nz, ny, nx)
+    g = grading or (None, None, None)
+    xs = _axis_points(nx, lo[0], hi[0], g[0]); ys = _axis_points(ny, lo[1], hi[1], g[1]); zs = _axis_points(nz, lo[2], hi[2], g[2])
+    Z, Y, X = np.meshgrid(zs, ys, xs, indexing="ij")
+    points = np.stack([X.ravel(), Y.ravel(), Z.ravel()], axis=1)
+
+    def pid(i, j, k):
+        return (i + (nx + 1) * (j + (ny + 1) * k)).astype(np.int64)
+
+    quad = {0: lambda i, j, k: np.stack([pid(i, j, k), pid(i, j + 1, k), pid(i, j + 1, k + 1), pid(i, j, k + 1)], -1),
+            1: lambda i, j, k: np.stack([pid(i, j, k), pid(i, j, k + 1), pid(i + 1, j, k + 1), pid(i + 1, j, k)], -1),
+            2: lambda i, j, k: np.stack([pid(i, j, k), pid(i + 1, j, k), pid(i + 1, j + 1, k), pid(i, j + 1, k)], -1)}
+    cmap = np.full((nz + 2, ny + 2, nx + 2), -1, np.int64)         # padded: index + 1
+    cmap[1:-1, 1:-1, 1:-1][keep] = np.arange(int(keep.sum()))
+    inside = np.zeros((nz + 2, ny + 2, nx + 2), bool); inside[1:-1, 1:-1, 1:-1] = True
+    int_own, int_nb, int_f = [], [], []
+    side_own = {s: [] for s in SIDES}; side_f = {s: [] for s in SIDES}
+    hole_own, hole_f = [], []
+    for d, ax in ((0, 2), (1, 1), (2, 0)):                          # direction d runs along padded-array axis ax
+        nd = (nx, ny, nz)[d]
+        slA = [slice(1, -1)] * 3; slB = [slice(1, -1)] * 3
+        slA[ax] = slice(0, nd + 1); slB[ax] = slice(1, nd + 2)        # A = cell before the plane, B = cell after it
+        A, B = cmap[tuple(slA)], cmap[tuple(slB)]
+        inA, inB = inside[tuple(slA)], inside[tuple(slB)]
+        shp = A.shape
+        K, J, I = np.meshgrid(np.arange(shp[0]), np.arange(shp[1]), np.arange(shp[2]), indexing="ij")   # plane / cell indices
+        A, B, inA, inB, I, J, K = [a.ravel() for a in (A, B, inA, inB, I, J, K)]
+        f = quad[d](I, J, K)                                         # the index along d is already the plane index
+        both = (A >= 0) & (B >= 0)
+        int_own.append(A[both]); int_nb.append(B[both]); int_f.append(f[both])
+        onlyA = (A >= 0) & (B < 0); onlyB = (B >= 0) & (A < 0)
+        name = "xyz"[d]
+        m = onlyA & ~inB; side_own[name + "+"].append(A[m]); side_f[name + "+"].append(f[m])
+        m = onlyB & ~inA; side_own[name + "-"].append(B[m]); side_f[name + "-"].append(f[m][:, ::-1])
+        m = onlyA & inB; hole_own.append(A[m]); hole_f.append(f[m])
+        m = onlyB & inA; hole_own.append(B[m]); hole_f.append(f[m][:, ::-1])
+    own = np.concatenate(int_own); nb = np.concatenate(int_nb); fcs = np.concatenate(int_f)
+    order = np.lexsort((nb, own))
+    own, nb, fcs = own[order], nb[order], fcs[order]
+    boundary = OrderedDict()
+    b_owner, b_faces = [], []
+    start = len(own)
+    used = set()
+    plist = list(patches) + [(hole[0], hole[1], None, hole[2])]
+    for name, ptype, sides, extra in plist:
+        if sides is None:
+            o = np.concatenate(hole_own); f = np.concatenate(hole_f)
+        else:
+            for s in sides:
+                assert s in SIDES and s not in used, s
+                used.add(s)
+            o = np.concatenate([x for s in sides for x in side_own[s]] or [np.zeros(0, np.int64)])
+            f = np.concatenate([x for s in sides for x in side_f[s]] or [np.zeros((0, 4), np.int64)])
+        dct = OrderedDict(type=ptype, nFaces=int(len(o)), startFace=int(start))
+        dct.update(extra or {})
+        boundary[name] = dct
+        b_owner.append(o); b_faces.append(f.reshape(-1, 4))
+        start += len(o)
+    assert used == set(SIDES), "every box side needs a patch: missing %s" % (set(SIDES) - used)
+    return PolyMesh(points, np.concatenate([fcs] + b_faces), np.concatenate([own] + b_owner), nb, boundary)

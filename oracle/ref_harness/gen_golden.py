@@ -256,7 +256,41 @@ def case_cyl2d():
                 mid="[-0.8e-3,0.1e-3,1e-4]", amp="1e-1", width="2.5e6", nSteps=4, writeInterval=2, dt=2e-9)
 
 
-CASES = {"cyl2d": case_cyl2d, "box_cyclic": case_box_cyclic, "tube": case_tube, "box_walls": case_box_walls, "box_upt": case_box_upt}
+
+def case_step2d():
+    """Mach-3 forward-facing step of reference templates/forwardStep.py / cases/forwardStep (config 3 of BASELINE.json)
+    on a coarse mesh: box [0,3]x[0,1] minus the step x>0.6, y<0.2 (the three blocks of its blockMeshDict), one cell
+    in the span with `empty` faces, non-dimensional gas Cp=2.5 (c=1 at T=1), inviscid (mu=0), fixedValue inlet,
+    inletOutlet/zeroGradient outlet, symmetryPlane top and bottom, slip obstacle, pressure-force objective on the
+    obstacle (templates/forwardStep.py:8-28), source perturbation at the inlet cells (:32-40 uses the same idea)."""
+    nx, ny = 30, 10
+    lo, hi = (0., 0., -0.05), (3., 1., 0.05)
+    K, J, I = np.meshgrid(np.arange(1), np.arange(ny), np.arange(nx), indexing="ij")
+    keep = ~((I >= 6) & (J < 2))
+    poly = hexmesh.masked_box_mesh((nx, ny, 1), lo, hi, keep, [
+        ("inlet", "patch", ["x-"], {}),
+        ("outlet", "patch", ["x+"], {}),
+        ("bottom", "symmetryPlane", ["y-"], {}),
+        ("top", "symmetryPlane", ["y+"], {}),
+        ("defaultFaces", "empty", ["z-", "z+"], {})], hole=("obstacle", "patch", {}))
+    m = build_mesh(poly)
+    cc = m.cellCentres[:m.nInternalCells]
+    s = np.sin(2 * np.pi * cc[:, 0] / 3.) * np.cos(np.pi * cc[:, 1])
+    U = np.stack([3. + 0.05 * s, 0.02 * s, 0 * s], axis=1)
+    T = (1. + 0.01 * s).reshape(-1, 1)
+    p = (1. + 0.02 * s).reshape(-1, 1)
+    bU = {"inlet": {"type": "fixedValue", "value": "uniform (3 0 0)"}, "outlet": {"type": "inletOutlet", "inletValue": "uniform (3 0 0)", "value": "uniform (3 0 0)"},
+          "bottom": {"type": "symmetryPlane"}, "top": {"type": "symmetryPlane"}, "obstacle": {"type": "slip"}, "defaultFaces": {"type": "empty"}}
+    bT = {"inlet": {"type": "fixedValue", "value": "uniform 1"}, "outlet": {"type": "inletOutlet", "inletValue": "uniform 1", "value": "uniform 1"},
+          "bottom": {"type": "symmetryPlane"}, "top": {"type": "symmetryPlane"}, "obstacle": {"type": "zeroGradient"}, "defaultFaces": {"type": "empty"}}
+    bp = {"inlet": {"type": "fixedValue", "value": "uniform 1"}, "outlet": {"type": "zeroGradient"},
+          "bottom": {"type": "symmetryPlane"}, "top": {"type": "symmetryPlane"}, "obstacle": {"type": "zeroGradient"}, "defaultFaces": {"type": "empty"}}
+    return dict(poly=poly, fields={"U": (U, bU), "T": (T, bT), "p": (p, bp)},
+                objective=OBJ_PATCH_PA.format(patch="obstacle"), obj_spec={"kind": "patch_pA", "patch": "obstacle"},
+                rcf_extra=", Cp=2.5, mu=lambda T: 0., CFL=1.2", mid="[0.3,0.3,0.]", amp="1e-2", width="20", nSteps=4, writeInterval=2, dt=1e-3)
+
+
+CASES = {"step2d": case_step2d, "cyl2d": case_cyl2d, "box_cyclic": case_box_cyclic, "tube": case_tube, "box_walls": case_box_walls, "box_upt": case_box_upt}
 
 
 def run(cmd, cwd):
