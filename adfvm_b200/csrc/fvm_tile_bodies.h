@@ -134,6 +134,26 @@ __device__ __forceinline__ void cp_async_arrive(unsigned long long* bar) {
     asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
+
+// L2 prefetch of the index data a later tile needs before its first round. i = job of the calling lane:
+//   0..6      halo cell list of tile tn (up to 7 lines of 128 B)          } tn runs one wave of CTAs after this tile; its
+//   7..6+NW   first metric chunk of each warp of tile tn                   } index lines were prefetched one wave earlier,
+//   7+NW..    the index lines (round_start, halo_start, halo_round) of tile tnn, two waves ahead
+template <typename R, int NW, class Ch> __device__ __forceinline__ void tile_prefetch_meta(const MeshDev<R>& m, int tn, int tnn, int i) {
+    if (i < 7) {
+        const int hs = m.halo_start[tn], he = m.halo_start[tn + 1];
+        const int* p = m.halo_cell + hs + 32 * i;
+        if (p < m.halo_cell + he) prefetch_l2(p);
+    } else if (i < 7 + NW) {
+        const int r = m.round_start[tn * NW + (i - 7)];
+        if (r < m.round_start[tn * NW + (i - 7) + 1]) bulk_prefetch_l2(m.chunks + (long)r * Ch::kScalars, (unsigned)Ch::kBytes);
+    } else if (tnn < m.nTiles) {
+        if (i == 7 + NW) prefetch_l2(m.round_start + tnn * NW);
+        else if (i == 8 + NW) prefetch_l2(m.halo_start + tnn);
+        else if (i == 9 + NW) prefetch_l2(m.halo_round + tnn * NW);
+    }
+}
+
 // shared-memory carve-up common to both kernels: [qg 20*TS][extra ...][one chunk per warp][2 + T/32 mbarriers]
 template <typename R, int T, int TS, int EXTRA> struct TileSmem {
     static constexpr int NW = T / 32;
@@ -266,10 +286,18 @@ template <typename R, int T, int TS> struct FluxTileBody {
             bulk_g2s(chunk, m.chunks + (long)r0 * Ch::kScalars, (unsigned)Ch::kBytes, bar_chunk);
         }
         // halo rows: asynchronous gather, consumed from round `hr` on (the rounds before it only touch the tile's own cells)
-        for (int h = tid; h < nh; h += T) {
-            const int cell = m.halo_cell[h0 + h];
-            for (int k = 0; k < 5; k++) cp_async_elem<sizeof(R)>(qg + k * TS + T + h, Q + (long)k * m.sN + cell);
-            for (int k = 0; k < 15; k++) cp_async_elem<sizeof(R)>(qg + (5 + k) * TS + T + h, G + (long)k * m.sN + cell);
+        {
+            constexpr int kIter = (TS - T + T - 1) / T;          // halo slots per thread
+            int hc[kIter];
+            #pragma unroll
+            for (int i = 0; i < kIter; i++) { const int h = tid + i * T; hc[i] = h < nh ? m.halo_cell[h0 + h] : -1; }   // all index loads in flight at once
+            #pragma unroll
+            for (int i = 0; i < kIter; i++) {
+                const int h = tid + i * T, cell = hc[i];
+                if (cell < 0) continue;
+                for (int k = 0; k < 5; k++) cp_async_elem<sizeof(R)>(qg + k * TS + T + h, Q + (long)k * m.sN + cell);
+                for (int k = 0; k < 15; k++) cp_async_elem<sizeof(R)>(qg + (5 + k) * TS + T + h, G + (long)k * m.sN + cell);
+            }
         }
         cp_async_arrive(bar_halo);
         // pull the rows of the tile that will run in this CTA slot one wave later into L2: its first loads then see an
@@ -281,10 +309,8 @@ template <typename R, int T, int TS> struct FluxTileBody {
                 if (lane < 5) bulk_prefetch_l2(Q + (long)lane * m.sN + cn, kRow);
                 else if (lane < 20) bulk_prefetch_l2(G + (long)(lane - 5) * m.sN + cn, kRow);
                 else if (lane == 20) bulk_prefetch_l2(m.vol + cn, kRow);
-                else if (lane == 21) prefetch_l2(m.round_start + tn * NW);
-                else if (lane == 22) prefetch_l2(m.halo_start + tn);
-                else if (lane == 23) prefetch_l2(m.halo_round + tn * NW);
             }
+            if (tn < m.nTiles && w == (NW > 1 ? NW - 2 : 0)) tile_prefetch_meta<R, NW, Ch>(m, tn, tn + kPrefetchDistance, lane);
         }
         if (nr == 0) return;                       // sub-tile beyond the last internal cell
         mbar_wait(bar_rows, 0);
@@ -448,13 +474,21 @@ template <typename R, int T, int TS> struct FluxGradTileBody {
             mbar_expect_tx(bar_chunk, (unsigned)Ch::kBytes);
             bulk_g2s(chunk, m.chunks + (long)r0 * Ch::kScalars, (unsigned)Ch::kBytes, bar_chunk);
         }
-        for (int h = tid; h < nh; h += T) {
-            const int cell = m.halo_cell[h0 + h], slot = T + h;
-            for (int k = 0; k < 5; k++) cp_async_elem<sizeof(R)>(qg + k * TS + slot, Q + (long)k * m.sN + cell);
-            for (int k = 0; k < 15; k++) cp_async_elem<sizeof(R)>(qg + (5 + k) * TS + slot, G + (long)k * m.sN + cell);
-            if (cell < m.nInternalCells) {
-                for (int k = 0; k < 5; k++) cp_async_elem<sizeof(R)>(ab + k * TS + slot, abar + (long)k * m.sC + cell);
-                cp_async_elem<sizeof(R)>(vol + slot, m.vol + cell);
+        {
+            constexpr int kIter = (TS - T + T - 1) / T;
+            int hc[kIter];
+            #pragma unroll
+            for (int i = 0; i < kIter; i++) { const int h = tid + i * T; hc[i] = h < nh ? m.halo_cell[h0 + h] : -1; }
+            #pragma unroll
+            for (int i = 0; i < kIter; i++) {
+                const int cell = hc[i], slot = T + tid + i * T;
+                if (cell < 0) continue;
+                for (int k = 0; k < 5; k++) cp_async_elem<sizeof(R)>(qg + k * TS + slot, Q + (long)k * m.sN + cell);
+                for (int k = 0; k < 15; k++) cp_async_elem<sizeof(R)>(qg + (5 + k) * TS + slot, G + (long)k * m.sN + cell);
+                if (cell < m.nInternalCells) {
+                    for (int k = 0; k < 5; k++) cp_async_elem<sizeof(R)>(ab + k * TS + slot, abar + (long)k * m.sC + cell);
+                    cp_async_elem<sizeof(R)>(vol + slot, m.vol + cell);
+                }
             }
         }
         cp_async_arrive(bar_halo);
@@ -466,10 +500,8 @@ template <typename R, int T, int TS> struct FluxGradTileBody {
                 else if (lane < 20) bulk_prefetch_l2(G + (long)(lane - 5) * m.sN + cn, kRow);
                 else if (lane < 25) bulk_prefetch_l2(abar + (long)(lane - 20) * m.sC + cn, kRow);
                 else if (lane == 25) bulk_prefetch_l2(m.vol + cn, kRow);
-                else if (lane == 26) prefetch_l2(m.round_start + tn * NW);
-                else if (lane == 27) prefetch_l2(m.halo_start + tn);
-                else if (lane == 28) prefetch_l2(m.halo_round + tn * NW);
             }
+            if (tn < m.nTiles && w == (NW > 1 ? NW - 2 : 0)) tile_prefetch_meta<R, NW, Ch>(m, tn, tn + kPrefetchDistance, lane);
         }
         if (nr == 0) return;
         mbar_wait(bar_rows, 0);
