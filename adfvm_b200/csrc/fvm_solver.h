@@ -60,6 +60,7 @@ public:
     int *bcells = 0; int nBcells = 0;
     TilePlan plan; int tile_cells = 128; R* tile_partial = 0; double tile_evals_per_cell = 0; int tile_colours = 0, tile_max_halo = 0;
     int tile_variant = 0;
+    long tile_rounds_total = 0;               // rounds of all sub-tiles (32 lanes each; introspection)
     int nEarlyTiles = 0;                      // tiles [0,nEarlyTiles) and their cells do not depend on processor-patch data
     std::vector<int> tile_halo_hist;          // tiles per halo-size bin of 32 slots (introspection)
     enum { kHalo128s = 192, kHalo128 = 256, kHalo64 = 384,
@@ -195,6 +196,7 @@ public:
             ex.sync();
         }
         tile_evals_per_cell = plan.evals_per_cell(); tile_colours = plan.maxColours; tile_max_halo = plan.maxHalo;
+        tile_rounds_total = (long)(plan.ent_face.size() / kRound);
         tile_halo_hist.assign(32, 0);
         for (int t = 0; t < plan.nTiles; t++) tile_halo_hist[std::min(31, (plan.halo_start[t + 1] - plan.halo_start[t]) / 32)]++;
         // the plan's host vectors are only needed for the I/O permutation, which lives on the device: release them

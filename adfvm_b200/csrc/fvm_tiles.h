@@ -27,12 +27,16 @@
 //     so patch ranges and the halo layout are untouched.
 #pragma once
 #include <algorithm>
+#include <cmath>
 #include <cstdint>
 #include <cstring>
 #include <numeric>
 #include <stdexcept>
 #include <unordered_map>
 #include <vector>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 
 namespace fvm {
 
@@ -98,14 +102,87 @@ void integrate_centres(int C, int Fi, const int* owner, const int* neigh, const 
     for (size_t i = 0; i < p.size(); i++) pos[i] = (float)p[i];
 }
 
-// recursive coordinate bisection of idx[lo,hi) into leaves of T cells (splits at multiples of T)
-inline void rcb(std::vector<int>& idx, const std::vector<float>& pos, long lo, long hi, int T) {
+// Axis-aligned lattice detection: when the cell centres of the mesh sit on planes x = x_i, y = y_j, z = z_k (uniform or
+// graded blocks, boxes with holes), lat[3c+d] = index of cell c's plane along d. Returns false for anything else
+// (warped or unstructured meshes), which then use plain coordinate bisection.
+inline bool detect_lattice(const std::vector<float>& pos, int C, std::vector<int>& lat) {
+    if (C < 64) return false;
+    lat.assign((size_t)3 * C, 0);
+    const long nsample = std::min<long>(C, 2000000);
+    std::vector<float> sample, planes;
+    for (int d = 0; d < 3; d++) {
+        sample.clear();
+        // scattered sample (a regular stride would alias with the lattice and miss whole planes); a missed plane is
+        // caught by the verification pass below, which then rejects the lattice
+        for (long i = 0; i < nsample; i++) sample.push_back(pos[3 * (size_t)(nsample == C ? i : (long)(((unsigned long long)i * 2654435761ull) % (unsigned long long)C)) + d]);
+        std::sort(sample.begin(), sample.end());
+        const float span = sample.back() - sample.front();
+        const float tol = std::max(span * 1e-5f, 1e-30f);
+        planes.clear();
+        for (size_t i = 0; i < sample.size();) {              // clusters of values closer than tol = one plane
+            size_t j = i; double sum = 0;
+            while (j < sample.size() && sample[j] - sample[i] <= tol) sum += sample[j++];
+            planes.push_back((float)(sum / (double)(j - i)));
+            i = j;
+            if (planes.size() > 8192) return false;
+        }
+        if ((double)planes.size() * planes.size() * planes.size() > 64.0 * C && planes.size() > 64) return false;   // not a lattice
+        for (long c = 0; c < C; c++) {
+            const float x = pos[3 * (size_t)c + d];
+            size_t k = std::lower_bound(planes.begin(), planes.end(), x) - planes.begin();
+            if (k == planes.size() || (k > 0 && x - planes[k - 1] < planes[k] - x)) k--;
+            if (std::fabs(x - planes[k]) > 2 * tol) return false;
+            lat[3 * (size_t)c + d] = (int)k;
+        }
+    }
+    return true;
+}
+
+// Recursive bisection of idx[lo,hi) into leaves of T cells, always splitting at a multiple of T so that every leaf but
+// the last is full. With lattice indices (lat != NULL) the cut is a lattice plane whose index, counted from the
+// range's first plane, is a multiple of 8 (else 4, 2, 1) as close to the middle as possible: blocks whose extents are
+// multiples of 4 / 8 then decompose into exact 4x4x8 tiles and 4x4x2 sub-tiles whatever the block size (a plain
+// halving of 368 = 16*23 planes ends in 23-plane slabs and ragged tiles). Ranges without such a plane, and meshes
+// without a lattice, are cut by cell count at the median coordinate (nth_element).
+inline void rcb(std::vector<int>& idx, const std::vector<float>& pos, const int* lat, long lo, long hi, int T) {
     struct Range { long lo, hi; };
     std::vector<Range> stack; stack.push_back({lo, hi});
+    std::vector<long> hist;
     while (!stack.empty()) {
         Range r = stack.back(); stack.pop_back();
         const long n = r.hi - r.lo;
         if (n <= T) continue;
+        if (lat) {
+            int mn[3] = {1 << 30, 1 << 30, 1 << 30}, mx[3] = {-1, -1, -1};
+            for (long i = r.lo; i < r.hi; i++)
+                for (int k = 0; k < 3; k++) { const int v = lat[3 * (size_t)idx[i] + k]; mn[k] = std::min(mn[k], v); mx[k] = std::max(mx[k], v); }
+            int order[3] = {0, 1, 2};
+            std::sort(order, order + 3, [&](int a, int b) { return (mx[a] - mn[a]) != (mx[b] - mn[b]) ? (mx[a] - mn[a]) > (mx[b] - mn[b]) : a < b; });
+            bool done = false;
+            for (int oi = 0; oi < 3 && !done; oi++) {
+                const int dim = order[oi], ext = mx[dim] - mn[dim] + 1;
+                if (ext < 2) break;
+                hist.assign(ext + 1, 0);
+                for (long i = r.lo; i < r.hi; i++) hist[lat[3 * (size_t)idx[i] + dim] - mn[dim] + 1]++;
+                for (int p = 1; p <= ext; p++) hist[p] += hist[p - 1];           // hist[p] = cells on planes < mn+p
+                int best = -1, bestClass = -1; long bestDist = 0;
+                for (int p = 1; p < ext; p++) {
+                    if (hist[p] % T || hist[p] == 0 || hist[p] == n) continue;
+                    if (hist[p] * 5 < n || hist[p] * 5 > 4 * n) continue;          // keep the two sides within 1:4
+                    const int cls = (p % 8 == 0) ? 3 : (p % 4 == 0) ? 2 : (p % 2 == 0) ? 1 : 0;
+                    const long dist = std::labs(2 * hist[p] - n);
+                    if (cls > bestClass || (cls == bestClass && dist < bestDist)) { best = p; bestClass = cls; bestDist = dist; }
+                }
+                if (best < 0) continue;
+                const int cut = mn[dim] + best;
+                auto mid = std::stable_partition(idx.begin() + r.lo, idx.begin() + r.hi, [&](int c) { return lat[3 * (size_t)c + dim] < cut; });
+                const long left = mid - (idx.begin() + r.lo);
+                stack.push_back({r.lo + left, r.hi});
+                stack.push_back({r.lo, r.lo + left});
+                done = true;
+            }
+            if (done) continue;
+        }
         float mn[3] = {1e30f, 1e30f, 1e30f}, mx[3] = {-1e30f, -1e30f, -1e30f};
         for (long i = r.lo; i < r.hi; i++)
             for (int k = 0; k < 3; k++) { const float v = pos[3 * (size_t)idx[i] + k]; mn[k] = std::min(mn[k], v); mx[k] = std::max(mx[k], v); }
@@ -122,6 +199,9 @@ inline void rcb(std::vector<int>& idx, const std::vector<float>& pos, long lo, l
     }
 }
 
+}  // namespace detail
+
+namespace detail {
 
 // Schedule of one sub-tile: entries -> (round, lane). home[e]/other[e]: local cell (0..31) of the entry's home /
 // of its other cell when that is in the sub-tile too (else -1); both-in entries may be re-oriented (swap).
@@ -238,18 +318,28 @@ template <typename R>
 TilePlan build_tile_plan(int C, int Fi, int F, const int* owner, const int* neigh, const int* cellFaces,
                          const R* deltas, const R* deltasUnit, const unsigned char* bkind, int T, int nLocalFaces) {
     if (T <= 0 || T > 512 || T % kRound) throw std::runtime_error("tile size out of range");
+    const bool verbose = std::getenv("ADFVM_TILE_TIMING") != nullptr;
+    auto t_start = std::chrono::steady_clock::now();
+    auto lap = [&](const char* what) { if (verbose) { auto now = std::chrono::steady_clock::now();
+        std::fprintf(stderr, "[tile plan] %-22s %.2f s\n", what, std::chrono::duration<double>(now - t_start).count()); t_start = now; } };
     TilePlan P; P.T = T; P.NW = T / kRound;
     P.nTiles = (C + T - 1) / T;
     const int NW = P.NW;
     // ---- cell order: tiles of T cells, inside a tile sub-tiles of 32 cells, inside a sub-tile ascending old ids
     std::vector<float> pos;
     detail::integrate_centres(C, Fi, owner, neigh, cellFaces, deltas, deltasUnit, pos);
+    lap("cell centres");
     P.cell_new2old.resize(C);
     std::iota(P.cell_new2old.begin(), P.cell_new2old.end(), 0);
-    detail::rcb(P.cell_new2old, pos, 0, C, T);
-    for (int t = 0; t < P.nTiles; t++) detail::rcb(P.cell_new2old, pos, (long)t * T, std::min<long>((long)(t + 1) * T, C), kRound);
+    std::vector<int> lattice;
+    const int* lat = detail::detect_lattice(pos, C, lattice) ? lattice.data() : nullptr;
+    lap("lattice detection");
+    detail::rcb(P.cell_new2old, pos, lat, 0, C, T);
+    lap("bisection into tiles");
+    for (int t = 0; t < P.nTiles; t++) detail::rcb(P.cell_new2old, pos, lat, (long)t * T, std::min<long>((long)(t + 1) * T, C), kRound);
     for (long b = 0; b < C; b += kRound)
         std::sort(P.cell_new2old.begin() + b, P.cell_new2old.begin() + std::min<long>(b + kRound, C));
+    lap("sub-tiles");
     P.nEarly = P.nTiles;
     if (nLocalFaces < F) {
         std::vector<char> rb(C, 0), late(P.nTiles, 0);
@@ -285,6 +375,7 @@ TilePlan build_tile_plan(int C, int Fi, int F, const int* owner, const int* neig
     int nextFace = 0;
     std::vector<int> faces;
     detail::SubTileSchedule sch;
+    std::unordered_map<uint64_t, std::vector<detail::SubTileSchedule>> memo;
     const int N = C + (F - Fi);
     std::vector<int> slot_of(N, -1), slot_tile(N, -1);
     P.halo_start.assign(P.nTiles + 1, 0);
@@ -320,7 +411,21 @@ TilePlan build_tile_plan(int C, int Fi, int F, const int* owner, const int* neig
                     faces.push_back(f); sch.E.push_back(e);
                 }
             }
-            sch.solve();
+            {   // sub-tiles with the same local face graph (all interior sub-tiles of a structured block) share one schedule
+                uint64_t key = 1469598103934665603ull;
+                for (const auto& e : sch.E) { key ^= (uint64_t)(e.a | (e.b + 1) << 6 | (int)e.both << 13 | e.pref << 14); key *= 1099511628211ull; }
+                auto& bucket = memo[key];
+                const detail::SubTileSchedule* hit = nullptr;
+                for (const auto& m_ : bucket) {
+                    if (m_.E.size() != sch.E.size()) continue;
+                    bool same = true;
+                    for (size_t i = 0; i < sch.E.size() && same; i++)
+                        same = m_.E[i].a == sch.E[i].a && m_.E[i].b == sch.E[i].b && m_.E[i].both == sch.E[i].both && m_.E[i].pref == sch.E[i].pref;
+                    if (same) { hit = &m_; break; }
+                }
+                if (hit) { sch.home = hit->home; sch.other = hit->other; sch.round = hit->round; sch.R = hit->R; }
+                else { sch.solve(); if (memo.size() < 65536) bucket.push_back(sch); }
+            }
             const int Rw = faces.empty() ? 0 : sch.R;
             P.maxColours = std::max(P.maxColours, Rw);
             std::vector<int> at((size_t)Rw * kRound, -1), from((size_t)Rw * kRound, -1);
@@ -353,6 +458,7 @@ TilePlan build_tile_plan(int C, int Fi, int F, const int* owner, const int* neig
         P.maxHalo = std::max(P.maxHalo, nHalo);
         P.halo_start[t + 1] = (int)P.halo_cell.size();
     }
+    lap("entries + schedules");
     if (nextFace != Fi) throw std::runtime_error("internal face not reachable from any cell (broken cellFaces)");
     return P;
 }

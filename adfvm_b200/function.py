@@ -276,6 +276,12 @@ class PrimalFunction:
         self.c.lib.check(self.c.lib.dll.adfvm_tile_stats(self.c.ctx, C.byref(a), C.byref(b), C.byref(c_), C.byref(d)))
         return a.value, b.value, c_.value, d.value
 
+    def tile_rounds(self):
+        """(rounds summed over all sub-tiles, sub-tiles, early tiles): rounds/sub-tiles = 4.0 on a regular hex block"""
+        a, b, e = C.c_int64(), C.c_int64(), C.c_int32()
+        self.c.lib.check(self.c.lib.dll.adfvm_tile_rounds(self.c.ctx, C.byref(a), C.byref(b), C.byref(e)))
+        return a.value, b.value, e.value
+
     def tile_halo_stats(self):
         """(largest tile halo, kernel variant, tiles per halo-size bin of 32 slots)"""
         a, b = C.c_int32(), C.c_int32()

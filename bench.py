@@ -17,6 +17,7 @@ periodic box, halo over NCCL inside the library.
 import argparse
 import json
 import os
+import resource
 import subprocess
 import sys
 import threading
@@ -109,6 +110,38 @@ def cpu_oracle_rate(n, steps=1, dtype=np.float64):
             torch.get_num_threads(), tp + ta)
 
 
+HOST_BYTES_PER_CELL = 1100          # numpy inputs (mesh metrics, connectivity, state) + pinned buffers + tile plan, measured at 368^3
+
+
+def host_memory_available():
+    """bytes of host memory this job may still use (cgroup limit aware)"""
+    avail = None
+    try:
+        import psutil
+        avail = psutil.virtual_memory().available
+    except Exception:
+        pass
+    try:
+        mx = open("/sys/fs/cgroup/memory.max").read().strip()
+        cur = int(open("/sys/fs/cgroup/memory.current").read().strip())
+        if mx != "max":
+            lim = int(mx) - cur
+            avail = lim if avail is None else min(avail, lim)
+    except Exception:
+        pass
+    return avail
+
+
+def default_size(world):
+    """368^3 per GPU (BASELINE.json config 5) unless the host cannot hold the inputs of all ranks; then 256^3, said in config"""
+    n, note = 368, None
+    avail = host_memory_available()
+    need = HOST_BYTES_PER_CELL * 368 ** 3 * world * 1.25
+    if avail is not None and avail < need:
+        n, note = 256, "host memory %.0f GB < %.0f GB needed for %d ranks at 368^3: 256^3 per GPU instead" % (avail / 1e9, need / 1e9, world)
+    return n, note
+
+
 def run_reference(args, rank):
     if rank != 0:
         return
@@ -134,13 +167,18 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--size", dest="n", type=int, default=int(os.environ.get("ADFVM_BENCH_N", "256")), help="cells per side per GPU")
+    ap.add_argument("--size", dest="n", type=int, default=int(os.environ.get("ADFVM_BENCH_N", "0")),
+                    help="cells per side per GPU (default: 368 = the ~50M cells/GPU of BASELINE.json config 5, or 256 when the "
+                         "host memory cannot hold the input arrays of all ranks)")
     ap.add_argument("--dtype", default="f64", choices=["f64", "f32"])
     ap.add_argument("--cpu-n", type=int, default=64, help="box size of the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    size_note = None
+    if args.n <= 0 and (args.impl == "reference" or world == 1):
+        args.n, size_note = default_size(max(world, args.gpus if args.impl == "reference" else 1))
     if args.impl == "reference":
         run_reference(args, rank)
         return
@@ -156,6 +194,10 @@ def main():
     s = np.dtype(dtype).itemsize
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        if args.n <= 0:                       # rank 0 decides, everybody follows
+            box = [default_size(world) if rank == 0 else None]
+            dist.broadcast_object_list(box, src=0)
+            args.n, size_note = box[0]
     W = max(args.warmup, 3)
     K = args.steps
 
@@ -298,7 +340,8 @@ def main():
             "config": {"workload": "periodic_hex_box_n%d" % args.n, "cells_per_gpu": C, "rk_stages": 3,
                        "step": "1 primal step + 1 adjoint step (incl. forward recompute)",
                        "l2": "working set per step (%.0f MB) exceeds the 126 MB L2; no explicit flush" % (f.device_bytes / 1e6),
-                       "device_bytes": f.device_bytes},
+                       "device_bytes": f.device_bytes, "host_rss_gb": round(resource.getrusage(resource.RUSAGE_SELF).ru_maxrss / 1e6, 1),
+                       "size_note": size_note},
             "primal": vp, "adjoint": va, "primal_ms": tp_ms / K, "adjoint_ms": ta_ms / K,
             "e2e": {"value": 2 * 3 * cells_total * e2e_K / e2e_s / 1e6, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
                     "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_s * 1e3 / e2e_K,

@@ -120,6 +120,10 @@ int adfvm_tile_stats(adfvm_ctx* ctx, double* evals_per_cell, int32_t* max_colour
  * histogram of tiles per halo size in bins of 32 slots */
 int adfvm_tile_halo_stats(adfvm_ctx* ctx, int32_t* max_halo, int32_t* variant, int32_t* hist, int32_t nbins);
 
+/* rounds (32 lanes, one face evaluation each) summed over all sub-tiles, the number of sub-tiles, and the number of
+ * tiles that do not depend on processor-patch data (the range that overlaps the halo exchange) */
+int adfvm_tile_rounds(adfvm_ctx* ctx, int64_t* rounds, int64_t* subtiles, int32_t* early_tiles);
+
 /* per-kernel device timing (CUDA events on the launching stream around every launch while enabled).
  * adfvm_kernel_report writes lines "<kernel> <launches> <total_ms>\n" into buf. Counterpart of the reference's
  * `-o/--profile` per-kernel prints (adpy/adpy/variable.py:437-467). */
