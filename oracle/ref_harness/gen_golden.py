@@ -298,9 +298,9 @@ def run(cmd, cwd):
     subprocess.check_call(cmd, cwd=cwd)
 
 
-def generate(name, fp32=False):
+def write_case(name, tag):
+    """case directory (mesh, fields, case file) of one golden case under SCRATCH; returns (dict, case dir, case file)"""
     c = CASES[name]()
-    tag = name + ("_fp32" if fp32 else "")
     case = os.path.join(SCRATCH, tag)
     if os.path.exists(case):
         shutil.rmtree(case)
@@ -313,6 +313,33 @@ def generate(name, fp32=False):
         f.write(CASEFILE_HEAD + c["objective"] + CASEFILE_TAIL.format(
             case=case, rcf_extra=c["rcf_extra"], mid=c["mid"], amp=c["amp"], width=c["width"],
             nSteps=c["nSteps"], writeInterval=c["writeInterval"], dt=c["dt"]))
+    return c, case, casefile
+
+
+def run_dropin(name, lib, runs=("orig", "perturb", "adjoint")):
+    """Run the reference's own drivers (apps/problem.py, apps/adjoint.py, unmodified) on a golden case with their
+    compiled `primal` / `primal_grad` functions replaced by adfvm_b200's Function objects over the native library
+    `lib` (refshim drop-in mode). Returns the lines of objective.txt the reference wrote."""
+    c, case, casefile = write_case(name, name + "_dropin")
+    env = dict(os.environ, ADFVM_DROPIN_LIB=lib, ADFVM_DROPIN_OBJECTIVE=json.dumps(c["obj_spec"]))
+    runner = os.path.join(HERE, "run_ref.py")
+    py = sys.executable
+    for r in runs:
+        app = "adjoint" if r == "adjoint" else "problem"
+        argv = [casefile, "-c"] + (["perturb"] if r == "perturb" else [])
+        print("+ drop-in", r, flush=True)
+        out = subprocess.run([py, runner, app, os.path.join(case, "rec_%s.npz" % r), "--"] + argv, cwd=case, env=env,
+                             stdout=subprocess.PIPE, text=True, check=True).stdout
+        served = [l for l in out.split("\n") if l.startswith("[dropin] served")]
+        assert served and int(served[-1].split()[2]) > 0, "the drop-in functions were not called"
+        print(served[-1], flush=True)
+    with open(os.path.join(case, "objective.txt")) as f:
+        return f.read().strip().split("\n")
+
+
+def generate(name, fp32=False):
+    tag = name + ("_fp32" if fp32 else "")
+    c, case, casefile = write_case(name, tag)
     runner = os.path.join(HERE, "run_ref.py")
     flag = ["--fp32"] if fp32 else []
     py = sys.executable
