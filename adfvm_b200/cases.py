@@ -143,3 +143,77 @@ def walled_box(n=(8, 6, 4), dtype=np.float64, warp=0.02, dt=2e-6, nonuniform=Tru
               ("p", "inlet", "Tt"): (305 + v(nin)).reshape(-1, 1), ("p", "inlet", "pt"): (103000 + 100 * v(nin)).reshape(-1, 1)}
     spec = _spec(mesh, bcs, {"kind": "drag", "patch": "lid", "direction": 0}, mu={"law": "constant", "value": 2.5e-5})
     return Case(mesh, spec, conservative(U, T, p), gaussian_source(cc, (1.0, 0.5, 0.25), 1e2, 20.), bcvals, dt, dtype)
+
+
+def cylinder2d(nr=185, nt=250, dtype=np.float64, dt=2e-9):
+    """2-D laminar cylinder at the size of the reference's cases/cylinder mesh (C = 46 250 cells, BASELINE.json config 2;
+    the shipped blockMeshDict cannot be meshed here and its outlet BC has no class in BCs.py): half annulus around a
+    cylinder of radius 0.5 mm, geometric radial spacing, one cell in the span with cyclic z1/z2, no-slip wall,
+    CBC_UPT far field with the Lax-Friedrichs boundary solver, symmetry planes on the axis, mu = 2.5e-5, drag
+    objective (templates/cylinder.py:9-19). Same set-up as the golden fixture `cyl2d` (12 x 16 cells)."""
+    r0, r1 = 0.5e-3, 8e-3
+
+    def warp(p):
+        r = r0 * (r1 / r0) ** p[:, 0]
+        th = np.pi * p[:, 1]
+        return np.stack([r * np.cos(th), r * np.sin(th), p[:, 2]], axis=1)
+    poly = hexmesh.box_mesh((nr, nt, 1), (0., 0., 0.), (1., 1., 2e-4), warp=warp, patches=[
+        ("cylinder", "patch", ["x-"], {}), ("far", "patch", ["x+"], {}), ("axis", "symmetryPlane", ["y-", "y+"], {}),
+        ("z1", "cyclic", ["z-"], {"neighbourPatch": "z2"}), ("z2", "cyclic", ["z+"], {"neighbourPatch": "z1"})])
+    mesh = build_mesh(poly)
+    mesh.boundary["far"]["type"] = "characteristic"          # what CBC_UPT.__init__ does (BCs.py:142)
+    C = mesh.nInternalCells
+    cc = mesh.cellCentres[:C]
+    r = np.linalg.norm(cc[:, :2], axis=1)
+    th = np.arctan2(cc[:, 1], cc[:, 0])
+    U0 = 33.
+    f = 1 - (r0 / r) ** 2
+    U = np.stack([U0 * (1 - (r0 / r) ** 2 * np.cos(2 * th)) * f, -U0 * (r0 / r) ** 2 * np.sin(2 * th) * f, 0 * r], axis=1)
+    T = (300 + 2 * np.exp(-((r - r0) / 1e-3) ** 2)).reshape(-1, 1)
+    p = (101325 + 0.5 * 1.17 * (U0 ** 2 - (U ** 2).sum(axis=1))).reshape(-1, 1)
+    k0 = {"keys": []}
+    cyc = {"z1": dict(type="cyclic", **k0), "z2": dict(type="cyclic", **k0)}
+    bcs = {"U": dict(cyc, cylinder={"type": "fixedValue", "keys": ["value"]}, far=dict(type="calculated", **k0), axis=dict(type="symmetryPlane", **k0)),
+           "T": dict(cyc, cylinder=dict(type="zeroGradient", **k0), far=dict(type="calculated", **k0), axis=dict(type="symmetryPlane", **k0)),
+           "p": dict(cyc, cylinder=dict(type="zeroGradient", **k0), far={"type": "CBC_UPT", "keys": ["U0", "T0", "p0"]}, axis=dict(type="symmetryPlane", **k0))}
+    ncyl, nfar = mesh.boundary["cylinder"]["nFaces"], mesh.boundary["far"]["nFaces"]
+    Ufar = np.zeros((nfar, 3)); Ufar[:, 0] = U0
+    bcvals = {("U", "cylinder", "value"): np.zeros((ncyl, 3)), ("p", "far", "U0"): Ufar,
+              ("p", "far", "T0"): np.full((nfar, 1), 300.), ("p", "far", "p0"): np.full((nfar, 1), 101325.)}
+    spec = _spec(mesh, bcs, {"kind": "drag", "patch": "cylinder", "direction": 0}, mu={"law": "constant", "value": 2.5e-5},
+                 briemann="eulerLaxFriedrichs")
+    return Case(mesh, spec, conservative(U, T, p), gaussian_source(cc, (-0.8e-3, 0.1e-3, 1e-4), 1e-1, 2.5e6), bcvals, dt, dtype)
+
+
+def forward_step(nx=240, ny=80, dtype=np.float64, dt=1e-4):
+    """Mach-3 forward-facing step at the size of the reference's cases/forwardStep mesh (C = 16 128 cells, BASELINE.json
+    config 3): box [0,3]x[0,1] minus the step x > 0.6, y < 0.2, one cell in the span with `empty` faces, Cp = 2.5,
+    inviscid, fixedValue inlet, inletOutlet (= zeroGradient, BCs.py:137) outlet, symmetryPlane top/bottom, slip
+    (= symmetryPlane, BCs.py:135) obstacle, pressure-force objective on the obstacle (templates/forwardStep.py); BC types
+    are given by the names of the classes they resolve to, as the reference's own objects report them. Same set-up as the golden fixture `step2d` (30 x 10 cells)."""
+    lo, hi = (0., 0., -0.05), (3., 1., 0.05)
+    K, J, I = np.meshgrid(np.arange(1), np.arange(ny), np.arange(nx), indexing="ij")
+    keep = ~((I >= nx // 5) & (J < ny // 5))
+    poly = hexmesh.masked_box_mesh((nx, ny, 1), lo, hi, keep, [
+        ("inlet", "patch", ["x-"], {}), ("outlet", "patch", ["x+"], {}), ("bottom", "symmetryPlane", ["y-"], {}),
+        ("top", "symmetryPlane", ["y+"], {}), ("defaultFaces", "empty", ["z-", "z+"], {})], hole=("obstacle", "patch", {}))
+    mesh = build_mesh(poly)
+    C = mesh.nInternalCells
+    cc = mesh.cellCentres[:C]
+    s = np.sin(2 * np.pi * cc[:, 0] / 3.) * np.cos(np.pi * cc[:, 1])
+    U = np.stack([3. + 0.05 * s, 0.02 * s, 0 * s], axis=1)
+    T = (1. + 0.01 * s).reshape(-1, 1)
+    p = (1. + 0.02 * s).reshape(-1, 1)
+    k0 = {"keys": []}
+    fv = {"type": "fixedValue", "keys": ["value"]}
+    bcs = {"U": {"inlet": fv, "outlet": dict(type="zeroGradient", **k0), "bottom": dict(type="symmetryPlane", **k0),
+                 "top": dict(type="symmetryPlane", **k0), "obstacle": dict(type="symmetryPlane", **k0), "defaultFaces": dict(type="zeroGradient", **k0)},
+           "T": {"inlet": fv, "outlet": dict(type="zeroGradient", **k0), "bottom": dict(type="symmetryPlane", **k0),
+                 "top": dict(type="symmetryPlane", **k0), "obstacle": dict(type="zeroGradient", **k0), "defaultFaces": dict(type="zeroGradient", **k0)},
+           "p": {"inlet": fv, "outlet": dict(type="zeroGradient", **k0), "bottom": dict(type="symmetryPlane", **k0),
+                 "top": dict(type="symmetryPlane", **k0), "obstacle": dict(type="zeroGradient", **k0), "defaultFaces": dict(type="zeroGradient", **k0)}}
+    nin = mesh.boundary["inlet"]["nFaces"]
+    Uin = np.zeros((nin, 3)); Uin[:, 0] = 3.
+    bcvals = {("U", "inlet", "value"): Uin, ("T", "inlet", "value"): np.ones((nin, 1)), ("p", "inlet", "value"): np.ones((nin, 1))}
+    spec = _spec(mesh, bcs, {"kind": "patch_pA", "patch": "obstacle"}, mu={"law": "constant", "value": 0.}, Cp=2.5)
+    return Case(mesh, spec, conservative(U, T, p, Cp=2.5), gaussian_source(cc, (0.3, 0.3, 0.), 1e-2, 20.), bcvals, dt, dtype)

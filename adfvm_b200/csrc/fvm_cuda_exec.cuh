@@ -4,6 +4,7 @@
 // the 148 SMs stay covered by several waves; reductions are two-pass fixed-order trees (deterministic).
 #pragma once
 #include <cuda_runtime.h>
+#include <cstdlib>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -101,12 +102,53 @@ struct CudaExec {
         timing->recs.clear();
     }
 
+    // ---- CUDA graphs of whole steps: small meshes (the shipped cases: 500 - 50 000 cells) are bound by the launch
+    // latency of the ~20 (primal) / ~45 (adjoint) kernels of a step. A step with a given key (time step, buffer
+    // rotation, ...) runs eagerly the first time, is captured the second time and replayed from then on.
+    struct GraphEntry { cudaGraphExec_t exec = nullptr; long launches = 0; int seen = 0; };
+    struct Graphs { bool enabled = true; bool capturing = false; std::map<std::vector<unsigned long long>, GraphEntry> cache; };
+    Graphs* graphs = nullptr;    // shared by copies of the executor
+    // (the legacy default stream cannot be captured: graphs need a context created on an explicit stream)
+    bool graph_usable() const { return stream != nullptr && graphs && graphs->enabled && !graphs->capturing && !(timing && timing->on); }
+    bool graph_launch(const std::vector<unsigned long long>& key, long& launches) {
+        auto it = graphs->cache.find(key);
+        if (it == graphs->cache.end() || !it->second.exec) return false;
+        FVM_CUDA_CHECK(cudaGraphLaunch(it->second.exec, stream));
+        launches = it->second.launches;
+        return true;
+    }
+    bool graph_first_time(const std::vector<unsigned long long>& key) {
+        if (graphs->cache.size() > 64) { for (auto& kv : graphs->cache) if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec); graphs->cache.clear(); }
+        return graphs->cache[key].seen++ == 0;
+    }
+    bool graph_begin() {
+        if (cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) { cudaGetLastError(); graphs->enabled = false; return false; }
+        graphs->capturing = true;
+        return true;
+    }
+    // ends the capture, instantiates and launches the graph once; false (graphs disabled) if anything failed: the caller
+    // then runs the step eagerly
+    bool graph_end_launch(const std::vector<unsigned long long>& key, long launches) {
+        graphs->capturing = false;
+        cudaGraph_t g = nullptr;
+        cudaGraphExec_t e = nullptr;
+        if (cudaStreamEndCapture(stream, &g) != cudaSuccess || !g || cudaGraphInstantiate(&e, g, 0) != cudaSuccess) {
+            cudaGetLastError(); if (g) cudaGraphDestroy(g); graphs->enabled = false; return false;
+        }
+        cudaGraphDestroy(g);
+        GraphEntry& ge = graphs->cache[key]; ge.exec = e; ge.launches = launches;
+        FVM_CUDA_CHECK(cudaGraphLaunch(e, stream));
+        return true;
+    }
+
     void init(int dev, void* strm) {
         device = dev;
         FVM_CUDA_CHECK(cudaSetDevice(dev));
         stream = (cudaStream_t)strm;
         FVM_CUDA_CHECK(cudaMalloc(&partial, kRedMaxBlocks * sizeof(double)));
         timing = new Timing();
+        graphs = new Graphs();
+        if (const char* e = getenv("ADFVM_NO_GRAPH")) graphs->enabled = !(e[0] && e[0] != '0');
     }
     void* stream_handle() const { return (void*)stream; }
     void* alloc(size_t bytes) { void* p = nullptr; FVM_CUDA_CHECK(cudaMalloc(&p, bytes ? bytes : 1)); return p; }

@@ -51,6 +51,8 @@ public:
     std::vector<PatchDev<R>> patches_dev_h;  // host mirror of the device table
     HaloComm<R>* comm = nullptr;
     long launches = 0;                        // kernels launched so far (bench "gpu_launches")
+    long graph_replays = 0;                   // steps served by replaying a captured CUDA graph (introspection)
+    unsigned long long epoch = 0;             // bumped by every set_* call: part of the CUDA-graph keys (kernel arguments are baked into graphs)
     long bytes_allocated = 0;
 
     // device buffers
@@ -91,6 +93,7 @@ public:
         return dst;
     }
     void set_physics(double gamma, double Cp, double Pr, int mu_law, double mu_value, int riemann, int briemann) {
+        epoch++;
         ph.gamma = (R)gamma; ph.Cp = (R)Cp; ph.Pr = (R)Pr; ph.Cv = (R)(Cp / gamma);
         ph.gm1 = (R)(gamma - 1.); ph.iCv = (R)(gamma / Cp); ph.iCvgm1 = (R)(gamma / (Cp * (gamma - 1.)));
         ph.g_gm1 = (R)(gamma / (gamma - 1.)); ph.CpPr = (R)(Cp / Pr);
@@ -246,6 +249,7 @@ public:
     // BC value arrays (static inputs created by BoundaryCondition.createInput, adFVM/BCs.py:45-54); host AoS [nFaces][d]
     enum BCKey { KEY_VALUE_U = 0, KEY_VALUE_T, KEY_VALUE_P, KEY_U0, KEY_T0, KEY_P0, KEY_TT, KEY_PT, KEY_DIR };
     void set_bc_value(int patch, int key, const R* host) {
+        epoch++;
         if (patch < 0 || patch >= (int)patches.size()) throw std::runtime_error("bad patch index");
         const int n = patches[patch].nFaces;
         const int d = (key == KEY_VALUE_U || key == KEY_U0 || key == KEY_DIR) ? 3 : 1;
@@ -272,6 +276,7 @@ public:
         }
     }
     void set_objective(int kind, int patch, int dir) {
+        epoch++;
         if (kind != OBJ_NONE && kind != OBJ_CELL_TV && (patch < 0 || patch >= (int)patches.size())) throw std::runtime_error("objective patch out of range");
         obj.kind = kind; obj.patch = patch; obj.dir = dir;
     }
@@ -377,17 +382,36 @@ public:
         run_tiles_range(t0, nt, fb);
     }
 
+    // runs `body` (a whole step: kernel launches on the executor's stream only, no host synchronisation) as a CUDA graph
+    // keyed by everything the launches depend on; eager on the first occurrence of a key and wherever graphs do not apply
+    // (multi-rank steps use a second stream and NCCL, per-kernel timing records events)
+    static unsigned long long bits(double v) { unsigned long long u; std::memcpy(&u, &v, 8); return u; }
+    template <class F> void with_graph(const std::vector<unsigned long long>& key, F&& body) {
+        if (!ex.graph_usable() || comm || m.nRemoteCells > 0) { body(); return; }
+        long n = 0;
+        if (ex.graph_launch(key, n)) { launches += n; graph_replays++; return; }
+        if (ex.graph_first_time(key) || !ex.graph_begin()) { body(); return; }
+        const long l0 = launches;
+        body();
+        if (!ex.graph_end_launch(key, launches - l0)) { launches = l0; body(); }
+    }
+
     // primal step; state W[0] -> W[0]. keep=true keeps every stage (Q[s], G[s], W[s]) for the reverse sweep.
     void primal_step(R dt, bool keep = false) {
         if (!have_mesh || !have_state) throw std::runtime_error("mesh/state not set");
         check_bcs();
         if (keep) ensure_adjoint_buffers();
-        for (int s = 0; s < 3; s++) {
-            R* Qs = keep ? Q[s] : Q[s % 2];
-            R* Gs = keep ? G[s] : G[0];
-            R* Qn = (s < 2) ? (keep ? Q[s + 1] : Q[(s + 1) % 2]) : nullptr;
-            stage(s, dt, Qs, Gs, Qn, s == 1 && !keep, !(keep && s == 2));
-        }
+        auto body = [&]() {
+            for (int s = 0; s < 3; s++) {
+                R* Qs = keep ? Q[s] : Q[s % 2];
+                R* Gs = keep ? G[s] : G[0];
+                R* Qn = (s < 2) ? (keep ? Q[s + 1] : Q[(s + 1) % 2]) : nullptr;
+                stage(s, dt, Qs, Gs, Qn, s == 1 && !keep, !(keep && s == 2));
+            }
+        };
+        if (keep) body();                          // part of the adjoint step's graph
+        else with_graph({1ull, epoch, bits((double)dt), (unsigned long long)W[0], (unsigned long long)W[3], (unsigned long long)obj.kind,
+                         (unsigned long long)obj.patch, (unsigned long long)obj.dir, (unsigned long long)patches_dev}, body);
         if (!keep) { R* t = W[0]; W[0] = W[3]; W[3] = t; }
     }
     // dtc (max over ranks not applied here: the reference returns the rank-local max, adFVM/density.py:405-413)
@@ -420,6 +444,10 @@ public:
     void adjoint_step_resident(R dt, R obja, bool chain) {
         ensure_adjoint_buffers();
         if (chain) { R* t = A[0]; A[0] = A[3]; A[3] = t; }
+        with_graph({2ull, epoch, bits((double)dt), bits((double)obja), (unsigned long long)W[0], (unsigned long long)A[0], (unsigned long long)A[3],
+                    (unsigned long long)obj.kind, (unsigned long long)obj.patch, (unsigned long long)obj.dir}, [&]() { adjoint_step_body(dt, obja); });
+    }
+    void adjoint_step_body(R dt, R obja) {
         primal_step(dt, true);
         const int C = m.nInternalCells;
         for (int s = 2; s >= 0; s--) {

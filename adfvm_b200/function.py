@@ -358,6 +358,11 @@ class PrimalFunction:
         return int(self.c.lib.dll.adfvm_launch_count(self.c.ctx))
 
     @property
+    def graph_replays(self):
+        """steps served by replaying a captured CUDA graph"""
+        return int(self.c.lib.dll.adfvm_graph_replays(self.c.ctx))
+
+    @property
     def device_bytes(self):
         return int(self.c.lib.dll.adfvm_device_bytes(self.c.ctx))
 

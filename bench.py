@@ -208,7 +208,8 @@ def main():
     else:
         case = cases.periodic_box(args.n, dtype)
     C = case.mesh.nInternalCells
-    stream = torch.cuda.current_stream().cuda_stream
+    torch.cuda.set_stream(torch.cuda.Stream())            # an explicit stream (events below are recorded on it); the legacy
+    stream = torch.cuda.current_stream().cuda_stream      # default stream would rule out the CUDA graphs of whole steps
     f = function.PrimalFunction(case.spec, dtype, device=local, stream=stream)
     fa = f.grad()
     if world > 1:

@@ -120,6 +120,10 @@ int adfvm_tile_stats(adfvm_ctx* ctx, double* evals_per_cell, int32_t* max_colour
  * histogram of tiles per halo size in bins of 32 slots */
 int adfvm_tile_halo_stats(adfvm_ctx* ctx, int32_t* max_halo, int32_t* variant, int32_t* hist, int32_t nbins);
 
+/* whole steps are captured into CUDA graphs (the second time a step with the same time step and buffer rotation runs)
+ * and replayed afterwards; number of steps served by a replay so far (set ADFVM_NO_GRAPH=1 to run every step eagerly) */
+int64_t adfvm_graph_replays(adfvm_ctx* ctx);
+
 /* rounds (32 lanes, one face evaluation each) summed over all sub-tiles, the number of sub-tiles, and the number of
  * tiles that do not depend on processor-patch data (the range that overlaps the halo exchange) */
 int adfvm_tile_rounds(adfvm_ctx* ctx, int64_t* rounds, int64_t* subtiles, int32_t* early_tiles);

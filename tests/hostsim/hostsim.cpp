@@ -31,6 +31,11 @@ struct HostExec {
         #pragma omp parallel for schedule(static)
         for (int i = first; i < first + n; i++) b(i);
     }
+    bool graph_usable() const { return false; }
+    bool graph_launch(const std::vector<unsigned long long>&, long&) { return false; }
+    bool graph_first_time(const std::vector<unsigned long long>&) { return true; }
+    bool graph_begin() { return false; }
+    bool graph_end_launch(const std::vector<unsigned long long>&, long) { return false; }
     void side_begin() {}
     void side_end() {}
     void join() {}

@@ -77,6 +77,43 @@ def test_bitwise_deterministic(cudalib):
         assert np.array_equal(a, b)
 
 
+def test_graph_replay_matches_eager(cudalib):
+    """whole steps run eagerly the first time, are captured into a CUDA graph the second time and replayed afterwards
+    (per buffer rotation): same inputs must give identical bits in all three modes, primal and adjoint"""
+    import torch
+    case = cases.walled_box((10, 8, 4))
+    stream = torch.cuda.Stream()                      # the legacy default stream cannot be captured
+    f = function.PrimalFunction(case.spec, np.float64, stream=stream.cuda_stream)
+    fa = f.grad()
+    adj = _adj_seed(case)
+    outs, grads = [], []
+    for rep in range(8):
+        out = f(*case.inputs(), replace_reusable=True, return_reusable=True)
+        outs.append([o.copy() for o in out])
+        g = fa(*case.adjoint_inputs(case.state, adj), return_static=True, zero_static=True)
+        grads.append([x.copy() for x in g])
+    for rep in range(1, 8):
+        for a, b in zip(outs[0], outs[rep]):
+            assert np.array_equal(a, b), rep
+        for a, b in zip(grads[0], grads[rep]):
+            assert np.array_equal(a, b), rep
+    assert f.graph_replays >= 4, f.graph_replays          # the later repetitions really were replays
+    # resident stepping (the replayed path) against one host round trip per step
+    f2 = function.PrimalFunction(case.spec, np.float64)
+    state = case.state
+    for s in range(7):
+        out = f2(*case.inputs(state), replace_reusable=True, return_reusable=True)
+        state = list(out[:3])
+    f3 = function.PrimalFunction(case.spec, np.float64, stream=stream.cuda_stream)
+    f3(*case.inputs(), replace_reusable=True, return_reusable=False)
+    for s in range(5):
+        f3.step_resident(case.dt)
+    out3 = f3(*case.inputs(), replace_reusable=False, return_reusable=True)
+    assert f3.graph_replays >= 1
+    for a, b in zip(out3, out):
+        assert np.array_equal(a, b)
+
+
 def test_resident_equals_host_roundtrip(cudalib):
     case = cases.periodic_box(20)
     f1 = function.PrimalFunction(case.spec, np.float64)
