@@ -153,7 +153,9 @@ def run_reference(args, rank):
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": secs * 1e3 / max(1, min(args.steps, 3)), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "periodic_hex_box_n%d" % args.n, "cells_per_gpu": args.n ** 3, "rk_stages": 3},
+            "config": {"workload": "periodic_hex_box_n%d" % args.n, "cells_per_gpu": args.n ** 3, "rk_stages": 3,
+                       "step": "1 primal step + 1 adjoint step (incl. forward recompute)",
+                       "sample": "each step = one primal + adjoint step of a %d^3 box of the same workload on the host cores" % n},
             "primal": vp, "adjoint": va,
             "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                              "sample": "oracle port (torch CPU fp64), %d^3 periodic box, %d primal+adjoint steps" % (n, max(1, min(args.steps, 3)))},
@@ -171,7 +173,7 @@ def main():
                     help="cells per side per GPU (default: 368 = the ~50M cells/GPU of BASELINE.json config 5, or 256 when the "
                          "host memory cannot hold the input arrays of all ranks)")
     ap.add_argument("--dtype", default="f64", choices=["f64", "f32"])
-    ap.add_argument("--cpu-n", type=int, default=64, help="box size of the bounded CPU-baseline sample")
+    ap.add_argument("--cpu-n", type=int, default=112, help="box size of the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
