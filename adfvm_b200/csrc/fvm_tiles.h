@@ -424,7 +424,7 @@ TilePlan build_tile_plan(int C, int Fi, int F, const int* owner, const int* neig
                     if (same) { hit = &m_; break; }
                 }
                 if (hit) { sch.home = hit->home; sch.other = hit->other; sch.round = hit->round; sch.R = hit->R; }
-                else { sch.solve(); if (memo.size() < 65536) bucket.push_back(sch); }
+                else { sch.solve(); if (memo.size() < 8192) bucket.push_back(sch); }
             }
             const int Rw = faces.empty() ? 0 : sch.R;
             P.maxColours = std::max(P.maxColours, Rw);

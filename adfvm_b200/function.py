@@ -271,7 +271,7 @@ class PrimalFunction:
         self.c = _Context(spec, precision, device, stream, lib, tile_cells)
 
     def tile_stats(self):
-        """(flux evaluations per cell, max colours per tile, tiles, cells per tile) of the device layout"""
+        """(flux evaluations per cell, most rounds of a sub-tile, tiles, cells per tile) of the device layout"""
         a, b, c_, d = C.c_double(), C.c_int32(), C.c_int32(), C.c_int32()
         self.c.lib.check(self.c.lib.dll.adfvm_tile_stats(self.c.ctx, C.byref(a), C.byref(b), C.byref(c_), C.byref(d)))
         return a.value, b.value, c_.value, d.value

@@ -112,9 +112,9 @@ int64_t adfvm_device_bytes(adfvm_ctx* ctx);
 /* Tiling of the flux kernels (internal data layout): cells are regrouped into tiles of `cells`
  * consecutive cells, one CTA per tile. adfvm_set_tile_cells (64 or 128; default 128, with automatic fallback to 64 on 1-D/2-D meshes) must precede adfvm_set_mesh.
  * adfvm_tile_stats reports flux evaluations per cell (3 = every face once, 6 = cell-centred gather), the largest
- * number of colours of a tile, the number of tiles and the tile size. */
+ * number of rounds of a 32-cell sub-tile (4 on a regular hex block), the number of tiles and the tile size. */
 int adfvm_set_tile_cells(adfvm_ctx* ctx, int32_t cells);
-int adfvm_tile_stats(adfvm_ctx* ctx, double* evals_per_cell, int32_t* max_colours, int32_t* n_tiles, int32_t* tile_cells);
+int adfvm_tile_stats(adfvm_ctx* ctx, double* evals_per_cell, int32_t* max_rounds, int32_t* n_tiles, int32_t* tile_cells);
 
 /* largest halo (slots beyond the tile's own cells) of any tile, the kernel variant chosen from it and a
  * histogram of tiles per halo size in bins of 32 slots */
