@@ -108,7 +108,9 @@ void integrate_centres(int C, int Fi, const int* owner, const int* neigh, const 
 inline bool detect_lattice(const std::vector<float>& pos, int C, std::vector<int>& lat) {
     if (C < 64) return false;
     lat.assign((size_t)3 * C, 0);
-    const long nsample = std::min<long>(C, 2000000);
+    long cap = 2000000;
+    if (const char* e = std::getenv("ADFVM_LATTICE_SAMPLE")) cap = std::max(64L, std::atol(e));     // tests exercise the sampling path on small meshes
+    const long nsample = std::min<long>(C, cap);
     std::vector<float> sample, planes;
     for (int d = 0; d < 3; d++) {
         sample.clear();
