@@ -36,7 +36,8 @@ EXPORTS = ["adfvm_last_error", "adfvm_version", "adfvm_is_cuda", "adfvm_create",
            "adfvm_primal_grad", "adfvm_primal_step_resident", "adfvm_adjoint_step_resident", "adfvm_get_dtc_obj",
            "adfvm_get_state", "adfvm_sync", "adfvm_launch_count", "adfvm_device_bytes", "adfvm_comm_unique_id",
            "adfvm_comm_init", "adfvm_kernel_timing", "adfvm_kernel_report", "adfvm_set_tile_cells", "adfvm_tile_stats", "adfvm_tile_halo_stats",
-           "adfvm_host_alloc", "adfvm_host_free", "adfvm_tile_rounds", "adfvm_graph_replays"]
+           "adfvm_host_alloc", "adfvm_host_free", "adfvm_tile_rounds", "adfvm_graph_replays",
+           "adfvm_set_state", "adfvm_primal_block", "adfvm_adjoint_block", "adfvm_set_adjoint", "adfvm_get_adjoint"]
 
 
 class Lib:
@@ -74,6 +75,11 @@ class Lib:
         d.adfvm_comm_unique_id.argtypes = [vp]
         d.adfvm_host_alloc.argtypes = [C.POINTER(vp), C.c_size_t]
         d.adfvm_host_free.argtypes = [vp]
+        d.adfvm_primal_block.argtypes = [vp, i32, C.POINTER(f64), C.POINTER(f64), C.POINTER(f64)]
+        d.adfvm_adjoint_block.argtypes = [vp, i32, C.POINTER(f64), f64]
+        d.adfvm_set_adjoint.argtypes = [vp, vp, vp, vp]
+        d.adfvm_set_state.argtypes = [vp, vp, vp, vp]
+        d.adfvm_get_adjoint.argtypes = [vp, vp, vp, vp, vp, vp, vp, i32]
         d.adfvm_graph_replays.argtypes = [vp]; d.adfvm_graph_replays.restype = C.c_int64
         d.adfvm_tile_rounds.argtypes = [vp, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(i32)]
         d.adfvm_comm_init.argtypes = [vp, vp, i32, i32]

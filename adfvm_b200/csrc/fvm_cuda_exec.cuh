@@ -156,6 +156,7 @@ struct CudaExec {
     void zero(void* p, size_t bytes) { if (bytes) FVM_CUDA_CHECK(cudaMemsetAsync(p, 0, bytes, stream)); }
     void upload(void* dst, const void* src, size_t bytes) { if (bytes) FVM_CUDA_CHECK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, stream)); }
     void download(void* dst, const void* src, size_t bytes) { if (bytes) FVM_CUDA_CHECK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, stream)); }
+    void copy(void* dst, const void* src, size_t bytes) { if (bytes) FVM_CUDA_CHECK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, stream)); }
     void sync() { FVM_CUDA_CHECK(cudaStreamSynchronize(stream)); }
 
     template <class Body> void run(int n, const Body& b) { run_range(0, n, b); }

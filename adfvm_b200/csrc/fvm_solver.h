@@ -481,6 +481,46 @@ public:
             run(nBcells, GhostPrimAdjBody<R>{ph, m, obj, oa, bcells, Q[s], Qb, rQ, W[s], A[s]});
         }
     }
+    // ---- device-side checkpoint block. The reference's Solver.run(mode='forward') returns every
+    // state of a checkpoint block to the host and Adjoint.run feeds them back one by one (adFVM/solver.py:376-382,
+    // apps/adjoint.py:217-291); here the block stays in HBM: primal_block stores the state at the start of each of its
+    // steps, adjoint_block walks the block backwards with the adjoint fields resident.
+    std::vector<R*> block; R* block_red = nullptr; int block_cap = 0;
+    void block_reserve(int nsteps) {
+        if (nsteps <= (int)block.size() && nsteps <= block_cap) return;
+        while ((int)block.size() < nsteps) block.push_back(dalloc<R>((size_t)5 * m.sC + kRowSlack));
+        if (nsteps > block_cap) { block_red = dalloc<R>((size_t)2 * nsteps); block_cap = nsteps; }
+    }
+    // nsteps primal steps from the resident state; dtc[k], objective[k] of step k (rank-local, like get_dtc_obj)
+    void primal_block(int nsteps, const double* dt, double* dtc, double* objective) {
+        if (!have_mesh || !have_state) throw std::runtime_error("mesh/state not set");
+        block_reserve(nsteps);
+        const size_t bytes = (size_t)5 * m.sC * sizeof(R);
+        for (int k = 0; k < nsteps; k++) {
+            ex.copy(block[k], W[0], bytes);
+            primal_step((R)dt[k], false);
+            ex.copy(block_red + 2 * k, red, 2 * sizeof(R));
+        }
+        std::vector<R> h((size_t)2 * nsteps);
+        ex.download(h.data(), block_red, h.size() * sizeof(R)); ex.sync();
+        for (int k = 0; k < nsteps; k++) {
+            if (dtc) dtc[k] = (double)h[2 * k];
+            if (objective) objective[k] = comm ? comm->allreduce_sum((double)h[2 * k + 1]) : (double)h[2 * k + 1];
+        }
+    }
+    // reverse sweep over the block stored by the last primal_block: the adjoint of the block's final state is resident
+    // (A[0], from adjoint_step or a previous adjoint_block); afterwards A[0] holds the adjoint of the block's first state,
+    // Sb the accumulated source-term gradient. The resident primal state is left at the block's first state.
+    void adjoint_block(int nsteps, const double* dt, R obja) {
+        if (nsteps > (int)block.size()) throw std::runtime_error("adjoint_block: no stored primal block of that length");
+        ensure_adjoint_buffers();
+        const size_t bytes = (size_t)5 * m.sC * sizeof(R);
+        for (int k = nsteps - 1; k >= 0; k--) {
+            ex.copy(W[0], block[k], bytes);
+            adjoint_step_resident((R)dt[k], obja, true);
+        }
+    }
+    void put_adjoint(const R* rhoa, const R* rhoUa, const R* rhoEa) { ensure_adjoint_buffers(); put5(A[0], rhoa, rhoUa, rhoEa); }
     void get_adjoint(R* rhoa, R* rhoUa, R* rhoEa) { get5(A[0], rhoa, rhoUa, rhoEa); }
     void get_source_grad(R* a, R* b, R* c, bool zero_after) {
         get5(Sb, a, b, c);

@@ -331,6 +331,25 @@ class PrimalFunction:
     def step_resident(self, dt):
         self.c.lib.check(self.c.lib.dll.adfvm_primal_step_resident(self.c.ctx, float(dt)))
 
+    def set_state(self, *inputs):
+        """upload mesh/BC/source (first time) and the state from a `primal` positional list, without stepping"""
+        c = self.c
+        P, _ = self._prepare(inputs, {})
+        C_ = c.sizes[2]
+        rho, rhoU, rhoE = P["state"]
+        c._arr(rho, (1,), "rho", C_); c._arr(rhoU, (3,), "rhoU", C_); c._arr(rhoE, (1,), "rhoE", C_)
+        c.lib.check(c.lib.dll.adfvm_set_state(c.ctx, _ptr(rho), _ptr(rhoU), _ptr(rhoE)))
+
+    def run_block(self, dts):
+        """len(dts) resident primal steps; the state at the start of every step stays on the device for
+        AdjointFunction.run_block (replaces the host-side `solutions` list of Solver.run(mode='forward'),
+        adFVM/solver.py:376-382). Returns (dtc[k], objective[k])."""
+        n = len(dts)
+        dt = (C.c_double * max(n, 1))(*[float(x) for x in dts])
+        dtc, obj = (C.c_double * max(n, 1))(), (C.c_double * max(n, 1))()
+        self.c.lib.check(self.c.lib.dll.adfvm_primal_block(self.c.ctx, n, dt, dtc, obj))
+        return np.array(dtc[:n]), np.array(obj[:n])
+
     def dtc_obj(self):
         a, b = C.c_double(), C.c_double()
         self.c.lib.check(self.c.lib.dll.adfvm_get_dtc_obj(self.c.ctx, C.byref(a), C.byref(b)))
@@ -404,6 +423,32 @@ class AdjointFunction:
 
     def step_resident(self, dt, obja=1.0, chain=True):
         self.c.lib.check(self.c.lib.dll.adfvm_adjoint_step_resident(self.c.ctx, float(dt), float(obja), int(chain)))
+
+    def set_fields(self, rhoa, rhoUa, rhoEa):
+        """upload the adjoint fields the next run_block / step_resident(chain=True) starts from"""
+        c = self.c
+        C_ = c.sizes[2]
+        c._arr(rhoa, (1,), "rhoa", C_); c._arr(rhoUa, (3,), "rhoUa", C_); c._arr(rhoEa, (1,), "rhoEa", C_)
+        c.lib.check(c.lib.dll.adfvm_set_adjoint(c.ctx, _ptr(rhoa), _ptr(rhoUa), _ptr(rhoEa)))
+
+    def run_block(self, dts, obja=1.0):
+        """reverse sweep over the block stored by PrimalFunction.run_block(dts) (the step loop of Adjoint.run,
+        apps/adjoint.py:250-291, without the host round trips): adjoint fields and source-term gradient stay resident"""
+        n = len(dts)
+        dt = (C.c_double * max(n, 1))(*[float(x) for x in dts])
+        self.c.lib.check(self.c.lib.dll.adfvm_adjoint_block(self.c.ctx, n, dt, float(obja)))
+
+    def fields(self, return_static=True, zero_static=False):
+        """(rhoa, rhoUa, rhoEa[, dJ/dS_rho, dJ/dS_rhoU, dJ/dS_rhoE]) currently resident"""
+        c = self.c
+        C_ = c.sizes[2]
+        outs = [c.pool.empty((C_, 1), c.dtype), c.pool.empty((C_, 3), c.dtype), c.pool.empty((C_, 1), c.dtype)]
+        grads = [None, None, None]
+        if return_static:
+            grads = [c.pool.empty((C_, 1), c.dtype), c.pool.empty((C_, 3), c.dtype), c.pool.empty((C_, 1), c.dtype)]
+        c.lib.check(c.lib.dll.adfvm_get_adjoint(c.ctx, _ptr(outs[0]), _ptr(outs[1]), _ptr(outs[2]),
+                                                _ptr(grads[0]), _ptr(grads[1]), _ptr(grads[2]), int(zero_static)))
+        return tuple(outs + grads)
 
 
 def spec_from_solver(primal, objective):

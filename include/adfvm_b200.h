@@ -120,6 +120,18 @@ int adfvm_tile_stats(adfvm_ctx* ctx, double* evals_per_cell, int32_t* max_rounds
  * histogram of tiles per halo size in bins of 32 slots */
 int adfvm_tile_halo_stats(adfvm_ctx* ctx, int32_t* max_halo, int32_t* variant, int32_t* hist, int32_t nbins);
 
+/* Device-side checkpoint block: what Solver.run(mode='forward') + the step loop of Adjoint.run do through host memory
+ * (adFVM/solver.py:376-382: every state of a block returned to numpy; apps/adjoint.py:217-291: fed back one by one).
+ * adfvm_primal_block runs nsteps steps from the resident state with time steps dt[k], keeps the state at the start of
+ * every step in HBM and returns the per-step dtc / objective. adfvm_adjoint_block then walks that block backwards from
+ * the resident adjoint fields (set by adfvm_set_adjoint, or left by a previous adjoint call/block; objective seed obja
+ * per step); adfvm_get_adjoint reads the adjoint fields (and, if g_* are given, the accumulated source-term gradient). */
+int adfvm_set_state(adfvm_ctx* ctx, const void* rho, const void* rhoU, const void* rhoE);   /* upload the resident state without stepping */
+int adfvm_primal_block(adfvm_ctx* ctx, int32_t nsteps, const double* dt, double* dtc, double* objective);
+int adfvm_adjoint_block(adfvm_ctx* ctx, int32_t nsteps, const double* dt, double obja);
+int adfvm_set_adjoint(adfvm_ctx* ctx, const void* rhoa, const void* rhoUa, const void* rhoEa);
+int adfvm_get_adjoint(adfvm_ctx* ctx, void* rhoa, void* rhoUa, void* rhoEa, void* g_rho, void* g_rhoU, void* g_rhoE, int32_t zero_static);
+
 /* whole steps are captured into CUDA graphs (the second time a step with the same time step and buffer rotation runs)
  * and replayed afterwards; number of steps served by a replay so far (set ADFVM_NO_GRAPH=1 to run every step eagerly) */
 int64_t adfvm_graph_replays(adfvm_ctx* ctx);

@@ -23,6 +23,7 @@ struct HostExec {
     void zero(void* p, size_t b) { std::memset(p, 0, b); }
     void upload(void* d, const void* s, size_t b) { std::memcpy(d, s, b); }
     void download(void* d, const void* s, size_t b) { std::memcpy(d, s, b); }
+    void copy(void* d, const void* s, size_t b) { std::memcpy(d, s, b); }
     void sync() {}
     void timing_enable(bool) {}
     std::string timing_report() { return ""; }

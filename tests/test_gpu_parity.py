@@ -114,6 +114,14 @@ def test_graph_replay_matches_eager(cudalib):
         assert np.array_equal(a, b)
 
 
+def test_block_equals_host_round_trips_on_device(cudalib):
+    """device-side checkpoint block (adfvm_primal_block / adfvm_adjoint_block) against one host round trip per step,
+    bit for bit, with whole steps replayed as CUDA graphs"""
+    import torch
+    from test_block import block_vs_stepwise
+    block_vs_stepwise(cudalib, stream=torch.cuda.Stream().cuda_stream)
+
+
 def test_resident_equals_host_roundtrip(cudalib):
     case = cases.periodic_box(20)
     f1 = function.PrimalFunction(case.spec, np.float64)
