@@ -1,0 +1,52 @@
+"""Edge cases of the path through the C ABI (CPU simulator of the device code): meshes smaller than a warp, a single
+cell, a 1-D row longer than a sub-tile, and a patch without faces - against the oracle, fp64 1e-10."""
+import numpy as np
+import pytest
+
+from adfvm_b200 import cases, function, hexmesh
+from adfvm_b200.metrics import build_mesh
+from oracle import adfvm_oracle as O
+
+TOL = 1e-10
+
+
+def _check(case, lib):
+    f = function.PrimalFunction(case.spec, np.float64, lib=lib)
+    out = f(*case.inputs(), replace_reusable=True, return_reusable=True)
+    ref = O.primal(case.spec, case.inputs())
+    for a, b in zip(out, ref):
+        assert np.abs(a - b).max() <= TOL * max(np.abs(b).max(), 1e-300)
+    adj = [np.ones_like(s) * w for s, w in zip(case.state, (1.0, 1e-2, 1e-5))]
+    g = f.grad()(*case.adjoint_inputs(case.state, adj))
+    gref = O.primal_grad(case.spec, case.adjoint_inputs(case.state, adj))
+    sc = [float(np.abs(s).max()) for s in case.state]
+    for grp in (slice(0, 3), slice(3, 6)):
+        num = max(np.abs(a - b).max() * s for a, b, s in zip(g[grp], gref[grp], sc))
+        den = max(np.abs(b).max() * s for b, s in zip(gref[grp], sc))
+        assert num <= TOL * den
+
+
+@pytest.mark.parametrize("n", [(1, 1, 1), (2, 2, 2), (3, 1, 2), (33, 1, 1)])
+def test_tiny_periodic_boxes(hostsim, n):
+    _check(cases.periodic_box(n), hostsim)
+
+
+def test_patch_without_faces(hostsim):
+    """a patch of zero faces (OpenFOAM decompositions produce them) between the others"""
+    lo, hi = (0., 0., 0.), (1., 1., 1.)
+    poly = hexmesh.box_mesh((4, 3, 2), lo, hi, patches=[
+        ("a_in", "patch", ["x-"], {}), ("b_none", "patch", [], {}), ("c_out", "patch", ["x+"], {}),
+        ("walls", "symmetryPlane", ["y-", "y+"], {}),
+        ("z1", "cyclic", ["z-"], {"neighbourPatch": "z2"}), ("z2", "cyclic", ["z+"], {"neighbourPatch": "z1"})])
+    mesh = build_mesh(poly)
+    C = mesh.nInternalCells
+    cc = mesh.cellCentres[:C]
+    U, T, p = cases.smooth_state(cc)
+    k0 = {"keys": []}
+    zg = dict(type="zeroGradient", **k0)
+    cyc = {"z1": dict(type="cyclic", **k0), "z2": dict(type="cyclic", **k0)}
+    bcs = {f: dict(cyc, a_in=zg, b_none=zg, c_out=zg, walls=dict(type="symmetryPlane", **k0)) for f in ("U", "T", "p")}
+    spec = cases._spec(mesh, bcs, {"kind": "patch_pA", "patch": "c_out"})
+    case = cases.Case(mesh, spec, cases.conservative(U, T, p), cases.gaussian_source(cc), {}, 1e-6)
+    assert mesh.boundary["b_none"]["nFaces"] == 0
+    _check(case, hostsim)
