@@ -18,7 +18,7 @@ namespace fvm {
 
 enum BCType { BC_CALCULATED = 0, BC_CYCLIC = 1, BC_ZEROGRADIENT = 2, BC_FIXEDVALUE = 3, BC_SYMMETRY = 4,
               BC_CBC_UPT = 5, BC_CBC_TOTAL_PT = 6, BC_PROCESSOR = 7 };
-enum ObjKind { OBJ_NONE = 0, OBJ_CELL_TV = 1, OBJ_PATCH_PA = 2, OBJ_DRAG = 3 };
+enum ObjKind { OBJ_NONE = 0, OBJ_CELL_TV = 1, OBJ_PATCH_PA = 2, OBJ_DRAG = 3, OBJ_PLANE_PTLOSS = 4 };
 enum { MAX_PATCHES = 255 };
 
 template <typename R> struct PatchDev {
@@ -50,7 +50,9 @@ template <typename R> struct MeshDev {
     const int* cell_perm;                // [C] device cell -> reference (host) cell
 };
 
-template <typename R> struct ObjDev { int kind, patch, dir; };
+// OBJ_PLANE_PTLOSS (reference adFVM/objectives/vane.py:36-66): cells / areas of a cut plane (device cell numbering),
+// inlet total pressure ptin, plane normal nrm, factor scale (the a = 0.4 of vane.py:120)
+template <typename R> struct ObjDev { int kind, patch, dir; const int* cells; const R* areas; int ncells; R ptin, scale, nrm[3]; };
 
 // ------------------------------------------------------------------------------------------ loads
 template <typename R> FVM_HD void load_prim(const R* Q, int sN, int c, Prim<R>& q) {
@@ -210,6 +212,68 @@ template <typename R> struct ObjectiveBody {
         return (Q[4 * m.sN + g] * m.normal[o.dir * m.sF + f] - mung) * m.area[f];
     }
 };
+// ---- mass-flow averaged total-pressure loss over a cut plane: obj = scale * S2/S1, S1 = sum m_i,
+// S2 = sum l_i m_i, m_i = rho_i (U_i.n) A_i, l_i = (ptin - pt_i)/ptin, pt = p (1 + (g-1)/2 M^2)^(g/(g-1))
+template <typename R> FVM_HD void plane_cell(const Phys<R>& ph, const ObjDev<R>& o, const R* Q, int sN, int i, R& mflux, R& loss, Prim<R>& dm, Prim<R>& dl) {
+    const int c = o.cells[i];
+    Prim<R> q; load_prim(Q, sN, c, q);
+    const R A = o.areas[i], g = ph.gamma, gm1 = ph.gm1;
+    const R Rg = ph.Cv * gm1;                       // rho = p / (Cv T (g-1))
+    const R rho = q.p / (Rg * q.T);
+    const R un = dot3(q.U, o.nrm);
+    mflux = rho * un * A;
+    const R c2 = g * q.p / rho;
+    const R M2 = dot3(q.U, q.U) / c2;
+    const R B = R(1) + R(0.5) * gm1 * M2, e = ph.g_gm1;
+    const R Be1 = pow(B, e - R(1));
+    const R pt = q.p * Be1 * B;
+    loss = (o.ptin - pt) / o.ptin;
+    // derivatives w.r.t. (U, T, p)
+    for (int k = 0; k < 3; k++) dm.U[k] = rho * o.nrm[k] * A;
+    dm.p = mflux / q.p; dm.T = -mflux / q.T;
+    const R f = q.p * e * Be1 * R(0.5) * gm1;       // d pt / d M2
+    const R ip = -R(1) / o.ptin;
+    for (int k = 0; k < 3; k++) dl.U[k] = ip * f * R(2) * q.U[k] / c2;
+    dl.T = ip * f * (-M2 / q.T);                    // c2 = g (Cv (g-1)) T
+    dl.p = ip * Be1 * B;
+}
+template <typename R> struct PlaneMassBody {       // pass 1: S1
+    static constexpr const char* kName = "objective";
+    Phys<R> ph; MeshDev<R> m; ObjDev<R> o; const R* Q;
+    FVM_HD R operator()(int i) const { R mf, l; Prim<R> a, b; plane_cell(ph, o, Q, m.sN, i, mf, l, a, b); return mf; }
+};
+template <typename R> struct PlaneLossBody {       // pass 2: scale * sum l_i m_i / S1  (S1 read from device memory)
+    static constexpr const char* kName = "objective";
+    Phys<R> ph; MeshDev<R> m; ObjDev<R> o; const R* Q; const R* S1;
+    FVM_HD R operator()(int i) const { R mf, l; Prim<R> a, b; plane_cell(ph, o, Q, m.sN, i, mf, l, a, b); return o.scale * l * mf / S1[0]; }
+};
+// reverse: Qb[cell] += obja * d obj / d(U,T,p); S1 = sum m, P2 = obj (= scale * S2/S1) from the two passes above
+template <typename R> struct PlaneLossAdjBody {
+    static constexpr const char* kName = "objective_adj";
+    Phys<R> ph; MeshDev<R> m; ObjDev<R> o; const R* Q; const R* S1; const R* P2; R obja; R* Qb;
+    FVM_HD void operator()(int i) const {
+        R mf, l; Prim<R> dm, dl; plane_cell(ph, o, Q, m.sN, i, mf, l, dm, dl);
+        const R s = obja * o.scale / S1[0];
+        const R lbar = P2[0] / o.scale;             // S2/S1
+        Prim<R> qb;
+        for (int k = 0; k < 3; k++) qb.U[k] = s * ((l - lbar) * dm.U[k] + mf * dl.U[k]);
+        qb.T = s * ((l - lbar) * dm.T + mf * dl.T);
+        qb.p = s * ((l - lbar) * dm.p + mf * dl.p);
+        add_prim(Qb, m.sN, o.cells[i], qb);          // the cells of a cut plane are distinct
+    }
+};
+// host cell ids -> device cell ids: inverse of cell_perm, then gather
+template <typename R> struct InvertPermBody {
+    static constexpr const char* kName = "invert_perm";
+    const int* perm; int* inv;
+    FVM_HD void operator()(int i) const { inv[perm[i]] = i; }
+};
+template <typename R> struct GatherIntBody {
+    static constexpr const char* kName = "gather_int";
+    const int* map; const int* in; int* out;
+    FVM_HD void operator()(int i) const { out[i] = map[in[i]]; }
+};
+
 // adjoint of the objective w.r.t. the ghost row of boundary face f (scaled by obja) ...
 template <typename R> FVM_HD void objective_ghost_adj(const Phys<R>& ph, const MeshDev<R>& m, const ObjDev<R>& o, const R* Q,
                                                       R obja, int f, Prim<R>& qb) {

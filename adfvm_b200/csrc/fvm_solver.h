@@ -71,7 +71,7 @@ public:
     std::vector<void*> owned;                 // everything to free
 
     explicit Solver(const Exec& e) : ex(e) {
-        std::memset(&m, 0, sizeof(m)); std::memset(&ph, 0, sizeof(ph)); obj.kind = OBJ_NONE; obj.patch = 0; obj.dir = 0;
+        std::memset(&m, 0, sizeof(m)); std::memset(&ph, 0, sizeof(ph)); std::memset(&obj, 0, sizeof(obj)); obj.kind = OBJ_NONE;
     }
     ~Solver() { for (void* p : owned) ex.free(p); }
 
@@ -280,6 +280,36 @@ public:
         if (kind != OBJ_NONE && kind != OBJ_CELL_TV && (patch < 0 || patch >= (int)patches.size())) throw std::runtime_error("objective patch out of range");
         obj.kind = kind; obj.patch = patch; obj.dir = dir;
     }
+    // cut-plane objective (reference adFVM/objectives/vane.py): cells in the reference's numbering, areas, constants
+    void set_objective_plane(int n, const int* cells, const R* areas, double ptin, const double* normal, double scale) {
+        epoch++;
+        if (!have_mesh) throw std::runtime_error("set the mesh before the objective");
+        if (m.nRemoteCells > 0) throw std::runtime_error("the cut-plane objective is not available on decomposed meshes yet (its mass flux needs an all-reduce between the two passes)");
+        const int C = m.nInternalCells;
+        for (int i = 0; i < n; i++) if (cells[i] < 0 || cells[i] >= C) throw std::runtime_error("objective plane cell out of range");
+        int* inv = (int*)ex.alloc((size_t)(C + 1) * 4);
+        int* d_in = (int*)ex.alloc((size_t)(n + 1) * 4);
+        int* d_cells = dalloc<int>(n + 1);
+        R* d_areas = dalloc<R>(n + 1);
+        ex.upload(d_in, cells, (size_t)n * 4); ex.upload(d_areas, areas, (size_t)n * sizeof(R));
+        run(C, InvertPermBody<R>{m.cell_perm, inv});
+        run(n, GatherIntBody<R>{inv, d_in, d_cells});
+        ex.sync(); ex.free(inv); ex.free(d_in);
+        obj.kind = OBJ_PLANE_PTLOSS; obj.patch = 0; obj.dir = 0; obj.cells = d_cells; obj.areas = d_areas; obj.ncells = n;
+        obj.ptin = (R)ptin; obj.scale = (R)scale;
+        for (int k = 0; k < 3; k++) obj.nrm[k] = (R)normal[k];
+    }
+    void objective_forward(const R* Qs) {            // -> red[1] (red[2] = plane mass flux)
+        const int C = m.nInternalCells;
+        if (obj.kind == OBJ_NONE) { ex.zero(red + 1, sizeof(R)); return; }
+        if (obj.kind == OBJ_PLANE_PTLOSS) {
+            ex.reduce_sum(obj.ncells, PlaneMassBody<R>{ph, m, obj, Qs}, red + 2);
+            ex.reduce_sum(obj.ncells, PlaneLossBody<R>{ph, m, obj, Qs, red + 2}, red + 1); launches += 4;
+            return;
+        }
+        const int n = (obj.kind == OBJ_CELL_TV) ? C : patches[obj.patch].nFaces;
+        ex.reduce_sum(n, ObjectiveBody<R>{ph, m, obj, Qs}, red + 1); launches += 2;
+    }
     void set_source(const R* s_rho, const R* s_rhoU, const R* s_rhoE) {
         const int C = m.nInternalCells;
         upload_aos(s_rho, C, 1, m.sC, S, m.cell_perm); upload_aos(s_rhoU, C, 3, m.sC, S + m.sC, m.cell_perm);
@@ -349,13 +379,7 @@ public:
         const int Ce = early_cells(), Te = early_tiles();
         run(nLB, GhostPrimBody<R>{ph, m, Qs});
         halo_begin(Qs, 5);
-        if (want_dtc_obj) {
-            if (obj.kind == OBJ_NONE) ex.zero(red + 1, sizeof(R));
-            else {
-                int n = (obj.kind == OBJ_CELL_TV) ? C : patches[obj.patch].nFaces;
-                ex.reduce_sum(n, ObjectiveBody<R>{ph, m, obj, Qs}, red + 1); launches += 2;
-            }
-        }
+        if (want_dtc_obj) objective_forward(Qs);
         run_range(0, Ce, GradCellBody<R>{m, Qs, Gs});                  // overlaps the exchange of U,T,p
         halo_end();
         run_range(Ce, C - Ce, GradCellBody<R>{m, Qs, Gs});
@@ -411,7 +435,7 @@ public:
         };
         if (keep) body();                          // part of the adjoint step's graph
         else with_graph({1ull, epoch, bits((double)dt), (unsigned long long)W[0], (unsigned long long)W[3], (unsigned long long)obj.kind,
-                         (unsigned long long)obj.patch, (unsigned long long)obj.dir, (unsigned long long)patches_dev}, body);
+                         (unsigned long long)obj.patch, (unsigned long long)obj.dir, (unsigned long long)patches_dev, (unsigned long long)obj.cells}, body);
         if (!keep) { R* t = W[0]; W[0] = W[3]; W[3] = t; }
     }
     // dtc (max over ranks not applied here: the reference returns the rank-local max, adFVM/density.py:405-413)
@@ -463,6 +487,11 @@ public:
             }
             const R* rG = halo_reverse_end();
             run(nBcells, GhostGradAdjBody<R>{m, bcells, Gb, rG});
+            if (s == 1 && obj.kind == OBJ_PLANE_PTLOSS && obja != R(0)) {      // seeds of the cut-plane objective (stage-1 primitives)
+                ex.reduce_sum(obj.ncells, PlaneMassBody<R>{ph, m, obj, Q[1]}, red + 4);
+                ex.reduce_sum(obj.ncells, PlaneLossBody<R>{ph, m, obj, Q[1], red + 4}, red + 5); launches += 4;
+                run(obj.ncells, PlaneLossAdjBody<R>{ph, m, obj, Q[1], red + 4, red + 5, obja, Qb});
+            }
             GradAdjUpdateBody<R> pb;
             pb.ph = ph; pb.m = m; pb.Gb = Gb; pb.Qb = Qb; pb.W = W[s];
             // a_s = sum_{k>=s} alpha[k][s] * a_{k+1}

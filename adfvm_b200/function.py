@@ -189,7 +189,10 @@ class _Context:
             for pid in self.sorted:
                 for key in self.spec["BCs"][field][pid]["keys"]:
                     bcs.append((field, pid, key, inputs[k])); k += 1
-        out.update(mesh=mesh, sizes=sizes, triples=triples, source=source, bcs=bcs, rest=list(inputs[k:]))
+        # extraArgs of the case file (adFVM/solver.py:58,317): the objective's own inputs; the adjoint seeds follow them
+        nx = int((self.spec.get("objective") or {}).get("nExtra", 0))
+        extra = list(inputs[k:k + nx]); k += nx
+        out.update(mesh=mesh, sizes=sizes, triples=triples, source=source, bcs=bcs, extra=extra, rest=list(inputs[k:]))
         return out
 
     def load_static(self, P):
@@ -235,8 +238,23 @@ class _Context:
         self.sizes = sizes
         self.patch_index = index
         o = self.spec.get("objective") or {"kind": "none"}
-        self.lib.check(d.adfvm_set_objective(self.ctx, _OBJ_KIND[o["kind"]],
-                                             index.get(o.get("patch"), 0), int(o.get("direction", 0))))
+        if o["kind"] == "plane_ptloss":
+            # adFVM/objectives/vane.py: extraArgs = (nPlaneCells, cells[n,1], areas[n,1], weights of the `pressure` and
+            # `suction` patches - those feed the heat-transfer term, whose coefficient b is 0 in the reference, :122)
+            ex = P["extra"]
+            if len(ex) < 3:
+                raise TypeError("the cut-plane objective expects its extraArgs (nPlaneCells, cells, areas, ...)")
+            n = int(ex[0])
+            cells = self._iarr(np.ascontiguousarray(ex[1]), "objective cells", n, 1)
+            areas = self._arr(ex[2], (1,), "objective areas", n)
+            nrm = (C.c_double * 3)(*[float(x) for x in o.get("normal", (1., 0., 0.))])
+            self.lib.check(d.adfvm_set_objective_plane(self.ctx, n, _ptr(cells), _ptr(areas), float(o.get("ptin", 175158.)),
+                                                       nrm, float(o.get("scale", 0.4))))
+        else:
+            if o["kind"] not in _OBJ_KIND:
+                raise NotImplementedError("objective %r (supported: %s, plane_ptloss)" % (o["kind"], ", ".join(_OBJ_KIND)))
+            self.lib.check(d.adfvm_set_objective(self.ctx, _OBJ_KIND[o["kind"]],
+                                                 index.get(o.get("patch"), 0), int(o.get("direction", 0))))
         self.load_replaceable(P)
         self.static_loaded = True
 

@@ -77,6 +77,11 @@ int adfvm_set_mesh(adfvm_ctx* ctx, const int32_t sizes[8],
 int adfvm_set_bc_value(adfvm_ctx* ctx, int32_t patch, int32_t key, const void* values);
 /* objective evaluated on the stage-1 state (adFVM/density.py:412-413); see DESIGN.md for the supported kinds */
 int adfvm_set_objective(adfvm_ctx* ctx, int32_t kind, int32_t patch, int32_t direction);
+/* the design objective of the reference's turbine-vane cases (adFVM/objectives/vane.py:36-66,83-139, templates/vane.py):
+ * scale x mass-flow averaged total-pressure loss (ptin - pt)/ptin over the cells of a cut plane. cells (reference
+ * numbering) and areas are the extraArgs the case file passes after the BC arrays (adFVM/solver.py:317). */
+int adfvm_set_objective_plane(adfvm_ctx* ctx, int32_t n, const int32_t* cells, const void* areas, double ptin,
+                              const double normal[3], double scale);
 /* source terms [C][1],[C][3],[C][1] (Solver.sourceTerms, adFVM/solver.py:116-133); static, re-settable */
 int adfvm_set_source(adfvm_ctx* ctx, const void* S_rho, const void* S_rhoU, const void* S_rhoE);
 

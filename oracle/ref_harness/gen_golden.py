@@ -91,6 +91,7 @@ def objective(fields, solver):
 
 CASEFILE_TAIL = '''
 primal = RCF('{case}/', objective=objective, fixedTimeStep=True{rcf_extra})
+{after_primal}
 
 def perturb(fields, mesh, t):
     x = mesh.cellCentres[:mesh.nInternalCells]
@@ -290,7 +291,60 @@ def case_step2d():
                 rcf_extra=", Cp=2.5, mu=lambda T: 0., CFL=1.2", mid="[0.3,0.3,0.]", amp="1e-2", width="20", nSteps=4, writeInterval=2, dt=1e-3)
 
 
-CASES = {"step2d": case_step2d, "cyl2d": case_cyl2d, "box_cyclic": case_box_cyclic, "tube": case_tube, "box_walls": case_box_walls, "box_upt": case_box_upt}
+
+OBJ_VANE = '''
+from adFVM.objectives.vane import objective, getWeights
+'''
+
+VANE_EXTRA = '''
+# cut plane of the pressure-loss objective (adFVM/objectives/vane.py:25-38 finds it with the Cython intersectPlane,
+# stubbed in this harness): the cells of the column x = xc and their cross-section areas, passed the same way
+_m = primal.mesh
+_cc = _m.cellCentres[:_m.nInternalCells]
+_sel = np.where(np.abs(_cc[:, 0] - {xc}) < 1e-9)[0].astype(np.int32)
+_area = _m.volumes[_sel] / {dx}
+primal.extraArgs.append((tensor.IntegerScalar(), len(_sel)))
+_n = primal.extraArgs[-1][0]
+primal.extraArgs.append((tensor.StaticIntegerVariable((_n, 1)), _sel.reshape(-1, 1)))
+primal.extraArgs.append((tensor.StaticVariable((_n, 1)), _area.reshape(-1, 1).astype(config.precision)))
+getWeights(primal)
+'''
+
+
+def case_channel_vane():
+    """Design objective of reference templates/vane.py (config 4 of BASELINE.json): adFVM/objectives/vane.py - mass-flow
+    averaged total-pressure loss over a cut plane (cell list + areas passed as extraArgs) and wall heat transfer on the
+    patches `pressure` / `suction` with coordinate-selected weights (coefficient b = 0 in the reference) - on a small
+    graded channel: total-pressure inlet, fixedValue-p outlet, isothermal no-slip `pressure` and `suction` walls,
+    cyclic span, Sutherland viscosity."""
+    lo, hi = (0., 0., 0.), (0.1, 0.04, 0.01)
+    nx = 10
+    poly = hexmesh.box_mesh((nx, 6, 3), lo, hi, grading=(1.0, 0.5, 1.0), patches=[
+        ("inlet", "patch", ["x-"], {}), ("outlet", "patch", ["x+"], {}),
+        ("pressure", "patch", ["y-"], {}), ("suction", "patch", ["y+"], {}),
+        ("z1", "cyclic", ["z-"], {"neighbourPatch": "z2"}), ("z2", "cyclic", ["z+"], {"neighbourPatch": "z1"})])
+    m = build_mesh(poly)
+    cc = m.cellCentres[:m.nInternalCells]
+    s3 = (cc - np.asarray(lo)) / (np.asarray(hi) - np.asarray(lo))
+    s = np.sin(2 * np.pi * s3[:, 0]) * np.cos(np.pi * s3[:, 1]) * np.cos(2 * np.pi * s3[:, 2])
+    U = np.stack([180 * (1 - (2 * s3[:, 1] - 1) ** 2) + 20 + 3 * s, 2 * s, 1 * s], axis=1)
+    T = (320 + 5 * s).reshape(-1, 1)
+    p = (140000 + 500 * s).reshape(-1, 1)
+    cyc = {"z1": {"type": "cyclic"}, "z2": {"type": "cyclic"}}
+    wallU = {"type": "fixedValue", "value": "uniform (0 0 0)"}
+    wallT = {"type": "fixedValue", "value": "uniform 300"}
+    bU = dict(cyc, inlet={"type": "calculated"}, outlet={"type": "zeroGradient"}, pressure=wallU, suction=wallU)
+    bT = dict(cyc, inlet={"type": "calculated"}, outlet={"type": "zeroGradient"}, pressure=wallT, suction=wallT)
+    bp = dict(cyc, inlet={"type": "CBC_TOTAL_PT", "Tt": "uniform 340", "pt": "uniform 175158", "value": "uniform 140000"},
+              outlet={"type": "fixedValue", "value": "uniform 139000"}, pressure={"type": "zeroGradient"}, suction={"type": "zeroGradient"})
+    dx = (hi[0] - lo[0]) / nx
+    return dict(poly=poly, fields={"U": (U, bU), "T": (T, bT), "p": (p, bp)}, objective=OBJ_VANE,
+                after_primal=VANE_EXTRA.format(xc=repr(lo[0] + 6.5 * dx), dx=repr(dx)),
+                obj_spec={"kind": "plane_ptloss", "ptin": 175158., "normal": [1., 0., 0.], "scale": 0.4, "nExtra": 5},
+                rcf_extra="", mid="[0.05,0.02,0.005]", amp="1e1", width="2e3", nSteps=4, writeInterval=2, dt=2e-8)
+
+
+CASES = {"channel_vane": case_channel_vane, "step2d": case_step2d, "cyl2d": case_cyl2d, "box_cyclic": case_box_cyclic, "tube": case_tube, "box_walls": case_box_walls, "box_upt": case_box_upt}
 
 
 def run(cmd, cwd):
@@ -311,7 +365,7 @@ def write_case(name, tag):
     casefile = os.path.join(case, "casefile.py")
     with open(casefile, "w") as f:
         f.write(CASEFILE_HEAD + c["objective"] + CASEFILE_TAIL.format(
-            case=case, rcf_extra=c["rcf_extra"], mid=c["mid"], amp=c["amp"], width=c["width"],
+            case=case, rcf_extra=c["rcf_extra"], after_primal=c.get("after_primal", ""), mid=c["mid"], amp=c["amp"], width=c["width"],
             nSteps=c["nSteps"], writeInterval=c["writeInterval"], dt=c["dt"]))
     return c, case, casefile
 

@@ -13,6 +13,7 @@ TOL = 1e-12
 # the drag on the half cylinder of `cyl2d` is a sum of pressure forces that cancel to 1e-4 of their size: the objective
 # is compared at the north-star tolerance there
 OBJ_TOL = {"cyl2d": 1e-10}
+ADJ_TOL = {}
 
 
 @pytest.mark.parametrize("name", CASES)
@@ -36,8 +37,8 @@ def test_oracle_adjoint_matches_reference(name):
     for ci, nm, inp, opt, out in g.calls("adjoint", "primal_grad"):
         r = O.primal_grad(g.spec, inp)
         sc = state_scales(inp)
-        assert group_relerr(r[:3], out[:3], sc) < TOL
-        assert group_relerr(r[3:6], out[3:6], sc) < TOL
+        assert group_relerr(r[:3], out[:3], sc) < ADJ_TOL.get(name, TOL)
+        assert group_relerr(r[3:6], out[3:6], sc) < ADJ_TOL.get(name, TOL)
         n += 1
     assert n >= 4
 
