@@ -76,6 +76,9 @@ template <typename R> struct NcclHalo : fvm::HaloComm<R> {
         FVM_CUDA_CHECK(cudaStreamSynchronize(stream));
         return r;
     }
+    void allreduce_sum_device(R* buf, int n, void* strm) override {
+        g_nccl.check(g_nccl.AllReduce(buf, buf, (size_t)n, sizeof(R) == 8 ? ncclDouble : ncclFloat, ncclSum, comm, (cudaStream_t)strm), "ncclAllReduce");
+    }
     double allreduce_sum(double v) override { return allreduce(v, ncclSum); }
     double allreduce_max(double v) override { return allreduce(v, ncclMax); }
 };

@@ -38,6 +38,8 @@ template <typename R> struct HaloComm {
     virtual ~HaloComm() {}
     virtual void exchange(const R* send, R* recv, int ncomp, const std::vector<PatchHost>& remote, void* stream) = 0;
     virtual double allreduce_sum(double v) = 0;
+    // in-place sum over ranks of n scalars in executor memory, ordered on `stream` (no host synchronisation on the device)
+    virtual void allreduce_sum_device(R* buf, int n, void* stream) = 0;
     virtual double allreduce_max(double v) = 0;
 };
 
@@ -284,7 +286,6 @@ public:
     void set_objective_plane(int n, const int* cells, const R* areas, double ptin, const double* normal, double scale) {
         epoch++;
         if (!have_mesh) throw std::runtime_error("set the mesh before the objective");
-        if (m.nRemoteCells > 0) throw std::runtime_error("the cut-plane objective is not available on decomposed meshes yet (its mass flux needs an all-reduce between the two passes)");
         const int C = m.nInternalCells;
         for (int i = 0; i < n; i++) if (cells[i] < 0 || cells[i] >= C) throw std::runtime_error("objective plane cell out of range");
         int* inv = (int*)ex.alloc((size_t)(C + 1) * 4);
@@ -303,7 +304,10 @@ public:
         const int C = m.nInternalCells;
         if (obj.kind == OBJ_NONE) { ex.zero(red + 1, sizeof(R)); return; }
         if (obj.kind == OBJ_PLANE_PTLOSS) {
+            // the mass flux of the whole plane normalises every rank's share (mpi_allreduce of w, objectives/vane.py:97-99);
+            // the shares themselves are summed over the ranks with the objective (get_dtc_obj)
             ex.reduce_sum(obj.ncells, PlaneMassBody<R>{ph, m, obj, Qs}, red + 2);
+            if (comm) comm->allreduce_sum_device(red + 2, 1, ex.stream_handle());
             ex.reduce_sum(obj.ncells, PlaneLossBody<R>{ph, m, obj, Qs, red + 2}, red + 1); launches += 4;
             return;
         }
@@ -489,7 +493,9 @@ public:
             run(nBcells, GhostGradAdjBody<R>{m, bcells, Gb, rG});
             if (s == 1 && obj.kind == OBJ_PLANE_PTLOSS && obja != R(0)) {      // seeds of the cut-plane objective (stage-1 primitives)
                 ex.reduce_sum(obj.ncells, PlaneMassBody<R>{ph, m, obj, Q[1]}, red + 4);
+                if (comm) comm->allreduce_sum_device(red + 4, 1, ex.stream_handle());
                 ex.reduce_sum(obj.ncells, PlaneLossBody<R>{ph, m, obj, Q[1], red + 4}, red + 5); launches += 4;
+                if (comm) comm->allreduce_sum_device(red + 5, 1, ex.stream_handle());
                 run(obj.ncells, PlaneLossAdjBody<R>{ph, m, obj, Q[1], red + 4, red + 5, obja, Qb});
             }
             GradAdjUpdateBody<R> pb;

@@ -108,6 +108,7 @@ template <typename R> struct ThreadHalo : fvm::HaloComm<R> {
     }
     double allreduce_sum(double v) override { return allreduce(v, false); }
     double allreduce_max(double v) override { return allreduce(v, true); }
+    void allreduce_sum_device(R* buf, int n, void*) override { for (int i = 0; i < n; i++) buf[i] = (R)allreduce((double)buf[i], false); }
 };
 }  // namespace
 
@@ -146,6 +147,7 @@ template <typename R> struct CallbackHalo : fvm::HaloComm<R> {
     }
     double allreduce_sum(double v) override { return ar(v, 0); }
     double allreduce_max(double v) override { return ar(v, 1); }
+    void allreduce_sum_device(R* buf, int n, void*) override { for (int i = 0; i < n; i++) buf[i] = (R)ar((double)buf[i], 0); }
 };
 }  // namespace
 extern "C" int adfvm_hostsim_comm_callback(adfvm_ctx* c, exchange_fn e, allreduce_fn a) {

@@ -147,3 +147,73 @@ def test_gloo_two_processes():
     assert sorted(r for r, _ in got) == [0, 1]
     for _, e in got:
         assert e < 1e-9
+
+
+# ---- the vane design objective (cut plane given as extraArgs) on a decomposed mesh: its mass flux is all-reduced on the
+# device between the two passes, forward and in the adjoint seeds (adFVM/objectives/vane.py:97-99 mpi_allreduce)
+PLANE = {"kind": "plane_ptloss", "ptin": 175158., "normal": [1., 0., 0.], "scale": 0.4, "nExtra": 5}
+
+
+def _plane_extras(case, ids_global, plane_global):
+    """extraArgs of a rank: the plane cells it owns (rank-local numbering) + areas; two dummy weight arrays"""
+    pos = {g: i for i, g in enumerate(ids_global)}
+    sel = [(pos[g], a) for g, a in plane_global if g in pos]
+    cells = np.array([c for c, _ in sel], np.int32).reshape(-1, 1)
+    areas = np.array([a for _, a in sel], np.float64).reshape(-1, 1)
+    return [len(sel), cells, areas, np.zeros((1, 1)), np.zeros((1, 1))]
+
+
+def _with_plane(case):
+    spec = dict(case.spec); spec["objective"] = PLANE
+    return spec
+
+
+def _plane_of(g):
+    """cells of the column x = 2.5 / N[0]*px of the global box with a per-cell 'area'"""
+    cc = g.mesh.cellCentres[:g.mesh.nInternalCells]
+    xs = np.unique(np.round(cc[:, 0], 12))
+    sel = np.where(np.abs(cc[:, 0] - xs[len(xs) // 2]) < 1e-9)[0]
+    return [(int(c), 1e-3 * (1 + 0.1 * np.sin(c))) for c in sel]
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_threads_plane_objective(world, hostsim):
+    g = decompose.global_box(N, world)
+    plane = _plane_of(g)
+    gids = list(range(g.mesh.nInternalCells))
+    ex_g = _plane_extras(g, gids, plane)
+    f = function.PrimalFunction(_with_plane(g), np.float64, lib=hostsim)
+    out = f(*(g.inputs() + ex_g), replace_reusable=True)
+    adj = _seed(g.state)
+    a = lambda v: np.array([[v]], np.float64)
+    grad = f.grad()(*(g.inputs() + ex_g + adj + [a(0.), a(1.), a(0.)]))
+    uid = C.create_string_buffer(128)
+    hostsim.check(hostsim.dll.adfvm_comm_unique_id(uid))
+    results, errors = {}, []
+
+    def run(rank):
+        try:
+            case = decompose.periodic_box_rank(N, rank, world)
+            ids = decompose.global_cell_ids(N, rank, world)
+            ex_r = _plane_extras(case, list(ids), plane)
+            fr = function.PrimalFunction(_with_plane(case), np.float64, lib=hostsim)
+            fr.c.attach_comm(uid.raw, rank, world)
+            o = fr(*(case.inputs() + ex_r), replace_reusable=True)
+            adj_r = [np.ascontiguousarray(x[ids]) for x in adj]
+            gr = fr.grad()(*(case.inputs() + ex_r + adj_r + [a(0.), a(1.), a(0.)]))
+            results[rank] = (ids, o, gr)
+        except Exception as e:      # pragma: no cover
+            errors.append(e)
+    ts = [threading.Thread(target=run, args=(r,)) for r in range(world)]
+    [t.start() for t in ts]
+    [t.join(timeout=300) for t in ts]
+    assert not errors, errors
+    assert abs(out[4][0, 0]) > 1e-6                      # a real objective value
+    sc = [float(np.abs(s).max()) for s in g.state]
+    for rank in range(world):
+        ids, o, gr = results[rank]
+        assert relerr(o[4], out[4]) < TOL
+        for grp in (slice(0, 3), slice(3, 6)):
+            num = max(np.abs(x - y[ids]).max() * s for x, y, s in zip(gr[grp], grad[grp], sc))
+            den = max(np.abs(y).max() * s for y, s in zip(grad[grp], sc))
+            assert num / den < TOL

@@ -50,6 +50,40 @@ for grp in (slice(0, 3), slice(3, 6)):
     num = max(np.abs(x - y[ids]).max() * s for x, y, s in zip(gr[grp], grad[grp], sc))
     den = max(np.abs(y).max() * s for y, s in zip(grad[grp], sc))
     errs.append(num / den)
+# ---- the vane design objective on the decomposed mesh: cut-plane cells as extraArgs, its mass flux all-reduced on the
+# device (ncclAllReduce on the compute stream) between the two passes, forward and in the adjoint seeds
+PLANE = {"kind": "plane_ptloss", "ptin": 175158., "normal": [1., 0., 0.], "scale": 0.4, "nExtra": 5}
+cc = g.mesh.cellCentres[:g.mesh.nInternalCells]
+xs = np.unique(np.round(cc[:, 0], 12))
+sel = np.where(np.abs(cc[:, 0] - xs[len(xs) // 2]) < 1e-9)[0]
+plane = [(int(c), 1e-3 * (1 + 0.1 * np.sin(c))) for c in sel]
+
+
+def extras(ids_global):
+    pos = {int(gid): i for i, gid in enumerate(ids_global)}
+    mine = [(pos[c], a_) for c, a_ in plane if c in pos]
+    return [len(mine), np.array([c for c, _ in mine], np.int32).reshape(-1, 1),
+            np.array([a_ for _, a_ in mine], np.float64).reshape(-1, 1), np.zeros((1, 1)), np.zeros((1, 1))]
+
+
+one = lambda v: np.array([[v]], np.float64)
+gspec = dict(g.spec); gspec["objective"] = PLANE
+fp = function.PrimalFunction(gspec, np.float64, device=local)
+exg = extras(range(g.mesh.nInternalCells))
+outp = fp(*(g.inputs() + exg), replace_reusable=True)
+gradp = fp.grad()(*(g.inputs() + exg + adj + [one(0.), one(1.), one(0.)]))
+cspec = dict(case.spec); cspec["objective"] = PLANE
+fr = function.PrimalFunction(cspec, np.float64, device=local)
+decompose.attach_comm(fr, rank, world)
+exr = extras(ids)
+op = fr(*(case.inputs() + exr), replace_reusable=True)
+grp_ = fr.grad()(*(case.inputs() + exr + [np.ascontiguousarray(x[ids]) for x in adj] + [one(0.), one(1.), one(0.)]))
+assert abs(outp[4][0, 0]) > 1e-6
+errs.append(relerr(op[4], outp[4]))
+for grp in (slice(0, 3), slice(3, 6)):
+    num = max(np.abs(x - y[ids]).max() * s for x, y, s in zip(grp_[grp], gradp[grp], sc))
+    den = max(np.abs(y).max() * s for y, s in zip(gradp[grp], sc))
+    errs.append(num / den)
 e = max(errs)
 print("rank %d of %d maxerr %.3e launches %d" % (rank, world, e, f.launches), flush=True)
 t = torch.tensor([e], dtype=torch.float64, device="cuda")
