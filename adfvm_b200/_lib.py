@@ -19,6 +19,7 @@ PATCH_WALL, PATCH_CYCLIC, PATCH_SYMMETRY, PATCH_EMPTY, PATCH_CHARACTERISTIC, PAT
 BC_CALCULATED, BC_CYCLIC, BC_ZEROGRADIENT, BC_FIXEDVALUE, BC_SYMMETRY, BC_CBC_UPT, BC_CBC_TOTAL_PT, BC_PROCESSOR = range(8)
 KEY_VALUE_U, KEY_VALUE_T, KEY_VALUE_P, KEY_U0, KEY_T0, KEY_P0, KEY_TT, KEY_PT, KEY_DIRECTION = range(9)
 OBJ_NONE, OBJ_CELL_TV, OBJ_PATCH_PA, OBJ_DRAG = range(4)
+OBJ_PLANE_PTLOSS, OBJ_CELL_T = 4, 5
 RETURN_STATIC, ZERO_STATIC, REPLACE_STATIC, RETURN_REUSABLE, REPLACE_REUSABLE = 1, 2, 4, 8, 16
 
 

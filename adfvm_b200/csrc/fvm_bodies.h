@@ -18,7 +18,8 @@ namespace fvm {
 
 enum BCType { BC_CALCULATED = 0, BC_CYCLIC = 1, BC_ZEROGRADIENT = 2, BC_FIXEDVALUE = 3, BC_SYMMETRY = 4,
               BC_CBC_UPT = 5, BC_CBC_TOTAL_PT = 6, BC_PROCESSOR = 7 };
-enum ObjKind { OBJ_NONE = 0, OBJ_CELL_TV = 1, OBJ_PATCH_PA = 2, OBJ_DRAG = 3, OBJ_PLANE_PTLOSS = 4 };
+enum ObjKind { OBJ_NONE = 0, OBJ_CELL_TV = 1, OBJ_PATCH_PA = 2, OBJ_DRAG = 3, OBJ_PLANE_PTLOSS = 4,
+               OBJ_CELL_T = 5 };     // sum of T over the cells, no volume weight (reference templates/box.py:10-16)
 enum { MAX_PATCHES = 255 };
 
 template <typename R> struct PatchDev {
@@ -202,6 +203,7 @@ template <typename R> struct ObjectiveBody {
     Phys<R> ph; MeshDev<R> m; ObjDev<R> o; const R* Q;
     FVM_HD R operator()(int i) const {
         if (o.kind == OBJ_CELL_TV) return Q[3 * m.sN + i] * m.vol[i];
+        if (o.kind == OBJ_CELL_T) return Q[3 * m.sN + i];
         const PatchDev<R>& P = m.patches[o.patch];
         const int f = P.startFace + i, g = m.neigh[f];
         if (o.kind == OBJ_PATCH_PA) return Q[4 * m.sN + g] * m.area[f];
@@ -347,7 +349,8 @@ template <typename R> struct GradAdjUpdateBody {
     const R* W;                // stage state the residual was evaluated at
     const R *A1, *A2, *A3;     // adjoints of later stage outputs (NULL when coefficient is 0)
     R c1, c2, c3;
-    R objT;                    // obja for OBJ_CELL_TV on the objective stage, else 0
+    R objT;                    // obja for OBJ_CELL_TV / OBJ_CELL_T on the objective stage, else 0
+    int objVol;                // 1: the cell objective is volume-weighted (OBJ_CELL_TV)
     R* Aout;                   // [5][sC]
     R* Sb; R s1, s2, s3;       // source gradient accumulation (only when Sb != NULL): Sb += s1*A1 + s2*A2 + s3*A3
     FVM_HD void operator()(int c) const {
@@ -382,7 +385,7 @@ template <typename R> struct GradAdjUpdateBody {
                 add_prim(Qb, sN, nbr[j], gq);
             }
         }
-        if (objT != R(0)) acc.T += objT * m.vol[c];
+        if (objT != R(0)) acc.T += objVol ? objT * m.vol[c] : objT;
         R rhoU[3] = {W[sC + c], W[2 * sC + c], W[3 * sC + c]};
         R out[5] = {0, 0, 0, 0, 0};
         primitive_vjp(ph, W[c], rhoU, W[4 * sC + c], acc, out[0], out + 1, out[4]);

@@ -279,7 +279,7 @@ public:
     }
     void set_objective(int kind, int patch, int dir) {
         epoch++;
-        if (kind != OBJ_NONE && kind != OBJ_CELL_TV && (patch < 0 || patch >= (int)patches.size())) throw std::runtime_error("objective patch out of range");
+        if (kind != OBJ_NONE && kind != OBJ_CELL_TV && kind != OBJ_CELL_T && (patch < 0 || patch >= (int)patches.size())) throw std::runtime_error("objective patch out of range");
         obj.kind = kind; obj.patch = patch; obj.dir = dir;
     }
     // cut-plane objective (reference adFVM/objectives/vane.py): cells in the reference's numbering, areas, constants
@@ -311,7 +311,7 @@ public:
             ex.reduce_sum(obj.ncells, PlaneLossBody<R>{ph, m, obj, Qs, red + 2}, red + 1); launches += 4;
             return;
         }
-        const int n = (obj.kind == OBJ_CELL_TV) ? C : patches[obj.patch].nFaces;
+        const int n = (obj.kind == OBJ_CELL_TV || obj.kind == OBJ_CELL_T) ? C : patches[obj.patch].nFaces;
         ex.reduce_sum(n, ObjectiveBody<R>{ph, m, obj, Qs}, red + 1); launches += 2;
     }
     void set_source(const R* s_rho, const R* s_rhoU, const R* s_rhoE) {
@@ -504,7 +504,8 @@ public:
             pb.A1 = (s <= 0 && RK_ALPHA[0][s] != 0.) ? A[1] : nullptr; pb.c1 = (R)(s <= 0 ? RK_ALPHA[0][s] : 0.);
             pb.A2 = (s <= 1 && RK_ALPHA[1][s] != 0.) ? A[2] : nullptr; pb.c2 = (R)(s <= 1 ? RK_ALPHA[1][s] : 0.);
             pb.A3 = (RK_ALPHA[2][s] != 0.) ? A[3] : nullptr; pb.c3 = (R)RK_ALPHA[2][s];
-            pb.objT = (s == 1 && obj.kind == OBJ_CELL_TV) ? obja : R(0);
+            pb.objT = (s == 1 && (obj.kind == OBJ_CELL_TV || obj.kind == OBJ_CELL_T)) ? obja : R(0);
+            pb.objVol = obj.kind == OBJ_CELL_TV;
             pb.Aout = A[s];
             pb.Sb = (s == 0) ? Sb : nullptr;
             pb.s1 = (R)RK_BETA[0] * dt; pb.s2 = (R)RK_BETA[1] * dt; pb.s3 = (R)RK_BETA[2] * dt;

@@ -44,7 +44,7 @@ _BC_TYPE = {"cyclic": L.BC_CYCLIC, "zeroGradient": L.BC_ZEROGRADIENT, "empty": L
 _BC_KEY = {("U", "value"): (L.KEY_VALUE_U, 3), ("T", "value"): (L.KEY_VALUE_T, 1), ("p", "value"): (L.KEY_VALUE_P, 1),
            ("p", "U0"): (L.KEY_U0, 3), ("p", "T0"): (L.KEY_T0, 1), ("p", "p0"): (L.KEY_P0, 1),
            ("p", "Tt"): (L.KEY_TT, 1), ("p", "pt"): (L.KEY_PT, 1), ("p", "direction"): (L.KEY_DIRECTION, 3)}
-_OBJ_KIND = {"none": L.OBJ_NONE, "cell_TV": L.OBJ_CELL_TV, "patch_pA": L.OBJ_PATCH_PA, "drag": L.OBJ_DRAG}
+_OBJ_KIND = {"none": L.OBJ_NONE, "cell_TV": L.OBJ_CELL_TV, "patch_pA": L.OBJ_PATCH_PA, "drag": L.OBJ_DRAG, "cell_T": L.OBJ_CELL_T}
 
 
 def _ptr(a):

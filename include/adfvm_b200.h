@@ -31,7 +31,8 @@ enum { ADFVM_BC_CALCULATED = 0, ADFVM_BC_CYCLIC = 1, ADFVM_BC_ZEROGRADIENT = 2, 
        ADFVM_BC_SYMMETRY = 4, ADFVM_BC_CBC_UPT = 5, ADFVM_BC_CBC_TOTAL_PT = 6, ADFVM_BC_PROCESSOR = 7 };   /* adFVM/BCs.py */
 enum { ADFVM_KEY_VALUE_U = 0, ADFVM_KEY_VALUE_T = 1, ADFVM_KEY_VALUE_P = 2, ADFVM_KEY_U0 = 3, ADFVM_KEY_T0 = 4,
        ADFVM_KEY_P0 = 5, ADFVM_KEY_TT = 6, ADFVM_KEY_PT = 7, ADFVM_KEY_DIRECTION = 8 };                     /* createInput keys */
-enum { ADFVM_OBJ_NONE = 0, ADFVM_OBJ_CELL_TV = 1, ADFVM_OBJ_PATCH_PA = 2, ADFVM_OBJ_DRAG = 3 };
+enum { ADFVM_OBJ_NONE = 0, ADFVM_OBJ_CELL_TV = 1, ADFVM_OBJ_PATCH_PA = 2, ADFVM_OBJ_DRAG = 3,
+       ADFVM_OBJ_PLANE_PTLOSS = 4 /* set by adfvm_set_objective_plane */, ADFVM_OBJ_CELL_T = 5 /* sum T, templates/box.py */ };
 /* option bits of adfvm_primal / adfvm_primal_grad == the kwargs of Function.__call__, adpy/adpy/variable.py:282-287 */
 enum { ADFVM_RETURN_STATIC = 1, ADFVM_ZERO_STATIC = 2, ADFVM_REPLACE_STATIC = 4, ADFVM_RETURN_REUSABLE = 8,
        ADFVM_REPLACE_REUSABLE = 16 };

@@ -50,3 +50,10 @@ def test_patch_without_faces(hostsim):
     case = cases.Case(mesh, spec, cases.conservative(U, T, p), cases.gaussian_source(cc), {}, 1e-6)
     assert mesh.boundary["b_none"]["nFaces"] == 0
     _check(case, hostsim)
+
+
+def test_sum_T_objective(hostsim):
+    """objective of reference templates/box.py:10-16 (sum of T over the cells, no volume weight)"""
+    case = cases.periodic_box((6, 5, 4), warp=0.02)
+    case.spec = dict(case.spec, objective={"kind": "cell_T"})
+    _check(case, hostsim)
