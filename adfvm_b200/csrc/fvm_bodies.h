@@ -8,9 +8,9 @@
 //   G  [15][sN]  gradients: dU_i/dx_j at 3*i+j, dT/dx_j at 9+j, dp/dx_j at 12+j
 //   face metrics [k][sF]; cell connectivity [6][sC]
 // No scatter of the reference (Tensor.collate -> atomicAdd, adpy/adpy/tensor.py:393-394) is an atomic here: the
-// flux kernels (fvm_tile_bodies.h) sum face contributions per tile in shared memory in colour order, the gradient
-// kernels are cell-centred gathers over the six faces of the hexahedron. All sums have a fixed order: results are
-// bitwise reproducible run to run, primal and adjoint.
+// flux kernels (fvm_tile_bodies.h) sum the face contributions of a cell in the registers of the lane that owns it, in
+// the fixed order of the sub-tile's schedule (fvm_tiles.h); the gradient kernels are cell-centred gathers over the six
+// faces of the hexahedron. All sums have a fixed order: results are bitwise reproducible run to run, primal and adjoint.
 #pragma once
 #include "fvm_math.h"
 
@@ -480,6 +480,34 @@ template <typename R> struct GhostPrimAdjBody {
         R out[5] = {0, 0, 0, 0, 0};
         primitive_vjp(ph, W[c], rhoU, W[4 * sC + c], acc, out[0], out + 1, out[4]);
         for (int k = 0; k < 5; k++) Aout[k * sC + c] += out[k];
+    }
+};
+
+// G. gradient with respect to ONE boundary-condition input array (parameters = ('BCs', field, patch, key), reference
+// apps/adjoint.py:108-116): the adjoint of the patch's ghost rows (+ objective seeds) pushed through the BC formula
+// (adFVM/BCs.py:111-184), accumulated over stages and steps into Pb [d][nFaces] like the source-term gradient.
+template <typename R> struct BCParamAdjBody {
+    static constexpr const char* kName = "bc_param_adj";
+    Phys<R> ph; MeshDev<R> m; ObjDev<R> o; R obja; int patch, key;   // key: Solver::BCKey
+    const R* Q; const R* Qb; R* Pb;
+    FVM_HD void operator()(int i) const {
+        const PatchDev<R>& P = m.patches[patch];
+        const int f = P.startFace + i, nf = P.nFaces, gcell = m.nInternalCells + (f - m.nInternalFaces);
+        Prim<R> q; load_prim(Qb, m.sN, gcell, q);
+        if (obja != R(0)) objective_ghost_adj(ph, m, o, Q, obja, f, q);
+        switch (key) {
+        case 0: case 3: for (int k = 0; k < 3; k++) Pb[k * nf + i] += q.U[k]; break;      // U value / U0: ghost U = input
+        case 1: case 4: Pb[i] += q.T; break;                                              // T value / T0
+        case 2: case 5: Pb[i] += q.p; break;                                              // p value / p0
+        case 6: case 7: {                                                                 // Tt, pt of CBC_TOTAL_PT (BCs.py:178-184)
+            const int own = m.owner[f];
+            const R To = Q[3 * m.sN + own], Tt = P.Tt[i], ex = ph.g_gm1;
+            const R ratio = pow(To / Tt, ex);
+            if (key == 7) Pb[i] += q.p * ratio;                                           // p_b = pt (To/Tt)^ex
+            else Pb[i] += q.T - q.p * P.pt[i] * ratio * ex / Tt;                           // T_b = Tt - Un^2/(2 Cp)
+        } break;
+        default: break;
+        }
     }
 };
 

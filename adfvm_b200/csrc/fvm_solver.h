@@ -268,6 +268,30 @@ public:
         *slot = dst;
         push_patches();
     }
+    // parameter block of the adjoint: the source terms (default) or one BC input array (reference apps/adjoint.py:101-120)
+    int param_patch = -1, param_key = -1, param_dim = 0; R* Pb = nullptr;
+    void set_parameter_source() { epoch++; param_patch = -1; param_key = -1; }
+    void set_parameter_bc(int patch, int key) {
+        epoch++;
+        if (patch < 0 || patch >= (int)patches.size()) throw std::runtime_error("bad patch index");
+        const PatchDev<R>& d = patches_dev_h[patch];
+        const bool ok = (key == KEY_VALUE_U && d.bc[0] == BC_FIXEDVALUE) || (key == KEY_VALUE_T && d.bc[1] == BC_FIXEDVALUE) ||
+                        (key == KEY_VALUE_P && d.bc[2] == BC_FIXEDVALUE) ||
+                        ((key == KEY_U0 || key == KEY_T0 || key == KEY_P0) && d.bc[2] == BC_CBC_UPT) ||
+                        ((key == KEY_TT || key == KEY_PT) && d.bc[2] == BC_CBC_TOTAL_PT);
+        if (!ok) throw std::runtime_error("this boundary condition has no such input to differentiate (or it is not supported: direction)");
+        param_patch = patch; param_key = key; param_dim = (key == KEY_VALUE_U || key == KEY_U0) ? 3 : 1;
+        Pb = dalloc<R>((size_t)param_dim * std::max(1, patches[patch].nFaces));
+    }
+    // host [nFaces][d] <- device [d][nFaces]
+    void get_param_grad(R* out, bool zero_after) {
+        if (param_patch < 0) throw std::runtime_error("no BC parameter selected");
+        const int n = patches[param_patch].nFaces, d = param_dim;
+        std::vector<R> h((size_t)n * d);
+        ex.download(h.data(), Pb, h.size() * sizeof(R)); ex.sync();
+        for (int i = 0; i < n; i++) for (int k = 0; k < d; k++) out[(size_t)i * d + k] = h[(size_t)k * n + i];
+        if (zero_after) ex.zero(Pb, h.size() * sizeof(R));
+    }
     void check_bcs() const {
         for (size_t p = 0; p < patches.size(); p++) {
             const PatchDev<R>& d = patches_dev_h[p];
@@ -473,7 +497,8 @@ public:
         ensure_adjoint_buffers();
         if (chain) { R* t = A[0]; A[0] = A[3]; A[3] = t; }
         with_graph({2ull, epoch, bits((double)dt), bits((double)obja), (unsigned long long)W[0], (unsigned long long)A[0], (unsigned long long)A[3],
-                    (unsigned long long)obj.kind, (unsigned long long)obj.patch, (unsigned long long)obj.dir}, [&]() { adjoint_step_body(dt, obja); });
+                    (unsigned long long)obj.kind, (unsigned long long)obj.patch, (unsigned long long)obj.dir, (unsigned long long)obj.cells,
+                    (unsigned long long)Pb, (unsigned long long)(param_patch * 16 + param_key + 1)}, [&]() { adjoint_step_body(dt, obja); });
     }
     void adjoint_step_body(R dt, R obja) {
         primal_step(dt, true);
@@ -515,6 +540,7 @@ public:
             const R* rQ = halo_reverse_end();
             const R oa = (s == 1) ? obja : R(0);
             run(nBcells, GhostPrimAdjBody<R>{ph, m, obj, oa, bcells, Q[s], Qb, rQ, W[s], A[s]});
+            if (param_patch >= 0) run(patches[param_patch].nFaces, BCParamAdjBody<R>{ph, m, obj, oa, param_patch, param_key, Q[s], Qb, Pb});
         }
     }
     // ---- device-side checkpoint block. The reference's Solver.run(mode='forward') returns every

@@ -256,6 +256,18 @@ class _Context:
             self.lib.check(d.adfvm_set_objective(self.ctx, _OBJ_KIND[o["kind"]],
                                                  index.get(o.get("patch"), 0), int(o.get("direction", 0))))
         self.load_replaceable(P)
+        # parameter block of the adjoint: 'source' (default) or ('BCs', field, patch, key) (apps/adjoint.py:101-120)
+        par = self.spec.get("parameters") or "source"
+        self.param_bc = None
+        if par != "source":
+            if not (isinstance(par, (list, tuple)) and len(par) == 4 and par[0] == "BCs"):
+                raise NotImplementedError("parameters=%r: supported are 'source' and ('BCs', field, patch, key)" % (par,))
+            _, field, pid, key = par
+            if (field, key) not in _BC_KEY or key == "direction":
+                raise NotImplementedError("no gradient with respect to BC input %s.%s" % (field, key))
+            kid, dim = _BC_KEY[(field, key)]
+            self.lib.check(d.adfvm_set_parameter_bc(self.ctx, self.patch_index[pid], kid))
+            self.param_bc = (self.patch[pid]["nFaces"], dim)
         self.static_loaded = True
 
     def load_replaceable(self, P):
@@ -432,11 +444,15 @@ class AdjointFunction:
         flags = (L.RETURN_STATIC if opts["return_static"] else 0) | (L.ZERO_STATIC if opts["zero_static"] else 0)
         outs = [c.pool.empty((C_, 1), c.dtype), c.pool.empty((C_, 3), c.dtype), c.pool.empty((C_, 1), c.dtype)]
         grads = [None, None, None]
-        if opts["return_static"]:
+        if c.param_bc is not None:                 # one BC input array is the parameter block
+            grads = [c.pool.empty(c.param_bc, c.dtype) if opts["return_static"] else None, None, None]
+        elif opts["return_static"]:
             grads = [c.pool.empty((C_, 1), c.dtype), c.pool.empty((C_, 3), c.dtype), c.pool.empty((C_, 1), c.dtype)]
         c.lib.check(c.lib.dll.adfvm_primal_grad(
             c.ctx, _ptr(rho), _ptr(rhoU), _ptr(rhoE), float(dt[0, 0]), _ptr(ra), _ptr(rUa), _ptr(rEa), dtca, obja, flags,
             _ptr(outs[0]), _ptr(outs[1]), _ptr(outs[2]), _ptr(grads[0]), _ptr(grads[1]), _ptr(grads[2])))
+        if c.param_bc is not None:
+            return tuple(outs + grads[:1])
         return tuple(outs + grads)
 
     def step_resident(self, dt, obja=1.0, chain=True):

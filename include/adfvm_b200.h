@@ -78,6 +78,10 @@ int adfvm_set_mesh(adfvm_ctx* ctx, const int32_t sizes[8],
 int adfvm_set_bc_value(adfvm_ctx* ctx, int32_t patch, int32_t key, const void* values);
 /* objective evaluated on the stage-1 state (adFVM/density.py:412-413); see DESIGN.md for the supported kinds */
 int adfvm_set_objective(adfvm_ctx* ctx, int32_t kind, int32_t patch, int32_t direction);
+/* parameter block of the adjoint (reference apps/adjoint.py:101-120): the source terms (default, patch < 0) or ONE
+ * boundary-condition input array - parameters = ('BCs', field, patch, key) - whose gradient [nFaces][d] adfvm_primal_grad
+ * then returns in its first gradient array (same static-accumulator options). key: ADFVM_KEY_* of adfvm_set_bc_value. */
+int adfvm_set_parameter_bc(adfvm_ctx* ctx, int32_t patch, int32_t key);
 /* the design objective of the reference's turbine-vane cases (adFVM/objectives/vane.py:36-66,83-139, templates/vane.py):
  * scale x mass-flow averaged total-pressure loss (ptin - pt)/ptin over the cells of a cut plane. cells (reference
  * numbering) and areas are the extraArgs the case file passes after the BC arrays (adFVM/solver.py:317). */

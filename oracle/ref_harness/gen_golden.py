@@ -104,6 +104,7 @@ def perturb(fields, mesh, t):
     return rho, rhoU, rhoE
 
 parameters = 'source'
+{param_block}
 nSteps = {nSteps}
 writeInterval = {writeInterval}
 startTime = 0.0
@@ -344,7 +345,28 @@ def case_channel_vane():
                 rcf_extra="", mid="[0.05,0.02,0.005]", amp="1e1", width="2e3", nSteps=4, writeInterval=2, dt=2e-8)
 
 
-CASES = {"channel_vane": case_channel_vane, "step2d": case_step2d, "cyl2d": case_cyl2d, "box_cyclic": case_box_cyclic, "tube": case_tube, "box_walls": case_box_walls, "box_upt": case_box_upt}
+
+BC_PT_PARAM = '''
+# sensitivity to a boundary-condition input instead of the source term (apps/adjoint.py:108-116, adFVM/solver.py:262-270):
+# the total pressure of the CBC_TOTAL_PT inlet, perturbed face by face
+def perturb(fields, mesh, t):
+    n = mesh.boundary['inlet']['nFaces']
+    return (50.*(1 + 0.5*np.cos(np.arange(n)))).reshape(-1, 1)
+
+parameters = ('BCs', 'p', 'inlet', 'pt')
+'''
+
+
+def case_box_walls_bcpt():
+    """box_walls with parameters = ('BCs', 'p', 'inlet', 'pt'): the adjoint returns the gradient with respect to the
+    inlet total-pressure array (a14: BC parameter block) and the perturbed run perturbs that array."""
+    c = case_box_walls()
+    c["param_block"] = BC_PT_PARAM
+    c["parameters"] = ["BCs", "p", "inlet", "pt"]
+    return c
+
+
+CASES = {"box_walls_bcpt": case_box_walls_bcpt, "channel_vane": case_channel_vane, "step2d": case_step2d, "cyl2d": case_cyl2d, "box_cyclic": case_box_cyclic, "tube": case_tube, "box_walls": case_box_walls, "box_upt": case_box_upt}
 
 
 def run(cmd, cwd):
@@ -365,7 +387,7 @@ def write_case(name, tag):
     casefile = os.path.join(case, "casefile.py")
     with open(casefile, "w") as f:
         f.write(CASEFILE_HEAD + c["objective"] + CASEFILE_TAIL.format(
-            case=case, rcf_extra=c["rcf_extra"], after_primal=c.get("after_primal", ""), mid=c["mid"], amp=c["amp"], width=c["width"],
+            case=case, rcf_extra=c["rcf_extra"], after_primal=c.get("after_primal", ""), param_block=c.get("param_block", ""), mid=c["mid"], amp=c["amp"], width=c["width"],
             nSteps=c["nSteps"], writeInterval=c["writeInterval"], dt=c["dt"]))
     return c, case, casefile
 
@@ -410,6 +432,8 @@ def generate(name, fp32=False):
             j = json.load(f)
         meta["spec"] = j["spec"]
         meta["spec"]["objective"] = c["obj_spec"]
+        if "parameters" in c:
+            meta["spec"]["parameters"] = c["parameters"]
         meta["runs"][runname] = j["calls"]
         for k in z.files:
             out["%s__%s" % (runname, k)] = z[k]

@@ -57,3 +57,22 @@ def test_sum_T_objective(hostsim):
     case = cases.periodic_box((6, 5, 4), warp=0.02)
     case.spec = dict(case.spec, objective={"kind": "cell_T"})
     _check(case, hostsim)
+
+
+@pytest.mark.parametrize("par", [("BCs", "U", "lid", "value"), ("BCs", "T", "lid", "value"), ("BCs", "p", "outlet", "value"),
+                                 ("BCs", "p", "inlet", "Tt"), ("BCs", "p", "inlet", "pt")])
+def test_bc_parameter_gradients(hostsim, par):
+    """adjoint with one BC input array as the parameter block (reference apps/adjoint.py:108-116; the reference-recorded
+    fixture box_walls_bcpt pins the pt case, the others are checked against the oracle's autograd)"""
+    case = cases.walled_box((6, 5, 3))
+    case.spec = dict(case.spec, parameters=list(par))
+    f = function.PrimalFunction(case.spec, np.float64, lib=hostsim)
+    adj = [np.ones_like(s) * w for s, w in zip(case.state, (1.0, 1e-2, 1e-5))]
+    g = f.grad()(*case.adjoint_inputs(case.state, adj))
+    gref = O.primal_grad(case.spec, case.adjoint_inputs(case.state, adj))
+    assert len(g) == 4 and g[3].shape == gref[3].shape
+    assert np.abs(gref[3]).max() > 0
+    assert np.abs(g[3] - gref[3]).max() <= TOL * np.abs(gref[3]).max()
+    # static accumulator: a second call without zero_static adds the same gradient again (adpy/adpy/variable.py:484-490)
+    g2 = f.grad()(*case.adjoint_inputs(case.state, adj), zero_static=False)
+    assert np.abs(g2[3] - 2 * gref[3]).max() <= 10 * TOL * np.abs(gref[3]).max()
