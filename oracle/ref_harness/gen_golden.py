@@ -96,11 +96,11 @@ primal = RCF('{case}/', objective=objective, fixedTimeStep=True{rcf_extra})
 def perturb(fields, mesh, t):
     x = mesh.cellCentres[:mesh.nInternalCells]
     mid = np.array({mid})
-    G = {amp}*np.exp(-{width}*np.linalg.norm(x-mid, axis=1, keepdims=1)**2)
+    G = ({amp}*np.exp(-{width}*np.linalg.norm(x-mid, axis=1, keepdims=1)**2)).astype(config.precision)
     rho = G
-    rhoU = np.zeros((mesh.nInternalCells, 3))
+    rhoU = np.zeros((mesh.nInternalCells, 3), config.precision)
     rhoU[:, 0] += G.flatten()*100
-    rhoE = G*2e5
+    rhoE = (G*2e5).astype(config.precision)
     return rho, rhoU, rhoE
 
 parameters = 'source'

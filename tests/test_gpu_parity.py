@@ -114,6 +114,13 @@ def test_graph_replay_matches_eager(cudalib):
         assert np.array_equal(a, b)
 
 
+@pytest.mark.parametrize("name", [c for c in available() if c.endswith("_fp32")])
+def test_fp32_matches_reference_fp32_on_device(name, cudalib):
+    """fp32 kernels against the reference's own fp32 mode (tests/test_fp32_golden.py), 2e-6 per call"""
+    from test_fp32_golden import replay_fp32
+    replay_fp32(name)
+
+
 def test_block_equals_host_round_trips_on_device(cudalib):
     """device-side checkpoint block (adfvm_primal_block / adfvm_adjoint_block) against one host round trip per step,
     bit for bit, with whole steps replayed as CUDA graphs"""
