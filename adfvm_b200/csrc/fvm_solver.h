@@ -11,6 +11,7 @@
 #include <string>
 #include <vector>
 #include <cstring>
+#include <cstdlib>
 #include "fvm_bodies.h"
 #include "fvm_tile_bodies.h"
 #include "fvm_tiles.h"
@@ -53,6 +54,7 @@ public:
     std::vector<PatchDev<R>> patches_dev_h;  // host mirror of the device table
     HaloComm<R>* comm = nullptr;
     long launches = 0;                        // kernels launched so far (bench "gpu_launches")
+    long overlap_min_cells = 1 << 20;         // adjoint_step: seeds uploaded concurrently with the forward sweep from this size on
     long graph_replays = 0;                   // steps served by replaying a captured CUDA graph (introspection)
     unsigned long long epoch = 0;             // bumped by every set_* call: part of the CUDA-graph keys (kernel arguments are baked into graphs)
     long bytes_allocated = 0;
@@ -74,6 +76,7 @@ public:
 
     explicit Solver(const Exec& e) : ex(e) {
         std::memset(&m, 0, sizeof(m)); std::memset(&ph, 0, sizeof(ph)); std::memset(&obj, 0, sizeof(obj)); obj.kind = OBJ_NONE;
+        if (const char* e = std::getenv("ADFVM_OVERLAP_MIN_CELLS")) overlap_min_cells = std::atol(e);   // tests force / forbid the overlapped path
     }
     ~Solver() { for (void* p : owned) ex.free(p); }
 
@@ -489,8 +492,20 @@ public:
     // source-term gradient accumulated into Sb (static accumulator semantics, adpy/adpy/variable.py:484-490).
     void adjoint_step(R dt, const R* rhoa, const R* rhoUa, const R* rhoEa, R obja) {
         ensure_adjoint_buffers();
+        // large single-rank meshes: the adjoint seeds travel host -> device on the side stream while the forward sweep
+        // (which only needs the state) already runs; the reverse sweep waits for them
+        const bool overlap = !comm && m.nRemoteCells == 0 && m.nInternalCells >= overlap_min_cells;
+        if (!overlap) {
+            put5(A[3], rhoa, rhoUa, rhoEa);
+            adjoint_step_resident(dt, obja, false);
+            return;
+        }
+        ex.side_begin();               // ordered after the state upload issued so far (it uses the same staging buffer)
         put5(A[3], rhoa, rhoUa, rhoEa);
-        adjoint_step_resident(dt, obja, false);
+        ex.side_end();
+        primal_step(dt, true);
+        ex.join();
+        adjoint_reverse(dt, obja);
     }
     // same on resident data: adjoint input already in A[3] (chain: take the previous call's result A[0])
     void adjoint_step_resident(R dt, R obja, bool chain) {
@@ -502,6 +517,9 @@ public:
     }
     void adjoint_step_body(R dt, R obja) {
         primal_step(dt, true);
+        adjoint_reverse(dt, obja);
+    }
+    void adjoint_reverse(R dt, R obja) {
         const int C = m.nInternalCells;
         for (int s = 2; s >= 0; s--) {
             const R coef = (R)(-RK_BETA[s]) * dt;

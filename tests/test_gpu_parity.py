@@ -121,6 +121,26 @@ def test_fp32_matches_reference_fp32_on_device(name, cudalib):
     replay_fp32(name)
 
 
+def test_overlapped_seed_upload_is_bitwise_equal(cudalib, monkeypatch):
+    """primal_grad from host arrays uploads the adjoint seeds on a side stream while the forward sweep runs (large
+    meshes); forced here on a small mesh and compared with the sequential path"""
+    case = cases.walled_box((10, 8, 4))
+    adj = _adj_seed(case)
+    res = []
+    for threshold in ("0", "1000000000"):
+        monkeypatch.setenv("ADFVM_OVERLAP_MIN_CELLS", threshold)
+        f = function.PrimalFunction(case.spec, np.float64)
+        fa = f.grad()
+        out = []
+        for rep in range(3):
+            g = fa(*case.adjoint_inputs(case.state, adj), return_static=True, zero_static=True)
+            out.append([x.copy() for x in g])
+        res.append(out)
+    for a, b in zip(res[0], res[1]):
+        for x, y in zip(a, b):
+            assert np.array_equal(x, y)
+
+
 def test_block_equals_host_round_trips_on_device(cudalib):
     """device-side checkpoint block (adfvm_primal_block / adfvm_adjoint_block) against one host round trip per step,
     bit for bit, with whole steps replayed as CUDA graphs"""
