@@ -28,6 +28,10 @@ class Patch(C.Structure):
                                          "neighbour_patch", "peer_rank", "tag")]
 
 
+class MetricPatch(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("startFace", "nFaces", "kind", "nbrStartFace")]
+
+
 class AdfvmError(RuntimeError):
     pass
 
@@ -38,7 +42,7 @@ EXPORTS = ["adfvm_last_error", "adfvm_version", "adfvm_is_cuda", "adfvm_create",
            "adfvm_get_state", "adfvm_sync", "adfvm_launch_count", "adfvm_device_bytes", "adfvm_comm_unique_id",
            "adfvm_comm_init", "adfvm_kernel_timing", "adfvm_kernel_report", "adfvm_set_tile_cells", "adfvm_tile_stats", "adfvm_tile_halo_stats",
            "adfvm_host_alloc", "adfvm_host_free", "adfvm_tile_rounds", "adfvm_graph_replays",
-           "adfvm_set_state", "adfvm_set_objective_plane", "adfvm_set_parameter_bc", "adfvm_primal_block", "adfvm_adjoint_block", "adfvm_set_adjoint", "adfvm_get_adjoint"]
+           "adfvm_set_state", "adfvm_mesh_metrics", "adfvm_set_objective_plane", "adfvm_set_parameter_bc", "adfvm_primal_block", "adfvm_adjoint_block", "adfvm_set_adjoint", "adfvm_get_adjoint"]
 
 
 class Lib:
@@ -82,6 +86,7 @@ class Lib:
         d.adfvm_adjoint_block.argtypes = [vp, i32, C.POINTER(f64), f64]
         d.adfvm_set_adjoint.argtypes = [vp, vp, vp, vp]
         d.adfvm_set_state.argtypes = [vp, vp, vp, vp]
+        d.adfvm_mesh_metrics.argtypes = [vp, i32, vp, i32, i32, i32, vp, vp, vp, vp, i32, C.POINTER(MetricPatch), vp] + [vp] * 10
         d.adfvm_get_adjoint.argtypes = [vp, vp, vp, vp, vp, vp, vp, i32]
         d.adfvm_graph_replays.argtypes = [vp]; d.adfvm_graph_replays.restype = C.c_int64
         d.adfvm_tile_rounds.argtypes = [vp, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(i32)]

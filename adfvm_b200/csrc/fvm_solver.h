@@ -15,6 +15,7 @@
 #include "fvm_bodies.h"
 #include "fvm_tile_bodies.h"
 #include "fvm_tiles.h"
+#include "fvm_metrics.h"
 
 namespace fvm {
 
@@ -561,6 +562,54 @@ public:
             if (param_patch >= 0) run(patches[param_patch].nFaces, BCParamAdjBody<R>{ph, m, obj, oa, param_patch, param_key, Q[s], Qb, Pb});
         }
     }
+    // ---- mesh metric build on the device (fvm_metrics.h); host AoS in, host AoS out.
+    // neighbour: all faces (boundary face b -> ghost cell nIC + b); cellCentres out: [nIC + nBoundary][3]
+    void mesh_metrics(int nP, const R* points, int nF, int nIF, int nIC, const int* faces, const int* owner, const int* neighbour,
+                      const int* cellFaces, int nPatches, const MetricPatch* mp, const R* remote,
+                      R* areas, R* normals, R* faceCentres, R* cellCentres, R* volumes, R* deltas, R* deltasUnit, R* weights,
+                      R* linW, R* quadW) {
+        const int nB = nF - nIF, nC = nIC + nB;
+        if (nP <= 0 || nF <= 0 || nIC <= 0 || nIF < 0 || nIF > nF) throw std::runtime_error("bad mesh sizes");
+        for (long i = 0; i < (long)nF * 4; i++) if (faces[i] < 0 || faces[i] >= nP) throw std::runtime_error("face point index out of range");
+        for (long f = 0; f < nF; f++) if (owner[f] < 0 || owner[f] >= nIC || neighbour[f] < 0 || neighbour[f] >= nC) throw std::runtime_error("owner/neighbour out of range");
+        for (long i = 0; i < (long)nIC * 6; i++) if (cellFaces[i] < 0 || cellFaces[i] >= nF) throw std::runtime_error("cellFaces out of range");
+        std::vector<unsigned char> bp(nB + 1, 255);
+        if (nPatches > 255) throw std::runtime_error("too many patches");
+        for (int p = 0; p < nPatches; p++) {
+            if (mp[p].nFaces && (mp[p].startFace < nIF || mp[p].startFace + mp[p].nFaces > nF)) throw std::runtime_error("patch face range out of bounds");
+            if (mp[p].kind == 1 && (mp[p].nbrStartFace < nIF || mp[p].nbrStartFace + mp[p].nFaces > nF)) throw std::runtime_error("cyclic partner out of bounds");
+            if (mp[p].kind == 2 && mp[p].nFaces && !remote) throw std::runtime_error("processor patch needs the neighbour rank's cell centres");
+            for (int i = 0; i < mp[p].nFaces; i++) bp[mp[p].startFace - nIF + i] = (unsigned char)p;
+        }
+        for (int b = 0; b < nB; b++) if (bp[b] == 255) throw std::runtime_error("boundary face not covered by any patch");
+        std::vector<void*> tmp;
+        auto up = [&](const void* h, size_t bytes) { void* d = ex.alloc(bytes + 16); tmp.push_back(d); if (h) ex.upload(d, h, bytes); return d; };
+        const R* d_pts = (const R*)up(points, (size_t)nP * 3 * sizeof(R));
+        const int* d_faces = (const int*)up(faces, (size_t)nF * 4 * 4);
+        const int* d_owner = (const int*)up(owner, (size_t)nF * 4);
+        const int* d_neigh = (const int*)up(neighbour, (size_t)nF * 4);
+        const int* d_cf = (const int*)up(cellFaces, (size_t)nIC * 6 * 4);
+        const MetricPatch* d_mp = (const MetricPatch*)up(mp, (size_t)std::max(1, nPatches) * sizeof(MetricPatch));
+        const unsigned char* d_bp = (const unsigned char*)up(bp.data(), bp.size());
+        const R* d_remote = remote ? (const R*)up(remote, (size_t)nB * 3 * sizeof(R)) : nullptr;
+        R* d_n = (R*)up(nullptr, (size_t)nF * 3 * sizeof(R)); R* d_fc = (R*)up(nullptr, (size_t)nF * 3 * sizeof(R));
+        R* d_a = (R*)up(nullptr, (size_t)nF * sizeof(R)); R* d_cc = (R*)up(nullptr, (size_t)nC * 3 * sizeof(R));
+        R* d_v = (R*)up(nullptr, (size_t)nIC * sizeof(R)); R* d_d = (R*)up(nullptr, (size_t)nF * sizeof(R));
+        R* d_du = (R*)up(nullptr, (size_t)nF * 3 * sizeof(R)); R* d_w = (R*)up(nullptr, (size_t)nF * sizeof(R));
+        R* d_lw = (R*)up(nullptr, (size_t)nF * 2 * sizeof(R)); R* d_qw = (R*)up(nullptr, (size_t)nF * 6 * sizeof(R));
+        run(nF, FaceGeomBody<R>{d_pts, d_faces, d_n, d_fc, d_a});
+        run(nIC, CellGeomBody<R>{d_cf, d_n, d_fc, d_a, d_cc, d_v});
+        run(nB, GhostCentreBody<R>{d_mp, d_bp, d_owner, d_fc, d_remote, nIF, nIC, d_cc});
+        run(nF, FaceWeightBody<R>{d_owner, d_neigh, d_cc, d_fc, d_n, d_d, d_du, d_w, d_lw, d_qw});
+        ex.download(areas, d_a, (size_t)nF * sizeof(R)); ex.download(normals, d_n, (size_t)nF * 3 * sizeof(R));
+        ex.download(faceCentres, d_fc, (size_t)nF * 3 * sizeof(R)); ex.download(cellCentres, d_cc, (size_t)nC * 3 * sizeof(R));
+        ex.download(volumes, d_v, (size_t)nIC * sizeof(R)); ex.download(deltas, d_d, (size_t)nF * sizeof(R));
+        ex.download(deltasUnit, d_du, (size_t)nF * 3 * sizeof(R)); ex.download(weights, d_w, (size_t)nF * sizeof(R));
+        ex.download(linW, d_lw, (size_t)nF * 2 * sizeof(R)); ex.download(quadW, d_qw, (size_t)nF * 6 * sizeof(R));
+        ex.sync();
+        for (void* q : tmp) ex.free(q);
+    }
+
     // ---- device-side checkpoint block. The reference's Solver.run(mode='forward') returns every
     // state of a checkpoint block to the host and Adjoint.run feeds them back one by one (adFVM/solver.py:376-382,
     // apps/adjoint.py:217-291); here the block stays in HBM: primal_block stores the state at the start of each of its

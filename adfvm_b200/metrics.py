@@ -59,10 +59,16 @@ class MeshData:
         return m
 
 
-def build_mesh(poly, remote_centres=None):
+def build_mesh(poly, remote_centres=None, device=None):
     """poly: hexmesh.PolyMesh (rank-local). remote_centres: for processor patches, dict
     patchID -> [nFaces,3] ghost cell centres (what the reference exchanges over MPI in
-    `createGhostCells`, mesh.py:784-805)."""
+    `createGhostCells`, mesh.py:784-805).
+    device: None -> the numpy restatement below (test infrastructure for synthetic inputs); a dict
+    {"lib": _lib.Lib, "device": 0, "precision": np.float64, "stream": None} -> the geometry (everything of
+    adFVM/cpp/cmesh.cpp:65-233 and the ghost-cell centres) is computed by the library on the device
+    (adfvm_mesh_metrics, csrc/fvm_metrics.h); the integer connectivity stays here."""
+    if device is not None:
+        return _build_mesh_device(poly, remote_centres, device)
     m = MeshData()
     points, faces = poly.points, poly.faces.astype(np.int64)
     owner = poly.owner.astype(np.int64)
@@ -327,4 +333,76 @@ def uniform_box(n, lo=(0., 0., 0.), hi=(1., 1., 1.), patches=None):
     m.cellFaces = np.ascontiguousarray(cellFaces, np.int32)
     m.cellNeighbours = np.ascontiguousarray(np.where(own_flag, fn, fo), np.int32)
     m.cellOwner = np.ascontiguousarray(own_flag, np.int32)
+    return m
+
+
+def _build_mesh_device(poly, remote_centres, dev):
+    """Connectivity and patch bookkeeping on the host (integer sorts), geometry by adfvm_mesh_metrics."""
+    import ctypes as C
+    from . import _lib as L
+    lib = dev.get("lib") or L.default_lib()
+    dtype = np.dtype(dev.get("precision", np.float64))
+    m = MeshData()
+    faces = np.ascontiguousarray(poly.faces, np.int32)
+    owner = np.ascontiguousarray(poly.owner, np.int32)
+    nb_int = np.ascontiguousarray(poly.neighbour, np.int32)
+    nF, nIF = len(owner), len(nb_int)
+    nIC = int(owner.max()) + 1
+    nG = nF - nIF
+    m.boundary = OrderedDict((k, dict(v)) for k, v in poly.boundary.items())
+    m.nFaces, m.nInternalFaces, m.nInternalCells = nF, nIF, nIC
+    m.nGhostCells, m.nCells, m.nBoundaryFaces = nG, nIC + nG, nG
+    cells_of_face = np.concatenate([owner.astype(np.int64), nb_int.astype(np.int64)])
+    face_ids = np.concatenate([np.arange(nF), np.arange(nIF)])
+    pri = np.concatenate([np.zeros(nF, np.int64), np.ones(nIF, np.int64)])
+    order = np.lexsort((face_ids, pri, cells_of_face))
+    assert len(order) == 6 * nIC, "hexahedral cells only (6 faces per cell)"
+    cellFaces = np.ascontiguousarray(face_ids[order].reshape(nIC, 6), np.int32)
+    neighbour = np.concatenate([nb_int, np.arange(nIC, nIC + nG, dtype=np.int32)]).astype(np.int32)
+    delta_cf = nIC - nIF
+    pids = sorted(m.boundary.keys(), key=lambda x: (m.boundary[x]["startFace"], m.boundary[x]["nFaces"]))
+    local, remote = [], []
+    nLocalCells = nIC
+    table = (L.MetricPatch * max(1, len(pids)))()
+    rc = np.zeros((nG, 3), dtype) if any(m.boundary[p]["type"] in PROCESSOR_PATCHES for p in pids) else None
+    for i, pid in enumerate(pids):
+        patch = m.boundary[pid]
+        patch["nFaces"] = int(patch["nFaces"]); patch["startFace"] = int(patch["startFace"])
+        patch["cellStartFace"] = patch["startFace"] + delta_cf
+        t = table[i]
+        t.startFace, t.nFaces, t.kind, t.nbrStartFace = patch["startFace"], patch["nFaces"], 0, 0
+        if patch["type"] in PROCESSOR_PATCHES:
+            remote.append(pid); t.kind = 2
+            assert remote_centres is not None and pid in remote_centres, "processor patch %s needs the neighbour rank's cell centres" % pid
+            s0 = patch["startFace"] - nIF
+            rc[s0:s0 + patch["nFaces"]] = remote_centres[pid]
+        else:
+            local.append(pid); nLocalCells += patch["nFaces"]
+            if patch["type"] in CYCLIC_PATCHES:
+                t.kind = 1; t.nbrStartFace = int(m.boundary[patch["neighbourPatch"]]["startFace"])
+    m.localPatches, m.remotePatches, m.sortedPatches = local, remote, sorted(local)
+    m.nLocalCells, m.nRemoteCells = nLocalCells, nIC + nG - nLocalCells
+    m.nLocalFaces = nLocalCells - nIC + nIF
+    points = np.ascontiguousarray(poly.points, dtype)
+    out = {"areas": (nF, 1), "normals": (nF, 3), "faceCentres": (nF, 3), "cellCentres": (nIC + nG, 3), "volumes": (nIC, 1),
+           "deltas": (nF, 1), "deltasUnit": (nF, 3), "weights": (nF, 1), "linearWeights": (nF, 2), "quadraticWeights": (nF, 2, 3)}
+    arr = {k: np.zeros(shp, dtype) for k, shp in out.items()}
+    ctx = C.c_void_p()
+    stream = dev.get("stream")
+    lib.check(lib.dll.adfvm_create(C.byref(ctx), int(dev.get("device", 0)), dtype.itemsize, C.c_void_p(stream) if stream else None))
+    try:
+        p = lambda a: None if a is None else a.ctypes.data_as(C.c_void_p)
+        lib.check(lib.dll.adfvm_mesh_metrics(ctx, len(points), p(points), nF, nIF, nIC, p(faces), p(owner), p(neighbour), p(cellFaces),
+                                             len(pids), table, p(rc), *[p(arr[k]) for k in out]))
+    finally:
+        lib.dll.adfvm_destroy(ctx)
+    for k, v in arr.items():
+        setattr(m, k, v)
+    own_flag = (owner[cellFaces] == np.arange(nIC)[:, None])
+    m.points, m.faces = poly.points, poly.faces
+    m.owner, m.neighbour, m.cellFaces = owner, neighbour, cellFaces
+    m.cellNeighbours = np.ascontiguousarray(np.where(own_flag, neighbour[cellFaces], owner[cellFaces]), np.int32)
+    m.cellOwner = np.ascontiguousarray(own_flag, np.int32)
+    m.volumesL = m.volumes[m.owner]
+    m.volumesR = m.volumes[m.neighbour[:nIF]]
     return m

@@ -130,6 +130,20 @@ int adfvm_tile_stats(adfvm_ctx* ctx, double* evals_per_cell, int32_t* max_rounds
  * histogram of tiles per halo size in bins of 32 slots */
 int adfvm_tile_halo_stats(adfvm_ctx* ctx, int32_t* max_halo, int32_t* variant, int32_t* hist, int32_t nbins);
 
+/* Mesh metric build on the device: replaces cmesh.build (adFVM/cpp/cmesh.cpp:65-270, called from adFVM/mesh.py:107) and the
+ * ghost-cell centres of Mesh.createGhostCells (adFVM/mesh.py:758-819). Host arrays in the reference's AoS layout:
+ * points [nPoints][3], faces [nFaces][4] (quads), owner [nFaces], neighbour [nFaces] (boundary face b -> ghost cell
+ * nInternalCells + b), cellFaces [nInternalCells][6]. patches: kind 0 plain (ghost centre = face centre), 1 cyclic
+ * (nbrStartFace = first face of neighbourPatch), 2 processor (centres taken from remote_centres [nBoundaryFaces][3]).
+ * Outputs: areas [nF], normals [nF][3], faceCentres [nF][3], cellCentres [nCells][3], volumes [nIC], deltas [nF],
+ * deltasUnit [nF][3], weights [nF], linearWeights [nF][2], quadraticWeights [nF][2][3]. */
+typedef struct { int32_t startFace, nFaces, kind, nbrStartFace; } adfvm_metric_patch;
+int adfvm_mesh_metrics(adfvm_ctx* ctx, int32_t nPoints, const void* points, int32_t nFaces, int32_t nInternalFaces,
+                       int32_t nInternalCells, const int32_t* faces, const int32_t* owner, const int32_t* neighbour,
+                       const int32_t* cellFaces, int32_t nPatches, const adfvm_metric_patch* patches, const void* remote_centres,
+                       void* areas, void* normals, void* faceCentres, void* cellCentres, void* volumes, void* deltas,
+                       void* deltasUnit, void* weights, void* linearWeights, void* quadraticWeights);
+
 /* Device-side checkpoint block: what Solver.run(mode='forward') + the step loop of Adjoint.run do through host memory
  * (adFVM/solver.py:376-382: every state of a block returned to numpy; apps/adjoint.py:217-291: fed back one by one).
  * adfvm_primal_block runs nsteps steps from the resident state with time steps dt[k], keeps the state at the start of

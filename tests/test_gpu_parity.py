@@ -141,6 +141,12 @@ def test_overlapped_seed_upload_is_bitwise_equal(cudalib, monkeypatch):
             assert np.array_equal(x, y)
 
 
+def test_mesh_metrics_on_device(cudalib):
+    """adfvm_mesh_metrics on the device against the restatement of cmesh.cpp, fp64 1e-12"""
+    from test_mesh_metrics_device import compare
+    compare(cudalib)
+
+
 def test_block_equals_host_round_trips_on_device(cudalib):
     """device-side checkpoint block (adfvm_primal_block / adfvm_adjoint_block) against one host round trip per step,
     bit for bit, with whole steps replayed as CUDA graphs"""
