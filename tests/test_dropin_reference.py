@@ -32,3 +32,20 @@ def test_reference_drivers_with_b200_functions(name, hostsim):
         # perturb = J(perturbed) - J(orig) cancels four digits: compare relative to the size of J
         scale = abs(float(gold[0].split()[3])) if g[0] == "perturb" else abs(float(r[3]))
         assert abs(float(g[3]) - float(r[3])) <= 1e-9 * scale, (got, ref)
+    # the field files the reference wrote (final state of the `orig` run - the perturbed run does not write fields - and
+    # the adjoint fields at the start time) hold what our
+    # functions computed: read them back with the package's OpenFOAM reader and compare with the recorded stock run
+    from adfvm_b200 import foam_io
+    from golden_util import Golden, relerr
+    case = os.path.join(gen_golden.SCRATCH, name + "_dropin")
+    poly = foam_io.read_polymesh(case)
+    n = int(poly.owner.max()) + 1
+    gold_calls = Golden(name)
+    last = [out for _, _, _, _, out in gold_calls.calls("orig", "primal") if out[0] is not None][-1]
+    times = sorted((d for d in os.listdir(case) if d.replace(".", "").isdigit() and d != "0"), key=float)
+    for fname, ref in zip(("rho", "rhoU", "rhoE"), last[:3]):
+        got, _ = foam_io.read_field(case, times[-1], fname, n, poly.boundary)
+        assert relerr(got, ref) < 1e-10, fname
+    for fname in ("rhoa", "rhoUa", "rhoEa"):
+        got, _ = foam_io.read_field(case, "0", fname, n, poly.boundary)
+        assert np.all(np.isfinite(got)) and np.abs(got).max() > 0
