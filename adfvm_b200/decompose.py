@@ -137,3 +137,115 @@ def attach_comm(f, rank, world, group=None):
     t = torch.tensor(list(buf.raw), dtype=torch.uint8, device=dev)
     dist.broadcast(t, 0, group=group)
     f.c.attach_comm(bytes(t.cpu().tolist()), rank, world)
+
+
+# ------------------------------------------------------------------------------------------ general meshes
+def slab_partition(cell_centres, nranks, axis=0):
+    """cell -> rank by equal-count slabs along `axis` (OpenFOAM decomposePar `simple` with n = (nranks 1 1))"""
+    order = np.lexsort((np.arange(len(cell_centres)), cell_centres[:, axis]))
+    rank = np.empty(len(cell_centres), np.int64)
+    rank[order] = (np.arange(len(order)) * nranks) // len(order)
+    return rank
+
+
+def decompose_polymesh(poly, cell_rank):
+    """Split a `hexmesh.PolyMesh` into rank-local meshes in the layout of OpenFOAM's decomposePar that the reference reads
+    (`processor<r>/constant/polyMesh`, adFVM/mesh.py:177-204, 238-249): local cells in ascending global order, the
+    rank's inner faces first, then EVERY physical patch (possibly with 0 faces, same order and attributes), then one
+    `processor` patch `procBoundary<r>to<q>` per neighbouring rank q whose faces are the cut faces in ascending global
+    face order on both sides (face i of r's patch is face i of q's), flipped on the side that held the neighbour cell so
+    that normals leave the local owner. Returns per rank a dict(poly, cellProcAddressing, faceProcAddressing [global
+    face of every local face], patchFaces {patch: positions of the local faces inside the global patch}).
+    Cyclic partners must stay on one rank (a cut through a periodic pair would need processorCyclic patches)."""
+    from collections import OrderedDict
+    from .hexmesh import PolyMesh
+    cell_rank = np.asarray(cell_rank, np.int64)
+    nranks = int(cell_rank.max()) + 1
+    owner = np.asarray(poly.owner, np.int64); neigh = np.asarray(poly.neighbour, np.int64)
+    nIF, nF = len(neigh), len(owner)
+    for name, p in poly.boundary.items():
+        if p["type"] == "cyclic" and p["nFaces"]:
+            q = poly.boundary[p["neighbourPatch"]]
+            a = cell_rank[owner[p["startFace"]:p["startFace"] + p["nFaces"]]]
+            b = cell_rank[owner[q["startFace"]:q["startFace"] + q["nFaces"]]]
+            if np.any(a != b):
+                raise NotImplementedError("the partition cuts the cyclic pair %s/%s" % (name, p["neighbourPatch"]))
+    ro, rn = cell_rank[owner[:nIF]], cell_rank[neigh]
+    out = []
+    for r in range(nranks):
+        cells = np.where(cell_rank == r)[0]
+        g2l = np.full(len(cell_rank), -1, np.int64); g2l[cells] = np.arange(len(cells))
+        inner = np.where((ro == r) & (rn == r))[0]
+        f_list, own_l, faces_l = [inner], [g2l[owner[inner]]], [poly.faces[inner]]
+        nb_l = g2l[neigh[inner]]
+        boundary = OrderedDict()
+        patch_faces = {}
+        start = len(inner)
+        for name, p in poly.boundary.items():
+            gf = np.arange(p["startFace"], p["startFace"] + p["nFaces"])
+            sel = gf[cell_rank[owner[gf]] == r]
+            d = OrderedDict((k, v) for k, v in p.items() if k not in ("nFaces", "startFace", "cellStartFace"))
+            d["nFaces"], d["startFace"] = int(len(sel)), int(start)
+            boundary[name] = d
+            patch_faces[name] = sel - p["startFace"]
+            f_list.append(sel); own_l.append(g2l[owner[sel]]); faces_l.append(poly.faces[sel])
+            start += len(sel)
+        cut = np.where((ro == r) != (rn == r))[0]                 # global inner faces with exactly one cell here
+        peers = np.where(ro[cut] == r, rn[cut], ro[cut])
+        for q in sorted(set(peers.tolist())):
+            sel = cut[peers == q]                                  # ascending global face order on both ranks
+            mine_is_owner = ro[sel] == r
+            fl = poly.faces[sel].copy()
+            fl[~mine_is_owner] = fl[~mine_is_owner][:, [0, 3, 2, 1]]   # normal must leave the local cell (OpenFOAM reverseFace:
+            # first vertex kept). NB the reference takes the normal from a face's first three points (cmesh.cpp:72-87): on
+            # non-planar faces a reversed face has a slightly different normal, so decomposition invariance is exact only
+            # for meshes with planar faces - with decomposePar and the reference as well
+            lo = np.where(mine_is_owner, g2l[owner[sel]], g2l[neigh[sel]])
+            boundary["procBoundary%dto%d" % (r, q)] = OrderedDict(type="processor", nFaces=int(len(sel)), startFace=int(start),
+                                                                  myProcNo=int(r), neighbProcNo=int(q), tag=0)
+            f_list.append(sel); own_l.append(lo); faces_l.append(fl)
+            start += len(sel)
+        out.append(dict(poly=PolyMesh(poly.points, np.concatenate(faces_l), np.concatenate(own_l), nb_l, boundary),
+                        cellProcAddressing=cells, faceProcAddressing=np.concatenate(f_list), patchFaces=patch_faces))
+    return out
+
+
+def remote_centres(parts, rank, global_cell_centres, global_owner, global_neighbour):
+    """ghost-cell centres of `rank`'s processor patches = centres of the peer's cells across the cut faces (what
+    Mesh.createGhostCells exchanges over MPI, adFVM/mesh.py:784-805); here taken from the undecomposed mesh"""
+    part = parts[rank]
+    mine = set(part["cellProcAddressing"].tolist())
+    res = {}
+    for name, p in part["poly"].boundary.items():
+        if p["type"] != "processor":
+            continue
+        gf = part["faceProcAddressing"][p["startFace"]:p["startFace"] + p["nFaces"]]
+        o, n = global_owner[gf], global_neighbour[gf]
+        other = np.where(np.isin(o, list(mine)), n, o)
+        res[name] = global_cell_centres[other]
+    return res
+
+
+def rank_cases(case, nranks, axis=0):
+    """Decompose a single-rank `cases.Case` (any PolyMesh-backed mesh with planar faces) into `nranks` rank-local cases:
+    slab partition -> decompose_polymesh -> metrics with the peers' cell centres -> state / source / BC arrays sliced by
+    cellProcAddressing and by the patch face maps. Returns [(Case, cellProcAddressing)]."""
+    from .hexmesh import PolyMesh
+    from .metrics import build_mesh
+    gm = case.mesh
+    C = gm.nInternalCells
+    poly = PolyMesh(gm.points, gm.faces, gm.owner, gm.neighbour[:gm.nInternalFaces],
+                    {k: {kk: vv for kk, vv in v.items() if kk != "cellStartFace"} for k, v in gm.boundary.items()})
+    parts = decompose_polymesh(poly, slab_partition(gm.cellCentres[:C], nranks, axis))
+    out = []
+    for r, part in enumerate(parts):
+        rc = remote_centres(parts, r, gm.cellCentres, np.asarray(gm.owner), np.asarray(gm.neighbour))
+        m = build_mesh(part["poly"], rc)
+        ids = part["cellProcAddressing"]
+        spec = dict(case.spec)
+        spec["patches"] = cases._spec(m, spec["BCs"], spec.get("objective"))["patches"]
+        spec["sortedPatches"] = list(m.sortedPatches)
+        bcvals = {(f, pid, key): v[part["patchFaces"][pid]] for (f, pid, key), v in case.bcvals.items()}
+        rcase = cases.Case(m, spec, [s[ids] for s in case.state], [s[ids] for s in case.source], bcvals, case.dt, case.dtype)
+        out.append((rcase, ids))
+    return out

@@ -217,3 +217,38 @@ def test_threads_plane_objective(world, hostsim):
             num = max(np.abs(x - y[ids]).max() * s for x, y, s in zip(gr[grp], grad[grp], sc))
             den = max(np.abs(y).max() * s for y, s in zip(grad[grp], sc))
             assert num / den < TOL
+
+
+# ---- a general (non-periodic, walled) mesh decomposed like OpenFOAM's decomposePar: physical patches split between the
+# ranks (some left without faces), processor patches from the cut faces, flipped faces on the neighbour side
+@pytest.mark.parametrize("world", [2, 4])
+def test_threads_decomposed_walled_mesh(world, hostsim):
+    from adfvm_b200 import cases
+    g = cases.walled_box((8, 6, 4), warp=0.0)            # planar faces: decomposition invariance is exact (see decompose.py)
+    f = function.PrimalFunction(g.spec, np.float64, lib=hostsim)
+    out = f(*g.inputs(), replace_reusable=True)
+    out2 = f(*g.inputs(list(out[:3])), replace_reusable=True)
+    adj = _seed(g.state)
+    grad = f.grad()(*g.adjoint_inputs(g.state, adj))
+    parts = decompose.rank_cases(g, world)
+    assert any(p[0].mesh.boundary["inlet"]["nFaces"] == 0 for p in parts)          # a rank without inlet faces
+    uid = C.create_string_buffer(128)
+    hostsim.check(hostsim.dll.adfvm_comm_unique_id(uid))
+    results, errors = {}, []
+
+    def run(rank):
+        try:
+            case, ids = parts[rank]
+            fr = function.PrimalFunction(case.spec, np.float64, lib=hostsim)
+            fr.c.attach_comm(uid.raw, rank, world)
+            o = fr(*case.inputs(), replace_reusable=True)
+            o2 = fr(*case.inputs(list(o[:3])), replace_reusable=True)
+            gr = fr.grad()(*case.adjoint_inputs(case.state, [np.ascontiguousarray(x[ids]) for x in adj]))
+            results[rank] = (ids, o, o2, gr)
+        except Exception as e:      # pragma: no cover
+            errors.append(e)
+    ts = [threading.Thread(target=run, args=(r,)) for r in range(world)]
+    [t.start() for t in ts]
+    [t.join(timeout=300) for t in ts]
+    assert not errors, errors
+    _check(world, (g, out, out2, adj, grad), results)
