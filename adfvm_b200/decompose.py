@@ -249,3 +249,43 @@ def rank_cases(case, nranks, axis=0):
         rcase = cases.Case(m, spec, [s[ids] for s in case.state], [s[ids] for s in case.source], bcvals, case.dt, case.dtype)
         out.append((rcase, ids))
     return out
+
+
+def write_decomposed_case(case_dir, parts):
+    """processor<r>/constant/polyMesh/* of every part (OpenFOAM binary, adfvm_b200.foam_io) + the addressing arrays"""
+    import os
+    from . import foam_io
+    for r, part in enumerate(parts):
+        d = os.path.join(case_dir, "processor%d" % r)
+        foam_io.write_polymesh(d, part["poly"])
+        np.save(os.path.join(d, "constant", "polyMesh", "cellProcAddressing.npy"), part["cellProcAddressing"])
+
+
+def load_decomposed_mesh(case_dir, rank, group=None):
+    """Rank-local mesh of an OpenFOAM-decomposed case as the reference builds it in every MPI rank
+    (Mesh.readFoam + createGhostCells, adFVM/mesh.py:177-204, 758-819): read `processor<rank>/constant/polyMesh`, compute
+    the cell centres of the own cells, exchange those next to processor patches with the peer ranks (torch.distributed
+    point-to-point, any backend) and build the metrics with them."""
+    import os
+    import torch
+    import torch.distributed as dist
+    from . import foam_io
+    from .metrics import build_mesh
+    poly = foam_io.read_polymesh(os.path.join(case_dir, "processor%d" % rank))
+    proc = [(k, v) for k, v in poly.boundary.items() if v["type"] in ("processor", "processorCyclic")]
+    for k, v in proc:
+        v.setdefault("tag", 0)
+    own = build_mesh(poly, {k: np.zeros((v["nFaces"], 3)) for k, v in proc})    # own-cell centres do not depend on ghosts
+    cc = own.cellCentres[:own.nInternalCells]
+    reqs, recv = [], {}
+    dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend(group) == "nccl" else torch.device("cpu")
+    for k, v in sorted(proc, key=lambda kv: (kv[1]["neighbProcNo"], int(kv[1].get("tag", 0)))):
+        s, n = v["startFace"], v["nFaces"]
+        send = torch.from_numpy(np.ascontiguousarray(cc[np.asarray(poly.owner[s:s + n], np.int64)])).to(dev)
+        buf = torch.empty((n, 3), dtype=torch.float64, device=dev)
+        recv[k] = buf
+        reqs.append(dist.isend(send, int(v["neighbProcNo"]), group=group, tag=int(v.get("tag", 0))))
+        reqs.append(dist.irecv(buf, int(v["neighbProcNo"]), group=group, tag=int(v.get("tag", 0))))
+    for q in reqs:
+        q.wait()
+    return build_mesh(poly, {k: b.cpu().numpy() for k, b in recv.items()})

@@ -252,3 +252,43 @@ def test_threads_decomposed_walled_mesh(world, hostsim):
     [t.join(timeout=300) for t in ts]
     assert not errors, errors
     _check(world, (g, out, out2, adj, grad), results)
+
+
+# ---- loading a decomposed case from disk the way every MPI rank of the reference does (processor<r>/constant/polyMesh in
+# OpenFOAM binary + exchange of the cell centres across processor patches), two real processes over gloo
+def _load_worker(rank, world, port, case_dir, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    import torch.distributed as dist
+    from adfvm_b200 import cases
+    from adfvm_b200.metrics import GRAD_FIELDS, INT_FIELDS
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        m = decompose.load_decomposed_mesh(case_dir, rank)
+        ref = decompose.rank_cases(cases.walled_box((8, 6, 4), warp=0.0), world)[rank][0].mesh
+        err = 0.
+        for a in GRAD_FIELDS:
+            err = max(err, float(np.abs(getattr(m, a) - getattr(ref, a)).max() / np.abs(getattr(ref, a)).max()))
+        ok = all(np.array_equal(getattr(m, a), getattr(ref, a)) for a in INT_FIELDS) and m.getScalar() == ref.getScalar()
+        q.put((rank, err, ok))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_load_decomposed_case_two_processes(tmp_path):
+    import torch.multiprocessing as mp
+    from adfvm_b200 import cases, hexmesh
+    g = cases.walled_box((8, 6, 4), warp=0.0).mesh
+    poly = hexmesh.PolyMesh(g.points, g.faces, g.owner, g.neighbour[:g.nInternalFaces],
+                            {k: {kk: vv for kk, vv in v.items() if kk != "cellStartFace"} for k, v in g.boundary.items()})
+    parts = decompose.decompose_polymesh(poly, decompose.slab_partition(g.cellCentres[:g.nInternalCells], 2))
+    decompose.write_decomposed_case(str(tmp_path), parts)
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + (os.getpid() % 2000)
+    ps = [ctx.Process(target=_load_worker, args=(r, 2, port, str(tmp_path), q)) for r in range(2)]
+    [p.start() for p in ps]
+    got = [q.get(timeout=300) for _ in ps]
+    [p.join(timeout=60) for p in ps]
+    assert sorted(r for r, _, _ in got) == [0, 1]
+    for _, err, ok in got:
+        assert ok and err < 1e-12
