@@ -148,7 +148,20 @@ struct CudaExec {
         FVM_CUDA_CHECK(cudaMalloc(&partial, kRedMaxBlocks * sizeof(double)));
         timing = new Timing();
         graphs = new Graphs();
+        configured = new std::map<const void*, size_t>();
         if (const char* e = getenv("ADFVM_NO_GRAPH")) graphs->enabled = !(e[0] && e[0] != '0');
+    }
+    std::map<const void*, size_t>* configured = nullptr;     // kernels whose shared-memory attribute has been raised
+    // releases what init() and the lazily created side stream / graphs hold; called once by the owner (Solver)
+    void destroy() {
+        if (!timing) return;
+        cudaStreamSynchronize(stream);
+        timing_collect();
+        for (auto& kv : graphs->cache) if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+        if (side) { cudaStreamSynchronize(side); cudaStreamDestroy(side); cudaEventDestroy(ev_fork); cudaEventDestroy(ev_join); side = nullptr; }
+        cudaFree(partial); partial = nullptr;
+        delete timing; delete graphs; delete configured;
+        timing = nullptr; graphs = nullptr; configured = nullptr;
     }
     void* stream_handle() const { return (void*)stream; }
     void* alloc(size_t bytes) { void* p = nullptr; FVM_CUDA_CHECK(cudaMalloc(&p, bytes ? bytes : 1)); return p; }
@@ -193,10 +206,12 @@ struct CudaExec {
     template <class Body> void run_tiles_range(int first, int nTiles, const Body& b) {
         if (nTiles <= 0) return;
         const size_t smem = Body::smem_bytes();
-        static size_t configured = 0;
-        if (smem > 48 * 1024 && smem > configured) {
-            FVM_CUDA_CHECK(cudaFuncSetAttribute(k_tile<Body>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            configured = smem;
+        if (smem > 48 * 1024) {          // opt in to large dynamic shared memory once per kernel and executor (the attribute is per device)
+            size_t& done = (*configured)[(const void*)k_tile<Body>];
+            if (smem > done) {
+                FVM_CUDA_CHECK(cudaFuncSetAttribute(k_tile<Body>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                done = smem;
+            }
         }
         tic(Body::kName);
         k_tile<Body><<<nTiles, Body::kThreads, smem, stream>>>(b, first);

@@ -79,7 +79,7 @@ public:
         std::memset(&m, 0, sizeof(m)); std::memset(&ph, 0, sizeof(ph)); std::memset(&obj, 0, sizeof(obj)); obj.kind = OBJ_NONE;
         if (const char* e = std::getenv("ADFVM_OVERLAP_MIN_CELLS")) overlap_min_cells = std::atol(e);   // tests force / forbid the overlapped path
     }
-    ~Solver() { for (void* p : owned) ex.free(p); }
+    ~Solver() { ex.sync(); for (void* p : owned) ex.free(p); ex.destroy(); }
 
     template <typename T> T* dalloc(size_t n) {
         T* p = (T*)ex.alloc(n * sizeof(T)); ex.zero(p, n * sizeof(T)); owned.push_back(p);

@@ -25,6 +25,7 @@ struct HostExec {
     void download(void* d, const void* s, size_t b) { std::memcpy(d, s, b); }
     void copy(void* d, const void* s, size_t b) { std::memcpy(d, s, b); }
     void sync() {}
+    void destroy() {}
     void timing_enable(bool) {}
     std::string timing_report() { return ""; }
     template <class B> void run(int n, const B& b) { run_range(0, n, b); }
