@@ -176,7 +176,7 @@ def _plane_of(g):
     return [(int(c), 1e-3 * (1 + 0.1 * np.sin(c))) for c in sel]
 
 
-@pytest.mark.parametrize("world", [2, 4])
+@pytest.mark.parametrize("world", [2, 4, 8])
 def test_threads_plane_objective(world, hostsim):
     g = decompose.global_box(N, world)
     plane = _plane_of(g)
@@ -221,7 +221,7 @@ def test_threads_plane_objective(world, hostsim):
 
 # ---- a general (non-periodic, walled) mesh decomposed like OpenFOAM's decomposePar: physical patches split between the
 # ranks (some left without faces), processor patches from the cut faces, flipped faces on the neighbour side
-@pytest.mark.parametrize("world", [2, 4])
+@pytest.mark.parametrize("world", [2, 4, 8])
 def test_threads_decomposed_walled_mesh(world, hostsim):
     from adfvm_b200 import cases
     g = cases.walled_box((8, 6, 4), warp=0.0)            # planar faces: decomposition invariance is exact (see decompose.py)
