@@ -151,25 +151,27 @@ def slab_partition(cell_centres, nranks, axis=0):
 def decompose_polymesh(poly, cell_rank):
     """Split a `hexmesh.PolyMesh` into rank-local meshes in the layout of OpenFOAM's decomposePar that the reference reads
     (`processor<r>/constant/polyMesh`, adFVM/mesh.py:177-204, 238-249): local cells in ascending global order, the
-    rank's inner faces first, then EVERY physical patch (possibly with 0 faces, same order and attributes), then one
-    `processor` patch `procBoundary<r>to<q>` per neighbouring rank q whose faces are the cut faces in ascending global
-    face order on both sides (face i of r's patch is face i of q's), flipped on the side that held the neighbour cell so
-    that normals leave the local owner. Returns per rank a dict(poly, cellProcAddressing, faceProcAddressing [global
-    face of every local face], patchFaces {patch: positions of the local faces inside the global patch}).
-    Cyclic partners must stay on one rank (a cut through a periodic pair would need processorCyclic patches)."""
+    rank's inner faces first, then EVERY physical patch (possibly with 0 faces, same order and attributes), then the
+    processor patches: `procBoundary<r>to<q>` with the cut faces in ascending global face order on both sides (face i of
+    r's patch is face i of q's), flipped on the side that held the neighbour cell so that normals leave the local owner;
+    and, where the partition separates the two cells of a cyclic pair, `procBoundary<r>to<q>through<cyc>` (type
+    processorCyclic, referPatch = the cyclic patch the local faces came from) in ascending pair order. Tags are equal on
+    the two ends of a connection and distinct between the connections of one pair of ranks (adFVM/mesh.py:746-756).
+    Returns per rank a dict(poly, cellProcAddressing, faceProcAddressing [global face of every local face], patchFaces
+    {patch: positions of the local faces inside the global patch})."""
     from collections import OrderedDict
     from .hexmesh import PolyMesh
     cell_rank = np.asarray(cell_rank, np.int64)
     nranks = int(cell_rank.max()) + 1
     owner = np.asarray(poly.owner, np.int64); neigh = np.asarray(poly.neighbour, np.int64)
-    nIF, nF = len(neigh), len(owner)
+    nIF = len(neigh)
+    names = list(poly.boundary)
+    # rank of the cell behind every boundary face of a cyclic patch (its partner face's owner), else -1
+    partner_rank = {}
     for name, p in poly.boundary.items():
-        if p["type"] == "cyclic" and p["nFaces"]:
+        if p["type"] == "cyclic":
             q = poly.boundary[p["neighbourPatch"]]
-            a = cell_rank[owner[p["startFace"]:p["startFace"] + p["nFaces"]]]
-            b = cell_rank[owner[q["startFace"]:q["startFace"] + q["nFaces"]]]
-            if np.any(a != b):
-                raise NotImplementedError("the partition cuts the cyclic pair %s/%s" % (name, p["neighbourPatch"]))
+            partner_rank[name] = cell_rank[owner[q["startFace"]:q["startFace"] + q["nFaces"]]]
     ro, rn = cell_rank[owner[:nIF]], cell_rank[neigh]
     out = []
     for r in range(nranks):
@@ -180,10 +182,23 @@ def decompose_polymesh(poly, cell_rank):
         nb_l = g2l[neigh[inner]]
         boundary = OrderedDict()
         patch_faces = {}
+        proc = []                                  # (peer, tag, name, dict, global faces, local owners, face vertices)
         start = len(inner)
         for name, p in poly.boundary.items():
             gf = np.arange(p["startFace"], p["startFace"] + p["nFaces"])
-            sel = gf[cell_rank[owner[gf]] == r]
+            mine = cell_rank[owner[gf]] == r
+            if name in partner_rank:               # faces whose periodic partner lives on another rank leave the cyclic patch
+                pr = partner_rank[name]
+                away = mine & (pr != r)
+                mine = mine & (pr == r)
+                ia, ib = names.index(name), names.index(p["neighbourPatch"])
+                for q in sorted(set(pr[away].tolist())):
+                    sel = gf[away & (pr == q)]
+                    tag = 1 + 2 * min(ia, ib) + (1 if ((r < q) == (ia < ib)) else 0)
+                    proc.append((q, tag, "procBoundary%dto%dthrough%s" % (r, q, name),
+                                 OrderedDict(type="processorCyclic", myProcNo=int(r), neighbProcNo=int(q), referPatch=name, tag=int(tag)),
+                                 sel, g2l[owner[sel]], poly.faces[sel]))
+            sel = gf[mine]
             d = OrderedDict((k, v) for k, v in p.items() if k not in ("nFaces", "startFace", "cellStartFace"))
             d["nFaces"], d["startFace"] = int(len(sel)), int(start)
             boundary[name] = d
@@ -201,8 +216,11 @@ def decompose_polymesh(poly, cell_rank):
             # non-planar faces a reversed face has a slightly different normal, so decomposition invariance is exact only
             # for meshes with planar faces - with decomposePar and the reference as well
             lo = np.where(mine_is_owner, g2l[owner[sel]], g2l[neigh[sel]])
-            boundary["procBoundary%dto%d" % (r, q)] = OrderedDict(type="processor", nFaces=int(len(sel)), startFace=int(start),
-                                                                  myProcNo=int(r), neighbProcNo=int(q), tag=0)
+            proc.append((q, 0, "procBoundary%dto%d" % (r, q),
+                         OrderedDict(type="processor", myProcNo=int(r), neighbProcNo=int(q), tag=0), sel, lo, fl))
+        for q, tag, name, d, sel, lo, fl in sorted(proc, key=lambda x: (x[0], x[1])):
+            d["nFaces"], d["startFace"] = int(len(sel)), int(start)
+            boundary[name] = d
             f_list.append(sel); own_l.append(lo); faces_l.append(fl)
             start += len(sel)
         out.append(dict(poly=PolyMesh(poly.points, np.concatenate(faces_l), np.concatenate(own_l), nb_l, boundary),
@@ -210,19 +228,25 @@ def decompose_polymesh(poly, cell_rank):
     return out
 
 
-def remote_centres(parts, rank, global_cell_centres, global_owner, global_neighbour):
-    """ghost-cell centres of `rank`'s processor patches = centres of the peer's cells across the cut faces (what
-    Mesh.createGhostCells exchanges over MPI, adFVM/mesh.py:784-805); here taken from the undecomposed mesh"""
+def remote_centres(parts, rank, global_mesh):
+    """ghost-cell centres of `rank`'s processor patches = centres of the peer's cells across the cut faces, shifted by the
+    periodic offset for processorCyclic patches (what Mesh.createGhostCells exchanges over MPI, adFVM/mesh.py:784-805);
+    here taken from the undecomposed mesh `global_mesh` (metrics.MeshData)"""
     part = parts[rank]
-    mine = set(part["cellProcAddressing"].tolist())
+    gm = global_mesh
+    o_all, n_all = np.asarray(gm.owner, np.int64), np.asarray(gm.neighbour, np.int64)
+    mine = np.zeros(gm.nInternalCells, bool); mine[part["cellProcAddressing"]] = True
     res = {}
     for name, p in part["poly"].boundary.items():
-        if p["type"] != "processor":
-            continue
         gf = part["faceProcAddressing"][p["startFace"]:p["startFace"] + p["nFaces"]]
-        o, n = global_owner[gf], global_neighbour[gf]
-        other = np.where(np.isin(o, list(mine)), n, o)
-        res[name] = global_cell_centres[other]
+        if p["type"] == "processor":
+            o, n = o_all[gf], n_all[gf]
+            res[name] = gm.cellCentres[np.where(mine[o], n, o)]
+        elif p["type"] == "processorCyclic":
+            ref = gm.boundary[p["referPatch"]]
+            nbp = gm.boundary[ref["neighbourPatch"]]
+            pf = nbp["startFace"] + (gf - ref["startFace"])                        # partner faces
+            res[name] = gm.cellCentres[o_all[pf]] + (gm.faceCentres[gf] - gm.faceCentres[pf])
     return res
 
 
@@ -239,7 +263,7 @@ def rank_cases(case, nranks, axis=0):
     parts = decompose_polymesh(poly, slab_partition(gm.cellCentres[:C], nranks, axis))
     out = []
     for r, part in enumerate(parts):
-        rc = remote_centres(parts, r, gm.cellCentres, np.asarray(gm.owner), np.asarray(gm.neighbour))
+        rc = remote_centres(parts, r, gm)
         m = build_mesh(part["poly"], rc)
         ids = part["cellProcAddressing"]
         spec = dict(case.spec)

@@ -292,3 +292,40 @@ def test_load_decomposed_case_two_processes(tmp_path):
     assert sorted(r for r, _, _ in got) == [0, 1]
     for _, err, ok in got:
         assert ok and err < 1e-12
+
+
+# ---- a fully periodic mesh through the general decomposer: the partition separates the two cells of every x-cyclic pair,
+# which turns those faces into processorCyclic patches next to the plain processor patch of the cut
+@pytest.mark.parametrize("world", [2, 3])
+def test_threads_decomposed_periodic_mesh(world, hostsim):
+    from adfvm_b200 import cases, hexmesh
+    from adfvm_b200.metrics import build_mesh
+    g = cases.periodic_box((6, 5, 4), mesh=build_mesh(hexmesh.box_mesh((6, 5, 4))))
+    f = function.PrimalFunction(g.spec, np.float64, lib=hostsim)
+    out = f(*g.inputs(), replace_reusable=True)
+    out2 = f(*g.inputs(list(out[:3])), replace_reusable=True)
+    adj = _seed(g.state)
+    grad = f.grad()(*g.adjoint_inputs(g.state, adj))
+    parts = decompose.rank_cases(g, world)
+    types = {p["type"] for c, _ in parts for p in c.mesh.boundary.values()}
+    assert "processorCyclic" in types and "processor" in types
+    uid = C.create_string_buffer(128)
+    hostsim.check(hostsim.dll.adfvm_comm_unique_id(uid))
+    results, errors = {}, []
+
+    def run(rank):
+        try:
+            case, ids = parts[rank]
+            fr = function.PrimalFunction(case.spec, np.float64, lib=hostsim)
+            fr.c.attach_comm(uid.raw, rank, world)
+            o = fr(*case.inputs(), replace_reusable=True)
+            o2 = fr(*case.inputs(list(o[:3])), replace_reusable=True)
+            gr = fr.grad()(*case.adjoint_inputs(case.state, [np.ascontiguousarray(x[ids]) for x in adj]))
+            results[rank] = (ids, o, o2, gr)
+        except Exception as e:      # pragma: no cover
+            errors.append(e)
+    ts = [threading.Thread(target=run, args=(r,)) for r in range(world)]
+    [t.start() for t in ts]
+    [t.join(timeout=300) for t in ts]
+    assert not errors, errors
+    _check(world, (g, out, out2, adj, grad), results)
