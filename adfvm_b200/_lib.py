@@ -42,7 +42,7 @@ EXPORTS = ["adfvm_last_error", "adfvm_version", "adfvm_is_cuda", "adfvm_create",
            "adfvm_get_state", "adfvm_sync", "adfvm_launch_count", "adfvm_device_bytes", "adfvm_comm_unique_id",
            "adfvm_comm_init", "adfvm_kernel_timing", "adfvm_kernel_report", "adfvm_set_tile_cells", "adfvm_tile_stats", "adfvm_tile_halo_stats",
            "adfvm_host_alloc", "adfvm_host_free", "adfvm_tile_rounds", "adfvm_graph_replays",
-           "adfvm_set_state", "adfvm_mesh_metrics", "adfvm_set_objective_plane", "adfvm_set_parameter_bc", "adfvm_primal_block", "adfvm_adjoint_block", "adfvm_set_adjoint", "adfvm_get_adjoint"]
+           "adfvm_set_state", "adfvm_mesh_metrics", "adfvm_set_objective_plane", "adfvm_set_parameter_bc", "adfvm_set_parameter_mesh", "adfvm_get_mesh_grad", "adfvm_primal_block", "adfvm_adjoint_block", "adfvm_set_adjoint", "adfvm_get_adjoint"]
 
 
 class Lib:
@@ -64,6 +64,8 @@ class Lib:
         d.adfvm_set_objective.argtypes = [vp, i32, i32, i32]
         d.adfvm_set_source.argtypes = [vp, vp, vp, vp]
         d.adfvm_set_parameter_bc.argtypes = [vp, i32, i32]
+        d.adfvm_set_parameter_mesh.argtypes = [vp]
+        d.adfvm_get_mesh_grad.argtypes = [vp] + [vp] * 10 + [i32]
         d.adfvm_set_objective_plane.argtypes = [vp, i32, vp, vp, f64, C.POINTER(f64), f64]
         d.adfvm_primal.argtypes = [vp, vp, vp, vp, f64, i32, vp, vp, vp, vp, vp]
         d.adfvm_primal_grad.argtypes = [vp, vp, vp, vp, f64, vp, vp, vp, f64, f64, i32, vp, vp, vp, vp, vp, vp]

@@ -511,6 +511,116 @@ template <typename R> struct BCParamAdjBody {
     }
 };
 
+// H. mesh sensitivities (parameters = 'mesh', reference apps/adjoint.py:105-107): gradient with respect to the ten metric
+// arrays of adFVM/mesh.py:27-31. One thread per face, after the reverse sweep of a stage (needs abar, the complete
+// gradient adjoints H = Gb/V, the ghost-row adjoints Qb and the forward Q, G of the stage); every output row belongs to
+// one face or one cell: no scatter. Accumulated over stages and steps like the source-term gradient.
+//   Mb rows [19][sF]: 0 areas, 1 volumesL, 2 volumesR, 3 weights, 4 deltas, 5-7 normals, 8-10 deltasUnit, 11-12 linearWeights,
+//   13-18 quadraticWeights (device face numbering)
+template <typename R> struct MeshGradFaceBody {
+    static constexpr const char* kName = "mesh_grad_face";
+    Phys<R> ph; MeshDev<R> m; ObjDev<R> o; R obja; R coef;
+    const R *Q, *G, *abar, *Qb, *Gb;              // Gb: internal rows hold H = Gb/V, ghost rows are never read here
+    const R *dunit, *linw, *quadw;                // face-indexed copies of the flux metrics [3][sF], [2][sF], [6][sF]
+    R* Mb;
+    FVM_HD void operator()(int f) const {
+        const int sN = m.sN, sF = m.sF, C = m.nInternalCells;
+        const int own = m.owner[f], nb = m.neigh[f];
+        const bool internal = f < m.nInternalFaces;
+        const int kind = face_kind(m, f);
+        Geom<R> gm;
+        gm.area = m.area[f]; gm.idelta = m.idelta[f];
+        for (int k = 0; k < 3; k++) { gm.n[k] = m.normal[(long)k * sF + f]; gm.d[k] = dunit[(long)k * sF + f]; }
+        gm.lw[0] = linw[f]; gm.lw[1] = linw[(long)sF + f];
+        for (int k = 0; k < 3; k++) { gm.qw[0][k] = quadw[(long)k * sF + f]; gm.qw[1][k] = quadw[(long)(3 + k) * sF + f]; }
+        Prim<R> qL, qR; Grad<R> gL, gR;
+        load_prim(Q, sN, own, qL); load_grad(G, sN, own, gL); load_prim(Q, sN, nb, qR); load_grad(G, sN, nb, gR);
+        // ---- flux: scatter weights A/V, then the flux per unit area
+        const R VL = m.vol[own], VR = internal ? m.vol[nb] : R(1);
+        R aL[5], aR[5];
+        for (int k = 0; k < 5; k++) { aL[k] = abar[(long)k * m.sC + own]; aR[k] = internal ? abar[(long)k * m.sC + nb] : R(0); }
+        Flux5<R> F; R wave;
+        face_flux(ph, kind, gm, qL, gL, qR, gR, F, wave);
+        const R Fk[5] = {F.rho, F.rhoU[0], F.rhoU[1], F.rhoU[2], F.rhoE};
+        R sL = R(0), sR = R(0);
+        for (int k = 0; k < 5; k++) { sL += Fk[k] * aL[k]; sR += Fk[k] * aR[k]; }
+        R Ab = coef * (sL / VL - (internal ? sR / VR : R(0)));
+        const R VLb = -coef * gm.area * sL / (VL * VL);
+        const R VRb = internal ? coef * gm.area * sR / (VR * VR) : R(0);
+        Flux5<R> Fb;
+        {
+            const R cL = coef * gm.area / VL, cR = internal ? coef * gm.area / VR : R(0);
+            Fb.rho = aL[0] * cL - aR[0] * cR; Fb.rhoE = aL[4] * cL - aR[4] * cR;
+            for (int k = 0; k < 3; k++) Fb.rhoU[k] = aL[1 + k] * cL - aR[1 + k] * cR;
+        }
+        Geom<R> gb;
+        gb.area = R(0); gb.idelta = R(0);
+        for (int k = 0; k < 3; k++) { gb.n[k] = gb.d[k] = gb.qw[0][k] = gb.qw[1][k] = R(0); }
+        gb.lw[0] = gb.lw[1] = R(0);
+        face_flux_metric_vjp(ph, kind, gm, qL, gL, qR, gR, Fb, gb);
+        // ---- Green-Gauss gradient (op.py:45-63): phi_f = w phi_o + (1-w) phi_n, G_o += phi_f S n / V_o, G_n -= phi_f S n / V_n
+        R wb = R(0);
+        {
+            const R w = m.weight[f];
+            const R pL[5] = {qL.U[0], qL.U[1], qL.U[2], qL.T, qL.p}, pR[5] = {qR.U[0], qR.U[1], qR.U[2], qR.T, qR.p};
+            for (int k = 0; k < 5; k++) {
+                const R pf = pL[k] * w + pR[k] * (R(1) - w);
+                R hn = R(0);
+                for (int j = 0; j < 3; j++) {
+                    // row of component k, direction j in Gb: U: 3k+j, T: 9+j, p: 12+j
+                    const int row = k < 3 ? 3 * k + j : (k == 3 ? 9 + j : 12 + j);
+                    const R dH = Gb[(long)row * sN + own] - (internal ? Gb[(long)row * sN + nb] : R(0));
+                    hn += gm.n[j] * dH;
+                    gb.n[j] += gm.area * pf * dH;
+                }
+                Ab += pf * hn;
+                wb += gm.area * (pL[k] - pR[k]) * hn;
+            }
+        }
+        // ---- boundary conditions that read the face normal, objective seeds on boundary faces
+        if (!internal && f < m.nLocalFaces) {
+            const PatchDev<R>& P = m.patches[m.bpatch[f - m.nInternalFaces]];
+            Prim<R> q; load_prim(Qb, sN, C + (f - m.nInternalFaces), q);
+            if (obja != R(0)) objective_ghost_adj(ph, m, o, Q, obja, f, q);
+            if (P.bc[0] == BC_SYMMETRY) {                       // ghost U = u - (u.n) n
+                const R un = dot3(qL.U, gm.n), qn = dot3(q.U, gm.n);
+                for (int k = 0; k < 3; k++) gb.n[k] += -(qn * qL.U[k] + un * q.U[k]);
+            }
+            if (P.bc[2] == BC_CBC_TOTAL_PT && !P.dir) {         // direction defaults to the normal (BCs.py:170-176)
+                const R Un = dot3(qL.U, gm.n), qd = dot3(q.U, gm.n);
+                for (int k = 0; k < 3; k++) gb.n[k] += qL.U[k] * qd + Un * q.U[k] - q.T * Un * qL.U[k] / ph.Cp;
+            }
+            if (obja != R(0) && (o.kind == OBJ_PATCH_PA || o.kind == OBJ_DRAG) && f >= m.patches[o.patch].startFace &&
+                f < m.patches[o.patch].startFace + m.patches[o.patch].nFaces) {
+                if (o.kind == OBJ_PATCH_PA) Ab += obja * qR.p;
+                else {
+                    const R mu = viscosity(ph, qR.T);
+                    const R du = qR.U[o.dir] - qL.U[o.dir];
+                    Ab += obja * (qR.p * gm.n[o.dir] - mu * du * gm.idelta);
+                    gb.n[o.dir] += obja * qR.p * gm.area;
+                    gb.idelta += -obja * mu * du * gm.area;
+                }
+            }
+        }
+        R* r = Mb + f;
+        r[0] += Ab; r[(long)sF] += VLb; r[2L * sF] += VRb; r[3L * sF] += wb;
+        r[4L * sF] += -gb.idelta * gm.idelta * gm.idelta;        // deltas = 1 / idelta
+        for (int k = 0; k < 3; k++) { r[(long)(5 + k) * sF] += gb.n[k]; r[(long)(8 + k) * sF] += gb.d[k]; }
+        r[11L * sF] += gb.lw[0]; r[12L * sF] += gb.lw[1];
+        for (int k = 0; k < 3; k++) { r[(long)(13 + k) * sF] += gb.qw[0][k]; r[(long)(16 + k) * sF] += gb.qw[1][k]; }
+    }
+};
+// `volumes` (gradCell divides by it; the cell objective sum T V): Vb_c = - H_c . G_c (+ obja T_c)
+template <typename R> struct MeshGradCellBody {
+    static constexpr const char* kName = "mesh_grad_cell";
+    MeshDev<R> m; const R *Q, *G, *Gb; R objTV; R* Vb;
+    FVM_HD void operator()(int c) const {
+        R s = R(0);
+        for (int k = 0; k < 15; k++) s += Gb[(long)k * m.sN + c] * G[(long)k * m.sN + c];
+        Vb[c] += -s + objTV * Q[3L * m.sN + c];
+    }
+};
+
 // ------------------------------------------------------------------------------------------ layout helpers
 template <typename R> struct ReciprocalBody {      // x <- 1/x (deltas -> idelta at mesh upload)
     static constexpr const char* kName = "reciprocal";

@@ -229,7 +229,8 @@ FVM_HD void roe_forward(const Phys<R>& ph, const Prim<R>& L, const Prim<R>& Rr, 
 // reverse: accumulates into Lb, Rb (U, p only; T untouched) and rLb, rRb (adjoint of rho_L, rho_R)
 template <typename R>
 FVM_HD void roe_reverse(const Phys<R>& ph, const Prim<R>& L, const Prim<R>& Rr, const Cons<R>& wL, const Cons<R>& wR,
-                        const R* N, const RoeTmp<R>& t, const Flux5<R>& Fb, Prim<R>& Lb, Prim<R>& Rb, R& rLb_out, R& rRb_out) {
+                        const R* N, const RoeTmp<R>& t, const Flux5<R>& Fb, Prim<R>& Lb, Prim<R>& Rb, R& rLb_out, R& rRb_out,
+                        R* Nb = nullptr) {       // Nb (optional): accumulates the adjoint of the face normal (mesh sensitivities)
     const R g = ph.gamma, gm1 = ph.gm1;
     const R rL = wL.rho, rR = wR.rho, irL = wL.irho, irR = wR.irho;
     const R h = R(0.5);
@@ -316,6 +317,10 @@ FVM_HD void roe_reverse(const Phys<R>& ph, const Prim<R>& L, const Prim<R>& Rr, 
     for (int i = 0; i < 3; i++) { Lb.U[i] += ULb[i]; Rb.U[i] += URb[i]; }
     Lb.p += pLb; Rb.p += pRb;
     rLb_out += rLb; rRb_out += rRb;
+    if (Nb) {   // unL = UL.N, unR = UR.N, central (pL+pR) N, unt = Ut.N, b5 = unt dr - dU.N, dissipation + b7 N
+        for (int i = 0; i < 3; i++)
+            Nb[i] += mLb * rL * L.U[i] + mRb * rR * Rr.U[i] + h * (L.p + Rr.p) * Fb.rhoU[i] + untb * t.Ut[i] - b5b * t.dU[i] + h * t.b7 * Fb.rhoU[i];
+    }
 }
 
 // ---------------------------------------------------------------- Lax-Friedrichs (riemann.py:6-18)
@@ -336,7 +341,7 @@ FVM_HD void lf_forward(const Phys<R>& ph, const Prim<R>& L, const Prim<R>& Rr, c
 // reverse: accumulates into Lb/Rb (U,p) and wLb/wRb (all conservative components)
 template <typename R>
 FVM_HD void lf_reverse(const Phys<R>& ph, const Prim<R>& L, const Prim<R>& Rr, const Cons<R>& wL, const Cons<R>& wR,
-                       const R* N, const Flux5<R>& Fb, Prim<R>& Lb, Prim<R>& Rb, Cons<R>& wLb, Cons<R>& wRb) {
+                       const R* N, const Flux5<R>& Fb, Prim<R>& Lb, Prim<R>& Rb, Cons<R>& wLb, Cons<R>& wRb, R* Nb = nullptr) {
     const R g = ph.gamma, h = R(0.5);
     R unL = dot3(L.U, N), unR = dot3(Rr.U, N);
     const R xL = g * L.p * wL.irho, xR = g * Rr.p * wR.irho;
@@ -362,6 +367,7 @@ FVM_HD void lf_reverse(const Phys<R>& ph, const Prim<R>& L, const Prim<R>& Rr, c
         Rb.p += aFb * g * h * icR * wR.irho; wRb.rho += -aFb * cR * h * wR.irho;
     }
     for (int i = 0; i < 3; i++) { Lb.U[i] += unLb * N[i]; Rb.U[i] += unRb * N[i]; }
+    if (Nb) for (int i = 0; i < 3; i++) Nb[i] += unLb * L.U[i] + unRb * Rr.U[i] + h * (L.p + Rr.p) * Fb.rhoU[i];
 }
 
 // ---------------------------------------------------------------- viscous flux (density.py:192-222)
@@ -396,7 +402,8 @@ FVM_HD void viscous_forward(const Phys<R>& ph, const Geom<R>& gm, R TL, R TR, co
 template <typename R>
 FVM_HD void viscous_reverse(const Phys<R>& ph, const Geom<R>& gm, R TL, R TR, const R* UL, const R* UR, R TF, const R* UF,
                             const R* gTF, const R* gUF, const Flux5<R>& Fb,
-                            R& TLb, R& TRb, R* ULb, R* URb, R& TFb, R* UFb, R* gTFb, R* gUFb) {
+                            R& TLb, R& TRb, R* ULb, R* URb, R& TFb, R* UFb, R* gTFb, R* gUFb,
+                            R* Db = nullptr, R* Nb = nullptr, R* idelb = nullptr) {   // optional: adjoints of deltasUnit, normal, 1/delta
     R mu = viscosity(ph, TF);
     R CpPr = ph.CpPr;
     R kappa = mu * CpPr;
@@ -439,10 +446,26 @@ FVM_HD void viscous_reverse(const Phys<R>& ph, const Geom<R>& gm, R TL, R TR, co
         R gD = gUb[3 * i] * D[0] + gUb[3 * i + 1] * D[1] + gUb[3 * i + 2] * D[2];
         for (int j = 0; j < 3; j++) gUFb[3 * i + j] += gUb[3 * i + j] - gD * D[j];
         URb[i] += gD * idel; ULb[i] -= gD * idel;
+        if (Db) {   // gU[3i+j] = gUF[3i+j] + (snU_i - gUF_i.D) D[j]
+            const R snU = (UR[i] - UL[i]) * idel;
+            const R gUD = gUF[3 * i] * D[0] + gUF[3 * i + 1] * D[1] + gUF[3 * i + 2] * D[2];
+            for (int j = 0; j < 3; j++) Db[j] += gUb[3 * i + j] * (snU - gUD) - gD * gUF[3 * i + j];
+            *idelb += gD * (UR[i] - UL[i]);
+        }
     }
     R gTbD = dot3(gTb, D);
     for (int j = 0; j < 3; j++) gTFb[j] += gTb[j] - gTbD * D[j];
     TRb += gTbD * idel; TLb -= gTbD * idel;
+    if (Db) {
+        for (int j = 0; j < 3; j++) Db[j] += gTb[j] * (snT - gTD) - gTbD * gTF[j];
+        *idelb += gTbD * (TR - TL);
+        // qF = kappa gT.N ; sig_i = mu (tmp2_i - 2/3 tr N_i), tmp2_i = sum_j (gU[3i+j] + gU[3j+i]) N_j
+        for (int j = 0; j < 3; j++) {
+            R v = qFb * kappa * gT[j] - R(2. / 3) * mu * tr * sigb[j];
+            for (int i = 0; i < 3; i++) v += mu * sigb[i] * (gU[3 * i + j] + gU[3 * j + i]);
+            Nb[j] += v;
+        }
+    }
     TFb += mub * viscosity_dT(ph, TF, mu);
 }
 
@@ -486,6 +509,83 @@ FVM_HD void face_flux(const Phys<R>& ph, int kind, const Geom<R>& gm, const Prim
     else lf_forward(ph, LF, RF, wL, wR, gm.n, F);
     viscous_forward(ph, gm, qL.T, qR.T, qL.U, qR.U, TF, UF, gTF, gUF, F);
     { const R x = ph.Cp * TF * ph.gm1; wave = fabs(dot3(UF, gm.n)) + x * rsqrt_fast(x); }
+}
+
+// Reverse of face_flux with respect to the FACE METRICS (mesh sensitivities, parameters = 'mesh' of the reference,
+// apps/adjoint.py:105-107): accumulates into gb.n, gb.d, gb.idelta, gb.lw, gb.qw for a given flux adjoint Fb (per unit
+// area; the scatter weights A/V are handled by the caller). Same three face kinds as face_flux.
+template <typename R>
+FVM_HD void face_flux_metric_vjp(const Phys<R>& ph, int kind, const Geom<R>& gm, const Prim<R>& qL, const Grad<R>& gL,
+                                 const Prim<R>& qR, const Grad<R>& gR, const Flux5<R>& Fb, Geom<R>& gb) {
+    const R h = R(0.5);
+    Prim<R> dumL, dumR; zero(dumL); zero(dumR);
+    R TFb = R(0), UFb[3] = {0, 0, 0}, gTFb[3] = {0, 0, 0}, gUFb[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+    if (kind == FACE_BOUNDARY) {
+        Cons<R> w; conservative(ph, qR, w);
+        const R unb = Fb.rho * w.rho + dot3(Fb.rhoU, w.rhoU) + Fb.rhoE * (w.rhoE + qR.p);
+        for (int i = 0; i < 3; i++) gb.n[i] += unb * qR.U[i] + qR.p * Fb.rhoU[i];
+        viscous_reverse(ph, gm, qL.T, qR.T, qL.U, qR.U, qR.T, qR.U, gR.T, gR.U, Fb,
+                        dumL.T, dumR.T, dumL.U, dumR.U, TFb, UFb, gTFb, gUFb, gb.d, gb.n, &gb.idelta);
+        return;
+    }
+    Prim<R> LF, RF;
+    reconstruct(qL, qR, gL, gm.lw[0], gm.qw[0], LF);
+    Cons<R> wL, wR;
+    conservative(ph, LF, wL);
+    Prim<R> LFb, RFb; zero(LFb); zero(RFb);
+    Cons<R> wLb, wRb;
+    wLb.rho = wRb.rho = wLb.rhoE = wRb.rhoE = R(0);
+    for (int i = 0; i < 3; i++) wLb.rhoU[i] = wRb.rhoU[i] = R(0);
+    const bool ch = (kind == FACE_CHARACTERISTIC);
+    R TF, UF[3], gTF[3], gUF[9];
+    if (ch) {
+        RF = qR; TF = qR.T;
+        for (int i = 0; i < 3; i++) { UF[i] = qR.U[i]; gTF[i] = gR.T[i]; }
+        for (int i = 0; i < 9; i++) gUF[i] = gR.U[i];
+    } else {
+        reconstruct(qR, qL, gR, gm.lw[1], gm.qw[1], RF);
+        TF = h * (LF.T + RF.T);
+        for (int i = 0; i < 3; i++) { UF[i] = h * (LF.U[i] + RF.U[i]); gTF[i] = h * (gL.T[i] + gR.T[i]); }
+        for (int i = 0; i < 9; i++) gUF[i] = h * (gL.U[i] + gR.U[i]);
+    }
+    conservative(ph, RF, wR);
+    viscous_reverse(ph, gm, qL.T, qR.T, qL.U, qR.U, TF, UF, gTF, gUF, Fb,
+                    dumL.T, dumR.T, dumL.U, dumR.U, TFb, UFb, gTFb, gUFb, gb.d, gb.n, &gb.idelta);
+    const int solver = ch ? ph.boundary_riemann : ph.riemann;
+    if (solver == RIEMANN_ROE) {
+        Flux5<R> F; RoeTmp<R> t;
+        roe_forward(ph, LF, RF, wL, wR, gm.n, F, t);
+        roe_reverse(ph, LF, RF, wL, wR, gm.n, t, Fb, LFb, RFb, wLb.rho, wRb.rho, gb.n);
+    } else {
+        lf_reverse(ph, LF, RF, wL, wR, gm.n, Fb, LFb, RFb, wLb, wRb, gb.n);
+    }
+    conservative_vjp(ph, LF, wL, wLb, LFb);
+    conservative_vjp(ph, RF, wR, wRb, RFb);
+    if (!ch) {
+        LFb.T += h * TFb; RFb.T += h * TFb;
+        for (int i = 0; i < 3; i++) { LFb.U[i] += h * UFb[i]; RFb.U[i] += h * UFb[i]; }
+    }
+    // reconstruction (interp.py:20-28): phiF = phiC + (phiD - phiC) lw + qw . grad(phiC)
+    {
+        R s = (qR.T - qL.T) * LFb.T + (qR.p - qL.p) * LFb.p;
+        for (int i = 0; i < 3; i++) s += (qR.U[i] - qL.U[i]) * LFb.U[i];
+        gb.lw[0] += s;
+        for (int j = 0; j < 3; j++) {
+            R v = gL.T[j] * LFb.T + gL.p[j] * LFb.p;
+            for (int i = 0; i < 3; i++) v += gL.U[3 * i + j] * LFb.U[i];
+            gb.qw[0][j] += v;
+        }
+    }
+    if (!ch) {
+        R s = (qL.T - qR.T) * RFb.T + (qL.p - qR.p) * RFb.p;
+        for (int i = 0; i < 3; i++) s += (qL.U[i] - qR.U[i]) * RFb.U[i];
+        gb.lw[1] += s;
+        for (int j = 0; j < 3; j++) {
+            R v = gR.T[j] * RFb.T + gR.p[j] * RFb.p;
+            for (int i = 0; i < 3; i++) v += gR.U[3 * i + j] * RFb.U[i];
+            gb.qw[1][j] += v;
+        }
+    }
 }
 
 // Compact form of the reverse of a COUPLED face (both sides reconstructed): everything the 40 input adjoints are

@@ -158,7 +158,9 @@ public:
             R* d_chunks = dalloc<R>((nslots / kRound) * (size_t)Chunk<R, kRound>::kScalars + 16);
             run((int)nslots, FillChunksBody<R, kRound>{t_face, t_word, m.sF, m.area, m.normal, m.idelta, t_dunit, t_linw, t_quadw, d_chunks});
             m.chunks = d_chunks;
-            ex.sync(); ex.free(t_dunit); ex.free(t_linw); ex.free(t_quadw); ex.free(t_face); ex.free(t_word);
+            ex.sync(); ex.free(t_face); ex.free(t_word);
+            if (mesh_param) { f_dunit = t_dunit; f_linw = t_linw; f_quadw = t_quadw; owned.push_back(t_dunit); owned.push_back(t_linw); owned.push_back(t_quadw); }
+            else { ex.free(t_dunit); ex.free(t_linw); ex.free(t_quadw); }
         }
         ex.sync(); ex.free(d_fperm);
         auto newcell = [&](int c) { return c < C ? plan.cell_old2new[c] : c; };
@@ -204,6 +206,7 @@ public:
             tile_partial = dalloc<R>((size_t)plan.nTiles * plan.NW + 1);
             ex.sync();
         }
+        if (mesh_param) { face_new2old_h = plan.face_new2old; cell_new2old_h = plan.cell_new2old; }
         tile_evals_per_cell = plan.evals_per_cell(); tile_colours = plan.maxColours; tile_max_halo = plan.maxHalo;
         tile_rounds_total = (long)(plan.ent_face.size() / kRound);
         tile_halo_hist.assign(32, 0);
@@ -274,6 +277,10 @@ public:
     }
     // parameter block of the adjoint: the source terms (default) or one BC input array (reference apps/adjoint.py:101-120)
     int param_patch = -1, param_key = -1, param_dim = 0; R* Pb = nullptr;
+    // parameters = 'mesh': must be chosen before set_mesh (the face-indexed flux metrics and the numbering maps are kept)
+    bool mesh_param = false; R *Mb = nullptr, *Vb = nullptr, *f_dunit = nullptr, *f_linw = nullptr, *f_quadw = nullptr;
+    std::vector<int> face_new2old_h, cell_new2old_h;
+    void set_parameter_mesh() { if (have_mesh) throw std::runtime_error("select parameters='mesh' before the mesh is set"); mesh_param = true; epoch++; }
     void set_parameter_source() { epoch++; param_patch = -1; param_key = -1; }
     void set_parameter_bc(int patch, int key) {
         epoch++;
@@ -295,6 +302,26 @@ public:
         ex.download(h.data(), Pb, h.size() * sizeof(R)); ex.sync();
         for (int i = 0; i < n; i++) for (int k = 0; k < d; k++) out[(size_t)i * d + k] = h[(size_t)k * n + i];
         if (zero_after) ex.zero(Pb, h.size() * sizeof(R));
+    }
+    // the ten gradient arrays in the reference's layout and numbering (adFVM/mesh.py:27-31): areas [F], volumesL [F],
+    // volumesR [Fi], weights [F], deltas [F], normals [F][3], deltasUnit [F][3], linearWeights [F][2], quadraticWeights [F][2][3],
+    // volumes [C]
+    void get_mesh_grad(R* const out[10], bool zero_after) {
+        if (!mesh_param || !Mb) throw std::runtime_error("parameters='mesh' was not selected (or no adjoint step has run)");
+        const int F = m.nFaces, Fi = m.nInternalFaces, C = m.nInternalCells;
+        std::vector<R> h((size_t)19 * m.sF), v((size_t)m.sC);
+        ex.download(h.data(), Mb, h.size() * sizeof(R)); ex.download(v.data(), Vb, v.size() * sizeof(R)); ex.sync();
+        auto row = [&](int r, long f) { return h[(size_t)r * m.sF + f]; };
+        for (long f = 0; f < F; f++) {
+            const long of = face_new2old_h[f];
+            out[0][of] = row(0, f); out[1][of] = row(1, f); if (of < Fi) out[2][of] = row(2, f);
+            out[3][of] = row(3, f); out[4][of] = row(4, f);
+            for (int k = 0; k < 3; k++) { out[5][of * 3 + k] = row(5 + k, f); out[6][of * 3 + k] = row(8 + k, f); }
+            out[7][of * 2] = row(11, f); out[7][of * 2 + 1] = row(12, f);
+            for (int k = 0; k < 6; k++) out[8][of * 6 + k] = row(13 + k, f);
+        }
+        for (long c = 0; c < C; c++) out[9][cell_new2old_h[c]] = v[c];
+        if (zero_after) { ex.zero(Mb, h.size() * sizeof(R)); ex.zero(Vb, v.size() * sizeof(R)); }
     }
     void check_bcs() const {
         for (size_t p = 0; p < patches.size(); p++) {
@@ -485,6 +512,7 @@ public:
         for (int k = 0; k < 4; k++) A[k] = dalloc<R>((size_t)5 * m.sC + kRowSlack);
         Qb = dalloc<R>((size_t)5 * m.sN); Gb = dalloc<R>((size_t)15 * m.sN);
         Sb = dalloc<R>((size_t)5 * m.sC);
+        if (mesh_param) { Mb = dalloc<R>((size_t)19 * m.sF); Vb = dalloc<R>((size_t)m.sC); }
         adjoint_ready = true;
     }
 
@@ -514,7 +542,7 @@ public:
         if (chain) { R* t = A[0]; A[0] = A[3]; A[3] = t; }
         with_graph({2ull, epoch, bits((double)dt), bits((double)obja), (unsigned long long)W[0], (unsigned long long)A[0], (unsigned long long)A[3],
                     (unsigned long long)obj.kind, (unsigned long long)obj.patch, (unsigned long long)obj.dir, (unsigned long long)obj.cells,
-                    (unsigned long long)Pb, (unsigned long long)(param_patch * 16 + param_key + 1)}, [&]() { adjoint_step_body(dt, obja); });
+                    (unsigned long long)Pb, (unsigned long long)(param_patch * 16 + param_key + 1), (unsigned long long)Mb}, [&]() { adjoint_step_body(dt, obja); });
     }
     void adjoint_step_body(R dt, R obja) {
         primal_step(dt, true);
@@ -560,6 +588,11 @@ public:
             const R oa = (s == 1) ? obja : R(0);
             run(nBcells, GhostPrimAdjBody<R>{ph, m, obj, oa, bcells, Q[s], Qb, rQ, W[s], A[s]});
             if (param_patch >= 0) run(patches[param_patch].nFaces, BCParamAdjBody<R>{ph, m, obj, oa, param_patch, param_key, Q[s], Qb, Pb});
+            if (mesh_param) {
+                if (m.nRemoteCells > 0) throw std::runtime_error("parameters='mesh' on decomposed meshes is not validated yet");
+                run(m.nFaces, MeshGradFaceBody<R>{ph, m, obj, oa, coef, Q[s], G[s], A[s + 1], Qb, Gb, f_dunit, f_linw, f_quadw, Mb});
+                run(C, MeshGradCellBody<R>{m, Q[s], G[s], Gb, (s == 1 && obj.kind == OBJ_CELL_TV) ? obja : R(0), Vb});
+            }
         }
     }
     // ---- mesh metric build on the device (fvm_metrics.h); host AoS in, host AoS out.

@@ -231,6 +231,8 @@ class _Context:
             t.neighbour_patch = index[p["neighbourPatch"]] if p["type"] == "cyclic" else -1
             t.peer_rank = int(p.get("neighbProcNo", -1)) if remote else -1
             t.tag = int(p.get("tag", 0))
+        if (self.spec.get("parameters") or "source") == "mesh":      # must precede the mesh upload (see adfvm_b200.h)
+            self.lib.check(d.adfvm_set_parameter_mesh(self.ctx))
         csizes = (C.c_int32 * 8)(*sizes)
         self.lib.check(d.adfvm_set_mesh(
             self.ctx, csizes, *[_ptr(m[n]) for n in GRAD_FIELDS], *[_ptr(m[n]) for n in INT_FIELDS],
@@ -259,9 +261,10 @@ class _Context:
         # parameter block of the adjoint: 'source' (default) or ('BCs', field, patch, key) (apps/adjoint.py:101-120)
         par = self.spec.get("parameters") or "source"
         self.param_bc = None
-        if par != "source":
+        self.param_mesh = par == "mesh"
+        if par != "source" and par != "mesh":
             if not (isinstance(par, (list, tuple)) and len(par) == 4 and par[0] == "BCs"):
-                raise NotImplementedError("parameters=%r: supported are 'source' and ('BCs', field, patch, key)" % (par,))
+                raise NotImplementedError("parameters=%r: supported are 'source', 'mesh' and ('BCs', field, patch, key)" % (par,))
             _, field, pid, key = par
             if (field, key) not in _BC_KEY or key == "direction":
                 raise NotImplementedError("no gradient with respect to BC input %s.%s" % (field, key))
@@ -444,16 +447,34 @@ class AdjointFunction:
         flags = (L.RETURN_STATIC if opts["return_static"] else 0) | (L.ZERO_STATIC if opts["zero_static"] else 0)
         outs = [c.pool.empty((C_, 1), c.dtype), c.pool.empty((C_, 3), c.dtype), c.pool.empty((C_, 1), c.dtype)]
         grads = [None, None, None]
-        if c.param_bc is not None:                 # one BC input array is the parameter block
+        if c.param_mesh:                           # the ten metric arrays: read after the call (adfvm_get_mesh_grad)
+            grads = [None, None, None]
+        elif c.param_bc is not None:               # one BC input array is the parameter block
             grads = [c.pool.empty(c.param_bc, c.dtype) if opts["return_static"] else None, None, None]
         elif opts["return_static"]:
             grads = [c.pool.empty((C_, 1), c.dtype), c.pool.empty((C_, 3), c.dtype), c.pool.empty((C_, 1), c.dtype)]
         c.lib.check(c.lib.dll.adfvm_primal_grad(
             c.ctx, _ptr(rho), _ptr(rhoU), _ptr(rhoE), float(dt[0, 0]), _ptr(ra), _ptr(rUa), _ptr(rEa), dtca, obja, flags,
             _ptr(outs[0]), _ptr(outs[1]), _ptr(outs[2]), _ptr(grads[0]), _ptr(grads[1]), _ptr(grads[2])))
+        if c.param_mesh:
+            if not opts["return_static"]:
+                if opts["zero_static"]:
+                    self.mesh_gradients(zero_static=True)
+                return tuple(outs + [None] * 10)
+            return tuple(outs + self.mesh_gradients(zero_static=opts["zero_static"]))
         if c.param_bc is not None:
             return tuple(outs + grads[:1])
         return tuple(outs + grads)
+
+    def mesh_gradients(self, zero_static=False):
+        """parameters='mesh': the accumulated gradients of the ten metric arrays, in Mesh.gradFields order
+        (adFVM/mesh.py:27-31), shaped like the inputs"""
+        c = self.c
+        F, Cn, Fi = c.sizes[1], c.sizes[2], c.sizes[3]
+        shapes = [(F, 1), (F, 1), (Fi, 1), (F, 1), (F, 1), (F, 3), (F, 3), (F, 2), (F, 2, 3), (Cn, 1)]
+        arrs = [np.zeros(sh, c.dtype) for sh in shapes]
+        c.lib.check(c.lib.dll.adfvm_get_mesh_grad(c.ctx, *[_ptr(a) for a in arrs], int(zero_static)))
+        return arrs
 
     def step_resident(self, dt, obja=1.0, chain=True):
         self.c.lib.check(self.c.lib.dll.adfvm_adjoint_step_resident(self.c.ctx, float(dt), float(obja), int(chain)))

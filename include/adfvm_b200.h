@@ -82,6 +82,13 @@ int adfvm_set_objective(adfvm_ctx* ctx, int32_t kind, int32_t patch, int32_t dir
  * boundary-condition input array - parameters = ('BCs', field, patch, key) - whose gradient [nFaces][d] adfvm_primal_grad
  * then returns in its first gradient array (same static-accumulator options). key: ADFVM_KEY_* of adfvm_set_bc_value. */
 int adfvm_set_parameter_bc(adfvm_ctx* ctx, int32_t patch, int32_t key);
+/* parameters = 'mesh' (apps/adjoint.py:105-107): gradient with respect to the ten metric arrays of adFVM/mesh.py:27-31.
+ * Select it BEFORE adfvm_set_mesh; after adjoint calls read the accumulated gradients (reference layout and numbering:
+ * areas [F], volumesL [F], volumesR [Fi], weights [F], deltas [F], normals [F][3], deltasUnit [F][3], linearWeights
+ * [F][2], quadraticWeights [F][2][3], volumes [C]) with adfvm_get_mesh_grad. */
+int adfvm_set_parameter_mesh(adfvm_ctx* ctx);
+int adfvm_get_mesh_grad(adfvm_ctx* ctx, void* areas, void* volumesL, void* volumesR, void* weights, void* deltas, void* normals,
+                        void* deltasUnit, void* linearWeights, void* quadraticWeights, void* volumes, int32_t zero_static);
 /* the design objective of the reference's turbine-vane cases (adFVM/objectives/vane.py:36-66,83-139, templates/vane.py):
  * scale x mass-flow averaged total-pressure loss (ptin - pt)/ptin over the cells of a cut plane. cells (reference
  * numbering) and areas are the extraArgs the case file passes after the BC arrays (adFVM/solver.py:317). */

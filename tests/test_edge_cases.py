@@ -76,3 +76,29 @@ def test_bc_parameter_gradients(hostsim, par):
     # static accumulator: a second call without zero_static adds the same gradient again (adpy/adpy/variable.py:484-490)
     g2 = f.grad()(*case.adjoint_inputs(case.state, adj), zero_static=False)
     assert np.abs(g2[3] - 2 * gref[3]).max() <= 10 * TOL * np.abs(gref[3]).max()
+
+
+@pytest.mark.parametrize("which", ["walls", "periodic", "cylinder", "step"])
+def test_mesh_parameter_gradients(hostsim, which):
+    """parameters = 'mesh' (reference apps/adjoint.py:105-107): gradient with respect to the ten metric arrays
+    (areas, volumesL, volumesR, weights, deltas, normals, deltasUnit, linearWeights, quadraticWeights, volumes) against the
+    oracle's reverse mode, every array to 1e-10 of its own size; BCs that read the normal (symmetryPlane, CBC_TOTAL_PT
+    without direction), the drag / p.A / T.V objectives, Roe and Lax-Friedrichs boundary solvers, inviscid and viscous"""
+    case = {"walls": lambda: cases.walled_box((6, 5, 3)), "periodic": lambda: cases.periodic_box((6, 5, 4), warp=0.03),
+            "cylinder": lambda: cases.cylinder2d(8, 10, dt=2e-9), "step": lambda: cases.forward_step(20, 10, dt=1e-3)}[which]()
+    case.spec = dict(case.spec, parameters="mesh")
+    f = function.PrimalFunction(case.spec, np.float64, lib=hostsim)
+    adj = [np.ones_like(s) * w for s, w in zip(case.state, (1.0, 1e-2, 1e-5))]
+    g = f.grad()(*case.adjoint_inputs(case.state, adj), zero_static=True)
+    gref = O.primal_grad(case.spec, case.adjoint_inputs(case.state, adj))
+    assert len(g) == 13
+    sc = [float(np.abs(s).max()) for s in case.state]
+    num = max(np.abs(a - b).max() * s for a, b, s in zip(g[:3], gref[:3], sc))
+    assert num <= TOL * max(np.abs(b).max() * s for b, s in zip(gref[:3], sc))
+    for a, b in zip(g[3:], gref[3:]):
+        b = np.asarray(b).reshape(a.shape)
+        assert np.abs(a - b).max() <= TOL * np.abs(b).max()        # (an inviscid case has exactly zero deltas / deltasUnit gradients)
+    assert sum(np.abs(np.asarray(b)).max() > 0 for b in gref[3:]) >= 8
+    g2 = f.grad()(*case.adjoint_inputs(case.state, adj))          # accumulator was zeroed: same gradients again
+    for a, b in zip(g2[3:], g[3:]):
+        assert np.abs(a - b).max() <= 1e-12 * max(np.abs(b).max(), 1e-300)

@@ -141,6 +141,22 @@ def test_overlapped_seed_upload_is_bitwise_equal(cudalib, monkeypatch):
             assert np.array_equal(x, y)
 
 
+def test_mesh_parameter_gradients_on_device(cudalib):
+    """parameters = 'mesh': the ten metric-array gradients from the device against the oracle's reverse mode, 1e-10"""
+    from oracle import adfvm_oracle as O
+    for make in (lambda: cases.walled_box((6, 5, 3)), lambda: cases.cylinder2d(8, 10, dt=2e-9)):
+        case = make()
+        case.spec = dict(case.spec, parameters="mesh")
+        f = function.PrimalFunction(case.spec, np.float64)
+        adj = _adj_seed(case)
+        g = f.grad()(*case.adjoint_inputs(case.state, adj), zero_static=True)
+        gref = O.primal_grad(case.spec, case.adjoint_inputs(case.state, adj))
+        assert len(g) == 13
+        for a, b in zip(g[3:], gref[3:]):
+            b = np.asarray(b).reshape(a.shape)
+            assert np.abs(a - b).max() <= 1e-10 * np.abs(b).max()
+
+
 def test_mesh_metrics_on_device(cudalib):
     """adfvm_mesh_metrics on the device against the restatement of cmesh.cpp, fp64 1e-12"""
     from test_mesh_metrics_device import compare
