@@ -366,7 +366,29 @@ def case_box_walls_bcpt():
     return c
 
 
-CASES = {"box_walls_bcpt": case_box_walls_bcpt, "channel_vane": case_channel_vane, "step2d": case_step2d, "cyl2d": case_cyl2d, "box_cyclic": case_box_cyclic, "tube": case_tube, "box_walls": case_box_walls, "box_upt": case_box_upt}
+
+MESH_PARAM = '''
+# mesh sensitivities (apps/adjoint.py:105-107, templates/cylinder.py:45-60): the parameter block is the ten metric arrays,
+# the perturbation a uniform dilation of the points pushed through the reference's own metric build
+def perturb(fields, mesh, t):
+    if not hasattr(perturb, 'perturbation'):
+        points = 1e-6*mesh.points
+        perturb.perturbation = mesh.getPointsPerturbation(points)
+    return perturb.perturbation
+
+parameters = 'mesh'
+'''
+
+
+def case_box_walls_mesh():
+    """box_walls with parameters = 'mesh': the adjoint returns the gradients with respect to the ten metric arrays"""
+    c = case_box_walls()
+    c["param_block"] = MESH_PARAM
+    c["parameters"] = "mesh"
+    return c
+
+
+CASES = {"box_walls_mesh": case_box_walls_mesh, "box_walls_bcpt": case_box_walls_bcpt, "channel_vane": case_channel_vane, "step2d": case_step2d, "cyl2d": case_cyl2d, "box_cyclic": case_box_cyclic, "tube": case_tube, "box_walls": case_box_walls, "box_upt": case_box_upt}
 
 
 def run(cmd, cwd):

@@ -157,6 +157,12 @@ def test_mesh_parameter_gradients_on_device(cudalib):
             assert np.abs(a - b).max() <= 1e-10 * np.abs(b).max()
 
 
+def test_mesh_gradients_match_reference_on_device(cudalib):
+    """fixture box_walls_mesh (the reference's own parameters='mesh' adjoint) replayed on the device, 1e-10 per array"""
+    from test_mesh_param_golden import replay
+    replay()
+
+
 def test_mesh_metrics_on_device(cudalib):
     """adfvm_mesh_metrics on the device against the restatement of cmesh.cpp, fp64 1e-12"""
     from test_mesh_metrics_device import compare
