@@ -589,7 +589,6 @@ public:
             run(nBcells, GhostPrimAdjBody<R>{ph, m, obj, oa, bcells, Q[s], Qb, rQ, W[s], A[s]});
             if (param_patch >= 0) run(patches[param_patch].nFaces, BCParamAdjBody<R>{ph, m, obj, oa, param_patch, param_key, Q[s], Qb, Pb});
             if (mesh_param) {
-                if (m.nRemoteCells > 0) throw std::runtime_error("parameters='mesh' on decomposed meshes is not validated yet");
                 run(m.nFaces, MeshGradFaceBody<R>{ph, m, obj, oa, coef, Q[s], G[s], A[s + 1], Qb, Gb, f_dunit, f_linw, f_quadw, Mb});
                 run(C, MeshGradCellBody<R>{m, Q[s], G[s], Gb, (s == 1 && obj.kind == OBJ_CELL_TV) ? obja : R(0), Vb});
             }

@@ -329,3 +329,56 @@ def test_threads_decomposed_periodic_mesh(world, hostsim):
     [t.join(timeout=300) for t in ts]
     assert not errors, errors
     _check(world, (g, out, out2, adj, grad), results)
+
+
+# ---- parameters = 'mesh' on a decomposed mesh: every rank returns the gradients with respect to ITS OWN metric arrays (the
+# reference's ranks hold their own mesh files); the sensitivity to a perturbation of the points, summed over the ranks
+# (cmesh.computeSensitivity + parallel.sum, apps/adjoint.py:337-341), must equal the single-rank one
+@pytest.mark.parametrize("world", [2, 4])
+def test_threads_mesh_sensitivity(world, hostsim):
+    from adfvm_b200 import cases, hexmesh
+    from adfvm_b200.metrics import build_mesh, GRAD_FIELDS
+    g = cases.walled_box((8, 6, 4), warp=0.0)
+    g.spec = dict(g.spec, parameters="mesh")
+    adj = _seed(g.state)
+    grads = function.PrimalFunction(g.spec, np.float64, lib=hostsim).grad()(*g.adjoint_inputs(g.state, adj))[3:]
+    parts = decompose.rank_cases(g, world)
+    gm = g.mesh
+
+    def poly_of(mesh, pts):
+        return hexmesh.PolyMesh(pts, mesh.faces, mesh.owner, mesh.neighbour[:mesh.nInternalFaces],
+                                {k: {kk: vv for kk, vv in v.items() if kk != "cellStartFace"} for k, v in mesh.boundary.items()})
+    # directional derivative of every metric array along a smooth displacement of the points (central difference)
+    eps = 1e-6
+    disp = np.stack([0.3 * np.sin(2 * gm.points[:, 1]), 0.2 * gm.points[:, 0] * gm.points[:, 2], 0.1 * np.cos(gm.points[:, 0])], axis=1)
+    mp, mm = build_mesh(poly_of(gm, gm.points + eps * disp)), build_mesh(poly_of(gm, gm.points - eps * disp))
+    S_single = sum(float((np.asarray(gr).reshape(getattr(mp, a).shape) * (getattr(mp, a) - getattr(mm, a)) / (2 * eps)).sum())
+                   for a, gr in zip(GRAD_FIELDS, grads))
+    uid = C.create_string_buffer(128)
+    hostsim.check(hostsim.dll.adfvm_comm_unique_id(uid))
+    results, errors = {}, []
+
+    def run(rank):
+        try:
+            case, ids = parts[rank]
+            case.spec = dict(case.spec, parameters="mesh")
+            fr = function.PrimalFunction(case.spec, np.float64, lib=hostsim)
+            fr.c.attach_comm(uid.raw, rank, world)
+            results[rank] = fr.grad()(*case.adjoint_inputs(case.state, [np.ascontiguousarray(x[ids]) for x in adj]))[3:]
+        except Exception as e:      # pragma: no cover
+            errors.append(e)
+    ts = [threading.Thread(target=run, args=(r,)) for r in range(world)]
+    [t.start() for t in ts]
+    [t.join(timeout=300) for t in ts]
+    assert not errors, errors
+    # the ranks' meshes rebuilt from the displaced points (same partition, ghost centres from the displaced global mesh)
+    S_ranks = 0.
+    for sign, gmesh in ((+1, mp), (-1, mm)):
+        gmesh.boundary = {k: dict(v) for k, v in gmesh.boundary.items()}
+        pr = decompose.decompose_polymesh(poly_of(gmesh, gmesh.points), decompose.slab_partition(gm.cellCentres[:gm.nInternalCells], world))
+        for r in range(world):
+            mr = build_mesh(pr[r]["poly"], decompose.remote_centres(pr, r, gmesh))
+            S_ranks += sign * sum(float((np.asarray(gr).reshape(getattr(mr, a).shape) * getattr(mr, a)).sum())
+                                  for a, gr in zip(GRAD_FIELDS, results[r])) / (2 * eps)
+    assert abs(S_single) > 0
+    assert abs(S_ranks - S_single) <= 1e-6 * abs(S_single), (S_ranks, S_single)
