@@ -102,3 +102,27 @@ def test_mesh_parameter_gradients(hostsim, which):
     g2 = f.grad()(*case.adjoint_inputs(case.state, adj))          # accumulator was zeroed: same gradients again
     for a, b in zip(g2[3:], g[3:]):
         assert np.abs(a - b).max() <= 1e-12 * max(np.abs(b).max(), 1e-300)
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_random_holes(hostsim, seed):
+    """irregular topologies: a 3-D box with random cells removed (ragged sub-tiles, cells with several boundary faces,
+    possibly disconnected pieces) - the tile schedule must stay consistent (the simulator checks every entry) and the
+    results must match the oracle"""
+    rng = np.random.RandomState(seed)
+    n = (7, 6, 5)
+    keep = rng.rand(n[2], n[1], n[0]) > 0.25
+    lo, hi = (0., 0., 0.), (1.4, 1.2, 1.0)
+    poly = hexmesh.masked_box_mesh(n, lo, hi, keep, [
+        ("inlet", "patch", ["x-"], {}), ("outlet", "patch", ["x+"], {}), ("walls", "symmetryPlane", ["y-", "y+"], {}),
+        ("z1", "patch", ["z-"], {}), ("z2", "patch", ["z+"], {})], hole=("holes", "patch", {}))
+    mesh = build_mesh(poly)
+    C = mesh.nInternalCells
+    cc = mesh.cellCentres[:C]
+    U, T, p = cases.smooth_state(cc, lo, hi)
+    k0 = {"keys": []}
+    zg, sym = dict(type="zeroGradient", **k0), dict(type="symmetryPlane", **k0)
+    bcs = {f: dict(inlet=zg, outlet=zg, walls=sym, z1=zg, z2=zg, holes=sym if f == "U" else zg) for f in ("U", "T", "p")}
+    spec = cases._spec(mesh, bcs, {"kind": "patch_pA", "patch": "holes"})
+    case = cases.Case(mesh, spec, cases.conservative(U, T, p), cases.gaussian_source(cc, (0.7, 0.6, 0.5)), {}, 1e-6)
+    _check(case, hostsim)
