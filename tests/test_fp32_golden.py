@@ -42,3 +42,23 @@ def replay_fp32(name, **kw):
 def test_fp32_matches_reference_fp32(name, hostsim):
     assert CASES32
     replay_fp32(name, lib=hostsim)
+
+
+@pytest.mark.parametrize("make", [lambda: __import__("adfvm_b200.cases", fromlist=["x"]).periodic_box((10, 8, 6), np.float32, warp=0.03),
+                                  lambda: __import__("adfvm_b200.cases", fromlist=["x"]).walled_box((8, 6, 4), np.float32)])
+def test_fp32_against_fp64_oracle(hostsim, make):
+    """the stated fp32 tolerance of the north star: 1e-5 relative against the fp64 oracle (one step, primal and adjoint)"""
+    from oracle import adfvm_oracle as O
+    case = make()
+    f = function.PrimalFunction(case.spec, np.float32, lib=hostsim)
+    out = f(*case.inputs(), replace_reusable=True, return_reusable=True)
+    inp64 = [np.asarray(a, np.float64) if isinstance(a, np.ndarray) and a.dtype == np.float32 else a for a in case.inputs()]
+    ref = O.primal(case.spec, inp64)
+    sc = state_scales(inp64)
+    assert group_relerr(out[:3], ref[:3], sc) < 1e-5
+    adj = [np.ascontiguousarray(np.ones_like(s) * w, np.float32) for s, w in zip(case.state, (1.0, 1e-2, 1e-5))]
+    g = f.grad()(*case.adjoint_inputs(case.state, adj))
+    a64 = [np.asarray(a, np.float64) if isinstance(a, np.ndarray) and a.dtype == np.float32 else a for a in case.adjoint_inputs(case.state, adj)]
+    gref = O.primal_grad(case.spec, a64)
+    assert group_relerr(g[:3], gref[:3], sc) < 1e-5
+    assert group_relerr(g[3:6], gref[3:6], sc) < 1e-5
