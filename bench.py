@@ -3,16 +3,18 @@
 primal + adjoint Mcell-updates/s per RK stage; HBM GB/s as % of peak).
 
 A "step" = one primal time step (3 SSPRK stages) + one adjoint time step (forward recompute + reverse sweep,
-3 stages) of the synthetic periodic hex box, i.e. 2*3*C cell-updates.
-  value        device-resident stepping (inputs already in HBM)
+3 stages) of the synthetic periodic hex box, i.e. 2*3*C cell-updates. Default workload: 368^3 = 49.8 M
+cells per GPU (BASELINE.json config 5; 256^3 if the host cannot hold the input arrays of all ranks, said in config).
+  value        device-resident stepping (inputs already in HBM), CUDA events on the library's stream
   e2e          the same work through PrimalFunction/AdjointFunction.__call__ with pinned HOST buffers:
                state + adjoint uploaded and results downloaded every call
-  roofline     dominant kernel (flux_grad), algorithmic bytes / CUDA-event kernel time / measured peak
-  cpu_baseline the oracle port timed on this host on a bounded sample
+  roofline     dominant kernel, algorithmic bytes (DESIGN.md) / CUDA-event kernel time per pass / measured peak;
+               stage_model = whole-stage byte model of BASELINE.md over the step time
+  cpu_baseline the oracle port timed on this host on a bounded sample (112^3)
 
 `--impl reference` times the CPU oracle port only (rank 0), same metric and config.
 Multi-GPU: one rank per GPU (torchrun), weak scaling: every rank owns an n^3 block of a (n*px, n*py, n*pz)
-periodic box, halo over NCCL inside the library.
+periodic box, halo over NCCL inside the library, overlapped with the tiles that do not depend on it.
 """
 import argparse
 import json
