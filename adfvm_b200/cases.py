@@ -106,6 +106,29 @@ def periodic_box(n, dtype=np.float64, warp=0.0, dt=None, mesh=None):
     return Case(mesh, spec, conservative(U, T, p), gaussian_source(cc), {}, dt, dtype)
 
 
+def shock_tube(n=500, width=0.06, dtype=np.float64, dt=1e-5):
+    """BASELINE.json config 1: the geometry of the reference's cases/shockTube (n x 1 x 1 cells on [-5,5] x [-1,1]^2, patches
+    `sides` = {x=+5, x=-5} zeroGradient, `empty` = the 4n lateral faces), tanh-smoothed Sod initial condition
+    sigma = (1 - tanh(x/width))/2 (the shipped sharp one NaNs in the reference), inviscid, objective
+    sum_{sides} p_ghost * area, source perturbation G = 1e3 exp(-((x+4.5)/0.2)^2) (BASELINE.md §5 anchor B)."""
+    lo, hi = (-5., -1., -1.), (5., 1., 1.)
+    poly = hexmesh.box_mesh((n, 1, 1), lo, hi, patches=[("sides", "patch", ["x+", "x-"], {}),
+                                                        ("empty", "empty", ["y-", "z+", "y+", "z-"], {})])
+    mesh = build_mesh(poly)
+    C = mesh.nInternalCells
+    cc = mesh.cellCentres[:C]
+    sig = 0.5 * (1 - np.tanh(cc[:, 0] / width))
+    p = (1e4 + 9e4 * sig).reshape(-1, 1)
+    rho = (0.125 + 0.875 * sig).reshape(-1, 1)
+    R = 1004.5 - 1004.5 / 1.4
+    T = p / (rho * R)
+    U = np.zeros((C, 3))
+    k0 = {"keys": []}
+    bcs = {f: {"sides": dict(type="zeroGradient", **k0), "empty": dict(type="zeroGradient", **k0)} for f in ("U", "T", "p")}   # class names, as the reference reports them (empty = zeroGradient, BCs.py)
+    spec = _spec(mesh, bcs, {"kind": "patch_pA", "patch": "sides"}, mu={"law": "constant", "value": 0.})
+    return Case(mesh, spec, conservative(U, T, p), gaussian_source(cc, (-4.5, 0., 0.), 1e3, 25.), {}, dt, dtype)
+
+
 def walled_box(n=(8, 6, 4), dtype=np.float64, warp=0.02, dt=2e-6, nonuniform=True):
     """Channel exercising every supported BC: CBC_TOTAL_PT inlet, fixedValue-p outlet, symmetryPlane floor,
     no-slip isothermal lid (fixedValue U,T), one cyclic pair; constant viscosity; drag objective on the lid.

@@ -375,6 +375,15 @@ public:
         upload_aos(s_rhoE, C, 1, m.sC, S + 4 * (size_t)m.sC, m.cell_perm);
     }
     void set_state(const R* rho, const R* rhoU, const R* rhoE) { put5(W[0], rho, rhoU, rhoE); have_state = true; }
+    // primal_grad from host arrays must not disturb the resident state of `primal` (the reference keeps that one under the
+    // reuse ids primal_0..2 of Function_primal, adpy/adpy/variable.py:382-388): the adjoint's start state goes to a spare
+    // buffer that takes the place of W[0] for the duration of the call
+    R* Wspare = nullptr;
+    void adjoint_state_begin(const R* rho, const R* rhoU, const R* rhoE) {
+        if (have_state) { if (!Wspare) Wspare = dalloc<R>((size_t)5 * m.sC + kRowSlack); std::swap(W[0], Wspare); }
+        put5(W[0], rho, rhoU, rhoE);
+    }
+    void adjoint_state_end() { if (have_state) std::swap(W[0], Wspare); }
     void get_state(R* rho, R* rhoU, R* rhoE) { get5(W[0], rho, rhoU, rhoE); }
     // host (rho[C][1], rhoU[C][3], rhoE[C][1]) in reference cell order <-> device [5][sC] in tile order
     void put5(R* dst, const R* a, const R* b, const R* c) {
@@ -682,8 +691,12 @@ public:
         }
     }
     void put_adjoint(const R* rhoa, const R* rhoUa, const R* rhoEa) { ensure_adjoint_buffers(); put5(A[0], rhoa, rhoUa, rhoEa); }
-    void get_adjoint(R* rhoa, R* rhoUa, R* rhoEa) { get5(A[0], rhoa, rhoUa, rhoEa); }
+    void get_adjoint(R* rhoa, R* rhoUa, R* rhoEa) {
+        if (!adjoint_ready) throw std::runtime_error("no adjoint data: call primal_grad / set_adjoint first");
+        get5(A[0], rhoa, rhoUa, rhoEa);
+    }
     void get_source_grad(R* a, R* b, R* c, bool zero_after) {
+        if (!adjoint_ready) throw std::runtime_error("no adjoint data: call primal_grad / set_adjoint first");
         get5(Sb, a, b, c);
         if (zero_after) ex.zero(Sb, (size_t)5 * m.sC * sizeof(R));
     }

@@ -391,6 +391,47 @@ def case_box_walls_mesh():
 CASES = {"box_walls_mesh": case_box_walls_mesh, "box_walls_bcpt": case_box_walls_bcpt, "channel_vane": case_channel_vane, "step2d": case_step2d, "cyl2d": case_cyl2d, "box_cyclic": case_box_cyclic, "tube": case_tube, "box_walls": case_box_walls, "box_upt": case_box_upt}
 
 
+# ---- BASELINE.md section 5 reproducibility anchors, at their own sizes. Too large to store call by call: the fixture keeps
+# objective.txt, the per-step time series and a strided sample + norms of the final state / final adjoint fields.
+def case_anchor_box48():
+    """Anchor A: 48^3 periodic unit box, cell id = i + 48 (j + 48 k), 4 steps, dt = 1e-6, objective sum T*V"""
+    lo, hi = (0., 0., 0.), (1., 1., 1.)
+    poly = hexmesh.box_mesh((48, 48, 48), lo, hi)
+    m = build_mesh(poly)
+    U, T, p = smooth_fields(m.cellCentres[:m.nInternalCells], lo, hi)
+    bf = {k: {"type": "cyclic"} for k in poly.boundary}
+    return dict(poly=poly, fields={"U": (U, bf), "T": (T, bf), "p": (p, bf)}, objective=OBJ_CELL_TV,
+                obj_spec={"kind": "cell_TV"}, rcf_extra="", mid="[0.5,0.5,0.5]", amp="1e2", width="50", nSteps=4, writeInterval=2, dt=1e-6,
+                builder={"kind": "periodic_box", "n": [48, 48, 48]})
+
+
+def case_anchor_tube500():
+    """Anchor B: cases/shockTube geometry (500 x 1 x 1 cells on [-5,5] x [-1,1]^2), smoothed Sod initial condition
+    sigma = (1 - tanh(x/0.06))/2, inviscid, objective sum_{sides} p_ghost * area, 20 steps, dt = 1e-5"""
+    lo, hi = (-5., -1., -1.), (5., 1., 1.)
+    poly = hexmesh.box_mesh((500, 1, 1), lo, hi, patches=[
+        ("sides", "patch", ["x+", "x-"], {}),
+        ("empty", "empty", ["y-", "z+", "y+", "z-"], {})])
+    m = build_mesh(poly)
+    x = m.cellCentres[:m.nInternalCells, 0]
+    sig = 0.5 * (1 - np.tanh(x / 0.06))
+    pr = 1e4 + 9e4 * sig
+    rho = 0.125 + 0.875 * sig
+    R = 1004.5 - 1004.5 / 1.4
+    T = (pr / (rho * R)).reshape(-1, 1)
+    U = np.zeros((len(x), 3))
+    bf = {"sides": {"type": "zeroGradient"}, "empty": {"type": "empty"}}
+    return dict(poly=poly, fields={"U": (U, bf), "T": (T, bf), "p": (pr.reshape(-1, 1), bf)},
+                objective=OBJ_PATCH_PA.format(patch="sides"),
+                obj_spec={"kind": "patch_pA", "patch": "sides"}, rcf_extra=", mu=lambda T: 0.",
+                mid="[-4.5,0.,0.]", amp="1e3", width="25", nSteps=20, writeInterval=10, dt=1e-5,
+                builder={"kind": "tube", "n": 500, "width": 0.06})
+
+
+ANCHORS = {"anchor_box48": case_anchor_box48, "anchor_tube500": case_anchor_tube500}
+CASES.update(ANCHORS)          # write_case looks them up; the plain generator below skips them (see __main__)
+
+
 def run(cmd, cwd):
     print("+", " ".join(cmd), flush=True)
     subprocess.check_call(cmd, cwd=cwd)
@@ -469,8 +510,57 @@ def generate(name, fp32=False):
     print("wrote", tag, meta["objective_txt"])
 
 
+def _sample(arrs, stride):
+    """strided rows + [sum, sum of squares, max |.|] per column of each array"""
+    out = {}
+    for k, a in arrs.items():
+        a = np.asarray(a, np.float64).reshape(len(a), -1)
+        out[k + "_sample"] = a[::stride].copy()
+        out[k + "_norms"] = np.stack([a.sum(axis=0), (a * a).sum(axis=0), np.abs(a).max(axis=0)])
+    return out
+
+
+def generate_anchor(name, stride=97):
+    """runs the unmodified reference like generate(); keeps objective.txt, time series and samples of the final fields"""
+    c, case, casefile = write_case(name, name)
+    runner = os.path.join(HERE, "run_ref.py")
+    py = sys.executable
+    run([py, runner, "problem", os.path.join(case, "rec_orig.npz"), "--", casefile, "-c"], case)
+    run([py, runner, "problem", os.path.join(case, "rec_perturb.npz"), "--", casefile, "-c", "perturb"], case)
+    run([py, runner, "adjoint", os.path.join(case, "rec_adjoint.npz"), "--", casefile, "-c"], case)
+    out = {}
+    meta = {"case": name, "stride": stride, "builder": c["builder"]}
+    for runname, fname in (("orig", "primal"), ("perturb", "primal"), ("adjoint", "primal_grad")):
+        z = np.load(os.path.join(case, "rec_%s.npz" % runname))
+        with open(os.path.join(case, "rec_%s.json" % runname)) as f:
+            j = json.load(f)
+        meta["spec"] = j["spec"]
+        meta["spec"]["objective"] = c["obj_spec"]
+        last = max(ci for ci, cl in enumerate(j["calls"]) if cl["name"] == fname)
+        meta[runname + "_calls"] = sum(1 for cl in j["calls"] if cl["name"] == fname)
+        names = ("rho", "rhoU", "rhoE") if fname == "primal" else ("rhoa", "rhoUa", "rhoEa", "gS_rho", "gS_rhoU", "gS_rhoE")
+        arrs = {"%s_%s" % (runname, n): z["c%d_o%d" % (last, oi)] for oi, n in enumerate(names)}
+        out.update(_sample(arrs, stride))
+        if runname == "orig":       # initial state (inputs 0-2 of the first call) and the source perturbation used by `perturb`
+            first = min(ci for ci, cl in enumerate(j["calls"]) if cl["name"] == fname)
+            out.update(_sample({"initial_%s" % n: z["c%d_i%d" % (first, ii)] for ii, n in enumerate(names)}, stride))
+    with open(os.path.join(case, "objective.txt")) as f:
+        meta["objective_txt"] = f.read().strip().split("\n")
+    out["timeSeries_orig"] = np.loadtxt(os.path.join(case, "timeSeries.txt"), ndmin=1)
+    out["timeSeries_perturb"] = np.loadtxt(os.path.join(case, "timeSeries_0.txt"), ndmin=1)
+    out["sensTimeSeries"] = np.loadtxt(os.path.join(case, "sensTimeSeries.txt"), ndmin=1)
+    meta["casefile"] = {k: c[k] for k in ("nSteps", "writeInterval", "dt", "mid", "amp", "width", "rcf_extra")}
+    np.savez_compressed(os.path.join(GOLDEN, name + ".npz"), **out)
+    with open(os.path.join(GOLDEN, name + ".json"), "w") as f:
+        json.dump(meta, f, indent=1)
+    print("wrote", name, meta["objective_txt"])
+
+
 if __name__ == "__main__":
     args = [a for a in sys.argv[1:] if not a.startswith("--")]
     fp32 = "--fp32" in sys.argv
-    for nm in (args or list(CASES)):
-        generate(nm, fp32=fp32)
+    for nm in (args or [n for n in CASES if n not in ANCHORS]):
+        if nm in ANCHORS:
+            generate_anchor(nm)
+        else:
+            generate(nm, fp32=fp32)

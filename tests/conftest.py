@@ -17,8 +17,9 @@ def build_hostsim():
     """CPU simulator of the device code (test infrastructure, see tests/hostsim/hostsim.cpp)."""
     d = os.path.join(ROOT, "tests", "hostsim")
     so = os.path.join(d, "libadfvm_hostsim.so")
-    srcs = [os.path.join(d, "hostsim.cpp")] + [os.path.join(ROOT, "adfvm_b200", "csrc", f) for f in
-                                               ("fvm_math.h", "fvm_bodies.h", "fvm_tile_bodies.h", "fvm_tiles.h", "fvm_solver.h", "fvm_capi.inc")]
+    csrc = os.path.join(ROOT, "adfvm_b200", "csrc")
+    srcs = [os.path.join(d, "hostsim.cpp")] + [os.path.join(csrc, f) for f in sorted(os.listdir(csrc)) if f.endswith((".h", ".inc"))] + \
+           [os.path.join(ROOT, "include", "adfvm_b200.h")]
     if not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
         subprocess.check_call(["g++", "-std=c++17", "-O2", "-fPIC", "-shared", "-fopenmp", "-o", so, srcs[0]], cwd=d)
     return so

@@ -38,7 +38,42 @@ class Golden:
 
 
 def available():
-    return sorted(f[:-5] for f in os.listdir(GOLDEN) if f.endswith(".json"))
+    """fixtures recorded call by call (the anchors of BASELINE.md section 5 are listed by anchors())"""
+    return sorted(f[:-5] for f in os.listdir(GOLDEN) if f.endswith(".json") and not f.startswith("anchor_"))
+
+
+def anchors():
+    return sorted(f[:-5] for f in os.listdir(GOLDEN) if f.endswith(".json") and f.startswith("anchor_"))
+
+
+class Anchor:
+    """objective.txt, time series and strided samples of the final fields of one anchor run of the unmodified reference
+    (oracle/ref_harness/gen_golden.py generate_anchor)"""
+
+    def __init__(self, name):
+        with open(os.path.join(GOLDEN, name + ".json")) as f:
+            self.meta = json.load(f)
+        self.z = np.load(os.path.join(GOLDEN, name + ".npz"))
+        self.spec, self.stride = self.meta["spec"], int(self.meta["stride"])
+        self.cf = self.meta["casefile"]
+        self.objective = {ln.split()[0]: float(ln.split()[3]) for ln in self.meta["objective_txt"]}
+
+    def check_fields(self, prefix, names, arrs, tol, scales=None):
+        """compare arrays with the stored strided sample and norms of `<prefix>_<name>`; error relative to the group's max"""
+        scales = scales or [1.0] * len(arrs)
+        num = den = 0.0
+        ssq_den = max(float(self.z["%s_%s_norms" % (prefix, n)][1].max()) * s * s for n, s in zip(names, scales))
+        for n, a, s in zip(names, arrs, scales):
+            a = np.asarray(a, np.float64).reshape(len(a), -1)
+            ref = self.z["%s_%s_sample" % (prefix, n)]
+            num = max(num, float(np.abs(a[::self.stride] - ref).max()) * s)
+            den = max(den, float(self.z["%s_%s_norms" % (prefix, n)][2].max()) * s)
+            nr = self.z["%s_%s_norms" % (prefix, n)]
+            ssq = (a * a).sum(axis=0)
+            assert np.all(np.abs(ssq - nr[1]) * s * s <= 10 * tol * max(ssq_den, 1e-300)), (prefix, n, "sum of squares")
+        err = num / max(den, 1e-300)
+        assert err < tol, (prefix, err)
+        return err
 
 
 def relerr(a, b):

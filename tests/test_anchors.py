@@ -1,0 +1,80 @@
+"""Reproducibility anchors of BASELINE.md section 5 at their own sizes (48^3 periodic box, 4 steps; 500-cell shock tube,
+20 steps), recorded from the UNMODIFIED reference (oracle/ref_harness/gen_golden.py generate_anchor ->
+tests/golden/anchor_*.{npz,json}: objective.txt, per-step time series, strided samples + norms of the final fields).
+
+tests/minidriver.py restates the drivers' time loops; the same loops run the oracle, the CPU simulator of the device code
+and - in the `gpu` tests - the CUDA library, and must reproduce the reference's objective.txt: `orig` to 1e-10, the
+adjoint sensitivity to 1e-9 (the north-star tolerances), the finite difference `perturb` to 2e-12 of the objective it is a
+difference of, and the final state / final adjoint fields at the sampled cells to 1e-10."""
+import numpy as np
+import pytest
+
+import minidriver
+from golden_util import Anchor
+from adfvm_b200 import cases, function
+from oracle import adfvm_oracle as O
+
+NAMES = ("rho", "rhoU", "rhoE")
+ANAMES = ("rhoa", "rhoUa", "rhoEa")
+
+
+def build(name):
+    a = Anchor(name)
+    b = a.meta["builder"]
+    case = cases.periodic_box(tuple(b["n"])) if b["kind"] == "periodic_box" else cases.shock_tube(b["n"], b["width"])
+    # the static description the reference reported for its own objects must be the one our builder produces
+    assert [(p["name"], p["type"], p["startFace"], p["nFaces"]) for p in a.spec["patches"]] == \
+           [(p["name"], p["type"], p["startFace"], p["nFaces"]) for p in case.spec["patches"]]
+    assert a.spec["mu"] == case.spec["mu"] and a.spec["BCs"] == case.spec["BCs"]
+    case.spec = a.spec
+    case.dt = a.cf["dt"]
+    a.check_fields("initial", NAMES, case.state, 1e-13)
+    return a, case
+
+
+def replay(a, case, primal, grad, tol_obj=1e-10, tol_adj=1e-9, tol_field=1e-10):
+    nSteps, wi = a.cf["nSteps"], a.cf["writeInterval"]
+    pert = case.source                                   # the case builders carry the perturbation of the source terms
+    orig, state, series = minidriver.run_primal(primal, case, nSteps)
+    assert abs(orig - a.objective["orig"]) <= tol_obj * abs(a.objective["orig"])
+    assert np.allclose(series, a.z["timeSeries_orig"], rtol=tol_obj, atol=0)
+    a.check_fields("orig", NAMES, state, tol_field)
+    pval, pstate, _ = minidriver.run_primal(primal, case, nSteps, source=pert)
+    assert abs((pval - orig) - a.objective["perturb"]) <= 2e-12 * abs(a.objective["orig"])
+    a.check_fields("perturb", NAMES, pstate, tol_field)
+    adj, fields, sens = minidriver.run_adjoint(primal, grad, case, nSteps, wi, pert)
+    assert abs(adj - a.objective["adjoint"]) <= tol_adj * abs(a.objective["adjoint"]), (adj, a.objective["adjoint"])
+    assert np.allclose(sens, a.z["sensTimeSeries"], rtol=tol_adj, atol=tol_adj * np.abs(a.z["sensTimeSeries"]).max())
+    sc = [float(np.abs(s).max()) for s in case.state]
+    a.check_fields("adjoint", ANAMES, fields, tol_field, sc)
+    # the reference's own end-to-end criterion: adjoint sensitivity vs finite difference, 1e-3 (tests/test_adjoint.py:33)
+    assert abs(adj - (pval - orig)) < 1e-3 * abs(adj)
+
+
+def oracle_functions(case):
+    return (lambda *inp, **kw: O.primal(case.spec, list(inp))), (lambda *inp, **kw: O.primal_grad(case.spec, list(inp)))
+
+
+def test_anchor_tube500_oracle():
+    a, case = build("anchor_tube500")
+    replay(a, case, *oracle_functions(case))
+
+
+def test_anchor_tube500_hostsim(hostsim):
+    a, case = build("anchor_tube500")
+    f = function.PrimalFunction(case.spec, np.float64, lib=hostsim)
+    replay(a, case, f, f.grad())
+
+
+def test_anchor_box48_hostsim(hostsim):
+    a, case = build("anchor_box48")
+    f = function.PrimalFunction(case.spec, np.float64, lib=hostsim)
+    replay(a, case, f, f.grad())
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["anchor_tube500", "anchor_box48"])
+def test_anchor_on_device(name, cudalib):
+    a, case = build(name)
+    f = function.PrimalFunction(case.spec, np.float64)
+    replay(a, case, f, f.grad())
