@@ -378,12 +378,14 @@ public:
     // primal_grad from host arrays must not disturb the resident state of `primal` (the reference keeps that one under the
     // reuse ids primal_0..2 of Function_primal, adpy/adpy/variable.py:382-388): the adjoint's start state goes to a spare
     // buffer that takes the place of W[0] for the duration of the call
-    R* Wspare = nullptr;
+    R* Wspare = nullptr; bool adj_had_state = false;
     void adjoint_state_begin(const R* rho, const R* rhoU, const R* rhoE) {
+        adj_had_state = have_state;
         if (have_state) { if (!Wspare) Wspare = dalloc<R>((size_t)5 * m.sC + kRowSlack); std::swap(W[0], Wspare); }
         put5(W[0], rho, rhoU, rhoE);
+        have_state = true;
     }
-    void adjoint_state_end() { if (have_state) std::swap(W[0], Wspare); }
+    void adjoint_state_end() { if (adj_had_state) std::swap(W[0], Wspare); have_state = adj_had_state; }
     void get_state(R* rho, R* rhoU, R* rhoE) { get5(W[0], rho, rhoU, rhoE); }
     // host (rho[C][1], rhoU[C][3], rhoE[C][1]) in reference cell order <-> device [5][sC] in tile order
     void put5(R* dst, const R* a, const R* b, const R* c) {

@@ -64,6 +64,80 @@ def test_oracle_parity(make, dtype, tol, cudalib):
     assert group_relerr(g[3:6], gref[3:6], sc) < tol
 
 
+# ---- the code path that is benchmarked (regular 4x4x8 tiles on lattice planes, the 444-tile L2 prefetch distance, several
+# waves of CTAs) and the other two kernel variants, against the REFERENCE's own compiled step functions (oracle/_ref, built from
+# the unmodified reference's generated code by oracle/ref_harness/build_ref_graph.py; the oracle port if it did not travel)
+LARGE = [((64, 64, 64), 0.0, 0, 128),      # variant (T,TS) = (128,320): regular tiles, 2048 tiles = 4.6 waves of 444 CTAs
+         ((92, 92, 23), 0.0, 2, 64),       # ragged lattice (23 planes): 64-cell tiles
+         ((46, 46, 46), 0.0, 2, 64),
+         ((40, 36, 28), 0.02, 1, 128)]     # warped (no lattice): coordinate bisection, halo > 192 -> (128,384)
+
+
+def _reference_functions(case):
+    from oracle import refgraph
+    if refgraph.available("box_cyclic"):
+        R = refgraph.RefGraph("box_cyclic")
+        R.initialize(case.mesh)
+        return R.primal, R.primal_grad, "reference"
+    return (lambda *inp, **kw: O.primal(case.spec, list(inp))), (lambda *inp, **kw: O.primal_grad(case.spec, list(inp))), "port"
+
+
+@pytest.mark.parametrize("n,warp,variant,tcells", LARGE)
+def test_large_parity_against_reference(n, warp, variant, tcells, cudalib):
+    case = cases.periodic_box(n, warp=warp)
+    rp, rg, kind = _reference_functions(case)
+    f = function.PrimalFunction(case.spec, np.float64)
+    state = rstate = case.state
+    for step in range(2):
+        out = f(*case.inputs(state), replace_reusable=(step == 0), return_reusable=True)
+        ref = rp(*case.inputs(rstate), replace_reusable=True)
+        for a, b in zip(out, ref):
+            assert relerr(a, b) < TOL64, (kind, step, relerr(a, b))
+        state, rstate = list(out[:3]), [np.ascontiguousarray(x) for x in ref[:3]]
+    assert f.tile_halo_stats()[1] == variant and f.tile_stats()[3] == tcells      # the kernel variant this case is meant to cover
+    adj = _adj_seed(case)
+    g = f.grad()(*case.adjoint_inputs(case.state, adj))
+    gref = rg(*case.adjoint_inputs(case.state, adj))
+    sc = state_scales(case.state)
+    assert group_relerr(g[:3], gref[:3], sc) < TOL64
+    assert group_relerr(g[3:6], gref[3:6], sc) < TOL64
+    # component by component as well (a group norm hides the small ones): each array against its own max, 1e-9
+    for a, b in zip(g, gref):
+        assert relerr(a, b) < 1e-9
+
+
+def test_large_parity_fp32(cudalib):
+    """fp32 kernels at 64^3 against the fp64 reference, stated fp32 tolerance 1e-5"""
+    case = cases.periodic_box(64, np.float32)
+    case64 = cases.periodic_box(64)
+    rp, rg, kind = _reference_functions(case64)
+    f = function.PrimalFunction(case.spec, np.float32)
+    out = f(*case.inputs(), replace_reusable=True)
+    ref = rp(*case64.inputs(), replace_reusable=True)
+    for a, b in zip(out, ref):
+        assert relerr(a, b) < TOL32
+    adj = _adj_seed(case)
+    g = f.grad()(*case.adjoint_inputs(case.state, adj))
+    gref = rg(*case64.adjoint_inputs(case64.state, [a.astype(np.float64) for a in adj]))
+    sc = state_scales(case64.state)
+    assert group_relerr(g[:3], gref[:3], sc) < TOL32 and group_relerr(g[3:6], gref[3:6], sc) < TOL32
+
+
+def test_large_walled_parity(cudalib):
+    """12 288-cell walled channel (every boundary condition class, 96 tiles) against the oracle"""
+    case = cases.walled_box((32, 24, 16))
+    f = function.PrimalFunction(case.spec, np.float64)
+    out = f(*case.inputs(), replace_reusable=True)
+    ref = O.primal(case.spec, case.inputs())
+    for a, b in zip(out, ref):
+        assert relerr(a, b) < TOL64
+    adj = _adj_seed(case)
+    g = f.grad()(*case.adjoint_inputs(case.state, adj))
+    gref = O.primal_grad(case.spec, case.adjoint_inputs(case.state, adj))
+    sc = state_scales(case.state)
+    assert group_relerr(g[:3], gref[:3], sc) < TOL64 and group_relerr(g[3:6], gref[3:6], sc) < TOL64
+
+
 def test_bitwise_deterministic(cudalib):
     """no float atomics anywhere: two runs give identical bits, primal and adjoint"""
     case = cases.periodic_box(24, warp=0.02)

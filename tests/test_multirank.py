@@ -24,7 +24,7 @@ def _seed(state):
     return [np.ascontiguousarray(rng.randn(*s.shape) * w) for s, w in zip(state, (1.0, 1e-2, 1e-5))]
 
 
-def _single(world, lib):
+def _single(world, lib, N=N):
     g = decompose.global_box(N, world)
     f = function.PrimalFunction(g.spec, np.float64, lib=lib)
     out = f(*g.inputs(), replace_reusable=True)
@@ -34,7 +34,7 @@ def _single(world, lib):
     return g, out, out2, adj, grad
 
 
-def _rank_run(rank, world, lib, uid, adj_global, results, attach):
+def _rank_run(rank, world, lib, uid, adj_global, results, attach, N=N, tiles=None):
     case = decompose.periodic_box_rank(N, rank, world)
     f = function.PrimalFunction(case.spec, np.float64, lib=lib)
     attach(f, rank, world, uid)
@@ -43,10 +43,12 @@ def _rank_run(rank, world, lib, uid, adj_global, results, attach):
     ids = decompose.global_cell_ids(N, rank, world)
     adj = [np.ascontiguousarray(a[ids]) for a in adj_global]
     grad = f.grad()(*case.adjoint_inputs(case.state, adj))
+    if tiles is not None:
+        tiles[rank] = (f.tile_rounds()[2], f.tile_stats()[2])
     results[rank] = (ids, out, out2, grad)
 
 
-def _check(world, single, results):
+def _check(world, single, results, N=N):
     g, out, out2, adj, grad = single
     for rank in range(world):
         ids, o, o2, gr = results[rank]
@@ -84,6 +86,33 @@ def test_threads(world, hostsim):
     [t.join(timeout=300) for t in ts]
     assert not errors, errors
     _check(world, single, results)
+
+
+@pytest.mark.parametrize("world,block", [(2, (16, 8, 8)), (4, (16, 16, 8))])
+def test_threads_overlap_split(world, block, hostsim):
+    """blocks large enough to have tiles that touch no processor patch: the step runs split into early tiles / cells (while
+    the halo is in flight) and late ones, forward and reverse (fvm_solver.h stage / adjoint_reverse) - the only
+    order-sensitive part of the multi-rank step - and must still reproduce the single-rank run"""
+    single = _single(world, hostsim, block)
+    uid = C.create_string_buffer(128)
+    hostsim.check(hostsim.dll.adfvm_comm_unique_id(uid))
+    results, tiles, errors = {}, {}, []
+
+    def attach(f, rank, world_, uid_):
+        f.c.attach_comm(uid_.raw, rank, world_)
+
+    def run(rank):
+        try:
+            _rank_run(rank, world, hostsim, uid, single[3], results, attach, block, tiles)
+        except Exception as e:      # pragma: no cover
+            errors.append(e)
+    ts = [threading.Thread(target=run, args=(r,)) for r in range(world)]
+    [t.start() for t in ts]
+    [t.join(timeout=300) for t in ts]
+    assert not errors, errors
+    for r in range(world):
+        assert 0 < tiles[r][0] < tiles[r][1], tiles
+    _check(world, single, results, block)
 
 
 def _gloo_worker(rank, world, port, q):

@@ -16,12 +16,13 @@ import torch.distributed as dist  # noqa: E402
 from adfvm_b200 import decompose, function  # noqa: E402
 
 ap = argparse.ArgumentParser()
-ap.add_argument("--n", type=int, default=12)
+ap.add_argument("--n", type=int, default=48, help="cells per side of every rank's block (48: tiles that do not touch a processor "
+                                                   "patch exist, so the overlapped early/late path really runs)")
 a = ap.parse_args()
 rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ.get("LOCAL_RANK", "0"))
 torch.cuda.set_device(local)
 dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-N = (a.n, a.n - 2, a.n - 4)
+N = (a.n, a.n - 4, a.n - 8) if a.n >= 24 else (a.n, a.n - 2, a.n - 4)
 
 
 def relerr(x, y):
@@ -41,6 +42,9 @@ f = function.PrimalFunction(case.spec, np.float64, device=local)
 decompose.attach_comm(f, rank, world)
 o = f(*case.inputs(), replace_reusable=True)
 o2 = f(*case.inputs(list(o[:3])), replace_reusable=True)
+early_tiles, all_tiles = f.tile_rounds()[2], f.tile_stats()[2]
+if a.n >= 24:
+    assert 0 < early_tiles < all_tiles, "the overlapped early/late split is not exercised (early %d of %d tiles)" % (early_tiles, all_tiles)
 ids = decompose.global_cell_ids(N, rank, world)
 gr = f.grad()(*case.adjoint_inputs(case.state, [np.ascontiguousarray(x[ids]) for x in adj]))
 errs = [relerr(x, y[ids]) for x, y in zip(o[:3], out[:3])] + [relerr(x, y[ids]) for x, y in zip(o2[:3], out2[:3])]
@@ -104,7 +108,7 @@ for grp in (slice(0, 3), slice(3, 6)):
     den = max(np.abs(y).max() * s for y, s in zip(gradw[grp], scw))
     errs.append(num / den)
 e = max(errs)
-print("rank %d of %d maxerr %.3e launches %d" % (rank, world, e, f.launches), flush=True)
+print("rank %d of %d maxerr %.3e launches %d early_tiles %d of %d" % (rank, world, e, f.launches, early_tiles, all_tiles), flush=True)
 t = torch.tensor([e], dtype=torch.float64, device="cuda")
 dist.all_reduce(t, op=dist.ReduceOp.MAX)
 dist.destroy_process_group()
