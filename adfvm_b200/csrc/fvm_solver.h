@@ -70,7 +70,7 @@ public:
     long tile_rounds_total = 0;               // rounds of all sub-tiles (32 lanes each; introspection)
     int nEarlyTiles = 0;                      // tiles [0,nEarlyTiles) and their cells do not depend on processor-patch data
     std::vector<int> tile_halo_hist;          // tiles per halo-size bin of 32 slots (introspection)
-    enum { kHalo128s = 192, kHalo128 = 256, kHalo64 = 384,
+    enum { kHalo128r = 160, kHalo128s = 192, kHalo128 = 256, kHalo64 = 384,
            kRowSlack = 128 };   // the tile kernels bulk-copy whole T-cell rows: the last tile may read past the last row   // halo slots of the two tile-kernel instantiations (T=128: TS=384, T=64: TS=448)
     bool have_mesh = false, have_state = false, adjoint_ready = false;
     std::vector<void*> owned;                 // everything to free
@@ -139,8 +139,9 @@ public:
         if (tile_cells == 128 && plan.maxHalo > kHalo128)
             plan = build_tile_plan<R>(C, Fi, F, owner, neighbour, cellFaces, deltas, deltasUnit, bkind.data(), 64, m.nLocalFaces);
         if (plan.T == 64 && plan.maxHalo > kHalo64) throw std::runtime_error("tile halo exceeds the kernel's capacity");
-        // kernel variant: (T, TS) = (128, 320) for compact 3-D tiles (halo <= 192; ragged box sizes reach 170: three fp64 forward CTAs and two reverse CTAs per SM), (128, 384), (64, 448)
-        tile_variant = plan.T == 64 ? 2 : (plan.maxHalo <= kHalo128s ? 0 : 1);
+        // kernel variant (T, TS): 0 = (128, 288) regular 4x4x8 tiles of a hex block (halo = its 160 face neighbours: three fp64 CTAs per
+        // SM forward AND reverse), 1 = (128, 320) compact 3-D tiles (halo <= 192), 2 = (128, 384), 3 = (64, 448)
+        tile_variant = plan.T == 64 ? 3 : (plan.maxHalo <= kHalo128r ? 0 : (plan.maxHalo <= kHalo128s ? 1 : 2));
         m.T = plan.T; m.nTiles = plan.nTiles; nEarlyTiles = plan.nEarly;
         int* d_cperm = dalloc<int>(m.sC); ex.upload(d_cperm, plan.cell_new2old.data(), (size_t)C * 4); m.cell_perm = d_cperm;
         int* d_fperm = (int*)ex.alloc((size_t)(F + 1) * 4); ex.upload(d_fperm, plan.face_new2old.data(), (size_t)F * 4);
@@ -459,8 +460,9 @@ public:
         for (int part = 0; part < 2; part++) {                          // early tiles overlap the exchange of the gradients
             const int t0 = part ? Te : 0, nt = part ? m.nTiles - Te : Te;
             if (part) halo_end();
-            if (tile_variant == 0) run_flux_tile<128, 128 + kHalo128s>(s, dt, Qs, Gs, Qnext, want_dtc_obj, t0, nt);
-            else if (tile_variant == 1) run_flux_tile<128, 128 + kHalo128>(s, dt, Qs, Gs, Qnext, want_dtc_obj, t0, nt);
+            if (tile_variant == 0) run_flux_tile<128, 128 + kHalo128r>(s, dt, Qs, Gs, Qnext, want_dtc_obj, t0, nt);
+            else if (tile_variant == 1) run_flux_tile<128, 128 + kHalo128s>(s, dt, Qs, Gs, Qnext, want_dtc_obj, t0, nt);
+            else if (tile_variant == 2) run_flux_tile<128, 128 + kHalo128>(s, dt, Qs, Gs, Qnext, want_dtc_obj, t0, nt);
             else run_flux_tile<64, 64 + kHalo64>(s, dt, Qs, Gs, Qnext, want_dtc_obj, t0, nt);
         }
         if (want_dtc_obj) { ex.reduce_max_buffer(tile_partial, m.nTiles * (m.T / kRound), red); launches += 2; }
@@ -567,8 +569,9 @@ public:
             // late tiles first: they produce the ghost-row adjoints that travel; the early tiles overlap the exchange
             for (int part = 1; part >= 0; part--) {
                 const int t0 = part ? Te : 0, nt = part ? m.nTiles - Te : Te;
-                if (tile_variant == 0) run_tiles_range(t0, nt, FluxGradTileBody<R, 128, 128 + kHalo128s>{ph, m, Q[s], G[s], A[s + 1], coef, Qb, Gb});
-                else if (tile_variant == 1) run_tiles_range(t0, nt, FluxGradTileBody<R, 128, 128 + kHalo128>{ph, m, Q[s], G[s], A[s + 1], coef, Qb, Gb});
+                if (tile_variant == 0) run_tiles_range(t0, nt, FluxGradTileBody<R, 128, 128 + kHalo128r>{ph, m, Q[s], G[s], A[s + 1], coef, Qb, Gb});
+                else if (tile_variant == 1) run_tiles_range(t0, nt, FluxGradTileBody<R, 128, 128 + kHalo128s>{ph, m, Q[s], G[s], A[s + 1], coef, Qb, Gb});
+                else if (tile_variant == 2) run_tiles_range(t0, nt, FluxGradTileBody<R, 128, 128 + kHalo128>{ph, m, Q[s], G[s], A[s + 1], coef, Qb, Gb});
                 else run_tiles_range(t0, nt, FluxGradTileBody<R, 64, 64 + kHalo64>{ph, m, Q[s], G[s], A[s + 1], coef, Qb, Gb});
                 if (part) halo_reverse_begin(Gb, 15);
             }

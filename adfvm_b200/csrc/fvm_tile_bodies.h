@@ -17,7 +17,7 @@
 //   * face metrics live in HBM as per-round CHUNKS [16][32] R + [32] u32 (area, n, 1/delta, dUnit, linW, quadW and the
 //     packed entry word) in the order the warp consumes them; one bulk copy per warp and round streams a chunk into the
 //     warp's own buffer, issued one round ahead of its use, completion on the warp's own mbarrier;
-//   * forward:  vol [T]          reverse:  ab [5][TS] = abar, vol [TS].
+//   * forward:  vol [T]          reverse:  ab [5][TS] = abar (own slots scaled by 1/V once staged), volh [TS-T] = V of halo slots.
 // After the staging the warps of a CTA never synchronise with each other. The CPU simulator (tests/hostsim) runs the
 // same face / share functions round by round in the same order.
 #pragma once
@@ -363,32 +363,37 @@ template <typename R, int T, int TS> struct FluxTileBody {
 template <typename R, int T, int TS> struct FluxGradTileBody {
     static constexpr const char* kName = "flux_grad_tile";
     static constexpr int kThreads = T, NW = T / 32;
-    static constexpr int kMinBlocks = sizeof(R) == 8 ? 2 : 4;     // register cap: 255 (fp64), 128 (fp32)
+    // fp64: 254 registers and 2 CTAs per SM leave the fp64 pipe half idle (8 warps per SM, profiles/README.md); the compact
+    // variant (TS <= 288: every tile of a regular hex block) fits three CTAs in shared memory and is compiled for 168 registers
+    static constexpr int kMinBlocks = sizeof(R) == 8 ? (TS <= 288 ? 3 : 2) : 4;
     static constexpr int kPrefetchDistance = 148 * kMinBlocks;
     typedef Chunk<R, 32> Ch;
     Phys<R> ph; MeshDev<R> m;
     const R *Q, *G; const R* abar; R coef;
     R *Qb, *Gb;
 #if defined(__CUDACC__)
-    typedef TileSmem<R, T, TS, 6 * TS> Smem;
+    typedef TileSmem<R, T, TS, 5 * TS + (TS - T)> Smem;
     static size_t smem_bytes() { return Smem::kBytes; }
 #endif
 
-    // ab [5][TS]: abar of the slot's cell, vol [TS]; ghost slots are never read (boundary faces scatter to their owner only)
-    FVM_HD void stage_ab(R* ab, R* vol, int slot, int cell) const {
-        if (cell < m.nInternalCells) { for (int k = 0; k < 5; k++) ab[k * TS + slot] = abar[(long)k * m.sC + cell]; vol[slot] = m.vol[cell]; }
+    // ab [5][TS]: abar of the slot's cell - slots [0,T) (the tile's own cells) already divided by the cell volume, halo slots raw
+    // with their volume in volh [TS-T]; ghost slots are never read (boundary faces scatter to their owner only)
+    FVM_HD void stage_ab(R* ab, R* volh, int slot, int cell) const {
+        if (cell >= m.nInternalCells) return;
+        if (slot < T) { const R iv = R(1) / m.vol[cell]; for (int k = 0; k < 5; k++) ab[k * TS + slot] = abar[(long)k * m.sC + cell] * iv; }
+        else { for (int k = 0; k < 5; k++) ab[k * TS + slot] = abar[(long)k * m.sC + cell]; volh[slot - T] = m.vol[cell]; }
     }
     // one entry of the lane whose cell sits in slot lo: own[20] += the home cell's input adjoints; snd[20] = the other
     // cell's (set when e.sn; zero otherwise); ghost >= 0: global row of the other cell when it is a ghost cell, whose
     // adjoints are stored straight to Qb/Gb
-    FVM_HD void face(const Geom<R>& gm, const TileEntry& e, int lo, int ghost, const R* qg, const R* ab, R ivh, const R* vol, R* own, R* snd) const {
+    FVM_HD void face(const Geom<R>& gm, const TileEntry& e, int lo, int ghost, const R* qg, const R* ab, const R* volh, R* own, R* snd) const {
         Prim<R> qL, qR; Grad<R> gL, gR;
         tile_load_cell<R, TS>(qg, lo, qL, gL); tile_load_cell<R, TS>(qg, e.ln, qR, gR);
-        const R sO = gm.area * coef * ivh;
+        const R sO = gm.area * coef;
         R d[5];
         for (int k = 0; k < 5; k++) d[k] = ab[k * TS + lo] * sO;
         if (!e.ghost) {
-            const R sN_ = gm.area * coef * rcp(vol[e.ln]);
+            const R sN_ = e.ln >= T ? sO * rcp(volh[e.ln - T]) : sO;
             for (int k = 0; k < 5; k++) d[k] -= ab[k * TS + e.ln] * sN_;
         }
         Flux5<R> Fb; Fb.rho = d[0]; Fb.rhoU[0] = d[1]; Fb.rhoU[1] = d[2]; Fb.rhoU[2] = d[3]; Fb.rhoE = d[4];
@@ -417,12 +422,12 @@ template <typename R, int T, int TS> struct FluxGradTileBody {
 #if !defined(__CUDACC__)
     void host_tile(int t) const {
         const int c0 = t * T, nc = (m.nInternalCells - c0 < T) ? m.nInternalCells - c0 : T;
-        const R nan = std::numeric_limits<R>::quiet_NaN();       // ghost slots of ab / vol must never be read
-        std::vector<R> qg((size_t)20 * TS, R(0)), ab((size_t)5 * TS, nan), vol(TS, nan);
-        for (int l = 0; l < nc; l++) { tile_stage_cell<R, TS>(qg.data(), l, Q, G, m.sN, c0 + l); stage_ab(ab.data(), vol.data(), l, c0 + l); }
+        const R nan = std::numeric_limits<R>::quiet_NaN();       // ghost slots of ab / volh must never be read
+        std::vector<R> qg((size_t)20 * TS, R(0)), ab((size_t)5 * TS, nan), volh(TS - T, nan);
+        for (int l = 0; l < nc; l++) { tile_stage_cell<R, TS>(qg.data(), l, Q, G, m.sN, c0 + l); stage_ab(ab.data(), volh.data(), l, c0 + l); }
         for (int h = m.halo_start[t]; h < m.halo_start[t + 1]; h++) {
             const int slot = T + h - m.halo_start[t];
-            tile_stage_cell<R, TS>(qg.data(), slot, Q, G, m.sN, m.halo_cell[h]); stage_ab(ab.data(), vol.data(), slot, m.halo_cell[h]);
+            tile_stage_cell<R, TS>(qg.data(), slot, Q, G, m.sN, m.halo_cell[h]); stage_ab(ab.data(), volh.data(), slot, m.halo_cell[h]);
         }
         for (int w = 0; w < NW; w++) {
             R acc[32][20], snd[32][20];
@@ -437,11 +442,11 @@ template <typename R, int T, int TS> struct FluxGradTileBody {
                     if (e[i].ghost != (e[i].ln >= T && m.halo_cell[m.halo_start[t] + e[i].ln - T] >= m.nInternalCells)) throw std::runtime_error("ghost flag inconsistent");
                     if (e[i].kind != FACE_COUPLED && !e[i].ghost) throw std::runtime_error("boundary-kind entry without a ghost cell");
                     Geom<R> gm; tile_load_geom<R, 32>(chunk, i, gm);
-                    face(gm, e[i], w * 32 + i, ghost_of(t, e[i]), qg.data(), ab.data(), R(1) / vol[w * 32 + i], vol.data(), acc[i], snd[i]);
+                    face(gm, e[i], w * 32 + i, ghost_of(t, e[i]), qg.data(), ab.data(), volh.data(), acc[i], snd[i]);
                 }
                 for (int i = 0; i < 32; i++) if (e[i].has_src) for (int k = 0; k < 20; k++) acc[i][k] += snd[e[i].src][k];
             }
-            for (int l = w * 32; l < nc && l < w * 32 + 32; l++) finish(c0 + l, acc[l - w * 32], R(1) / vol[l]);
+            for (int l = w * 32; l < nc && l < w * 32 + 32; l++) finish(c0 + l, acc[l - w * 32], R(1) / m.vol[c0 + l]);
         }
     }
 #else
@@ -450,7 +455,7 @@ template <typename R, int T, int TS> struct FluxGradTileBody {
         const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
         R* qg = reinterpret_cast<R*>(smem);
         R* ab = qg + 20 * TS;
-        R* vol = ab + 5 * TS;
+        R* volh = ab + 5 * TS;
         R* chunk = reinterpret_cast<R*>(smem + Smem::kChunkOff) + w * Ch::kScalars;
         unsigned long long* bars = reinterpret_cast<unsigned long long*>(smem + Smem::kBarOff);
         unsigned long long *bar_rows = &bars[0], *bar_halo = &bars[1], *bar_chunk = &bars[2 + w];
@@ -464,16 +469,16 @@ template <typename R, int T, int TS> struct FluxGradTileBody {
         }
         __syncthreads();
         if (tid == 0) {
-            mbar_expect_tx(bar_rows, 26u * kRow);
+            mbar_expect_tx(bar_rows, 25u * kRow);
             for (int k = 0; k < 5; k++) bulk_g2s(qg + k * TS, Q + (long)k * m.sN + c0, kRow, bar_rows);
             for (int k = 0; k < 15; k++) bulk_g2s(qg + (5 + k) * TS, G + (long)k * m.sN + c0, kRow, bar_rows);
             for (int k = 0; k < 5; k++) bulk_g2s(ab + k * TS, abar + (long)k * m.sC + c0, kRow, bar_rows);
-            bulk_g2s(vol, m.vol + c0, kRow, bar_rows);
         }
         if (lane == 0 && nr > 0) {
             mbar_expect_tx(bar_chunk, (unsigned)Ch::kBytes);
             bulk_g2s(chunk, m.chunks + (long)r0 * Ch::kScalars, (unsigned)Ch::kBytes, bar_chunk);
         }
+        const R vown = m.vol[c0 + tid];             // (rows past the last cell: allocated slack)
         {
             constexpr int kIter = (TS - T + T - 1) / T;
             int hc[kIter];
@@ -487,7 +492,7 @@ template <typename R, int T, int TS> struct FluxGradTileBody {
                 for (int k = 0; k < 15; k++) cp_async_elem<sizeof(R)>(qg + (5 + k) * TS + slot, G + (long)k * m.sN + cell);
                 if (cell < m.nInternalCells) {
                     for (int k = 0; k < 5; k++) cp_async_elem<sizeof(R)>(ab + k * TS + slot, abar + (long)k * m.sC + cell);
-                    cp_async_elem<sizeof(R)>(vol + slot, m.vol + cell);
+                    cp_async_elem<sizeof(R)>(volh + slot - T, m.vol + cell);
                 }
             }
         }
@@ -503,9 +508,13 @@ template <typename R, int T, int TS> struct FluxGradTileBody {
             }
             if (tn < m.nTiles && w == (NW > 1 ? NW - 2 : 0)) tile_prefetch_meta<R, NW, Ch>(m, tn, tn + kPrefetchDistance, lane);
         }
-        if (nr == 0) return;
+        // the tile's own abar rows are consumed divided by the cell volume, by every warp of the CTA: scale them in place once
         mbar_wait(bar_rows, 0);
-        const R ivh = tid < nc ? rcp(vol[tid]) : R(0);
+        const R ivh = tid < nc ? rcp(vown) : R(0);
+        #pragma unroll
+        for (int k = 0; k < 5; k++) ab[k * TS + tid] *= ivh;
+        __syncthreads();
+        if (nr == 0) return;
         R acc[20];
         for (int k = 0; k < 20; k++) acc[k] = R(0);
         for (int r = 0; r < nr; r++) {
@@ -521,7 +530,7 @@ template <typename R, int T, int TS> struct FluxGradTileBody {
             }
             R snd[20];
             for (int k = 0; k < 20; k++) snd[k] = R(0);
-            if (e.valid) face(gm, e, tid, ghost_of(t, e), qg, ab, ivh, vol, acc, snd);
+            if (e.valid) face(gm, e, tid, ghost_of(t, e), qg, ab, volh, acc, snd);
             if (__any_sync(0xffffffffu, e.has_src)) {
                 for (int k = 0; k < 20; k++) { const R v = __shfl_sync(0xffffffffu, snd[k], e.src); if (e.has_src) acc[k] += v; }
             }

@@ -22,6 +22,7 @@ adFVM/density.py:108-110): 0-2 state | 3 dt | 4-13 gradFields | 14-18 intFields 
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import numpy as np
 
@@ -70,8 +71,12 @@ class _PinnedPool:
     are fresh numpy arrays over recycled page-locked blocks: the device-to-host copies run asynchronously at the
     full PCIe rate instead of staging through pageable memory."""
 
-    def __init__(self, lib, keep=8):
-        self.lib, self.free, self.keep = lib, {}, keep
+    def __init__(self, lib, keep_bytes=None):
+        # recycled blocks are kept up to a byte budget (a checkpoint block of the reference's adjoint driver holds one state per
+        # step alive, apps/adjoint.py:217; allocating page-locked memory is slow, ~0.5 s per GB)
+        if keep_bytes is None:
+            keep_bytes = int(float(os.environ.get("ADFVM_PINNED_POOL_GB", "16")) * 2 ** 30)
+        self.lib, self.free, self.keep_bytes, self.pooled = lib, {}, keep_bytes, 0
 
     def empty(self, shape, dtype):
         n = int(np.prod(shape)) * np.dtype(dtype).itemsize
@@ -79,6 +84,7 @@ class _PinnedPool:
         lst = self.free.get(nbytes)
         if lst:
             ptr = lst.pop()
+            self.pooled -= nbytes
         else:
             p = C.c_void_p()
             self.lib.check(self.lib.dll.adfvm_host_alloc(C.byref(p), nbytes))
@@ -88,8 +94,9 @@ class _PinnedPool:
 
     def _release(self, ptr, nbytes):
         lst = self.free.setdefault(nbytes, [])
-        if len(lst) < self.keep:
+        if self.pooled + nbytes <= self.keep_bytes or nbytes <= 4096:
             lst.append(ptr)
+            self.pooled += nbytes
         else:
             try:
                 self.lib.dll.adfvm_host_free(C.c_void_p(ptr))
@@ -103,7 +110,7 @@ class _PinnedPool:
                     self.lib.dll.adfvm_host_free(C.c_void_p(ptr))
                 except Exception:
                     pass
-        self.free = {}
+        self.free, self.pooled = {}, 0
 
 
 class _Context:

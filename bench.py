@@ -408,7 +408,7 @@ def measure(case, dtype, rank, world, local, stream, K, W, want_kernels=True, wa
 
     # ---- end to end through the public call with pinned host buffers: a checkpoint block as Adjoint.run drives it
     if want_e2e:
-        B = max(2, min(K, 5))
+        B = max(2, min(K, 3))
         pin = lambda a: torch.from_numpy(np.ascontiguousarray(a)).pin_memory().numpy()
         hstate = [pin(a) for a in case.state]
         hadj0 = [pin(a) for a in adj0]

@@ -104,3 +104,75 @@ class RefGraph:
 
     def primal_grad(self, *args, **kwargs):
         return self._call("primal_grad", args, kwargs)
+
+
+# ---- one mesh per process. The reference's runtime keeps its static buffers (gradient accumulators, adpy/adpy/cpp/include/
+# common.hpp:312-327 `shared_acquire`) in a process-wide table keyed by variable id and sized by the FIRST mesh it sees, as a
+# solver process of the reference only ever has one mesh. Checks that visit several meshes therefore run each RefGraph in
+# its own child process.
+def _serve(conn, name, fp32):
+    try:
+        g = RefGraph(name, fp32)
+        devnull = os.open(os.devnull, os.O_WRONLY)
+        os.dup2(devnull, 1)                           # "Initializing C++ interface"
+        conn.send(("ok", g.variant))
+        while True:
+            msg = conn.recv()
+            if msg[0] == "close":
+                break
+            try:
+                if msg[0] == "initialize":
+                    g.initialize(msg[1]); conn.send(("ok", None))
+                else:
+                    conn.send(("ok", getattr(g, msg[0])(*msg[1], **msg[2])))
+            except Exception as e:      # noqa: BLE001
+                conn.send(("error", repr(e)))
+    except Exception as e:              # noqa: BLE001
+        conn.send(("error", repr(e)))
+    os._exit(0)                                       # skip the module's exit hook
+
+
+class IsolatedRefGraph:
+    """RefGraph in a child process (same methods); close() or garbage collection ends the child"""
+
+    def __init__(self, name="box_cyclic", fp32=False):
+        import multiprocessing as mp
+        if not available(name, fp32):
+            raise FileNotFoundError(module_path(name, fp32))
+        ctx = mp.get_context("spawn")
+        self.conn, child = ctx.Pipe()
+        self.proc = ctx.Process(target=_serve, args=(child, name, fp32), daemon=True)
+        self.proc.start()
+        self.variant = self._reply()
+
+    def _reply(self):
+        status, val = self.conn.recv()
+        if status != "ok":
+            raise RuntimeError("reference process: %s" % val)
+        return val
+
+    def initialize(self, mesh):
+        self.conn.send(("initialize", mesh)); self._reply()
+
+    def primal(self, *args, **kwargs):
+        self.conn.send(("primal", args, kwargs)); return self._reply()
+
+    def primal_grad(self, *args, **kwargs):
+        self.conn.send(("primal_grad", args, kwargs)); return self._reply()
+
+    def close(self):
+        if self.proc is not None:
+            try:
+                self.conn.send(("close",))
+            except Exception:
+                pass
+            self.proc.join(timeout=10)
+            if self.proc.is_alive():
+                self.proc.kill()
+            self.proc = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

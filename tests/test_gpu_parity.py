@@ -67,16 +67,17 @@ def test_oracle_parity(make, dtype, tol, cudalib):
 # ---- the code path that is benchmarked (regular 4x4x8 tiles on lattice planes, the 444-tile L2 prefetch distance, several
 # waves of CTAs) and the other two kernel variants, against the REFERENCE's own compiled step functions (oracle/_ref, built from
 # the unmodified reference's generated code by oracle/ref_harness/build_ref_graph.py; the oracle port if it did not travel)
-LARGE = [((64, 64, 64), 0.0, 0, 128),      # variant (T,TS) = (128,320): regular tiles, 2048 tiles = 4.6 waves of 444 CTAs
-         ((92, 92, 23), 0.0, 2, 64),       # ragged lattice (23 planes): 64-cell tiles
-         ((46, 46, 46), 0.0, 2, 64),
-         ((40, 36, 28), 0.02, 1, 128)]     # warped (no lattice): coordinate bisection, halo > 192 -> (128,384)
+LARGE = [((64, 64, 64), 0.0, 0, 128),      # variant 0, (T,TS) = (128,288): regular tiles, 2048 tiles = 4.6 waves of 444 CTAs
+         ((92, 92, 23), 0.0, 3, 64),       # ragged lattice (23 planes): 64-cell tiles (64,448)
+         ((46, 46, 46), 0.0, 3, 64),
+         ((40, 36, 28), 0.02, 2, 128),     # warped (no lattice): coordinate bisection, halo 193 -> (128,384)
+         ((16, 14, 12), 0.03, 1, 128)]     # halo 190 -> (128,320)
 
 
 def _reference_functions(case):
     from oracle import refgraph
     if refgraph.available("box_cyclic"):
-        R = refgraph.RefGraph("box_cyclic")
+        R = refgraph.IsolatedRefGraph("box_cyclic")       # one mesh per reference process (see oracle/refgraph.py)
         R.initialize(case.mesh)
         return R.primal, R.primal_grad, "reference"
     return (lambda *inp, **kw: O.primal(case.spec, list(inp))), (lambda *inp, **kw: O.primal_grad(case.spec, list(inp))), "port"
