@@ -49,6 +49,7 @@ template <typename R> struct MeshDev {
     const int* halo_round;               // [nTiles*T/32] first round (relative to round_start) whose entries read halo slots
     const int* halo_start; const int* halo_cell;    // tile t's halo slots T.. hold cells halo_cell[halo_start[t]..halo_start[t+1])
     const int* cell_perm;                // [C] device cell -> reference (host) cell
+    const unsigned short* nbrSlot;       // [6][sC] tile slot of the cell's j-th neighbour (own cells [0,T), halo slots from T on); bit 15: ghost cell
 };
 
 // OBJ_PLANE_PTLOSS (reference adFVM/objectives/vane.py:36-66): cells / areas of a cut plane (device cell numbering),
@@ -341,65 +342,8 @@ template <typename R> struct GhostGradAdjBody {
 //   a ghost neighbour has no gradient of its own and receives (1-a_j) SN_j . H_c in its Qb row (exclusive writer).
 //   Then a_s = sum_k alpha_k a_k + (dQ/dW)^T Qb_c (+ cell objective seed, + source-gradient accumulation on the last
 //   reverse stage). Cells next to a boundary get the share of their ghost rows later (GhostPrimAdjBody, linear).
-template <typename R> struct GradAdjUpdateBody {
-    static constexpr const char* kName = "grad_adj_update";
-    static constexpr int kMinBlocks = sizeof(R) == 8 ? 4 : 6;      // a latency-bound gather: 16 (fp64) / 24 (fp32) warps per SM
-    Phys<R> ph; MeshDev<R> m;
-    const R* Gb; R* Qb;
-    const R* W;                // stage state the residual was evaluated at
-    const R *A1, *A2, *A3;     // adjoints of later stage outputs (NULL when coefficient is 0)
-    R c1, c2, c3;
-    R objT;                    // obja for OBJ_CELL_TV / OBJ_CELL_T on the objective stage, else 0
-    int objVol;                // 1: the cell objective is volume-weighted (OBJ_CELL_TV)
-    R* Aout;                   // [5][sC]
-    R* Sb; R s1, s2, s3;       // source gradient accumulation (only when Sb != NULL): Sb += s1*A1 + s2*A2 + s3*A3
-    FVM_HD void operator()(int c) const {
-        const int sC = m.sC, sN = m.sN, C = m.nInternalCells;
-        const R* FVM_RESTRICT gb = Gb; const R* FVM_RESTRICT cfm = m.cfm; const int* FVM_RESTRICT cn = m.cellNbr;
-        R H[15];
-        for (int k = 0; k < 15; k++) H[k] = gb[(long)k * sN + c];
-        Prim<R> acc; load_prim(Qb, sN, c, acc);
-        int nbr[6];
-        for (int j = 0; j < 6; j++) nbr[j] = cn[(long)j * sC + c];
-        unsigned ghosts = 0;
-        for (int j = 0; j < 6; j++) {
-            const int nb = nbr[j];
-            const R SN[3] = {cfm[(long)(4 * j) * sC + c], cfm[(long)(4 * j + 1) * sC + c], cfm[(long)(4 * j + 2) * sC + c]};
-            const R a = cfm[(long)(4 * j + 3) * sC + c];
-            R D[15];
-            if (nb >= C) { ghosts |= 1u << j; for (int k = 0; k < 15; k++) D[k] = H[k]; }
-            else for (int k = 0; k < 15; k++) D[k] = H[k] - gb[(long)k * sN + nb];
-            for (int i = 0; i < 3; i++) acc.U[i] += a * (SN[0] * D[3 * i] + SN[1] * D[3 * i + 1] + SN[2] * D[3 * i + 2]);
-            acc.T += a * (SN[0] * D[9] + SN[1] * D[10] + SN[2] * D[11]);
-            acc.p += a * (SN[0] * D[12] + SN[1] * D[13] + SN[2] * D[14]);
-        }
-        if (ghosts) {
-            for (int j = 0; j < 6; j++) {
-                if (!((ghosts >> j) & 1u)) continue;
-                const R SN[3] = {cfm[(long)(4 * j) * sC + c], cfm[(long)(4 * j + 1) * sC + c], cfm[(long)(4 * j + 2) * sC + c]};
-                const R wp = R(1) - cfm[(long)(4 * j + 3) * sC + c];
-                Prim<R> gq;
-                for (int i = 0; i < 3; i++) gq.U[i] = wp * (SN[0] * H[3 * i] + SN[1] * H[3 * i + 1] + SN[2] * H[3 * i + 2]);
-                gq.T = wp * (SN[0] * H[9] + SN[1] * H[10] + SN[2] * H[11]);
-                gq.p = wp * (SN[0] * H[12] + SN[1] * H[13] + SN[2] * H[14]);
-                add_prim(Qb, sN, nbr[j], gq);
-            }
-        }
-        if (objT != R(0)) acc.T += objVol ? objT * m.vol[c] : objT;
-        R rhoU[3] = {W[sC + c], W[2 * sC + c], W[3 * sC + c]};
-        R out[5] = {0, 0, 0, 0, 0};
-        primitive_vjp(ph, W[c], rhoU, W[4 * sC + c], acc, out[0], out + 1, out[4]);
-        for (int k = 0; k < 5; k++) {
-            R v = out[k];
-            R x1 = A1 ? A1[k * sC + c] : R(0), x2 = A2 ? A2[k * sC + c] : R(0), x3 = A3 ? A3[k * sC + c] : R(0);
-            if (A1) v += c1 * x1;
-            if (A2) v += c2 * x2;
-            if (A3) v += c3 * x3;
-            Aout[k * sC + c] = v;
-            if (Sb) Sb[k * sC + c] += s1 * x1 + s2 * x2 + s3 * x3;
-        }
-    }
-};
+// (the kernel itself is GradAdjTileBody in fvm_tile_bodies.h: one CTA per tile, the gradient adjoints of the tile and of its halo
+// staged in shared memory)
 // cell-face metrics (mesh upload, one-off): rows 4j..4j+2 = +-S_f n_f (outward of the cell), row 4j+3 = weight of the
 // cell's own value in the face interpolate (adFVM/op.py:52-58: w' = w + o - 2 w o is the NEIGHBOUR's weight)
 template <typename R> struct CellFaceMetricBody {

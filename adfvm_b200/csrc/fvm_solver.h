@@ -205,6 +205,7 @@ public:
             int* d_hs = dalloc<int>(plan.halo_start.size()); ex.upload(d_hs, plan.halo_start.data(), plan.halo_start.size() * 4); m.halo_start = d_hs;
             int* d_hc = dalloc<int>(plan.halo_cell.size() + 1); ex.upload(d_hc, plan.halo_cell.data(), plan.halo_cell.size() * 4); m.halo_cell = d_hc;
             tile_partial = dalloc<R>((size_t)plan.nTiles * plan.NW + 1);
+            unsigned short* d_ns = dalloc<unsigned short>((size_t)6 * m.sC); run(C, NbrSlotBody<R>{m, d_ns}); m.nbrSlot = d_ns;
             ex.sync();
         }
         if (mesh_param) { face_new2old_h = plan.face_new2old; cell_new2old_h = plan.cell_new2old; }
@@ -523,7 +524,7 @@ public:
         Q[2] = dalloc<R>((size_t)5 * m.sN + kRowSlack);
         G[1] = dalloc<R>((size_t)15 * m.sN + kRowSlack); G[2] = dalloc<R>((size_t)15 * m.sN + kRowSlack);
         for (int k = 0; k < 4; k++) A[k] = dalloc<R>((size_t)5 * m.sC + kRowSlack);
-        Qb = dalloc<R>((size_t)5 * m.sN); Gb = dalloc<R>((size_t)15 * m.sN);
+        Qb = dalloc<R>((size_t)5 * m.sN); Gb = dalloc<R>((size_t)15 * m.sN + kRowSlack);
         Sb = dalloc<R>((size_t)5 * m.sC);
         if (mesh_param) { Mb = dalloc<R>((size_t)19 * m.sF); Vb = dalloc<R>((size_t)m.sC); }
         adjoint_ready = true;
@@ -561,6 +562,20 @@ public:
         primal_step(dt, true);
         adjoint_reverse(dt, obja);
     }
+    template <int T, int TS> void run_grad_adj_tile(int s, R dt, R obja, int t0, int nt) {
+        GradAdjTileBody<R, T, TS> pb;
+        pb.ph = ph; pb.m = m; pb.Gb = Gb; pb.Qb = Qb; pb.W = W[s];
+        // a_s = sum_{k>=s} alpha[k][s] * a_{k+1}
+        pb.A1 = (s <= 0 && RK_ALPHA[0][s] != 0.) ? A[1] : nullptr; pb.c1 = (R)(s <= 0 ? RK_ALPHA[0][s] : 0.);
+        pb.A2 = (s <= 1 && RK_ALPHA[1][s] != 0.) ? A[2] : nullptr; pb.c2 = (R)(s <= 1 ? RK_ALPHA[1][s] : 0.);
+        pb.A3 = (RK_ALPHA[2][s] != 0.) ? A[3] : nullptr; pb.c3 = (R)RK_ALPHA[2][s];
+        pb.objT = (s == 1 && (obj.kind == OBJ_CELL_TV || obj.kind == OBJ_CELL_T)) ? obja : R(0);
+        pb.objVol = obj.kind == OBJ_CELL_TV;
+        pb.Aout = A[s];
+        pb.Sb = (s == 0) ? Sb : nullptr;
+        pb.s1 = (R)RK_BETA[0] * dt; pb.s2 = (R)RK_BETA[1] * dt; pb.s3 = (R)RK_BETA[2] * dt;
+        run_tiles_range(t0, nt, pb);
+    }
     void adjoint_reverse(R dt, R obja) {
         const int C = m.nInternalCells;
         for (int s = 2; s >= 0; s--) {
@@ -584,20 +599,15 @@ public:
                 if (comm) comm->allreduce_sum_device(red + 5, 1, ex.stream_handle());
                 run(obj.ncells, PlaneLossAdjBody<R>{ph, m, obj, Q[1], red + 4, red + 5, obja, Qb});
             }
-            GradAdjUpdateBody<R> pb;
-            pb.ph = ph; pb.m = m; pb.Gb = Gb; pb.Qb = Qb; pb.W = W[s];
-            // a_s = sum_{k>=s} alpha[k][s] * a_{k+1}
-            pb.A1 = (s <= 0 && RK_ALPHA[0][s] != 0.) ? A[1] : nullptr; pb.c1 = (R)(s <= 0 ? RK_ALPHA[0][s] : 0.);
-            pb.A2 = (s <= 1 && RK_ALPHA[1][s] != 0.) ? A[2] : nullptr; pb.c2 = (R)(s <= 1 ? RK_ALPHA[1][s] : 0.);
-            pb.A3 = (RK_ALPHA[2][s] != 0.) ? A[3] : nullptr; pb.c3 = (R)RK_ALPHA[2][s];
-            pb.objT = (s == 1 && (obj.kind == OBJ_CELL_TV || obj.kind == OBJ_CELL_T)) ? obja : R(0);
-            pb.objVol = obj.kind == OBJ_CELL_TV;
-            pb.Aout = A[s];
-            pb.Sb = (s == 0) ? Sb : nullptr;
-            pb.s1 = (R)RK_BETA[0] * dt; pb.s2 = (R)RK_BETA[1] * dt; pb.s3 = (R)RK_BETA[2] * dt;
-            run_range(Ce, C - Ce, pb);               // late cells first: they complete the ghost rows of U,T,p that travel
-            halo_reverse_begin(Qb, 5);
-            run_range(0, Ce, pb);
+            // late tiles first: they complete the ghost rows of U,T,p that travel
+            for (int part = 1; part >= 0; part--) {
+                const int t0 = part ? Te : 0, nt = part ? m.nTiles - Te : Te;
+                if (tile_variant == 0) run_grad_adj_tile<128, 128 + kHalo128r>(s, dt, obja, t0, nt);
+                else if (tile_variant == 1) run_grad_adj_tile<128, 128 + kHalo128s>(s, dt, obja, t0, nt);
+                else if (tile_variant == 2) run_grad_adj_tile<128, 128 + kHalo128>(s, dt, obja, t0, nt);
+                else run_grad_adj_tile<64, 64 + kHalo64>(s, dt, obja, t0, nt);
+                if (part) halo_reverse_begin(Qb, 5);
+            }
             const R* rQ = halo_reverse_end();
             const R oa = (s == 1) ? obja : R(0);
             run(nBcells, GhostPrimAdjBody<R>{ph, m, obj, oa, bcells, Q[s], Qb, rQ, W[s], A[s]});

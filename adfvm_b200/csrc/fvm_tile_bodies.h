@@ -540,4 +540,142 @@ template <typename R, int T, int TS> struct FluxGradTileBody {
 #endif
 };
 
+// ------------------------------------------------------------------------------------------ reverse of gradCell (+ primitive + RK)
+// C + F of fvm_bodies.h, one CTA per tile, one thread per cell: the rows H = Gb/V of the tile's own cells arrive by bulk
+// copy, those of its halo cells (the face neighbours in other tiles) by the asynchronous gather, and the six-neighbour
+// gather of 15 values each reads shared memory instead of L2 (it was bound by the latency of those loads).
+// nbrSlot (mesh upload): shared-memory slot of every neighbour; bit 15 marks ghost cells, which have no gradient of their own.
+enum { kGhostSlot = 0x8000 };
+template <typename R> struct NbrSlotBody {
+    static constexpr const char* kName = "nbr_slot";
+    MeshDev<R> m; unsigned short* out;
+    FVM_HD void operator()(int c) const {
+        const int t = c / m.T, c0 = t * m.T, h0 = m.halo_start[t], nh = m.halo_start[t + 1] - h0;
+        for (int j = 0; j < 6; j++) {
+            const int nb = m.cellNbr[(long)j * m.sC + c];
+            int slot = -1;
+            if (nb >= c0 && nb < c0 + m.T && nb < m.nInternalCells) slot = nb - c0;
+            else for (int h = 0; h < nh; h++) if (m.halo_cell[h0 + h] == nb) { slot = m.T + h; break; }
+            // every face neighbour outside the tile is a halo slot of the tile (fvm_tiles.h); 0x7fff would fault loudly
+            out[(long)j * m.sC + c] = (unsigned short)((slot < 0 ? 0x7fff : slot) | (nb >= m.nInternalCells ? kGhostSlot : 0));
+        }
+    }
+};
+
+template <typename R, int T, int TS> struct GradAdjTileBody {
+    static constexpr const char* kName = "grad_adj_update";
+    static constexpr int kThreads = T;
+    static constexpr int kMinBlocks = sizeof(R) == 8 ? 4 : 5;      // register cap 128 (fp64) / 102 (fp32)
+    static constexpr int kPrefetchDistance = 148 * kMinBlocks;
+    Phys<R> ph; MeshDev<R> m;
+    const R* Gb; R* Qb;
+    const R* W;                // stage state the residual was evaluated at
+    const R *A1, *A2, *A3;     // adjoints of later stage outputs (NULL when coefficient is 0)
+    R c1, c2, c3;
+    R objT;                    // obja for OBJ_CELL_TV / OBJ_CELL_T on the objective stage, else 0
+    int objVol;                // 1: the cell objective is volume-weighted (OBJ_CELL_TV)
+    R* Aout;                   // [5][sC]
+    R* Sb; R s1, s2, s3;       // source gradient accumulation (only when Sb != NULL): Sb += s1*A1 + s2*A2 + s3*A3
+#if defined(__CUDACC__)
+    static constexpr size_t kBarOff = ((size_t)15 * TS * sizeof(R) + 15) / 16 * 16;
+    static size_t smem_bytes() { return kBarOff + 16; }
+#endif
+    // cell c of tile t (slot lo); gbs [15][TS]: H rows of the tile's slots (ghost slots never read)
+    FVM_HD void cell(int t, int c, int lo, const R* gbs) const {
+        const int sC = m.sC, sN = m.sN;
+        const R* FVM_RESTRICT cfm = m.cfm;
+        R H[15];
+        for (int k = 0; k < 15; k++) H[k] = gbs[k * TS + lo];
+        Prim<R> acc; load_prim(Qb, sN, c, acc);
+        unsigned ghosts = 0; int slots[6];
+        for (int j = 0; j < 6; j++) {
+            const int s = m.nbrSlot[(long)j * sC + c];
+            slots[j] = s & 0x7fff;
+            const R SN[3] = {cfm[(long)(4 * j) * sC + c], cfm[(long)(4 * j + 1) * sC + c], cfm[(long)(4 * j + 2) * sC + c]};
+            const R a = cfm[(long)(4 * j + 3) * sC + c];
+            R D[15];
+            if (s & kGhostSlot) { ghosts |= 1u << j; for (int k = 0; k < 15; k++) D[k] = H[k]; }
+            else { const R* nb = gbs + slots[j]; for (int k = 0; k < 15; k++) D[k] = H[k] - nb[k * TS]; }
+            for (int i = 0; i < 3; i++) acc.U[i] += a * (SN[0] * D[3 * i] + SN[1] * D[3 * i + 1] + SN[2] * D[3 * i + 2]);
+            acc.T += a * (SN[0] * D[9] + SN[1] * D[10] + SN[2] * D[11]);
+            acc.p += a * (SN[0] * D[12] + SN[1] * D[13] + SN[2] * D[14]);
+        }
+        if (ghosts) {
+            for (int j = 0; j < 6; j++) {
+                if (!((ghosts >> j) & 1u)) continue;
+                const R SN[3] = {cfm[(long)(4 * j) * sC + c], cfm[(long)(4 * j + 1) * sC + c], cfm[(long)(4 * j + 2) * sC + c]};
+                const R wp = R(1) - cfm[(long)(4 * j + 3) * sC + c];
+                Prim<R> gq;
+                for (int i = 0; i < 3; i++) gq.U[i] = wp * (SN[0] * H[3 * i] + SN[1] * H[3 * i + 1] + SN[2] * H[3 * i + 2]);
+                gq.T = wp * (SN[0] * H[9] + SN[1] * H[10] + SN[2] * H[11]);
+                gq.p = wp * (SN[0] * H[12] + SN[1] * H[13] + SN[2] * H[14]);
+                add_prim(Qb, sN, m.halo_cell[m.halo_start[t] + slots[j] - T], gq);      // the ghost row of that face (exclusive writer)
+            }
+        }
+        if (objT != R(0)) acc.T += objVol ? objT * m.vol[c] : objT;
+        R rhoU[3] = {W[sC + c], W[2 * sC + c], W[3 * sC + c]};
+        R out[5] = {0, 0, 0, 0, 0};
+        primitive_vjp(ph, W[c], rhoU, W[4 * sC + c], acc, out[0], out + 1, out[4]);
+        for (int k = 0; k < 5; k++) {
+            R v = out[k];
+            R x1 = A1 ? A1[k * sC + c] : R(0), x2 = A2 ? A2[k * sC + c] : R(0), x3 = A3 ? A3[k * sC + c] : R(0);
+            if (A1) v += c1 * x1;
+            if (A2) v += c2 * x2;
+            if (A3) v += c3 * x3;
+            Aout[k * sC + c] = v;
+            if (Sb) Sb[k * sC + c] += s1 * x1 + s2 * x2 + s3 * x3;
+        }
+    }
+#if !defined(__CUDACC__)
+    void host_tile(int t) const {
+        const int c0 = t * T, nc = (m.nInternalCells - c0 < T) ? m.nInternalCells - c0 : T;
+        const R nan = std::numeric_limits<R>::quiet_NaN();
+        std::vector<R> gbs((size_t)15 * TS, nan);
+        for (int l = 0; l < nc; l++) for (int k = 0; k < 15; k++) gbs[(size_t)k * TS + l] = Gb[(long)k * m.sN + c0 + l];
+        for (int h = m.halo_start[t]; h < m.halo_start[t + 1]; h++) {
+            const int cellh = m.halo_cell[h];
+            if (cellh < m.nInternalCells) for (int k = 0; k < 15; k++) gbs[(size_t)k * TS + T + h - m.halo_start[t]] = Gb[(long)k * m.sN + cellh];
+        }
+        for (int l = 0; l < nc; l++) cell(t, c0 + l, l, gbs.data());
+    }
+#else
+    __device__ __forceinline__ void device_tile(int t, unsigned char* smem) const {
+        const int c0 = t * T, nc = min(T, m.nInternalCells - c0);
+        const int tid = threadIdx.x;
+        R* gbs = reinterpret_cast<R*>(smem);
+        unsigned long long* bars = reinterpret_cast<unsigned long long*>(smem + kBarOff);
+        unsigned long long *bar_rows = &bars[0], *bar_halo = &bars[1];
+        const int h0 = m.halo_start[t], nh = m.halo_start[t + 1] - h0;
+        constexpr unsigned kRow = T * (unsigned)sizeof(R);
+        if (tid == 0) { mbar_init(bar_rows, 1); mbar_init(bar_halo, T); mbar_fence_init(); }
+        __syncthreads();
+        if (tid == 0) {
+            mbar_expect_tx(bar_rows, 15u * kRow);
+            for (int k = 0; k < 15; k++) bulk_g2s(gbs + k * TS, Gb + (long)k * m.sN + c0, kRow, bar_rows);
+        }
+        {
+            constexpr int kIter = (TS - T + T - 1) / T;
+            int hc[kIter];
+            #pragma unroll
+            for (int i = 0; i < kIter; i++) { const int h = tid + i * T; hc[i] = h < nh ? m.halo_cell[h0 + h] : -1; }
+            #pragma unroll
+            for (int i = 0; i < kIter; i++) {
+                const int cellh = hc[i], slot = T + tid + i * T;
+                if (cellh < 0 || cellh >= m.nInternalCells) continue;
+                for (int k = 0; k < 15; k++) cp_async_elem<sizeof(R)>(gbs + k * TS + slot, Gb + (long)k * m.sN + cellh);
+            }
+        }
+        cp_async_arrive(bar_halo);
+        {   // L2 prefetch of the rows of the tile that runs in this CTA slot one wave later
+            const int tn = t + kPrefetchDistance;
+            if (tn < m.nTiles && tid < 15) bulk_prefetch_l2(Gb + (long)tid * m.sN + (long)tn * T, kRow);
+            if (tn < m.nTiles && tid >= 32 && tid < 39) { const int* p = m.halo_cell + m.halo_start[tn] + 32 * (tid - 32); if (p < m.halo_cell + m.halo_start[tn + 1]) prefetch_l2(p); }
+        }
+        mbar_wait(bar_rows, 0);
+        mbar_wait(bar_halo, 0);
+        if (tid < nc) cell(t, c0 + tid, tid, gbs);
+    }
+#endif
+};
+
 }  // namespace fvm
