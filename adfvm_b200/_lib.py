@@ -19,7 +19,8 @@ PATCH_WALL, PATCH_CYCLIC, PATCH_SYMMETRY, PATCH_EMPTY, PATCH_CHARACTERISTIC, PAT
 BC_CALCULATED, BC_CYCLIC, BC_ZEROGRADIENT, BC_FIXEDVALUE, BC_SYMMETRY, BC_CBC_UPT, BC_CBC_TOTAL_PT, BC_PROCESSOR = range(8)
 KEY_VALUE_U, KEY_VALUE_T, KEY_VALUE_P, KEY_U0, KEY_T0, KEY_P0, KEY_TT, KEY_PT, KEY_DIRECTION = range(9)
 OBJ_NONE, OBJ_CELL_TV, OBJ_PATCH_PA, OBJ_DRAG = range(4)
-OBJ_PLANE_PTLOSS, OBJ_CELL_T = 4, 5
+OBJ_PLANE_PTLOSS, OBJ_CELL_T, OBJ_CALLBACK = 4, 5, 6
+OBJECTIVE_FN = C.CFUNCTYPE(C.c_double, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_double, C.c_void_p)
 RETURN_STATIC, ZERO_STATIC, REPLACE_STATIC, RETURN_REUSABLE, REPLACE_REUSABLE = 1, 2, 4, 8, 16
 
 
@@ -42,7 +43,8 @@ EXPORTS = ["adfvm_last_error", "adfvm_version", "adfvm_is_cuda", "adfvm_create",
            "adfvm_get_state", "adfvm_sync", "adfvm_launch_count", "adfvm_device_bytes", "adfvm_comm_unique_id",
            "adfvm_comm_init", "adfvm_kernel_timing", "adfvm_kernel_report", "adfvm_set_tile_cells", "adfvm_tile_stats", "adfvm_tile_halo_stats",
            "adfvm_host_alloc", "adfvm_host_free", "adfvm_tile_rounds", "adfvm_graph_replays",
-           "adfvm_set_state", "adfvm_mesh_metrics", "adfvm_set_objective_plane", "adfvm_set_parameter_bc", "adfvm_set_parameter_mesh", "adfvm_get_mesh_grad", "adfvm_primal_block", "adfvm_adjoint_block", "adfvm_set_adjoint", "adfvm_get_adjoint"]
+           "adfvm_set_state", "adfvm_mesh_metrics", "adfvm_set_objective_plane", "adfvm_set_parameter_bc", "adfvm_set_parameter_mesh", "adfvm_get_mesh_grad", "adfvm_primal_block", "adfvm_adjoint_block", "adfvm_set_adjoint", "adfvm_get_adjoint",
+           "adfvm_set_objective_callback", "adfvm_get_cell_perm"]
 
 
 class Lib:
@@ -93,6 +95,8 @@ class Lib:
         d.adfvm_graph_replays.argtypes = [vp]; d.adfvm_graph_replays.restype = C.c_int64
         d.adfvm_tile_rounds.argtypes = [vp, C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(i32)]
         d.adfvm_comm_init.argtypes = [vp, vp, i32, i32]
+        d.adfvm_set_objective_callback.argtypes = [vp, OBJECTIVE_FN, vp]
+        d.adfvm_get_cell_perm.argtypes = [vp, C.POINTER(i32)]
 
     @property
     def is_cuda(self):

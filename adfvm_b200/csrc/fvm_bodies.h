@@ -19,7 +19,8 @@ namespace fvm {
 enum BCType { BC_CALCULATED = 0, BC_CYCLIC = 1, BC_ZEROGRADIENT = 2, BC_FIXEDVALUE = 3, BC_SYMMETRY = 4,
               BC_CBC_UPT = 5, BC_CBC_TOTAL_PT = 6, BC_PROCESSOR = 7 };
 enum ObjKind { OBJ_NONE = 0, OBJ_CELL_TV = 1, OBJ_PATCH_PA = 2, OBJ_DRAG = 3, OBJ_PLANE_PTLOSS = 4,
-               OBJ_CELL_T = 5 };     // sum of T over the cells, no volume weight (reference templates/box.py:10-16)
+               OBJ_CELL_T = 5,       // sum of T over the cells, no volume weight (reference templates/box.py:10-16)
+               OBJ_CALLBACK = 6 };   // evaluated by the host layer from the case file's traced kernels (Solver::obj_fn)
 enum { MAX_PATCHES = 255 };
 
 template <typename R> struct PatchDev {
@@ -566,6 +567,11 @@ template <typename R> struct MeshGradCellBody {
 };
 
 // ------------------------------------------------------------------------------------------ layout helpers
+template <typename R> struct AddBody {             // y += x (objective seeds of the callback objective)
+    static constexpr const char* kName = "add";
+    R* y; const R* x;
+    FVM_HD void operator()(int i) const { y[i] += x[i]; }
+};
 template <typename R> struct ReciprocalBody {      // x <- 1/x (deltas -> idelta at mesh upload)
     static constexpr const char* kName = "reciprocal";
     R* x;

@@ -357,9 +357,23 @@ public:
         obj.ptin = (R)ptin; obj.scale = (R)scale;
         for (int k = 0; k < 3; k++) obj.nrm[k] = (R)normal[k];
     }
+    // objective evaluated by the host layer (any case-file objective, traced by the reference's own front-end)
+    typedef double (*ObjectiveFn)(void* user, const void* Q, long long stride, int want_seed, double obja, void* Qseed);
+    ObjectiveFn obj_fn = nullptr; void* obj_user = nullptr; R* Qseed = nullptr; R obj_host = R(0);
+    void set_objective_callback(ObjectiveFn fn, void* user) {
+        epoch++;
+        if (!fn) throw std::runtime_error("null objective callback");
+        obj_fn = fn; obj_user = user; obj.kind = OBJ_CALLBACK; obj.patch = 0; obj.dir = 0;
+    }
+    void get_cell_perm(int* out) { ex.download(out, m.cell_perm, (size_t)m.nInternalCells * 4); ex.sync(); }
     void objective_forward(const R* Qs) {            // -> red[1] (red[2] = plane mass flux)
         const int C = m.nInternalCells;
         if (obj.kind == OBJ_NONE) { ex.zero(red + 1, sizeof(R)); return; }
+        if (obj.kind == OBJ_CALLBACK) {
+            obj_host = (R)obj_fn(obj_user, Qs, (long long)m.sN, 0, 0., nullptr);
+            ex.upload(red + 1, &obj_host, sizeof(R));
+            return;
+        }
         if (obj.kind == OBJ_PLANE_PTLOSS) {
             // the mass flux of the whole plane normalises every rank's share (mpi_allreduce of w, objectives/vane.py:97-99);
             // the shares themselves are summed over the ranks with the objective (get_dtc_obj)
@@ -484,7 +498,7 @@ public:
     // (multi-rank steps use a second stream and NCCL, per-kernel timing records events)
     static unsigned long long bits(double v) { unsigned long long u; std::memcpy(&u, &v, 8); return u; }
     template <class F> void with_graph(const std::vector<unsigned long long>& key, F&& body) {
-        if (!ex.graph_usable() || comm || m.nRemoteCells > 0) { body(); return; }
+        if (!ex.graph_usable() || comm || m.nRemoteCells > 0 || obj.kind == OBJ_CALLBACK) { body(); return; }   // (host callbacks cannot be captured)
         long n = 0;
         if (ex.graph_launch(key, n)) { launches += n; graph_replays++; return; }
         if (ex.graph_first_time(key) || !ex.graph_begin()) { body(); return; }
@@ -598,6 +612,12 @@ public:
                 ex.reduce_sum(obj.ncells, PlaneLossBody<R>{ph, m, obj, Q[1], red + 4}, red + 5); launches += 4;
                 if (comm) comm->allreduce_sum_device(red + 5, 1, ex.stream_handle());
                 run(obj.ncells, PlaneLossAdjBody<R>{ph, m, obj, Q[1], red + 4, red + 5, obja, Qb});
+            }
+            if (s == 1 && obj.kind == OBJ_CALLBACK && obja != R(0)) {          // seeds of a traced objective: obja * dJ/d(U,T,p), all rows
+                if (!Qseed) Qseed = dalloc<R>((size_t)5 * m.sN);
+                ex.zero(Qseed, (size_t)5 * m.sN * sizeof(R));
+                obj_fn(obj_user, Q[1], (long long)m.sN, 1, (double)obja, Qseed);
+                run(5 * m.sN, AddBody<R>{Qb, Qseed});
             }
             // late tiles first: they complete the ghost rows of U,T,p that travel
             for (int part = 1; part >= 0; part--) {

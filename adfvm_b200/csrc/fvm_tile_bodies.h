@@ -363,9 +363,12 @@ template <typename R, int T, int TS> struct FluxTileBody {
 template <typename R, int T, int TS> struct FluxGradTileBody {
     static constexpr const char* kName = "flux_grad_tile";
     static constexpr int kThreads = T, NW = T / 32;
-    // fp64: 254 registers and 2 CTAs per SM leave the fp64 pipe half idle (8 warps per SM, profiles/README.md); the compact
-    // variant (TS <= 288: every tile of a regular hex block) fits three CTAs in shared memory and is compiled for 168 registers
-    static constexpr int kMinBlocks = sizeof(R) == 8 ? (TS <= 288 ? 3 : 2) : 4;
+    // fp64: 254 registers, 2 CTAs per SM. A third CTA (168 registers; the compact variant fits three in shared memory) was
+    // measured and is slower: 400 B of spills per thread, 1.20 ms instead of 0.76 ms at 128^3 (profiles/README.md, round 2)
+#ifndef ADFVM_FG_MINBLOCKS
+#define ADFVM_FG_MINBLOCKS 2
+#endif
+    static constexpr int kMinBlocks = sizeof(R) == 8 ? ADFVM_FG_MINBLOCKS : 4;
     static constexpr int kPrefetchDistance = 148 * kMinBlocks;
     typedef Chunk<R, 32> Ch;
     Phys<R> ph; MeshDev<R> m;
@@ -580,36 +583,47 @@ template <typename R, int T, int TS> struct GradAdjTileBody {
     static constexpr size_t kBarOff = ((size_t)15 * TS * sizeof(R) + 15) / 16 * 16;
     static size_t smem_bytes() { return kBarOff + 16; }
 #endif
-    // cell c of tile t (slot lo); gbs [15][TS]: H rows of the tile's slots (ghost slots never read)
-    FVM_HD void cell(int t, int c, int lo, const R* gbs) const {
-        const int sC = m.sC, sN = m.sN;
+    // per-cell inputs that do not depend on the staged rows: loaded BEFORE the CTA waits for its shared-memory rows, so that
+    // the two memory round trips overlap (cell-face metrics, neighbour slots, the cell's own Qb row)
+    struct Pre { R cfm[24]; int slots[6]; unsigned ghosts; Prim<R> acc; };
+    FVM_HD void preload(int c, Pre& p) const {
+        const int sC = m.sC;
         const R* FVM_RESTRICT cfm = m.cfm;
-        R H[15];
-        for (int k = 0; k < 15; k++) H[k] = gbs[k * TS + lo];
-        Prim<R> acc; load_prim(Qb, sN, c, acc);
-        unsigned ghosts = 0; int slots[6];
+        p.ghosts = 0;
         for (int j = 0; j < 6; j++) {
             const int s = m.nbrSlot[(long)j * sC + c];
-            slots[j] = s & 0x7fff;
-            const R SN[3] = {cfm[(long)(4 * j) * sC + c], cfm[(long)(4 * j + 1) * sC + c], cfm[(long)(4 * j + 2) * sC + c]};
-            const R a = cfm[(long)(4 * j + 3) * sC + c];
+            p.slots[j] = s & 0x7fff;
+            if (s & kGhostSlot) p.ghosts |= 1u << j;
+        }
+        for (int k = 0; k < 24; k++) p.cfm[k] = cfm[(long)k * sC + c];
+        load_prim(Qb, m.sN, c, p.acc);
+    }
+    // cell c of tile t (slot lo); gbs [15][TS]: H rows of the tile's slots (ghost slots never read)
+    FVM_HD void cell(int t, int c, int lo, const R* gbs, const Pre& p) const {
+        const int sC = m.sC, sN = m.sN;
+        R H[15];
+        for (int k = 0; k < 15; k++) H[k] = gbs[k * TS + lo];
+        Prim<R> acc = p.acc;
+        for (int j = 0; j < 6; j++) {
+            const R* SN = p.cfm + 4 * j;
+            const R a = p.cfm[4 * j + 3];
             R D[15];
-            if (s & kGhostSlot) { ghosts |= 1u << j; for (int k = 0; k < 15; k++) D[k] = H[k]; }
-            else { const R* nb = gbs + slots[j]; for (int k = 0; k < 15; k++) D[k] = H[k] - nb[k * TS]; }
+            if ((p.ghosts >> j) & 1u) { for (int k = 0; k < 15; k++) D[k] = H[k]; }
+            else { const R* nb = gbs + p.slots[j]; for (int k = 0; k < 15; k++) D[k] = H[k] - nb[k * TS]; }
             for (int i = 0; i < 3; i++) acc.U[i] += a * (SN[0] * D[3 * i] + SN[1] * D[3 * i + 1] + SN[2] * D[3 * i + 2]);
             acc.T += a * (SN[0] * D[9] + SN[1] * D[10] + SN[2] * D[11]);
             acc.p += a * (SN[0] * D[12] + SN[1] * D[13] + SN[2] * D[14]);
         }
-        if (ghosts) {
+        if (p.ghosts) {
             for (int j = 0; j < 6; j++) {
-                if (!((ghosts >> j) & 1u)) continue;
-                const R SN[3] = {cfm[(long)(4 * j) * sC + c], cfm[(long)(4 * j + 1) * sC + c], cfm[(long)(4 * j + 2) * sC + c]};
-                const R wp = R(1) - cfm[(long)(4 * j + 3) * sC + c];
+                if (!((p.ghosts >> j) & 1u)) continue;
+                const R* SN = p.cfm + 4 * j;
+                const R wp = R(1) - p.cfm[4 * j + 3];
                 Prim<R> gq;
                 for (int i = 0; i < 3; i++) gq.U[i] = wp * (SN[0] * H[3 * i] + SN[1] * H[3 * i + 1] + SN[2] * H[3 * i + 2]);
                 gq.T = wp * (SN[0] * H[9] + SN[1] * H[10] + SN[2] * H[11]);
                 gq.p = wp * (SN[0] * H[12] + SN[1] * H[13] + SN[2] * H[14]);
-                add_prim(Qb, sN, m.halo_cell[m.halo_start[t] + slots[j] - T], gq);      // the ghost row of that face (exclusive writer)
+                add_prim(Qb, sN, m.halo_cell[m.halo_start[t] + p.slots[j] - T], gq);      // the ghost row of that face (exclusive writer)
             }
         }
         if (objT != R(0)) acc.T += objVol ? objT * m.vol[c] : objT;
@@ -636,7 +650,7 @@ template <typename R, int T, int TS> struct GradAdjTileBody {
             const int cellh = m.halo_cell[h];
             if (cellh < m.nInternalCells) for (int k = 0; k < 15; k++) gbs[(size_t)k * TS + T + h - m.halo_start[t]] = Gb[(long)k * m.sN + cellh];
         }
-        for (int l = 0; l < nc; l++) cell(t, c0 + l, l, gbs.data());
+        for (int l = 0; l < nc; l++) { Pre p; preload(c0 + l, p); cell(t, c0 + l, l, gbs.data(), p); }
     }
 #else
     __device__ __forceinline__ void device_tile(int t, unsigned char* smem) const {
@@ -671,9 +685,11 @@ template <typename R, int T, int TS> struct GradAdjTileBody {
             if (tn < m.nTiles && tid < 15) bulk_prefetch_l2(Gb + (long)tid * m.sN + (long)tn * T, kRow);
             if (tn < m.nTiles && tid >= 32 && tid < 39) { const int* p = m.halo_cell + m.halo_start[tn] + 32 * (tid - 32); if (p < m.halo_cell + m.halo_start[tn + 1]) prefetch_l2(p); }
         }
+        Pre p;
+        if (tid < nc) preload(c0 + tid, p);
         mbar_wait(bar_rows, 0);
         mbar_wait(bar_halo, 0);
-        if (tid < nc) cell(t, c0 + tid, tid, gbs);
+        if (tid < nc) cell(t, c0 + tid, tid, gbs, p);
     }
 #endif
 };

@@ -126,6 +126,7 @@ class _Context:
             raise NotImplementedError("only the 3-stage SSPRK integrator is supported (the reference's euler "
                                       "integrator cannot compile either, SURVEY §3.1)")
         self.ctx = C.c_void_p()
+        self.device, self.stream = int(device), stream
         self.lib.check(self.lib.dll.adfvm_create(C.byref(self.ctx), int(device), self.dtype.itemsize,
                                                   C.c_void_p(stream) if stream else None))
         mu = spec["mu"]
@@ -199,7 +200,10 @@ class _Context:
         # extraArgs of the case file (adFVM/solver.py:58,317): the objective's own inputs; the adjoint seeds follow them
         nx = int((self.spec.get("objective") or {}).get("nExtra", 0))
         extra = list(inputs[k:k + nx]); k += nx
-        out.update(mesh=mesh, sizes=sizes, triples=triples, source=source, bcs=bcs, extra=extra, rest=list(inputs[k:]))
+        if (self.spec.get("objective") or {}).get("kind") == "traced":      # extraArgs: everything up to the adjoint seeds
+            nx = int(self.spec["objective"]["traced"].n_inputs) - k
+            extra = list(inputs[k:k + nx]); k += nx
+        out.update(mesh=mesh, sizes=sizes, triples=triples, source=source, bcs=bcs, extra=extra, rest=list(inputs[k:]), inputs=list(inputs[:k]))
         return out
 
     def load_static(self, P):
@@ -259,9 +263,11 @@ class _Context:
             nrm = (C.c_double * 3)(*[float(x) for x in o.get("normal", (1., 0., 0.))])
             self.lib.check(d.adfvm_set_objective_plane(self.ctx, n, _ptr(cells), _ptr(areas), float(o.get("ptin", 175158.)),
                                                        nrm, float(o.get("scale", 0.4))))
+        elif o["kind"] == "traced":
+            self._install_traced_objective(o["traced"], P)
         else:
             if o["kind"] not in _OBJ_KIND:
-                raise NotImplementedError("objective %r (supported: %s, plane_ptloss)" % (o["kind"], ", ".join(_OBJ_KIND)))
+                raise NotImplementedError("objective %r (supported: %s, plane_ptloss, traced)" % (o["kind"], ", ".join(_OBJ_KIND)))
             self.lib.check(d.adfvm_set_objective(self.ctx, _OBJ_KIND[o["kind"]],
                                                  index.get(o.get("patch"), 0), int(o.get("direction", 0))))
         self.load_replaceable(P)
@@ -279,6 +285,51 @@ class _Context:
             self.lib.check(d.adfvm_set_parameter_bc(self.ctx, self.patch_index[pid], kid))
             self.param_bc = (self.patch[pid]["nFaces"], dim)
         self.static_loaded = True
+
+    # ---- an arbitrary case-file objective, traced by the reference's own front-end (adpy_objective.TracedObjective)
+    def _install_traced_objective(self, traced, P):
+        import torch
+        d = self.lib.dll
+        C_, nCells = self.sizes[2], self.sizes[0]
+        perm = np.zeros(C_, np.int32)
+        self.lib.check(d.adfvm_get_cell_perm(self.ctx, perm.ctypes.data_as(C.POINTER(C.c_int32))))
+        rows = np.arange(nCells, dtype=np.int64)
+        rows[perm] = np.arange(C_)                       # reference cell -> device row; ghost rows keep their place
+        cuda = self.lib.is_cuda
+        dev = torch.device("cuda", self.device) if cuda else torch.device("cpu")
+        tdtype = torch.float64 if self.dtype == np.float64 else torch.float32
+        traced.bind(P["inputs"], dev, tdtype, torch.as_tensor(rows, device=dev))
+        self.traced, self.traced_error = traced, None
+        itemsize = self.dtype.itemsize
+
+        def view(ptr, stride):
+            if cuda:
+                class _Dev:
+                    __cuda_array_interface__ = {"shape": (5, int(stride)), "typestr": "<f%d" % itemsize, "data": (int(ptr), False), "version": 2}
+                return torch.as_tensor(_Dev(), device=dev)
+            buf = (C.c_char * (5 * int(stride) * itemsize)).from_address(int(ptr))
+            return torch.from_numpy(np.frombuffer(buf, self.dtype).reshape(5, int(stride)))
+
+        def callback(user, Q, stride, want_seed, obja, Qseed):
+            try:
+                Qt = view(Q, stride)
+                Qs = view(Qseed, stride) if want_seed else None
+                if cuda:
+                    strm = torch.cuda.ExternalStream(self.stream, device=dev) if self.stream else torch.cuda.default_stream(dev)
+                    with torch.cuda.stream(strm):
+                        return traced(Qt, bool(want_seed), float(obja), Qs)
+                return traced(Qt, bool(want_seed), float(obja), Qs)
+            except BaseException as e:      # noqa: BLE001  (must not propagate through the C frames)
+                self.traced_error = e
+                return float("nan")
+        self._objective_cb = L.OBJECTIVE_FN(callback)          # keep the trampoline alive as long as the context
+        self.lib.check(d.adfvm_set_objective_callback(self.ctx, self._objective_cb, None))
+
+    def check_traced(self):
+        """re-raise what the objective callback caught during the last native call"""
+        e, self.traced_error = getattr(self, "traced_error", None), None
+        if e is not None:
+            raise e
 
     def load_replaceable(self, P):
         """source terms + BC value arrays: static in the reference, but re-settable here (fixes the
@@ -358,8 +409,10 @@ class PrimalFunction:
         if opts["return_reusable"]:
             outs = [c.pool.empty((C_, 1), c.dtype), c.pool.empty((C_, 3), c.dtype), c.pool.empty((C_, 1), c.dtype)]
         dtc, obj = np.zeros((1, 1), c.dtype), np.zeros((1, 1), c.dtype)
-        c.lib.check(c.lib.dll.adfvm_primal(c.ctx, _ptr(rho), _ptr(rhoU), _ptr(rhoE), float(dt[0, 0]), flags,
-                                           _ptr(outs[0]), _ptr(outs[1]), _ptr(outs[2]), _ptr(dtc), _ptr(obj)))
+        rc = c.lib.dll.adfvm_primal(c.ctx, _ptr(rho), _ptr(rhoU), _ptr(rhoE), float(dt[0, 0]), flags,
+                                    _ptr(outs[0]), _ptr(outs[1]), _ptr(outs[2]), _ptr(dtc), _ptr(obj))
+        c.check_traced()
+        c.lib.check(rc)
         return (outs[0], outs[1], outs[2], dtc, obj)
 
     def grad(self):
@@ -460,9 +513,11 @@ class AdjointFunction:
             grads = [c.pool.empty(c.param_bc, c.dtype) if opts["return_static"] else None, None, None]
         elif opts["return_static"]:
             grads = [c.pool.empty((C_, 1), c.dtype), c.pool.empty((C_, 3), c.dtype), c.pool.empty((C_, 1), c.dtype)]
-        c.lib.check(c.lib.dll.adfvm_primal_grad(
+        rc = c.lib.dll.adfvm_primal_grad(
             c.ctx, _ptr(rho), _ptr(rhoU), _ptr(rhoE), float(dt[0, 0]), _ptr(ra), _ptr(rUa), _ptr(rEa), dtca, obja, flags,
-            _ptr(outs[0]), _ptr(outs[1]), _ptr(outs[2]), _ptr(grads[0]), _ptr(grads[1]), _ptr(grads[2])))
+            _ptr(outs[0]), _ptr(outs[1]), _ptr(outs[2]), _ptr(grads[0]), _ptr(grads[1]), _ptr(grads[2]))
+        c.check_traced()
+        c.lib.check(rc)
         if c.param_mesh:
             if not opts["return_static"]:
                 if opts["zero_static"]:

@@ -32,7 +32,8 @@ enum { ADFVM_BC_CALCULATED = 0, ADFVM_BC_CYCLIC = 1, ADFVM_BC_ZEROGRADIENT = 2, 
 enum { ADFVM_KEY_VALUE_U = 0, ADFVM_KEY_VALUE_T = 1, ADFVM_KEY_VALUE_P = 2, ADFVM_KEY_U0 = 3, ADFVM_KEY_T0 = 4,
        ADFVM_KEY_P0 = 5, ADFVM_KEY_TT = 6, ADFVM_KEY_PT = 7, ADFVM_KEY_DIRECTION = 8 };                     /* createInput keys */
 enum { ADFVM_OBJ_NONE = 0, ADFVM_OBJ_CELL_TV = 1, ADFVM_OBJ_PATCH_PA = 2, ADFVM_OBJ_DRAG = 3,
-       ADFVM_OBJ_PLANE_PTLOSS = 4 /* set by adfvm_set_objective_plane */, ADFVM_OBJ_CELL_T = 5 /* sum T, templates/box.py */ };
+       ADFVM_OBJ_PLANE_PTLOSS = 4 /* set by adfvm_set_objective_plane */, ADFVM_OBJ_CELL_T = 5 /* sum T, templates/box.py */,
+       ADFVM_OBJ_CALLBACK = 6 /* set by adfvm_set_objective_callback */ };
 /* option bits of adfvm_primal / adfvm_primal_grad == the kwargs of Function.__call__, adpy/adpy/variable.py:282-287 */
 enum { ADFVM_RETURN_STATIC = 1, ADFVM_ZERO_STATIC = 2, ADFVM_REPLACE_STATIC = 4, ADFVM_RETURN_REUSABLE = 8,
        ADFVM_REPLACE_REUSABLE = 16 };
@@ -94,6 +95,16 @@ int adfvm_get_mesh_grad(adfvm_ctx* ctx, void* areas, void* volumesL, void* volum
  * numbering) and areas are the extraArgs the case file passes after the BC arrays (adFVM/solver.py:317). */
 int adfvm_set_objective_plane(adfvm_ctx* ctx, int32_t n, const int32_t* cells, const void* areas, double ptin,
                               const double normal[3], double scale);
+/* ANY objective of a case file (the reference differentiates arbitrary adpy-DSL kernels, templates/cylinder_test.py:9-36,
+ * adFVM/objectives/vane.py:83-140, traced by adpy/adpy/tensor.py:444-485): the host layer evaluates the traced kernels and their
+ * reverse mode on the device arrays (adfvm_b200/adpy_objective.py) through this callback. It is called on the stage-1 primitives
+ * Q = [5][stride] (U_x,U_y,U_z,T,p; rows [0,nInternalCells) in DEVICE cell order - see adfvm_get_cell_perm - ghost rows in the
+ * reference's order) and returns the rank-local objective; with want_seed it also writes obja * dObjective/dQ into Qseed
+ * (same layout, zeroed by the library). Pointers are device pointers, work must be ordered on the context's stream. */
+typedef double (*adfvm_objective_fn)(void* user, const void* Q, int64_t stride, int32_t want_seed, double obja, void* Qseed);
+int adfvm_set_objective_callback(adfvm_ctx* ctx, adfvm_objective_fn fn, void* user);
+/* device cell order: perm[i] = reference (host) index of the cell in device row i, i < nInternalCells */
+int adfvm_get_cell_perm(adfvm_ctx* ctx, int32_t* perm);
 /* source terms [C][1],[C][3],[C][1] (Solver.sourceTerms, adFVM/solver.py:116-133); static, re-settable */
 int adfvm_set_source(adfvm_ctx* ctx, const void* S_rho, const void* S_rhoU, const void* S_rhoE);
 
