@@ -44,7 +44,7 @@ EXPORTS = ["adfvm_last_error", "adfvm_version", "adfvm_is_cuda", "adfvm_create",
            "adfvm_comm_init", "adfvm_kernel_timing", "adfvm_kernel_report", "adfvm_set_tile_cells", "adfvm_tile_stats", "adfvm_tile_halo_stats",
            "adfvm_host_alloc", "adfvm_host_free", "adfvm_tile_rounds", "adfvm_graph_replays",
            "adfvm_set_state", "adfvm_mesh_metrics", "adfvm_set_objective_plane", "adfvm_set_parameter_bc", "adfvm_set_parameter_mesh", "adfvm_get_mesh_grad", "adfvm_primal_block", "adfvm_adjoint_block", "adfvm_set_adjoint", "adfvm_get_adjoint",
-           "adfvm_set_objective_callback", "adfvm_get_cell_perm"]
+           "adfvm_set_objective_callback", "adfvm_get_cell_perm", "adfvm_init_fields", "adfvm_get_dtc_global"]
 
 
 class Lib:
@@ -97,6 +97,8 @@ class Lib:
         d.adfvm_comm_init.argtypes = [vp, vp, i32, i32]
         d.adfvm_set_objective_callback.argtypes = [vp, OBJECTIVE_FN, vp]
         d.adfvm_get_cell_perm.argtypes = [vp, C.POINTER(i32)]
+        d.adfvm_init_fields.argtypes = [vp] + [vp] * 6
+        d.adfvm_get_dtc_global.argtypes = [vp, C.POINTER(f64)]
 
     @property
     def is_cuda(self):

@@ -56,15 +56,18 @@ class _AllReduce:
 class TracedObjective:
     def __init__(self, function, field_vars, obj_var):
         """function: the reference's `primal` Function (inputs in call order); field_vars: the [U, T, p] Variables the case
-        file's objective received; obj_var: the Variable it returned"""
+        file's objective received - or a list of such triples, one per RK stage the objective was traced at (the step function
+        keeps the stage-1 one, adFVM/density.py:412-413): the triple the objective's graph reaches is used; obj_var: the Variable
+        it returned"""
         self.in_names = [v.name for v in function._inputs]
         self.n_inputs = len(self.in_names)
         self.in_kinds = [_cls(v) for v in function._inputs]
-        self.field_names = [v.name for v in field_vars]
+        candidates = field_vars if isinstance(field_vars[0], (list, tuple)) else [field_vars]
+        candidates = [[v.name for v in t] for t in candidates]
         self.final_allreduce = False
         # ---- ops between the objective's inputs and its output, in evaluation order
-        known = set(self.in_names) | set(self.field_names)
-        order, seen = [], set()
+        known = set(self.in_names) | set(n for t in candidates for n in t)
+        order, seen, hit = [], set(), set()
 
         def producer(var):                              # walk reference chains (x[offset]) down to the producing op
             while var.args and _cls(var.args[0]) not in ("TensorFunctionOp", "ExternalFunctionOp"):
@@ -76,6 +79,7 @@ class TracedObjective:
             while stack:
                 v, done = stack.pop()
                 if v.name in known and not done:
+                    hit.add(v.name)
                     continue
                 op = producer(v)
                 if op is None:
@@ -93,6 +97,10 @@ class TracedObjective:
                 for a in op.args:
                     stack.append((a, False))
         visit(obj_var)
+        used = [t for t in candidates if hit & set(t)]
+        if len(used) > 1:
+            raise NotImplementedError("objective mixes the fields of several RK stages")
+        self.field_names = used[0] if used else candidates[0]
         self.ops = order
         self.out_name = obj_var.name
         if order and _cls(order[-1]) == "ExternalFunctionOp" and order[-1].name == "Function_mpi_allreduce":
@@ -107,11 +115,15 @@ class TracedObjective:
         self.error = None
 
     # ---- runtime
-    def bind(self, inputs, device, dtype, row_of_cell):
+    def bind(self, inputs, device, dtype, row_of_cell, mesh_param=False):
         """inputs: positional list of a `primal` call; row_of_cell: long tensor, device row of every reference cell index
-        (internal cells permuted into tile order, ghost rows in place)"""
+        (internal cells permuted into tile order, ghost rows in place); mesh_param: the adjoint's parameter block is the ten
+        mesh metric arrays (parameters = 'mesh', apps/adjoint.py:105-107) - the objective's own dependence on them is then
+        differentiated too and accumulated in `mesh_grad` (reference numbering, like the arrays themselves)"""
         import torch
         self.device, self.dtype = device, dtype
+        self.mesh_names = self.in_names[4:14] if mesh_param else []
+        self.mesh_grad = None
         vals = {}
         for name, kind, a in zip(self.in_names, self.in_kinds, inputs):
             if isinstance(a, np.ndarray):
@@ -121,6 +133,8 @@ class TracedObjective:
                     vals[name] = vals[name].reshape(-1, 1)
             else:
                 vals[name] = int(a)
+        for name in self.mesh_names:
+            vals[name].requires_grad_(True)
         self.bound = vals
         self.rows = row_of_cell
 
@@ -251,10 +265,27 @@ class TracedObjective:
         import torch
         if not want_seed:
             with torch.no_grad():
-                return float(self.evaluate(Q))
+                return float(self.evaluate(Q).detach())
         Qt = Q.detach().clone().requires_grad_(True)
         J = self.evaluate(Qt)
-        g, = torch.autograd.grad(J, Qt, allow_unused=True)
-        if g is not None:
-            Qseed.add_(g, alpha=obja)
-        return float(J)
+        mesh = [self.bound[n] for n in self.mesh_names]
+        grads = torch.autograd.grad(J, [Qt] + mesh, allow_unused=True)
+        if grads[0] is not None:
+            Qseed.add_(grads[0], alpha=obja)
+        if mesh:
+            if self.mesh_grad is None:
+                self.mesh_grad = [torch.zeros_like(t) for t in mesh]
+            for acc, g in zip(self.mesh_grad, grads[1:]):
+                if g is not None:
+                    acc.add_(g, alpha=obja)
+        return float(J.detach())
+
+    def take_mesh_grad(self, zero):
+        """accumulated obja * dJ/d(mesh arrays) as numpy arrays in Mesh.gradFields order (None if nothing was accumulated)"""
+        if self.mesh_grad is None:
+            return None
+        out = [g.detach().cpu().numpy().copy() for g in self.mesh_grad]
+        if zero:
+            for g in self.mesh_grad:
+                g.zero_()
+        return out

@@ -567,6 +567,17 @@ template <typename R> struct MeshGradCellBody {
 };
 
 // ------------------------------------------------------------------------------------------ layout helpers
+// conservative variables of every row (internal + ghost) from the primitives: the tail of the reference's `init` function
+// (adFVM/density.py:64-80), used when fields are written with their boundary values
+template <typename R> struct ConservativeAllBody {
+    static constexpr const char* kName = "conservative_all";
+    Phys<R> ph; int sN; const R* Q; R* out;
+    FVM_HD void operator()(int i) const {
+        Prim<R> q; load_prim(Q, sN, i, q);
+        Cons<R> w; conservative(ph, q, w);
+        out[i] = w.rho; out[sN + i] = w.rhoU[0]; out[2 * sN + i] = w.rhoU[1]; out[3 * sN + i] = w.rhoU[2]; out[4 * sN + i] = w.rhoE;
+    }
+};
 template <typename R> struct AddBody {             // y += x (objective seeds of the callback objective)
     static constexpr const char* kName = "add";
     R* y; const R* x;

@@ -424,6 +424,31 @@ public:
         ex.sync();
     }
 
+    // the reference's `init` function (Function('init', ...), adFVM/density.py:64-80): primitive -> ghost fill (BCs + halo) ->
+    // conservative on ALL rows; host arrays [nCells][d] out (reference numbering). Does not touch the resident state.
+    void init_fields(const R* rho, const R* rhoU, const R* rhoE, R* orho, R* orhoU, R* orhoE) {
+        if (!have_mesh) throw std::runtime_error("mesh not set");
+        check_bcs();
+        const int C = m.nInternalCells, N = m.nCells, nLB = m.nLocalFaces - m.nInternalFaces;
+        R* Wt = (R*)ex.alloc(((size_t)5 * m.sC + kRowSlack) * sizeof(R));
+        R* out = (R*)ex.alloc((size_t)5 * m.sN * sizeof(R));
+        R* aos = (R*)ex.alloc((size_t)5 * N * sizeof(R));
+        put5(Wt, rho, rhoU, rhoE);
+        run(C, PrimitiveBody<R>{ph, m.sC, m.sN, Wt, Q[0]});
+        run(nLB, GhostPrimBody<R>{ph, m, Q[0]});
+        halo_begin(Q[0], 5); halo_end();
+        run(N, ConservativeAllBody<R>{ph, m.sN, Q[0], out});
+        const int dims[3] = {1, 3, 1}; R* host[3] = {orho, orhoU, orhoE};
+        size_t off = 0; int row = 0;
+        for (int f = 0; f < 3; f++) {
+            run(C, SoaToAosBody<R>{out + (size_t)row * m.sN, aos + off, dims[f], m.sN, m.cell_perm});
+            run(N - C, SoaToAosBody<R>{out + (size_t)row * m.sN + C, aos + off + (size_t)C * dims[f], dims[f], m.sN, nullptr});
+            ex.download(host[f], aos + off, (size_t)N * dims[f] * sizeof(R));
+            off += (size_t)N * dims[f]; row += dims[f];
+        }
+        ex.sync();
+        ex.free(Wt); ex.free(out); ex.free(aos);
+    }
     // ---- processor-patch halo (replaces adFVM/cpp/parallel.cpp Function_mpi_init/mpi/mpi_end)
     std::vector<PatchHost> remote_patches() const {
         std::vector<PatchHost> r;
@@ -523,14 +548,19 @@ public:
         if (keep) body();                          // part of the adjoint step's graph
         else with_graph({1ull, epoch, bits((double)dt), (unsigned long long)W[0], (unsigned long long)W[3], (unsigned long long)obj.kind,
                          (unsigned long long)obj.patch, (unsigned long long)obj.dir, (unsigned long long)patches_dev, (unsigned long long)obj.cells}, body);
-        if (!keep) { R* t = W[0]; W[0] = W[3]; W[3] = t; }
+        if (!keep) { R* t = W[0]; W[0] = W[3]; W[3] = t; steps_done++; }
     }
-    // dtc (max over ranks not applied here: the reference returns the rank-local max, adFVM/density.py:405-413)
-    // and objective (allreduce-summed like mpi_allreduce, adFVM/cpp/parallel.cpp:214-232)
+    // dtc (max over ranks not applied here: the reference returns the rank-local max, adFVM/density.py:405-413; the global one
+    // is adfvm_get_dtc_global) and objective (allreduce-summed like mpi_allreduce, adFVM/cpp/parallel.cpp:214-232)
+    double obj_cached = 0.; long obj_cached_step = -1, steps_done = 0;
     void get_dtc_obj(double* dtc, double* objective) {
         R h[2]; ex.download(h, red, 2 * sizeof(R)); ex.sync();
         *dtc = (double)h[0];
-        *objective = comm ? comm->allreduce_sum((double)h[1]) : (double)h[1];
+        if (obj_cached_step != steps_done) {           // one collective per step, however often the pair is read
+            obj_cached = comm ? comm->allreduce_sum((double)h[1]) : (double)h[1];
+            obj_cached_step = steps_done;
+        }
+        *objective = obj_cached;
     }
 
     void ensure_adjoint_buffers() {

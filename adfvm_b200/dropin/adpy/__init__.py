@@ -34,7 +34,7 @@ __path__.append(_real)
 from . import tensor as _tensor          # noqa: E402  (the reference's modules, found through __path__)
 from . import variable as _variable      # noqa: E402
 
-_STATE = {"fields": None, "module": None}
+_STATE = {"fields": [], "module": None}
 
 
 def _solver():
@@ -62,8 +62,9 @@ def Kernel(func):
                 while fr is not None:
                     if fr.f_code is code:
                         fields = fr.f_locals.get(code.co_varnames[0])
-                        if isinstance(fields, (list, tuple)) and len(fields) == 3:
-                            _STATE["fields"] = list(fields)
+                        if isinstance(fields, (list, tuple)) and len(fields) == 3 and \
+                                not any(t[0] is fields[0] for t in _STATE["fields"]):
+                            _STATE["fields"].append(list(fields))       # one triple per RK stage the objective is traced at
                         break
                     fr = fr.f_back
             return inner(*args, **kwargs)
@@ -86,7 +87,7 @@ class _Module:
         self.solver = solver
         objective = {"kind": "none"}
         if getattr(solver, "objective", None) is not None:
-            if _STATE["fields"] is None:
+            if not _STATE["fields"]:
                 raise NotImplementedError("the objective of the case file did not trace any kernel on the fields it was given")
             traced = adpy_objective.TracedObjective(solver.map, _STATE["fields"], solver.map._outputs[4])
             objective = {"kind": "traced", "traced": traced}
@@ -98,7 +99,11 @@ class _Module:
         if par not in (None, [], ()):
             spec["parameters"] = par if isinstance(par, str) else tuple(par)
         device = int(os.environ.get("ADFVM_DEVICE", os.environ.get("LOCAL_RANK", "0")))
-        self.primal_f = b200.PrimalFunction(spec, config.precision, device=device)
+        lib = None
+        if os.environ.get("ADFVM_DROPIN_LIB"):               # tests: the CPU simulator of the device code
+            from adfvm_b200 import _lib
+            lib = _lib.Lib(os.environ["ADFVM_DROPIN_LIB"])
+        self.primal_f = b200.PrimalFunction(spec, config.precision, device=device, lib=lib)
         self.grad_f = self.primal_f.grad()
         self.np = np
 
@@ -112,6 +117,14 @@ class _Module:
         return self.grad_f(*args, **kwargs)
 
     def init(self, *args, **kwargs):
+        if not self.primal_f.c.static_loaded:
+            # `init` may come before the first step (fields written at start-up): load the static inputs from the positional list
+            # Solver.run would pass to `primal` (adFVM/solver.py:312-317)
+            s, mesh, np = self.solver, self.solver.mesh, self.np
+            from adFVM import config
+            full = list(args[:3]) + [np.zeros((1, 1), config.precision)] + mesh.getTensor() + mesh.getScalar() + \
+                [x[1] for x in s.sourceTerms] + s.getBoundaryTensor(1) + [x[1] for x in s.extraArgs]
+            self.primal_f.set_state(*full)
         return self.primal_f.init_fields(*args)
 
     def __getattr__(self, name):

@@ -298,7 +298,8 @@ class _Context:
         cuda = self.lib.is_cuda
         dev = torch.device("cuda", self.device) if cuda else torch.device("cpu")
         tdtype = torch.float64 if self.dtype == np.float64 else torch.float32
-        traced.bind(P["inputs"], dev, tdtype, torch.as_tensor(rows, device=dev))
+        traced.bind(P["inputs"], dev, tdtype, torch.as_tensor(rows, device=dev),
+                    mesh_param=(self.spec.get("parameters") or "source") == "mesh")
         self.traced, self.traced_error = traced, None
         itemsize = self.dtype.itemsize
 
@@ -415,6 +416,26 @@ class PrimalFunction:
         c.lib.check(rc)
         return (outs[0], outs[1], outs[2], dtc, obj)
 
+    def init_fields(self, *inputs):
+        """Drop-in for `solver.mapBoundary` (Function('init', ...), adFVM/density.py:64-80): inputs = (rho, rhoU, rhoE) + mesh
+        arrays + constants + patch triples + BC arrays; returns the conservative fields with ghost rows, [nCells][d]."""
+        c = self.c
+        ins = list(inputs)
+        if not c.static_loaded:           # `init` has no dt / source arguments: complete the list to the layout of `primal`
+            C_ = int(ins[3 + 15 + 2])
+            k = 3 + 15 + 8 + 3 * len(c.sorted)
+            full = ins[:3] + [np.zeros((1, 1), c.dtype)] + ins[3:k] + \
+                [np.zeros((C_, 1), c.dtype), np.zeros((C_, 3), c.dtype), np.zeros((C_, 1), c.dtype)] + ins[k:]
+            if (c.spec.get("objective") or {}).get("kind") == "traced":
+                raise RuntimeError("call primal once before init (the traced objective binds the inputs of `primal`)")
+            c.load_static(c.parse(full))
+        C_, N = c.sizes[2], c.sizes[0]
+        rho, rhoU, rhoE = ins[:3]
+        c._arr(rho, (1,), "rho", C_); c._arr(rhoU, (3,), "rhoU", C_); c._arr(rhoE, (1,), "rhoE", C_)
+        outs = [np.empty((N, 1), c.dtype), np.empty((N, 3), c.dtype), np.empty((N, 1), c.dtype)]
+        c.lib.check(c.lib.dll.adfvm_init_fields(c.ctx, _ptr(rho), _ptr(rhoU), _ptr(rhoE), _ptr(outs[0]), _ptr(outs[1]), _ptr(outs[2])))
+        return tuple(outs)
+
     def grad(self):
         """Counterpart of `primal.map.grad()` (adpy/adpy/variable.py:322-343): the reverse-mode function of
         this step for parameters='source' (apps/adjoint.py:94-126)."""
@@ -447,6 +468,16 @@ class PrimalFunction:
         a, b = C.c_double(), C.c_double()
         self.c.lib.check(self.c.lib.dll.adfvm_get_dtc_obj(self.c.ctx, C.byref(a), C.byref(b)))
         return a.value, b.value
+
+    def dtc_global(self):
+        """dtc of the last step maximised over the ranks (a collective; NCCL inside the library)"""
+        a = C.c_double()
+        self.c.lib.check(self.c.lib.dll.adfvm_get_dtc_global(self.c.ctx, C.byref(a)))
+        return a.value
+
+    def next_dt(self, dt, CFL, stepFactor=1.2, remaining=float("inf")):
+        """the adaptive time step of Solver.run (adFVM/solver.py:365): min(2*CFL/dtc over all ranks, dt*stepFactor, endTime-t)"""
+        return min(2. * CFL / self.dtc_global(), dt * stepFactor, remaining)
 
     def sync(self):
         self.c.lib.check(self.c.lib.dll.adfvm_sync(self.c.ctx))
@@ -536,6 +567,11 @@ class AdjointFunction:
         shapes = [(F, 1), (F, 1), (Fi, 1), (F, 1), (F, 1), (F, 3), (F, 3), (F, 2), (F, 2, 3), (Cn, 1)]
         arrs = [np.zeros(sh, c.dtype) for sh in shapes]
         c.lib.check(c.lib.dll.adfvm_get_mesh_grad(c.ctx, *[_ptr(a) for a in arrs], int(zero_static)))
+        traced = getattr(c, "traced", None)           # a traced objective differentiates its own use of the metrics (torch side)
+        extra = traced.take_mesh_grad(zero_static) if traced is not None else None
+        if extra is not None:
+            for a, e in zip(arrs, extra):
+                a += e.reshape(a.shape)
         return arrs
 
     def step_resident(self, dt, obja=1.0, chain=True):

@@ -95,6 +95,12 @@ int adfvm_get_mesh_grad(adfvm_ctx* ctx, void* areas, void* volumesL, void* volum
  * numbering) and areas are the extraArgs the case file passes after the BC arrays (adFVM/solver.py:317). */
 int adfvm_set_objective_plane(adfvm_ctx* ctx, int32_t n, const int32_t* cells, const void* areas, double ptin,
                               const double normal[3], double scale);
+/* == Function_init (adFVM/density.py:64-80; called by RCF.initFields / writeFields): conservative fields WITH ghost rows -
+ * primitive, ghost fill by the boundary conditions and the halo, conservative on every row. In: state [C][d]; out: host arrays
+ * [nCells][d] in the reference's numbering (internal cells, then one ghost row per boundary face). The resident state of
+ * adfvm_primal is not touched. */
+int adfvm_init_fields(adfvm_ctx* ctx, const void* rho, const void* rhoU, const void* rhoE,
+                      void* rho_out, void* rhoU_out, void* rhoE_out);
 /* ANY objective of a case file (the reference differentiates arbitrary adpy-DSL kernels, templates/cylinder_test.py:9-36,
  * adFVM/objectives/vane.py:83-140, traced by adpy/adpy/tensor.py:444-485): the host layer evaluates the traced kernels and their
  * reverse mode on the device arrays (adfvm_b200/adpy_objective.py) through this callback. It is called on the stage-1 primitives
@@ -130,6 +136,10 @@ int adfvm_primal_step_resident(adfvm_ctx* ctx, double dt);
 /* adjoint step on resident data; chain!=0 feeds the previous call's output adjoint back in as this call's input */
 int adfvm_adjoint_step_resident(adfvm_ctx* ctx, double dt, double obja, int32_t chain);
 int adfvm_get_dtc_obj(adfvm_ctx* ctx, double* dtc, double* obj);
+/* the same dtc maximised over all ranks of the communicator (a collective: every rank calls it once per step). This is the
+ * `parallel.min(2*CFL/dtc)` of the adaptive time step, adFVM/solver.py:365, for launches without mpi4py (torchrun + NCCL):
+ * dt_next = min(2*CFL/dtc_global, dt*stepFactor, endTime - t). */
+int adfvm_get_dtc_global(adfvm_ctx* ctx, double* dtc);
 int adfvm_get_state(adfvm_ctx* ctx, void* rho, void* rhoU, void* rhoE);
 int adfvm_sync(adfvm_ctx* ctx);
 /* kernels launched by this context so far */

@@ -197,13 +197,17 @@ def _install_recorder():
 
 
 # ----------------------------------------------------------------------------- entry point
-def install(fp32=False, argv=None):
-    """Call BEFORE importing adFVM. argv replaces sys.argv (adFVM.config parses it at import)."""
+def install(fp32=False, argv=None, overlay=None):
+    """Call BEFORE importing adFVM. argv replaces sys.argv (adFVM.config parses it at import).
+    overlay: a directory put in FRONT of the reference's on sys.path (the `adpy` drop-in overlay of adfvm_b200/dropin: the
+    equivalent of prepending it to PYTHONPATH); the recorder / compile overrides of this shim are then not installed."""
     if argv is not None:
         sys.argv = list(argv)
     for p in (os.path.join(REF, "adpy"), REF, os.path.join(REF, "apps")):
         if p not in sys.path:
             sys.path.insert(0, p)
+    if overlay:
+        sys.path.insert(0, overlay)
     _install_fake_mpi()
     _install_fake_ar()
     _install_fake_cfuncs()
@@ -266,6 +270,8 @@ def install(fp32=False, argv=None):
     for mod in (rmesh, rfield, rbcs, rsolver):
         if hasattr(mod, "extractField"):
             mod.extractField = extractField
+    if overlay:
+        return config
     _install_recorder()
     if DROPIN["lib"]:
         _install_dropin()

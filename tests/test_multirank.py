@@ -39,19 +39,22 @@ def _rank_run(rank, world, lib, uid, adj_global, results, attach, N=N, tiles=Non
     f = function.PrimalFunction(case.spec, np.float64, lib=lib)
     attach(f, rank, world, uid)
     out = f(*case.inputs(), replace_reusable=True)
+    dtc_global = f.dtc_global()          # collective: the parallel.min(2*CFL/dtc) of the adaptive time step (adFVM/solver.py:365)
     out2 = f(*case.inputs(list(out[:3])), replace_reusable=True)
     ids = decompose.global_cell_ids(N, rank, world)
     adj = [np.ascontiguousarray(a[ids]) for a in adj_global]
     grad = f.grad()(*case.adjoint_inputs(case.state, adj))
     if tiles is not None:
         tiles[rank] = (f.tile_rounds()[2], f.tile_stats()[2])
-    results[rank] = (ids, out, out2, grad)
+    results[rank] = (ids, out, out2, grad, dtc_global)
 
 
 def _check(world, single, results, N=N):
     g, out, out2, adj, grad = single
     for rank in range(world):
-        ids, o, o2, gr = results[rank]
+        ids, o, o2, gr = results[rank][:4]
+        if len(results[rank]) > 4:
+            assert relerr(results[rank][4], out[3][0, 0]) < TOL          # dtc_global: every rank holds the global maximum
         for a, b in zip(o[:3], out[:3]):
             assert relerr(a, b[ids]) < TOL
         for a, b in zip(o2[:3], out2[:3]):
@@ -156,7 +159,8 @@ def _gloo_worker(rank, world, port, q):
     _check_one = {rank: results[rank]}
     try:
         g, out, out2, adj, grad = single
-        ids, o, o2, gr = results[rank]
+        ids, o, o2, gr, dtc_global = results[rank]
+        assert relerr(dtc_global, out[3][0, 0]) < TOL          # every rank holds the global maximum
         errs = [relerr(a, b[ids]) for a, b in zip(o2[:3], out2[:3])] + [relerr(o[4], out[4])]
         errs += [relerr(a, b[ids]) for a, b in zip(gr[:3], grad[:3])]
         q.put((rank, max(errs)))
