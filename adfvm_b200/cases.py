@@ -240,3 +240,74 @@ def forward_step(nx=240, ny=80, dtype=np.float64, dt=1e-4):
     bcvals = {("U", "inlet", "value"): Uin, ("T", "inlet", "value"): np.ones((nin, 1)), ("p", "inlet", "value"): np.ones((nin, 1))}
     spec = _spec(mesh, bcs, {"kind": "patch_pA", "patch": "obstacle"}, mu={"law": "constant", "value": 0.}, Cp=2.5)
     return Case(mesh, spec, conservative(U, T, p, Cp=2.5), gaussian_source(cc, (0.3, 0.3, 0.), 1e-2, 20.), bcvals, dt, dtype)
+
+
+# ------------------------------------------------------------------------------------------ the shipped cases on their own meshes
+def forward_step_shipped(dtype=np.float64, dt=1e-4):
+    """BASELINE.json config 3 as the reference ships it: the mesh of cases/forwardStep/constant/polyMesh/blockMeshDict (3 blocks,
+    16 128 cells, generated by adfvm_b200.blockmesh; patch table = the shipped `boundary` file), the shipped initial fields
+    (cases/forwardStep/0: uniform U = (3,0,0), T = 1, p = 1) and the set-up of templates/forwardStep.py: Cp = 2.5, inviscid,
+    fixedValue inlet, inletOutlet outlet (= zeroGradient, BCs.py:137), symmetryPlane top / bottom, slip obstacle, `empty` span,
+    objective sum p_ghost * area over the obstacle. Source perturbation: a Gaussian just upstream of the step face (the template's
+    momentum source in the inlet cells, :32-40, cannot reach the obstacle within the 20 steps of the recorded anchor: its
+    sensitivity is exactly zero there)."""
+    from . import blockmesh
+    mesh = build_mesh(blockmesh.block_mesh(**blockmesh.forward_step_dict()))
+    C = mesh.nInternalCells
+    U = np.zeros((C, 3)); U[:, 0] = 3.
+    T = np.ones((C, 1)); p = np.ones((C, 1))
+    k0 = {"keys": []}
+    fv = {"type": "fixedValue", "keys": ["value"]}
+    zg, sym = dict(type="zeroGradient", **k0), dict(type="symmetryPlane", **k0)
+    bcs = {"U": {"inlet": fv, "outlet": zg, "bottom": sym, "top": sym, "obstacle": sym, "defaultFaces": zg},
+           "T": {"inlet": fv, "outlet": zg, "bottom": sym, "top": sym, "obstacle": zg, "defaultFaces": zg},
+           "p": {"inlet": fv, "outlet": zg, "bottom": sym, "top": sym, "obstacle": zg, "defaultFaces": zg}}
+    nin = mesh.boundary["inlet"]["nFaces"]
+    Uin = np.zeros((nin, 3)); Uin[:, 0] = 3.
+    bcvals = {("U", "inlet", "value"): Uin, ("T", "inlet", "value"): np.ones((nin, 1)), ("p", "inlet", "value"): np.ones((nin, 1))}
+    spec = _spec(mesh, bcs, {"kind": "patch_pA", "patch": "obstacle"}, mu={"law": "constant", "value": 0.}, Cp=2.5)
+    src = gaussian_source(mesh.cellCentres[:C], (0.58, 0.1, 0.), 1e-2, 2e3)
+    case = Case(mesh, spec, conservative(U, T, p, Cp=2.5), src, bcvals, dt, dtype)
+    case.primitive = (U, T, p)
+    return case
+
+
+def cylinder_shipped(dtype=np.float64, dt=2e-9):
+    """BASELINE.json config 2 on the mesh the reference ships: cases/cylinder/constant/polyMesh/blockMeshDict (upper half of the
+    cylinder, 10 blocks with arc edges, 46 250 cells; generated by adfvm_b200.blockmesh, patch table = the shipped `boundary` file)
+    with the two z planes made cyclic (z1 / z2) as the case's create_mesh.sh does. Boundary conditions of cases/cylinder/0 where the
+    reference has a class for them: no-slip cylinder (fixedValue U, zeroGradient T, p), CBC_UPT inflow on `left` (U0 = (33,0,0),
+    T0 = 300, p0 = 102325) with the Lax-Friedrichs boundary solver, isothermal no-slip `up`; the outlet `right` is
+    zeroGradient U, T + fixedValue p = 101325 (the shipped nonReflectingOutletPressure has no class in adFVM/BCs.py), `down` -
+    the mirror plane of create_mesh.sh - a symmetryPlane. mu = 2.5e-5, drag objective and upstream source perturbation of
+    templates/cylinder.py:9-19,66-78. Initial state: potential flow around the cylinder (the shipped uniform zero field has no
+    dynamics in a few steps)."""
+    from . import blockmesh
+    mesh = build_mesh(blockmesh.block_mesh(**blockmesh.cylinder_dict(cyclic_span=True)))
+    mesh.boundary["left"]["type"] = "characteristic"          # what CBC_UPT.__init__ does (BCs.py:142)
+    mesh.boundary["down"]["type"] = "symmetryPlane"
+    C = mesh.nInternalCells
+    cc = mesh.cellCentres[:C]
+    r0, U0 = 0.5 * 2.5e-4, 33.
+    r = np.linalg.norm(cc[:, :2], axis=1)
+    th = np.arctan2(cc[:, 1], cc[:, 0])
+    f = 1 - (r0 / r) ** 2
+    U = np.stack([U0 * (1 - (r0 / r) ** 2 * np.cos(2 * th)) * f, -U0 * (r0 / r) ** 2 * np.sin(2 * th) * f, 0 * r], axis=1)
+    T = np.full((C, 1), 300.)
+    p = (101325 + 0.5 * 1.17 * (U0 ** 2 - (U ** 2).sum(axis=1))).reshape(-1, 1)
+    k0 = {"keys": []}
+    fv = {"type": "fixedValue", "keys": ["value"]}
+    zg, sym, cyc, calc = dict(type="zeroGradient", **k0), dict(type="symmetryPlane", **k0), dict(type="cyclic", **k0), dict(type="calculated", **k0)
+    bcs = {"U": {"down": sym, "right": zg, "up": fv, "left": calc, "cylinder": fv, "z1": cyc, "z2": cyc},
+           "T": {"down": sym, "right": zg, "up": fv, "left": calc, "cylinder": zg, "z1": cyc, "z2": cyc},
+           "p": {"down": sym, "right": fv, "up": zg, "left": {"type": "CBC_UPT", "keys": ["U0", "T0", "p0"]}, "cylinder": zg, "z1": cyc, "z2": cyc}}
+    n = {k: mesh.boundary[k]["nFaces"] for k in ("up", "left", "right", "cylinder")}
+    Ul = np.zeros((n["left"], 3)); Ul[:, 0] = U0
+    bcvals = {("U", "up", "value"): np.zeros((n["up"], 3)), ("U", "cylinder", "value"): np.zeros((n["cylinder"], 3)),
+              ("T", "up", "value"): np.full((n["up"], 1), 300.), ("p", "right", "value"): np.full((n["right"], 1), 101325.),
+              ("p", "left", "U0"): Ul, ("p", "left", "T0"): np.full((n["left"], 1), 300.), ("p", "left", "p0"): np.full((n["left"], 1), 102325.)}
+    spec = _spec(mesh, bcs, {"kind": "drag", "patch": "cylinder", "direction": 0}, mu={"law": "constant", "value": 2.5e-5},
+                 briemann="eulerLaxFriedrichs")
+    case = Case(mesh, spec, conservative(U, T, p), gaussian_source(cc, (-0.0005, 0., 0.), 1e-3, 2.5e6), bcvals, dt, dtype)
+    case.primitive = (U, T, p)
+    return case

@@ -428,7 +428,51 @@ def case_anchor_tube500():
                 builder={"kind": "tube", "n": 500, "width": 0.06})
 
 
-ANCHORS = {"anchor_box48": case_anchor_box48, "anchor_tube500": case_anchor_tube500}
+def case_anchor_forwardstep():
+    """BASELINE.json config 3 as shipped: mesh of cases/forwardStep/constant/polyMesh/blockMeshDict (adfvm_b200.blockmesh; same patch
+    table as the shipped `boundary`), the shipped uniform initial fields, the set-up of templates/forwardStep.py; Gaussian source
+    perturbation just upstream of the step face (see adfvm_b200.cases.forward_step_shipped)"""
+    from adfvm_b200 import blockmesh, cases
+    poly = blockmesh.block_mesh(**blockmesh.forward_step_dict())
+    c = cases.forward_step_shipped()
+    U, T, p = c.primitive
+    bU = {"inlet": {"type": "fixedValue", "value": "uniform (3 0 0)"}, "outlet": {"type": "inletOutlet", "inletValue": "uniform (3 0 0)", "value": "uniform (3 0 0)"},
+          "bottom": {"type": "symmetryPlane"}, "top": {"type": "symmetryPlane"}, "obstacle": {"type": "slip"}, "defaultFaces": {"type": "empty"}}
+    bT = {"inlet": {"type": "fixedValue", "value": "uniform 1"}, "outlet": {"type": "inletOutlet", "inletValue": "uniform 1", "value": "uniform 1"},
+          "bottom": {"type": "symmetryPlane"}, "top": {"type": "symmetryPlane"}, "obstacle": {"type": "zeroGradient"}, "defaultFaces": {"type": "empty"}}
+    bp = {"inlet": {"type": "fixedValue", "value": "uniform 1"}, "outlet": {"type": "zeroGradient"},
+          "bottom": {"type": "symmetryPlane"}, "top": {"type": "symmetryPlane"}, "obstacle": {"type": "zeroGradient"}, "defaultFaces": {"type": "empty"}}
+    return dict(poly=poly, fields={"U": (U, bU), "T": (T, bT), "p": (p, bp)},
+                objective=OBJ_PATCH_PA.format(patch="obstacle"), obj_spec={"kind": "patch_pA", "patch": "obstacle"},
+                rcf_extra=", Cp=2.5, mu=lambda T: 0., CFL=1.2", mid="[0.58,0.1,0.]", amp="1e-2", width="2e3", nSteps=20, writeInterval=10, dt=1e-4,
+                builder={"kind": "forward_step_shipped"})
+
+
+def case_anchor_cylinder():
+    """BASELINE.json config 2 on the shipped mesh: cases/cylinder/constant/polyMesh/blockMeshDict (46 250 cells, arcs), z planes cyclic,
+    boundary conditions of cases/cylinder/0 where the reference has classes for them (adfvm_b200.cases.cylinder_shipped), drag
+    objective and upstream perturbation of templates/cylinder.py"""
+    from adfvm_b200 import blockmesh, cases
+    poly = blockmesh.block_mesh(**blockmesh.cylinder_dict(cyclic_span=True))
+    poly.boundary["down"]["type"] = "symmetryPlane"
+    c = cases.cylinder_shipped()
+    U, T, p = c.primitive
+    cyc = {"z1": {"type": "cyclic"}, "z2": {"type": "cyclic"}}
+    bU = dict(cyc, down={"type": "symmetryPlane"}, right={"type": "zeroGradient"}, up={"type": "fixedValue", "value": "uniform (0 0 0)"},
+              left={"type": "calculated"}, cylinder={"type": "fixedValue", "value": "uniform (0 0 0)"})
+    bT = dict(cyc, down={"type": "symmetryPlane"}, right={"type": "zeroGradient"}, up={"type": "fixedValue", "value": "uniform 300"},
+              left={"type": "calculated"}, cylinder={"type": "zeroGradient"})
+    bp = dict(cyc, down={"type": "symmetryPlane"}, right={"type": "fixedValue", "value": "uniform 101325"}, up={"type": "zeroGradient"},
+              left={"type": "CBC_UPT", "U0": "uniform (33 0 0)", "T0": "uniform 300", "p0": "uniform 102325", "value": "uniform 102325"},
+              cylinder={"type": "zeroGradient"})
+    return dict(poly=poly, fields={"U": (U, bU), "T": (T, bT), "p": (p, bp)},
+                objective=OBJ_DRAG.format(patch="cylinder"), obj_spec={"kind": "drag", "patch": "cylinder", "direction": 0},
+                rcf_extra=", mu=lambda T: 2.5e-5, boundaryRiemannSolver='eulerLaxFriedrichs'",
+                mid="[-0.0005,0.,0.]", amp="1e-3", width="2.5e6", nSteps=10, writeInterval=5, dt=2e-9, builder={"kind": "cylinder_shipped"})
+
+
+ANCHORS = {"anchor_box48": case_anchor_box48, "anchor_tube500": case_anchor_tube500,
+           "anchor_forwardstep": case_anchor_forwardstep, "anchor_cylinder": case_anchor_cylinder}
 CASES.update(ANCHORS)          # write_case looks them up; the plain generator below skips them (see __main__)
 
 

@@ -21,7 +21,8 @@ ANAMES = ("rhoa", "rhoUa", "rhoEa")
 def build(name):
     a = Anchor(name)
     b = a.meta["builder"]
-    case = cases.periodic_box(tuple(b["n"])) if b["kind"] == "periodic_box" else cases.shock_tube(b["n"], b["width"])
+    case = {"periodic_box": lambda: cases.periodic_box(tuple(b["n"])), "tube": lambda: cases.shock_tube(b["n"], b["width"]),
+            "forward_step_shipped": cases.forward_step_shipped, "cylinder_shipped": cases.cylinder_shipped}[b["kind"]]()
     # the static description the reference reported for its own objects must be the one our builder produces
     assert [(p["name"], p["type"], p["startFace"], p["nFaces"]) for p in a.spec["patches"]] == \
            [(p["name"], p["type"], p["startFace"], p["nFaces"]) for p in case.spec["patches"]]
@@ -72,8 +73,17 @@ def test_anchor_box48_hostsim(hostsim):
     replay(a, case, f, f.grad())
 
 
+# BASELINE.json configs 2 and 3 on the meshes the reference ships (cases/*/constant/polyMesh/blockMeshDict through
+# adfvm_b200.blockmesh), recorded from the unmodified reference at full size
+@pytest.mark.parametrize("name", ["anchor_forwardstep", "anchor_cylinder"])
+def test_anchor_shipped_mesh_hostsim(name, hostsim):
+    a, case = build(name)
+    f = function.PrimalFunction(case.spec, np.float64, lib=hostsim)
+    replay(a, case, f, f.grad())
+
+
 @pytest.mark.gpu
-@pytest.mark.parametrize("name", ["anchor_tube500", "anchor_box48"])
+@pytest.mark.parametrize("name", ["anchor_tube500", "anchor_box48", "anchor_forwardstep", "anchor_cylinder"])
 def test_anchor_on_device(name, cudalib):
     a, case = build(name)
     f = function.PrimalFunction(case.spec, np.float64)
