@@ -230,3 +230,86 @@ def cylinder_dict(cyclic_span=False):
                (zn[0], zn[2], z1, {"neighbourPatch": zn[1]} if cyclic_span else {}),
                (zn[1], zn[2], z2, {"neighbourPatch": zn[0]} if cyclic_span else {})]
     return dict(vertices=verts, blocks=blocks, edges=edges, patches=patches, scale=2.5e-4)
+
+
+def match_cyclic(poly, a, b, separation):
+    """reorder the faces of cyclic patch `b` so that its face i is the periodic image of face i of patch `a`
+    (centre_b = centre_a + separation): the pairing convention of the reference (adFVM/BCs.py:88-95)"""
+    A, B = poly.boundary[a], poly.boundary[b]
+    assert A["nFaces"] == B["nFaces"]
+    n, sa, sb = A["nFaces"], A["startFace"], B["startFace"]
+    ca = poly.points[poly.faces[sa:sa + n]].mean(axis=1) + np.asarray(separation, np.float64)
+    cb = poly.points[poly.faces[sb:sb + n]].mean(axis=1)
+    from scipy.spatial import cKDTree
+    dist, idx = cKDTree(cb).query(ca)
+    scale = np.abs(poly.points).max()
+    assert dist.max() < 1e-6 * scale and len(np.unique(idx)) == n, "cyclic patches %s / %s do not match" % (a, b)
+    poly.faces[sb:sb + n] = poly.faces[sb + idx]
+    poly.owner[sb:sb + n] = poly.owner[sb + idx]
+    return poly
+
+
+def vane_dict(nz=1, span=1.0):
+    """cases/vane_optim/foam/laminar/constant/polyMesh/blockMeshDict: one passage of the turbine-vane cascade (pitch 57.5 mm), 16
+    blocks of 25 x 25 cells with spline edges along the two blade surfaces (10 000 cells per layer). The dictionary has an empty
+    `boundary` list (the reference's patches were created afterwards); here: inlet, outlet, the blade surfaces `pressure` (blade
+    above the passage) and `suction` (blade below), the pitchwise periodic pair midplane1 / midplane2 and the spanwise pair
+    z1plane / z2plane, with the names and types of the reference's vane cases (cases/vane_optim/foam/laminar/constant/polyMesh/
+    boundary). nz layers over `span` mm in z (the dictionary is one layer of 1 mm)."""
+    xy = [(0.0, -57.49995), (3.895, -49.97595), (18.734, -52.79495), (26.338, -68.48795), (36.461, -109.80495), (0.0, 0.0), (4.081, -4.895),
+          (28.935, -34.724), (35.427, -51.465), (36.461, -52.305), (-10.0, -57.49995), (0.895, -42.97595), (23.734, -47.79495),
+          (33.338, -65.48795), (42.1967643635, -117.996470443), (-10.0, 0.0), (-2.919, -7.895), (26.935, -39.724), (32.427, -58.465),
+          (42.1967643635, -60.4965204429), (-100.0, -57.49995), (-100.0, -45.99996), (-100.0, -11.49999), (-100.0, 0.0),
+          (93.8186436351, -191.720154429), (93.8186436351, -180.220164429), (93.8186436351, -145.720194429), (93.8186436351, -134.220204429)]
+    nv = len(xy)
+    verts = [(x, y, 0.0) for x, y in xy] + [(x, y, -span) for x, y in xy]
+    quads2d = [((0, 10, 11, 1), (10, 1)), ((1, 11, 12, 2), (10, 1)), ((2, 12, 13, 3), (10, 1)), ((3, 13, 14, 4), (10, 1)),
+               ((5, 6, 16, 15), (1, 10)), ((6, 7, 17, 16), (1, 10)), ((7, 8, 18, 17), (1, 10)), ((8, 9, 19, 18), (1, 10)),
+               ((22, 16, 11, 21), (1, 1)), ((16, 17, 12, 11), (1, 1)), ((17, 18, 13, 12), (1, 1)), ((18, 26, 25, 13), (1, 1)),
+               ((21, 11, 10, 20), (1, 1)), ((23, 15, 16, 22), (1, 1)), ((19, 27, 26, 18), (1, 1)), ((13, 25, 24, 14), (1, 1))]
+    blocks = [(tuple(q) + tuple(v + nv for v in q), (25, 25, nz), (g[0], g[1], 1)) for q, g in quads2d]
+    splines = {(5, 6): [(0.0, 0.0), (0.185, -0.913), (0.927, -2.278), (1.669, -2.963), (2.782, -3.852), (4.081, -4.895)],
+               (6, 7): [(4.081, -4.895), (9.089, -9.023), (13.64, -13.062), (18.363, -18.038), (22.444, -23.229), (25.967, -28.85), (28.935, -34.724)],
+               (7, 8): [(28.935, -34.724), (31.347, -40.456), (33.757, -46.92), (34.87, -49.95), (35.427, -51.465)],
+               (8, 9): [(35.427, -51.465), (36.075, -52.312), (36.461, -52.305)],
+               (1, 0): [(3.895, -49.97595), (2.411, -51.64095), (1.484, -52.95195), (0.742, -54.20195), (0.185, -55.94595), (0.0, -57.49995)],
+               (2, 1): [(18.734, -52.79495), (11.871, -47.71695), (3.895, -49.97595)],
+               (3, 2): [(26.338, -68.48795), (23.0, -60.16295), (18.734, -52.79495)],
+               (4, 3): [(36.461, -109.80495), (36.814, -109.58695), (36.726, -107.97595), (36.355, -106.44095), (35.241, -101.83695),
+                        (33.201, -93.39695), (31.161, -85.11495), (28.75, -76.21295), (26.338, -68.48795)]}
+    edges = []
+    for (a, b), pts in splines.items():
+        edges.append(("spline", a, b, [(x, y, 0.0) for x, y in pts]))
+        edges.append(("spline", a + nv, b + nv, [(x, y, -span) for x, y in pts]))
+
+    def wall(pairs):
+        return [(a, b, b + nv, a + nv) for a, b in pairs]
+    patches = [("midplane1", "cyclic", wall([(23, 15), (15, 5), (9, 19), (19, 27)]), {"neighbourPatch": "midplane2"}),
+               ("midplane2", "cyclic", wall([(20, 10), (10, 0), (4, 14), (14, 24)]), {"neighbourPatch": "midplane1"}),
+               ("z1plane", "cyclic", [q for q, _ in quads2d], {"neighbourPatch": "z2plane"}),
+               ("z2plane", "cyclic", [tuple(v + nv for v in q) for q, _ in quads2d], {"neighbourPatch": "z1plane"}),
+               ("inlet", "patch", wall([(20, 21), (21, 22), (22, 23)]), {}),
+               ("outlet", "patch", wall([(24, 25), (25, 26), (26, 27)]), {}),
+               ("pressure", "patch", wall([(5, 6), (6, 7), (7, 8), (8, 9)]), {}),
+               ("suction", "patch", wall([(0, 1), (1, 2), (2, 3), (3, 4)]), {})]
+    return dict(vertices=verts, blocks=blocks, edges=edges, patches=patches, scale=1e-3)
+
+
+def start_faces_along(poly, normal):
+    """rotate every face's vertex cycle (orientation kept) so that its first edge v0 -> v1 is the one most nearly parallel to
+    the planes with the given normal. The reference's intersectPlane (adFVM/compat/cfuncs.pyx:60-69, see adfvm_b200.planecut)
+    cuts a face split 2/2 through its edges (v0,v3) and (v2,v1) whatever the geometry, which is the right pair exactly when
+    v0 -> v1 does not cross the plane; with this vertex order its cut areas are the geometric ones."""
+    P = poly.points[poly.faces]                                       # [F][4][3]
+    n = np.asarray(normal, np.float64)
+    e01 = np.abs((P[:, 1] - P[:, 0]) @ n)
+    e12 = np.abs((P[:, 2] - P[:, 1]) @ n)
+    rot = e12 < e01
+    poly.faces[rot] = np.roll(poly.faces[rot], -1, axis=1)
+    return poly
+
+
+def vane_mesh(nz=1, span=1.0, cut_normal=(1., 0., 0.)):
+    poly = block_mesh(**vane_dict(nz, span))
+    poly = match_cyclic(poly, "midplane1", "midplane2", (0., -57.49995e-3, 0.))
+    return start_faces_along(poly, cut_normal) if cut_normal is not None else poly

@@ -40,10 +40,11 @@ class Case:
         return self._static
 
     def inputs(self, state=None, dt=None):
-        """positional list for `primal`"""
+        """positional list for `primal` (extraArgs of the objective - `self.extra`, if any - after the BC arrays)"""
         mesh_args, source, bc = self.static_inputs()
         st = self.state if state is None else state
-        return list(st) + [np.array([[self.dt if dt is None else dt]], self.dtype)] + mesh_args + list(source) + bc
+        return list(st) + [np.array([[self.dt if dt is None else dt]], self.dtype)] + mesh_args + list(source) + bc + \
+            list(getattr(self, "extra", []))
 
     def adjoint_inputs(self, state, adj, obja=1.0, dtca=0.0, scaling=0.0, dt=None):
         """positional list for `primal_grad` (apps/adjoint.py:272-280)"""
@@ -310,4 +311,52 @@ def cylinder_shipped(dtype=np.float64, dt=2e-9):
                  briemann="eulerLaxFriedrichs")
     case = Case(mesh, spec, conservative(U, T, p), gaussian_source(cc, (-0.0005, 0., 0.), 1e-3, 2.5e6), bcvals, dt, dtype)
     case.primitive = (U, T, p)
+    return case
+
+
+def vane_cascade(nz=4, span=10.0, dtype=np.float64, dt=2e-8):
+    """BASELINE.json config 4: one passage of the turbine-vane cascade of cases/vane_optim/foam/laminar/constant/polyMesh/
+    blockMeshDict (16 blocks with spline edges, 10 000 cells per spanwise layer; adfvm_b200.blockmesh.vane_mesh), nz layers over
+    `span` mm, with the set-up of templates/vane.py: total-pressure inlet (CBC_TOTAL_PT, pt = 175158 Pa), fixed-pressure outlet,
+    isothermal no-slip blade surfaces `pressure` / `suction` (300 K), pitchwise and spanwise periodicity, Sutherland viscosity, the
+    design objective of adFVM/objectives/vane.py (mass-flow averaged total-pressure loss over the plane x = 52.641 mm, cut by
+    adfvm_b200.planecut as the reference's getPlane does; heat-transfer weights of getWeights), Gaussian source perturbation of
+    templates/vane.py:24-35. The reference ships no field files for this case: the initial state is a smooth turning flow."""
+    from . import blockmesh, planecut
+    poly = blockmesh.vane_mesh(nz, span)
+    mesh = build_mesh(poly)
+    mesh.points, mesh.faces = poly.points, poly.faces
+    mesh.boundary["inlet"]["type"] = "characteristic"         # what CBC_TOTAL_PT.__init__ does (BCs.py:167)
+    C = mesh.nInternalCells
+    cc = mesh.cellCentres[:C]
+    s = np.clip((cc[:, 0] + 0.01) / 0.06, 0., 1.)              # 0 upstream of the blades, 1 downstream
+    th = -np.deg2rad(55.) * s * s * (3 - 2 * s)
+    speed = 60. + 90. * s
+    U = np.stack([speed * np.cos(th), speed * np.sin(th), 0 * s], axis=1)
+    T = (330. - 15. * s).reshape(-1, 1)
+    p = (168000. - 30000. * s).reshape(-1, 1)
+    k0 = {"keys": []}
+    cyc, zg, calc = dict(type="cyclic", **k0), dict(type="zeroGradient", **k0), dict(type="calculated", **k0)
+    fv = {"type": "fixedValue", "keys": ["value"]}
+    per = {k: cyc for k in ("midplane1", "midplane2", "z1plane", "z2plane")}
+    bcs = {"U": dict(per, inlet=calc, outlet=zg, pressure=fv, suction=fv),
+           "T": dict(per, inlet=calc, outlet=zg, pressure=fv, suction=fv),
+           "p": dict(per, inlet={"type": "CBC_TOTAL_PT", "keys": ["Tt", "pt"]}, outlet=fv, pressure=zg, suction=zg)}
+    n = {k: mesh.boundary[k]["nFaces"] for k in ("inlet", "outlet", "pressure", "suction")}
+    bcvals = {("U", "pressure", "value"): np.zeros((n["pressure"], 3)), ("U", "suction", "value"): np.zeros((n["suction"], 3)),
+              ("T", "pressure", "value"): np.full((n["pressure"], 1), 300.), ("T", "suction", "value"): np.full((n["suction"], 1), 300.),
+              ("p", "inlet", "Tt"): np.full((n["inlet"], 1), 340.), ("p", "inlet", "pt"): np.full((n["inlet"], 1), 175158.),
+              ("p", "outlet", "value"): np.full((n["outlet"], 1), 138000.)}
+    spec = _spec(mesh, bcs, {"kind": "plane_ptloss", "ptin": 175158., "normal": [1., 0., 0.], "scale": 0.4, "nExtra": 5})
+    src = gaussian_source(cc, (0.05, -0.104, -0.5e-3 * span), 1e-1, 3e3)         # width of templates/vane.py:24-35, centred just upstream of the cut plane (the template's position needs thousands of steps to reach it)
+    case = Case(mesh, spec, conservative(U, T, p), src, bcvals, dt, dtype)
+    case.primitive = (U, T, p)
+    cells, areas = planecut.intersect_plane(mesh, (0.052641, -0.1, -0.5e-3 * span), (1., 0., 0.))
+    w = []
+    for pid, (x0, y1) in (("pressure", (0.033757, 0.04692)), ("suction", (0.035241, 0.044337))):            # vane.py getWeights
+        b = mesh.boundary[pid]
+        fc = mesh.faceCentres[b["startFace"]:b["startFace"] + b["nFaces"]]
+        w.append(np.ascontiguousarray(((fc[:, 0] >= x0) & (fc[:, 1] <= y1)).astype(case.dtype).reshape(-1, 1)))
+    case.extra = [len(cells), np.ascontiguousarray(cells.reshape(-1, 1)), np.ascontiguousarray(areas.reshape(-1, 1), case.dtype)] + w
+    case.extra_patches = ["pressure", "suction"]
     return case

@@ -271,6 +271,17 @@ def rank_cases(case, nranks, axis=0):
         spec["sortedPatches"] = list(m.sortedPatches)
         bcvals = {(f, pid, key): v[part["patchFaces"][pid]] for (f, pid, key), v in case.bcvals.items()}
         rcase = cases.Case(m, spec, [s[ids] for s in case.state], [s[ids] for s in case.source], bcvals, case.dt, case.dtype)
+        extras = getattr(case, "extra", None)
+        if extras is not None:
+            # extraArgs of the cut-plane objective (adFVM/objectives/vane.py): the plane cells owned by this rank with their areas,
+            # then one weight array per listed physical patch, restricted to the rank's faces of it
+            pos = -np.ones(C, np.int64); pos[ids] = np.arange(len(ids))
+            gcells = np.asarray(extras[1]).ravel()
+            mine = pos[gcells] >= 0
+            rcase.extra = [int(mine.sum()), np.ascontiguousarray(pos[gcells][mine].astype(np.int32).reshape(-1, 1)),
+                           np.ascontiguousarray(np.asarray(extras[2])[mine])]
+            for w, pid in zip(extras[3:], getattr(case, "extra_patches", [])):
+                rcase.extra.append(np.ascontiguousarray(np.asarray(w)[part["patchFaces"][pid]]))
         out.append((rcase, ids))
     return out
 

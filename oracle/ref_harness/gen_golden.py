@@ -471,7 +471,36 @@ def case_anchor_cylinder():
                 mid="[-0.0005,0.,0.]", amp="1e-3", width="2.5e6", nSteps=10, writeInterval=5, dt=2e-9, builder={"kind": "cylinder_shipped"})
 
 
-ANCHORS = {"anchor_box48": case_anchor_box48, "anchor_tube500": case_anchor_tube500,
+VANE_PLANE = '''
+# templates/vane.py:18-20: the cut plane (adFVM/objectives/vane.py getPlane -> the reference's own Cython intersectPlane) and the
+# heat-transfer weights become extraArgs of the step functions
+from adFVM.objectives.vane import getPlane
+getPlane(primal)
+getWeights(primal)
+'''
+
+
+def case_anchor_vane():
+    """BASELINE.json config 4: the vane cascade of cases/vane_optim/foam/laminar/constant/polyMesh/blockMeshDict, 4 spanwise layers
+    (40 000 cells), set-up of templates/vane.py (adfvm_b200.cases.vane_cascade), design objective of adFVM/objectives/vane.py"""
+    from adfvm_b200 import blockmesh, cases
+    c = cases.vane_cascade(nz=4)
+    poly = blockmesh.vane_mesh(4, 10.0)
+    U, T, p = c.primitive
+    cyc = {k: {"type": "cyclic"} for k in ("midplane1", "midplane2", "z1plane", "z2plane")}
+    wallU = {"type": "fixedValue", "value": "uniform (0 0 0)"}
+    wallT = {"type": "fixedValue", "value": "uniform 300"}
+    bU = dict(cyc, inlet={"type": "calculated"}, outlet={"type": "zeroGradient"}, pressure=wallU, suction=wallU)
+    bT = dict(cyc, inlet={"type": "calculated"}, outlet={"type": "zeroGradient"}, pressure=wallT, suction=wallT)
+    bp = dict(cyc, inlet={"type": "CBC_TOTAL_PT", "Tt": "uniform 340", "pt": "uniform 175158", "value": "uniform 168000"},
+              outlet={"type": "fixedValue", "value": "uniform 138000"}, pressure={"type": "zeroGradient"}, suction={"type": "zeroGradient"})
+    return dict(poly=poly, fields={"U": (U, bU), "T": (T, bT), "p": (p, bp)}, objective=OBJ_VANE, after_primal=VANE_PLANE,
+                obj_spec={"kind": "plane_ptloss", "ptin": 175158., "normal": [1., 0., 0.], "scale": 0.4, "nExtra": 5},
+                rcf_extra="", mid="[0.05,-0.104,-0.005]", amp="1e-1", width="3e3", nSteps=4, writeInterval=2, dt=2e-8,
+                builder={"kind": "vane_cascade", "nz": 4})
+
+
+ANCHORS = {"anchor_vane": case_anchor_vane, "anchor_box48": case_anchor_box48, "anchor_tube500": case_anchor_tube500,
            "anchor_forwardstep": case_anchor_forwardstep, "anchor_cylinder": case_anchor_cylinder}
 CASES.update(ANCHORS)          # write_case looks them up; the plain generator below skips them (see __main__)
 

@@ -81,10 +81,39 @@ def _install_fake_ar():
     sys.modules["ar"] = ar
 
 
+def _build_cfuncs():
+    """adFVM/compat/cfuncs.pyx (Cython: intersectPlane of the vane objective, ...) compiled from where it lies: cython writes
+    the C++ to a scratch directory (language level 2: the file has python-2 integer division, cfuncs.pyx:77), g++ the module
+    into oracle/_ref/"""
+    os.makedirs(OUT, exist_ok=True)
+    so = os.path.join(OUT, "cfuncs" + sysconfig.get_config_var("EXT_SUFFIX"))
+    pyx = os.path.join(REF, "adFVM", "compat", "cfuncs.pyx")
+    if os.path.exists(so) and os.path.getmtime(so) > os.path.getmtime(pyx):
+        return so
+    import tempfile
+    tmp = tempfile.mkdtemp(prefix="cfuncs_")
+    cpp = os.path.join(tmp, "cfuncs.cpp")
+    subprocess.check_call([sys.executable, "-m", "cython", "--cplus", "-2", pyx, "-o", cpp])
+    subprocess.check_call(["g++", "-O2", "-fPIC", "-shared", "-w", "-fopenmp", "-I" + sysconfig.get_paths()["include"],
+                           "-I" + np.get_include(), cpp, "-o", so])
+    return so
+
+
 def _install_fake_cfuncs():
-    """adFVM/compat/cfuncs.pyx is a Cython module (cut-plane geometry for the vane objective, SURVEY §2
-    row 27, out of scope); density.py imports postpro.py which imports it. Not on the hot path:
-    any call aborts."""
+    """adFVM/compat/cfuncs.pyx is a Cython module (cut-plane geometry for the vane objective); density.py
+    imports postpro.py which imports it. The reference's own module is used when it has been built into oracle/_ref
+    (_build_cfuncs); otherwise a stub whose functions abort (they are not on the hot path)."""
+    so = os.path.join(OUT, "cfuncs" + sysconfig.get_config_var("EXT_SUFFIX"))
+    if os.path.exists(so):
+        cf = _load_ext("cfuncs", so, "adFVM.compat.cfuncs")
+        pkg = types.ModuleType("adFVM.compat")
+        pkg.__path__ = []
+        pkg.cfuncs = cf
+        for n in ("intersectPlane", "reduceAbsMin", "selectMultipleRange", "reduceSum"):
+            setattr(pkg, n, getattr(cf, n))
+        sys.modules["adFVM.compat"] = pkg
+        return
+
     def _unavailable(*a, **k):
         raise RuntimeError("adFVM.compat.cfuncs is stubbed in the oracle harness")
     cf = types.ModuleType("adFVM.compat.cfuncs")

@@ -22,7 +22,8 @@ def build(name):
     a = Anchor(name)
     b = a.meta["builder"]
     case = {"periodic_box": lambda: cases.periodic_box(tuple(b["n"])), "tube": lambda: cases.shock_tube(b["n"], b["width"]),
-            "forward_step_shipped": cases.forward_step_shipped, "cylinder_shipped": cases.cylinder_shipped}[b["kind"]]()
+            "forward_step_shipped": cases.forward_step_shipped, "cylinder_shipped": cases.cylinder_shipped,
+            "vane_cascade": lambda: cases.vane_cascade(nz=b["nz"])}[b["kind"]]()
     # the static description the reference reported for its own objects must be the one our builder produces
     assert [(p["name"], p["type"], p["startFace"], p["nFaces"]) for p in a.spec["patches"]] == \
            [(p["name"], p["type"], p["startFace"], p["nFaces"]) for p in case.spec["patches"]]
@@ -75,7 +76,7 @@ def test_anchor_box48_hostsim(hostsim):
 
 # BASELINE.json configs 2 and 3 on the meshes the reference ships (cases/*/constant/polyMesh/blockMeshDict through
 # adfvm_b200.blockmesh), recorded from the unmodified reference at full size
-@pytest.mark.parametrize("name", ["anchor_forwardstep", "anchor_cylinder"])
+@pytest.mark.parametrize("name", ["anchor_forwardstep", "anchor_cylinder", "anchor_vane"])
 def test_anchor_shipped_mesh_hostsim(name, hostsim):
     a, case = build(name)
     f = function.PrimalFunction(case.spec, np.float64, lib=hostsim)
@@ -83,7 +84,7 @@ def test_anchor_shipped_mesh_hostsim(name, hostsim):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("name", ["anchor_tube500", "anchor_box48", "anchor_forwardstep", "anchor_cylinder"])
+@pytest.mark.parametrize("name", ["anchor_tube500", "anchor_box48", "anchor_forwardstep", "anchor_cylinder", "anchor_vane"])
 def test_anchor_on_device(name, cudalib):
     a, case = build(name)
     f = function.PrimalFunction(case.spec, np.float64)

@@ -415,3 +415,46 @@ def test_threads_mesh_sensitivity(world, hostsim):
                                   for a, gr in zip(GRAD_FIELDS, results[r])) / (2 * eps)
     assert abs(S_single) > 0
     assert abs(S_ranks - S_single) <= 1e-6 * abs(S_single), (S_ranks, S_single)
+
+
+# ---- BASELINE.json config 4: the vane cascade (blockMeshDict of cases/vane_optim, spline edges, 3-D: several spanwise layers) with
+# the reference's design objective (cut plane as extraArgs, its mass flux all-reduced) decomposed like decomposePar
+@pytest.mark.parametrize("world", [2, 4])
+def test_threads_vane_cascade(world, hostsim):
+    from adfvm_b200 import cases
+    g = cases.vane_cascade(nz=2)
+    f = function.PrimalFunction(g.spec, np.float64, lib=hostsim)
+    out = f(*g.inputs(), replace_reusable=True)
+    adj = _seed(g.state)
+    grad = f.grad()(*g.adjoint_inputs(g.state, adj))
+    assert abs(out[4][0, 0]) > 1e-3
+    parts = decompose.rank_cases(g, world)
+    assert sum(p[0].extra[0] for p in parts) == g.extra[0] and sum(1 for p in parts if p[0].extra[0] > 0) >= 1
+    uid = C.create_string_buffer(128)
+    hostsim.check(hostsim.dll.adfvm_comm_unique_id(uid))
+    results, errors = {}, []
+
+    def run(rank):
+        try:
+            case, ids = parts[rank]
+            fr = function.PrimalFunction(case.spec, np.float64, lib=hostsim)
+            fr.c.attach_comm(uid.raw, rank, world)
+            o = fr(*case.inputs(), replace_reusable=True)
+            gr = fr.grad()(*case.adjoint_inputs(case.state, [np.ascontiguousarray(x[ids]) for x in adj]))
+            results[rank] = (ids, o, gr)
+        except Exception as e:      # pragma: no cover
+            errors.append(e)
+    ts = [threading.Thread(target=run, args=(r,)) for r in range(world)]
+    [t.start() for t in ts]
+    [t.join(timeout=600) for t in ts]
+    assert not errors, errors
+    sc = [float(np.abs(s).max()) for s in g.state]
+    for rank in range(world):
+        ids, o, gr = results[rank]
+        for a, b in zip(o[:3], out[:3]):
+            assert relerr(a, b[ids]) < TOL
+        assert relerr(o[4], out[4]) < TOL
+        for grp in (slice(0, 3), slice(3, 6)):
+            num = max(np.abs(a - b[ids]).max() * s for a, b, s in zip(gr[grp], grad[grp], sc))
+            den = max(np.abs(b).max() * s for b, s in zip(grad[grp], sc))
+            assert num / den < TOL
