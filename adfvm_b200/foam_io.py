@@ -181,7 +181,13 @@ def read_field(case, time_dir, name, nInternalCells, boundary):
         raise ValueError("%s: no internalField" % path)
     if m.group(1) == b"uniform":
         e = data.index(b";", m.end())
-        vals = [float(x) for x in re.findall(rb"[-+0-9.eE]+", data[m.end():e])]
+        toks = data[m.end():e].replace(b"(", b" ").replace(b")", b" ").split()
+        try:
+            vals = [float(x) for x in toks]
+        except ValueError:
+            raise ValueError("%s: cannot parse uniform internalField %r" % (path, data[m.end():e]))
+        if len(vals) != width:
+            raise ValueError("%s: uniform internalField has %d components, expected %d" % (path, len(vals), width))
         internal = np.tile(np.array(vals, np.float64).reshape(1, width), (nInternalCells, 1))
         pos = e + 1
     else:
@@ -190,16 +196,31 @@ def read_field(case, time_dir, name, nInternalCells, boundary):
         internal = internal.reshape(-1, width)
         if len(internal) != nInternalCells:
             raise ValueError("%s: %d values for %d cells" % (path, len(internal), nInternalCells))
-    b0 = data.index(b"boundaryField", pos)
-    bfield = OrderedDict()
-    for patch in boundary:
-        pm = re.compile(rb"\b" + re.escape(patch.encode()) + rb"\s*\{").search(data, b0)
-        if not pm:
-            raise ValueError("%s: no boundaryField entry for patch %s" % (path, patch))
-        p, d = pm.end(), OrderedDict()
+    # boundaryField { patch { key value; ... } ... }: parsed sequentially, block by block; binary lists are skipped by their
+    # declared length, so that payload bytes can never be mistaken for a patch name or a key
+    bm = re.compile(rb"\s*boundaryField\s*\{").search(data, pos)
+    if not bm:
+        raise ValueError("%s: no boundaryField" % path)
+    p = bm.end()
+    found = OrderedDict()
+    name_re = re.compile(rb"\s*(\}|[^\s{};]+)\s*")
+    while True:
+        nm_ = name_re.match(data, p)
+        if not nm_:
+            raise ValueError("%s: malformed boundaryField" % path)
+        if nm_.group(1) == b"}":
+            break
+        pname, p = nm_.group(1).decode(), nm_.end()
+        if data[p:p + 1] != b"{":
+            raise ValueError("%s: expected '{' after patch name %s" % (path, pname))
+        p += 1
+        d = OrderedDict()
         while True:
             km = re.compile(rb"\s*(\}|[A-Za-z_]\w*)").match(data, p)
+            if not km:
+                raise ValueError("%s: malformed entry in patch %s" % (path, pname))
             if km.group(1) == b"}":
+                p = km.end()
                 break
             key, p = km.group(1).decode(), km.end()
             nm = re.compile(rb"\s+nonuniform\s+List<(scalar|vector)>\s*").match(data, p)
@@ -211,5 +232,10 @@ def read_field(case, time_dir, name, nInternalCells, boundary):
                 e = data.index(b";", p)
                 d[key] = data[p:e].decode().strip()
                 p = e + 1
-        bfield[patch] = d
+        found[pname] = d
+    bfield = OrderedDict()
+    for patch in boundary:
+        if patch not in found:
+            raise ValueError("%s: no boundaryField entry for patch %s" % (path, patch))
+        bfield[patch] = found[patch]
     return internal, bfield
