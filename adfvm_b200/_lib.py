@@ -21,7 +21,8 @@ KEY_VALUE_U, KEY_VALUE_T, KEY_VALUE_P, KEY_U0, KEY_T0, KEY_P0, KEY_TT, KEY_PT, K
 OBJ_NONE, OBJ_CELL_TV, OBJ_PATCH_PA, OBJ_DRAG = range(4)
 OBJ_PLANE_PTLOSS, OBJ_CELL_T, OBJ_CALLBACK = 4, 5, 6
 OBJECTIVE_FN = C.CFUNCTYPE(C.c_double, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_double, C.c_void_p)
-RETURN_STATIC, ZERO_STATIC, REPLACE_STATIC, RETURN_REUSABLE, REPLACE_REUSABLE = 1, 2, 4, 8, 16
+RETURN_STATIC, ZERO_STATIC, REPLACE_STATIC, RETURN_REUSABLE, REPLACE_REUSABLE, VISCOUS = 1, 2, 4, 8, 16, 32
+VISC = {None: 0, "abarbanel": 1, "turkel": 2, "uniform": 3}
 
 
 class Patch(C.Structure):
@@ -44,7 +45,8 @@ EXPORTS = ["adfvm_last_error", "adfvm_version", "adfvm_is_cuda", "adfvm_create",
            "adfvm_comm_init", "adfvm_kernel_timing", "adfvm_kernel_report", "adfvm_set_tile_cells", "adfvm_tile_stats", "adfvm_tile_halo_stats",
            "adfvm_host_alloc", "adfvm_host_free", "adfvm_tile_rounds", "adfvm_graph_replays",
            "adfvm_set_state", "adfvm_mesh_metrics", "adfvm_set_objective_plane", "adfvm_set_parameter_bc", "adfvm_set_parameter_mesh", "adfvm_get_mesh_grad", "adfvm_primal_block", "adfvm_adjoint_block", "adfvm_set_adjoint", "adfvm_get_adjoint",
-           "adfvm_set_objective_callback", "adfvm_get_cell_perm", "adfvm_init_fields", "adfvm_get_dtc_global"]
+           "adfvm_set_objective_callback", "adfvm_get_cell_perm", "adfvm_init_fields", "adfvm_get_dtc_global",
+           "adfvm_set_adjoint_viscosity", "adfvm_adjoint_viscous_resident", "adfvm_get_adjoint_viscosity", "adfvm_viscosity_iterations"]
 
 
 class Lib:
@@ -72,6 +74,11 @@ class Lib:
         d.adfvm_primal.argtypes = [vp, vp, vp, vp, f64, i32, vp, vp, vp, vp, vp]
         d.adfvm_primal_grad.argtypes = [vp, vp, vp, vp, f64, vp, vp, vp, f64, f64, i32, vp, vp, vp, vp, vp, vp]
         d.adfvm_primal_step_resident.argtypes = [vp, f64]
+        d.adfvm_set_adjoint_viscosity.argtypes = [vp, i32, f64, f64, i32]
+        d.adfvm_adjoint_viscous_resident.argtypes = [vp, f64]
+        d.adfvm_get_adjoint_viscosity.argtypes = [vp, vp, vp, vp, vp]
+        d.adfvm_viscosity_iterations.argtypes = [vp]
+        d.adfvm_viscosity_iterations.restype = C.c_int64
         d.adfvm_adjoint_step_resident.argtypes = [vp, f64, f64, i32]
         d.adfvm_get_dtc_obj.argtypes = [vp, C.POINTER(f64), C.POINTER(f64)]
         d.adfvm_get_state.argtypes = [vp, vp, vp, vp]

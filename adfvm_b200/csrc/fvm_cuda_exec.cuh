@@ -70,6 +70,37 @@ template <typename R, class Op> __global__ void __launch_bounds__(kRedBlock) k_r
     if (threadIdx.x == 0) *out = sm[0];
 }
 
+// five sums at once (the conjugate-gradient dot products of fvm_viscosity.h): same fixed-order two-pass tree, V = V5<R>
+template <class V, class Body> __global__ void __launch_bounds__(kRedBlock) k_reduce1_v5(const Body b, int n, V* partial) {
+    __shared__ V sm[kRedBlock];
+    V acc;
+    for (int k = 0; k < 5; k++) acc.v[k] = 0;
+    for (long i = (long)blockIdx.x * kRedBlock + threadIdx.x; i < n; i += (long)gridDim.x * kRedBlock) {
+        const V x = b((int)i);
+        for (int k = 0; k < 5; k++) acc.v[k] += x.v[k];
+    }
+    sm[threadIdx.x] = acc;
+    __syncthreads();
+    for (int s = kRedBlock / 2; s > 0; s >>= 1) {
+        if ((int)threadIdx.x < s) for (int k = 0; k < 5; k++) sm[threadIdx.x].v[k] += sm[threadIdx.x + s].v[k];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) partial[blockIdx.x] = sm[0];
+}
+template <class V, typename R> __global__ void __launch_bounds__(kRedBlock) k_reduce2_v5(const V* partial, int nb, R* out) {
+    __shared__ V sm[kRedBlock];
+    V acc;
+    for (int k = 0; k < 5; k++) acc.v[k] = 0;
+    for (int i = threadIdx.x; i < nb; i += kRedBlock) for (int k = 0; k < 5; k++) acc.v[k] += partial[i].v[k];
+    sm[threadIdx.x] = acc;
+    __syncthreads();
+    for (int s = kRedBlock / 2; s > 0; s >>= 1) {
+        if ((int)threadIdx.x < s) for (int k = 0; k < 5; k++) sm[threadIdx.x].v[k] += sm[threadIdx.x + s].v[k];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) for (int k = 0; k < 5; k++) out[k] = sm[0].v[k];
+}
+
 struct CudaExec {
     cudaStream_t stream = 0;
     int device = 0;
@@ -145,7 +176,7 @@ struct CudaExec {
         device = dev;
         FVM_CUDA_CHECK(cudaSetDevice(dev));
         stream = (cudaStream_t)strm;
-        FVM_CUDA_CHECK(cudaMalloc(&partial, kRedMaxBlocks * sizeof(double)));
+        FVM_CUDA_CHECK(cudaMalloc(&partial, 5 * kRedMaxBlocks * sizeof(double)));    // (five-component reductions: reduce_sum5)
         timing = new Timing();
         graphs = new Graphs();
         configured = new std::map<const void*, size_t>();
@@ -230,6 +261,18 @@ struct CudaExec {
         FVM_CUDA_CHECK(cudaPeekAtLastError());
     }
     template <class Body, typename R> void reduce_sum(int n, const Body& b, R* out) { reduce<R, OpSum, Body>(n, b, out); }
+    // out[0..4] = sum over i of b(i).v[0..4]; the body may update element i as a side effect (every i is visited exactly once)
+    template <class Body, typename R> void reduce_sum5(int n, const Body& b, R* out) {
+        typedef decltype(b(0)) V;
+        int nb = (n + kRedBlock - 1) / kRedBlock;
+        if (nb > kRedMaxBlocks) nb = kRedMaxBlocks;
+        if (nb < 1) nb = 1;
+        tic(Body::kName);
+        k_reduce1_v5<V, Body><<<nb, kRedBlock, 0, stream>>>(b, n, (V*)partial);
+        toc();
+        k_reduce2_v5<V, R><<<1, kRedBlock, 0, stream>>>((const V*)partial, nb, out);
+        FVM_CUDA_CHECK(cudaPeekAtLastError());
+    }
     template <class Body, typename R> void reduce_max(int n, const Body& b, R* out) { reduce<R, OpMax, Body>(n, b, out); }
 };
 

@@ -16,6 +16,7 @@
 #include "fvm_tile_bodies.h"
 #include "fvm_tiles.h"
 #include "fvm_metrics.h"
+#include "fvm_viscosity.h"
 
 namespace fvm {
 
@@ -754,6 +755,90 @@ public:
             ex.copy(W[0], block[k], bytes);
             adjoint_step_resident((R)dt[k], obja, true);
         }
+    }
+    // ---- adjoint artificial viscosity (fvm_viscosity.h): what `primal_grad_viscous` adds to
+    // `primal_grad` (apps/adjoint.py:127-141): M_2norm of the step's START state, then one implicit diffusion step of the
+    // adjoint fields the reverse sweep produced.
+    int visc_type = VISC_NONE, visc_maxit = 500; double visc_scaling = 0., visc_rtol = 0.; long visc_iterations = 0;
+    R *vlam = nullptr, *vM = nullptr, *vcf = nullptr, *vdg = nullptr, *vx = nullptr, *vr = nullptr, *vp = nullptr, *vq = nullptr, *vs = nullptr;
+    enum { VS_VTOT = 0, VS_N = 1, VS_RZA = 2, VS_RZB = 7, VS_PQ = 12, VS_BZ = 17, VS_SIZE = 24 };
+    void set_adjoint_viscosity(int type, double scaling, double rtol, int maxit) {
+        if (type < VISC_NONE || type > VISC_UNIFORM) throw std::runtime_error("unknown adjoint viscosity type");
+        visc_type = type; visc_scaling = scaling;
+        visc_rtol = rtol > 0. ? rtol : (sizeof(R) == 8 ? 1e-13 : 1e-6);
+        visc_maxit = maxit > 0 ? maxit : 500;
+    }
+    void ensure_visc_buffers() {
+        if (vlam) return;
+        vlam = dalloc<R>((size_t)m.sC); vM = dalloc<R>((size_t)m.sN); vcf = dalloc<R>((size_t)6 * m.sC); vdg = dalloc<R>((size_t)m.sC);
+        vx = dalloc<R>((size_t)5 * m.sN); vp = dalloc<R>((size_t)5 * m.sN); vr = dalloc<R>((size_t)5 * m.sC); vq = dalloc<R>((size_t)5 * m.sC);
+        vs = dalloc<R>(VS_SIZE);
+    }
+    // M_2norm (vM [nCells], ghost rows filled with the default boundary + halo) of the state whose primitives (ghost rows
+    // filled) and Green-Gauss gradients are Qs / Gs
+    void viscosity_field(const R* Qs, const R* Gs) {
+        if (visc_type == VISC_NONE) throw std::runtime_error("adjoint viscosity type not set (adfvm_set_adjoint_viscosity)");
+        ensure_visc_buffers();
+        const int C = m.nInternalCells, nLB = m.nLocalFaces - m.nInternalFaces;
+        run(C, ViscEigBody<R>{ph, m, visc_type, Qs, Gs, vlam});
+        ex.reduce_sum(C, ViscVolBody<R>{m.vol}, vs + VS_VTOT); ex.reduce_sum(C, ViscNormBody<R>{m.vol, vlam}, vs + VS_N); launches += 4;
+        if (comm) comm->allreduce_sum_device(vs + VS_VTOT, 2, ex.stream_handle());
+        run(C, ViscScaleBody<R>{vlam, vs, (R)visc_scaling, vM});
+        run(nLB, GhostScalarBody<R>{m, vM});
+        halo_begin(vM, 1); halo_end();
+    }
+    // one backward-Euler diffusion step (face conductance dt * areas * DT / deltas) of the volume-weighted adjoint fields Aio [5][sC]
+    void viscosity_apply(R* Aio, R dt) {
+        const int C = m.nInternalCells;
+        run(C, ViscCoefBody<R>{m, vM, dt, vcf, vdg});
+        run(C, ViscStartBody<R>{m, Aio, vx});
+        halo_begin(vx, 5); halo_end();
+        R* rz = vs + VS_RZA; R* rzn = vs + VS_RZB;
+        ex.reduce_sum5(C, ViscRhsNormBody<R>{m, vdg, Aio}, vs + VS_BZ);
+        ex.reduce_sum5(C, ViscInitBody<R>{m, vcf, vdg, Aio, vx, vr, vp}, rz); launches += 4;
+        if (comm) { comm->allreduce_sum_device(vs + VS_BZ, 5, ex.stream_handle()); comm->allreduce_sum_device(rz, 5, ex.stream_handle()); }
+        auto converged = [&](const R* z) {
+            R h[VS_SIZE]; ex.download(h, vs, sizeof(h)); ex.sync();
+            const R* hz = h + (z - vs); bool ok = true;
+            for (int k = 0; k < 5; k++) {
+                if (!(hz[k] == hz[k]) || !(h[VS_BZ + k] == h[VS_BZ + k])) throw std::runtime_error("adjoint viscosity: NaN in the diffusion solve");
+                if (hz[k] < R(0)) throw std::runtime_error("adjoint viscosity: the diffusion operator is indefinite (negative M_2norm?)");
+                if ((double)hz[k] > visc_rtol * visc_rtol * (double)h[VS_BZ + k]) ok = false;
+            }
+            return ok;
+        };
+        int it = 0;
+        bool done = converged(rz);
+        while (!done) {
+            if (it >= visc_maxit) throw std::runtime_error("adjoint viscosity: the diffusion solve did not converge");
+            for (int inner = 0; inner < 4; inner++, it++) {            // host looks at the residual every fourth iteration
+                halo_begin(vp, 5); halo_end();
+                ex.reduce_sum5(C, ViscSpmvBody<R>{m, vcf, vdg, vp, vq}, vs + VS_PQ);
+                if (comm) comm->allreduce_sum_device(vs + VS_PQ, 5, ex.stream_handle());
+                ex.reduce_sum5(C, ViscUpdateBody<R>{m, vdg, vp, vq, rz, vs + VS_PQ, vx, vr}, rzn); launches += 4;
+                if (comm) comm->allreduce_sum_device(rzn, 5, ex.stream_handle());
+                run(C, ViscDirBody<R>{m, vdg, vr, rz, rzn, vp});
+                std::swap(rz, rzn);
+            }
+            done = converged(rz);
+        }
+        visc_iterations = it;
+        run(C, ViscFinishBody<R>{m, vx, Aio});
+    }
+    void adjoint_viscous(R dt) { viscosity_field(Q[0], G[0]); viscosity_apply(A[0], dt); }
+    // diagnostic (the reference's write_M_2norm, apps/adjoint.py:26,139): M_2norm [nCells][1] of a host state, reference numbering
+    void get_adjoint_viscosity(const R* rho, const R* rhoU, const R* rhoE, R* M_out) {
+        if (!have_mesh) throw std::runtime_error("mesh not set");
+        check_bcs();
+        adjoint_state_begin(rho, rhoU, rhoE);
+        try { stage(0, R(0), Q[0], G[0], nullptr, false, false); viscosity_field(Q[0], G[0]); }
+        catch (...) { adjoint_state_end(); throw; }
+        adjoint_state_end();
+        const int C = m.nInternalCells, N = m.nCells;
+        run(C, SoaToAosBody<R>{vM, stage_aos, 1, m.sC, m.cell_perm});
+        ex.download(M_out, stage_aos, (size_t)C * sizeof(R));
+        ex.download(M_out + C, vM + C, (size_t)(N - C) * sizeof(R));
+        ex.sync();
     }
     void put_adjoint(const R* rhoa, const R* rhoUa, const R* rhoEa) { ensure_adjoint_buffers(); put5(A[0], rhoa, rhoUa, rhoEa); }
     void get_adjoint(R* rhoa, R* rhoUa, R* rhoEa) {

@@ -518,9 +518,41 @@ class AdjointFunction:
     name = "primal_grad"
     defaultOptions = PrimalFunction.defaultOptions
 
-    def __init__(self, primal):
+    def __init__(self, primal, viscosity=None, rtol=0., maxit=0):
         self.primal = primal
         self.c = primal.c
+        # viscosity: None, or the adjParams[1] of the case file ('abarbanel', 'turkel', 'uniform'): this object then is
+        # `adjoint.viscousMap` (Function('primal_grad_viscous'), apps/adjoint.py:127-141)
+        if viscosity not in L.VISC:
+            raise NotImplementedError("adjoint viscosity type %r (supported: abarbanel, turkel, uniform; 'entropy_hughes' is "
+                                      "generated Mathematica code + a generalised eigenproblem in the reference)" % (viscosity,))
+        self.viscosity, self.visc_rtol, self.visc_maxit = viscosity, float(rtol), int(maxit)
+
+    def viscous(self, viscosity, rtol=0., maxit=0):
+        """drop-in for `adjoint.viscousMap`: same inputs and outputs as this function; the returned adjoint fields have had one
+        step of the adjoint artificial viscosity applied (M_2norm of the step's start state scaled by the `scaling` input,
+        adFVM/postpro.py:491-720)"""
+        return AdjointFunction(self.primal, viscosity, rtol, maxit)
+
+    def adjoint_viscosity(self, rho, rhoU, rhoE, scaling):
+        """diagnostic (write_M_2norm of apps/adjoint.py): M_2norm [nCells,1] of a state for this function's viscosity type"""
+        c = self.c
+        C_ = c.sizes[2]
+        c._arr(rho, (1,), "rho", C_); c._arr(rhoU, (3,), "rhoU", C_); c._arr(rhoE, (1,), "rhoE", C_)
+        c.lib.check(c.lib.dll.adfvm_set_adjoint_viscosity(c.ctx, L.VISC[self.viscosity], float(scaling), self.visc_rtol, self.visc_maxit))
+        M = np.zeros((c.sizes[0], 1), c.dtype)
+        c.lib.check(c.lib.dll.adfvm_get_adjoint_viscosity(c.ctx, _ptr(rho), _ptr(rhoU), _ptr(rhoE), _ptr(M)))
+        return M
+
+    @property
+    def viscosity_iterations(self):
+        return int(self.c.lib.dll.adfvm_viscosity_iterations(self.c.ctx))
+
+    def viscous_resident(self, dt, scaling):
+        """the smoothing applied to the resident adjoint fields (after step_resident / run_block)"""
+        c = self.c
+        c.lib.check(c.lib.dll.adfvm_set_adjoint_viscosity(c.ctx, L.VISC[self.viscosity], float(scaling), self.visc_rtol, self.visc_maxit))
+        c.lib.check(c.lib.dll.adfvm_adjoint_viscous_resident(c.ctx, float(dt)))
 
     def __call__(self, *inputs, **options):
         c = self.c
@@ -536,6 +568,10 @@ class AdjointFunction:
         c._arr(ra, (1,), "rhoa", C_); c._arr(rUa, (3,), "rhoUa", C_); c._arr(rEa, (1,), "rhoEa", C_)
         dtca = float(c._arr(rest[3], (1,), "dtca", 1)[0, 0]); obja = float(c._arr(rest[4], (1,), "obja", 1)[0, 0])
         flags = (L.RETURN_STATIC if opts["return_static"] else 0) | (L.ZERO_STATIC if opts["zero_static"] else 0)
+        if self.viscosity is not None:
+            scaling = float(c._arr(rest[5], (1,), "scaling", 1)[0, 0])
+            c.lib.check(c.lib.dll.adfvm_set_adjoint_viscosity(c.ctx, L.VISC[self.viscosity], scaling, self.visc_rtol, self.visc_maxit))
+            flags |= L.VISCOUS
         outs = [c.pool.empty((C_, 1), c.dtype), c.pool.empty((C_, 3), c.dtype), c.pool.empty((C_, 1), c.dtype)]
         grads = [None, None, None]
         if c.param_mesh:                           # the ten metric arrays: read after the call (adfvm_get_mesh_grad)

@@ -36,7 +36,10 @@ enum { ADFVM_OBJ_NONE = 0, ADFVM_OBJ_CELL_TV = 1, ADFVM_OBJ_PATCH_PA = 2, ADFVM_
        ADFVM_OBJ_CALLBACK = 6 /* set by adfvm_set_objective_callback */ };
 /* option bits of adfvm_primal / adfvm_primal_grad == the kwargs of Function.__call__, adpy/adpy/variable.py:282-287 */
 enum { ADFVM_RETURN_STATIC = 1, ADFVM_ZERO_STATIC = 2, ADFVM_REPLACE_STATIC = 4, ADFVM_RETURN_REUSABLE = 8,
-       ADFVM_REPLACE_REUSABLE = 16 };
+       ADFVM_REPLACE_REUSABLE = 16,
+       ADFVM_VISCOUS = 32 /* adfvm_primal_grad acts as Function('primal_grad_viscous'), apps/adjoint.py:141,288-289 */ };
+/* adjoint artificial viscosity: adjParams[1] of the case file (apps/problem.py:22, adFVM/postpro.py:577-617) */
+enum { ADFVM_VISC_NONE = 0, ADFVM_VISC_ABARBANEL = 1, ADFVM_VISC_TURKEL = 2, ADFVM_VISC_UNIFORM = 3 };
 
 /* one boundary patch: the (startFace, nFaces, cellStartFace) triple of Mesh.getScalar (adFVM/mesh.py:874-881) plus
  * what the reference bakes into the generated code from mesh.boundary / field BC dicts at compile time */
@@ -133,6 +136,19 @@ int adfvm_primal_grad(adfvm_ctx* ctx, const void* rho, const void* rhoU, const v
 
 /* device-resident stepping (no host transfers): what Solver.run does between report steps (return_reusable=0) */
 int adfvm_primal_step_resident(adfvm_ctx* ctx, double dt);
+/* == adjoint artificial viscosity: Function('primal_grad_viscous') (apps/adjoint.py:127-141) ==
+ * Replaces computeAdjointViscosity (adFVM/postpro.py:491-697), Function_get_max_eigenvalue (adFVM/cpp/scaling.cpp:23-62 cusolver
+ * syevjBatched / :84-106 LAPACK dsyev), Function_apply_adjoint_viscosity (scaling.cpp:134-160) and Matop::heat_equation
+ * (adFVM/cpp/matop_cuda.cpp:180-235, matop_petsc.cpp:230-484). type: ADFVM_VISC_*; scaling: adjParams[0] (the `scaling` input of
+ * primal_grad); rtol / maxit of the diffusion solve (<= 0: 1e-13 fp64 / 1e-6 fp32, 500). Afterwards adfvm_primal_grad with
+ * ADFVM_VISCOUS smooths the adjoint fields it returns: M_2norm from the step's start state, one implicit diffusion step over dt. */
+int adfvm_set_adjoint_viscosity(adfvm_ctx* ctx, int32_t type, double scaling, double rtol, int32_t maxit);
+/* the same smoothing applied to the resident adjoint fields (after adfvm_adjoint_step_resident / adfvm_adjoint_block) */
+int adfvm_adjoint_viscous_resident(adfvm_ctx* ctx, double dt);
+/* diagnostic (write_M_2norm, apps/adjoint.py:26,139): M_2norm [nCells][1] of a host state, ghost rows filled; reference numbering */
+int adfvm_get_adjoint_viscosity(adfvm_ctx* ctx, const void* rho, const void* rhoU, const void* rhoE, void* M_2norm);
+/* conjugate-gradient iterations of the last diffusion solve */
+int64_t adfvm_viscosity_iterations(adfvm_ctx* ctx);
 /* adjoint step on resident data; chain!=0 feeds the previous call's output adjoint back in as this call's input */
 int adfvm_adjoint_step_resident(adfvm_ctx* ctx, double dt, double obja, int32_t chain);
 int adfvm_get_dtc_obj(adfvm_ctx* ctx, double* dtc, double* obj);

@@ -264,12 +264,14 @@ def install(fp32=False, argv=None, overlay=None):
     cppDir = os.path.join(REF, "adFVM", "cpp")
 
     def get_compiler_args():
-        return {"compiler": "gcc", "linker": "g++", "libs": [],
+        # LAPACK (only the adjoint-viscosity path calls it): abort stubs, or forwarders to the library named by ADFVM_LAPACK_SO
+        lapack = "lapack_fwd.cpp" if os.environ.get("ADFVM_LAPACK_SO") else "lapack_stub.cpp"
+        return {"compiler": "gcc", "linker": "g++", "libs": ["dl"] if lapack == "lapack_fwd.cpp" else [],
                 "incdirs": [os.path.join(cppDir, "include"), STUBS],
                 "libdirs": [],
                 "sources": [os.path.join(cppDir, x) for x in
                             ["external.cpp", "mesh.cpp", "parallel.cpp", "scaling.cpp"]] +
-                           [os.path.join(STUBS, "lapack_stub.cpp")],
+                           [os.path.join(STUBS, lapack)],
                 "extra_compile_args": ["-w"] + (["-DCPU_FLOAT32"] if fp32 else [])}
     config.get_compiler_args = get_compiler_args
 

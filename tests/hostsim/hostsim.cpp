@@ -52,6 +52,11 @@ struct HostExec {
     }
     template <typename R> void reduce_max_buffer(const R* in, int n, R* out) { R a = (R)-1e30; for (int i = 0; i < n; i++) if (in[i] > a) a = in[i]; *out = a; }
     template <class B, typename R> void reduce_sum(int n, const B& b, R* out) { R a = 0; for (int i = 0; i < n; i++) a += b(i); *out = a; }
+    template <class B, typename R> void reduce_sum5(int n, const B& b, R* out) {
+        R a[5] = {0, 0, 0, 0, 0};
+        for (int i = 0; i < n; i++) { const auto x = b(i); for (int k = 0; k < 5; k++) a[k] += x.v[k]; }
+        for (int k = 0; k < 5; k++) out[k] = a[k];
+    }
     template <class B, typename R> void reduce_max(int n, const B& b, R* out) { R a = (R)-1e30; for (int i = 0; i < n; i++) { R v = b(i); if (v > a) a = v; } *out = a; }
 };
 }  // namespace fvm

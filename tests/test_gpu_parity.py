@@ -299,3 +299,52 @@ def test_large_periodic_properties(cudalib):
         s0, s1 = (b * V).sum(axis=0), (a * V).sum(axis=0)
         assert np.all(np.abs(s1 - s0) <= 1e-12 * np.abs(b * V).sum(axis=0))
     assert np.isfinite(out[3]).all() and out[3][0, 0] > 0
+
+
+# ---- adjoint artificial viscosity: `primal_grad_viscous` on the device
+@pytest.mark.parametrize("name", ["box_walls", "box_cyclic", "cyl2d"])
+@pytest.mark.parametrize("vt", ["abarbanel", "turkel", "uniform"])
+def test_adjoint_viscosity_matches_reference_on_device(name, vt, cudalib):
+    """M_2norm against the recording of the unmodified reference (oracle/ref_harness/gen_viscosity.py)"""
+    import test_viscosity as tv
+    g, z, inputs = tv._fixture(name)
+    f = function.PrimalFunction(g.spec, np.float64)
+    f(*inputs, replace_reusable=True)
+    M = f.grad().viscous(vt).adjoint_viscosity(*inputs[:3], float(z["scaling"]))
+    assert relerr(M, z["M_2norm_" + vt]) < TOL64
+
+
+@pytest.mark.parametrize("name,vt,scaling", [("box_walls", "abarbanel", 3e4), ("box_cyclic", "turkel", 1e5), ("cyl2d", "abarbanel", 1e0)])
+def test_viscous_adjoint_step_on_device(name, vt, scaling, cudalib):
+    import test_viscosity as tv
+    g, inp, r, out, expect, fa = tv.viscous_case(name, vt, scaling, None)
+    sc = state_scales(inp)
+    assert group_relerr(r[:3], expect, sc) < TOL64
+    assert group_relerr(expect, out[:3], sc) > 1e-3
+    assert group_relerr(r[3:6], out[3:6], sc) < TOL64
+
+
+@pytest.mark.parametrize("dtype,tol", [(np.float64, TOL64), (np.float32, 2e-4)])
+def test_viscous_adjoint_large_against_oracle(dtype, tol, cudalib):
+    """32^3 periodic box (256 tiles, several CTAs per SM): M_2norm and the smoothed adjoint against the oracle (numpy
+    eigvalsh + direct sparse solve). fp32: the eigenvalue of a matrix with entries ~1e4 carries ~1e-4 relative error in
+    single precision whatever the solver - the reference's own fp32 build (cusolver Ssyevj) is in the same position."""
+    from oracle import adjoint_viscosity as AV
+    case, ref_case = cases.periodic_box((32, 32, 32), dtype, warp=0.03), cases.periodic_box((32, 32, 32), np.float64, warp=0.03)
+    scaling, vt = 3e2, "abarbanel"
+    adj = _adj_seed(ref_case)
+    inp = ref_case.adjoint_inputs(ref_case.state, adj); inp[-1] = np.array([[scaling]], np.float64)
+    M, DT = AV.adjoint_viscosity(ref_case.spec, inp, vt, scaling)
+    plain = O.primal_grad(ref_case.spec, ref_case.adjoint_inputs(ref_case.state, adj))
+    expect = AV.apply_adjoint_viscosity(ref_case.spec, inp, DT, plain[:3])
+    f = function.PrimalFunction(case.spec, dtype)
+    f(*case.inputs(), replace_reusable=True)
+    fa = f.grad().viscous(vt)
+    dinp = case.adjoint_inputs(case.state, [a.astype(dtype) for a in adj]); dinp[-1] = np.array([[scaling]], dtype)
+    r = fa(*dinp)
+    Md = fa.adjoint_viscosity(*case.state, scaling)
+    assert relerr(Md, M) < tol
+    sc = state_scales(inp)
+    assert group_relerr(expect, plain[:3], sc) > 1e-3
+    assert group_relerr(r[:3], expect, sc) < tol
+    assert 1 <= fa.viscosity_iterations <= 200
