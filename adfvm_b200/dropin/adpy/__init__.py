@@ -14,8 +14,9 @@ calling the compiler, the step functions are bound to the hand-written sm_100a k
   init         -> adfvm_init_fields                      (adFVM/density.py:64-80: ghost-filled conservative fields for writing)
 
 The case file's objective - arbitrary adpy-DSL code - is taken from the trace (adfvm_b200.adpy_objective) and evaluated /
-differentiated on the device arrays; nothing has to be declared. Anything else a case asks of the generated module
-(adjoint viscosity, `compute_energy`, dynamic meshes) raises NotImplementedError naming it.
+differentiated on the device arrays; nothing has to be declared. `primal_grad_viscous` (a case file with adjParams =
+[scaling, type, None]: adjoint artificial viscosity, apps/adjoint.py:127-141) -> AdjointFunction.viscous(type). Anything else a
+case asks of the generated module (`compute_energy` on the device, dynamic meshes) raises NotImplementedError naming it.
 """
 import os
 import sys
@@ -105,6 +106,7 @@ class _Module:
             lib = _lib.Lib(os.environ["ADFVM_DROPIN_LIB"])
         self.primal_f = b200.PrimalFunction(spec, config.precision, device=device, lib=lib)
         self.grad_f = self.primal_f.grad()
+        self.visc_f, self.viscous_calls = None, 0
         self.np = np
 
     def initialize(self, *args, **kwargs):
@@ -115,6 +117,18 @@ class _Module:
 
     def primal_grad(self, *args, **kwargs):
         return self.grad_f(*args, **kwargs)
+
+    def primal_grad_viscous(self, *args, **kwargs):
+        """`adjoint.viscousMap` (apps/adjoint.py:127-141,288-289): the viscosity type is adjParams[1] of the case file, which
+        apps/problem.py keeps as a module global (apps/problem.py:22,26-33); the scaling arrives as the last positional input"""
+        if self.visc_f is None:
+            prob = sys.modules.get("problem") or sys.modules.get("__main__")
+            adj = getattr(prob, "adjParams", None) or getattr(sys.modules.get("__main__"), "adjParams", None)
+            if not adj or adj[1] is None:
+                raise NotImplementedError("primal_grad_viscous called but the case file's adjParams names no viscosity type")
+            self.visc_f = self.grad_f.viscous(adj[1])
+        self.viscous_calls += 1
+        return self.visc_f(*args, **kwargs)
 
     def init(self, *args, **kwargs):
         if not self.primal_f.c.static_loaded:

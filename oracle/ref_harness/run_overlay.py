@@ -26,7 +26,8 @@ def main():
     runpy.run_path(script, run_name="__main__")
     import adpy
     mod = adpy._STATE["module"]
-    print("[overlay] adpy = %s; primal served by %s (%d kernel launches)" % (adpy.__file__, type(mod.primal_f).__name__, mod.primal_f.launches), flush=True)
+    print("[overlay] adpy = %s; primal served by %s (%d kernel launches); viscous calls %d" %
+          (adpy.__file__, type(mod.primal_f).__name__, mod.primal_f.launches, mod.viscous_calls), flush=True)
 
 
 if __name__ == "__main__":

@@ -45,8 +45,9 @@ def run_primal(primal, case, nSteps, source=None, state=None, keep=False):
     return (res, state, series, states) if keep else (res, state, series)
 
 
-def run_adjoint(primal, primal_grad, case, nSteps, writeInterval, perturbation):
-    """returns (result, final adjoint fields, per-step sensitivities in the order the reference appends them)"""
+def run_adjoint(primal, primal_grad, case, nSteps, writeInterval, perturbation, scaling=0.0):
+    """returns (result, final adjoint fields, per-step sensitivities in the order the reference appends them).
+    scaling: adjParams[0]; primal_grad is then the viscous function (viscousInterval = 1, apps/adjoint.py:250,288-289)"""
     C = case.mesh.nInternalCells
     adj = [np.zeros((C, 1), case.dtype), np.zeros((C, 3), case.dtype), np.zeros((C, 1), case.dtype)]
     # checkpoint states at multiples of writeInterval (the reference reads them back from disk)
@@ -58,7 +59,7 @@ def run_adjoint(primal, primal_grad, case, nSteps, writeInterval, perturbation):
         with source_terms(case, None):          # the adjoint run linearises about the unperturbed trajectory
             for step in range(writeInterval):
                 adjointIndex = writeInterval - 1 - step
-                out = primal_grad(*case.adjoint_inputs(block[adjointIndex], adj, obja=1.0, dtca=0.0, scaling=0.0),
+                out = primal_grad(*case.adjoint_inputs(block[adjointIndex], adj, obja=1.0, dtca=0.0, scaling=scaling),
                                   return_static=True, zero_static=True, return_reusable=True, replace_reusable=False,
                                   replace_static=(step == 0))
                 adj = [np.array(o, copy=True) for o in out[:3]]

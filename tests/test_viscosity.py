@@ -154,3 +154,79 @@ def test_threads_decomposition_invariance(world, hostsim):
         num = max(np.abs(a - b[ids]).max() * s for a, b, s in zip(out[:3], ref[:3], sc))
         den = max(np.abs(b).max() * s for b, s in zip(ref[:3], sc))
         assert num / den < TOL
+
+
+# ---- the drivers' time loop (tests/minidriver.py = Adjoint.run with viscousInterval = 1): oracle against the device code
+def oracle_viscous(case, vt):
+    from oracle import adfvm_oracle as O
+
+    def f(*inp, **kw):
+        inp = list(inp)
+        out = O.primal_grad(case.spec, inp)
+        M, DT = AV.adjoint_viscosity(case.spec, inp, vt, float(inp[-1][0, 0]))
+        return AV.apply_adjoint_viscosity(case.spec, inp, DT, out[:3]) + list(out[3:])
+    return f
+
+
+def test_adjoint_run_with_viscosity_oracle_vs_device_code(hostsim):
+    import minidriver
+    from adfvm_b200 import cases
+    from oracle import adfvm_oracle as O
+    case = cases.walled_box((6, 5, 4))
+    vt, scaling, nSteps, wi = "abarbanel", 3e4, 4, 2
+    f = function.PrimalFunction(case.spec, np.float64, lib=hostsim)
+    got, gfields, gsens = minidriver.run_adjoint(f, f.grad().viscous(vt), case, nSteps, wi, case.source, scaling=scaling)
+    oprimal = lambda *inp, **kw: O.primal(case.spec, list(inp))
+    ref, rfields, rsens = minidriver.run_adjoint(oprimal, oracle_viscous(case, vt), case, nSteps, wi, case.source, scaling=scaling)
+    plain, _, _ = minidriver.run_adjoint(f, f.grad(), case, nSteps, wi, case.source)
+    assert abs(ref - plain) > 1e-3 * abs(plain)                       # the smoothing changes the sensitivity
+    assert abs(got - ref) <= 1e-9 * abs(ref)
+    assert np.allclose(gsens, rsens, rtol=1e-9, atol=1e-9 * np.abs(rsens).max())
+    assert group_relerr(gfields, rfields, [float(np.abs(s).max()) for s in case.state]) < TOL
+
+
+# ---- the unmodified apps/adjoint.py with a case file that sets adjParams, served through the adpy overlay
+REF = os.environ.get("ADFVM_REFERENCE", "/root/reference")
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="needs the reference tree")
+def test_reference_adjoint_driver_with_viscosity_through_overlay(hostsim):
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, os.path.join(root, "oracle", "ref_harness"))
+    import gen_golden
+    vt, scaling = "abarbanel", 3e4
+    base = gen_golden.CASES["box_walls"]
+    gen_golden.CASES["box_walls_visc"] = lambda: dict(base(), param_block="adjParams = [%r, %r, None]\nviscousInterval = 1\n" % (scaling, vt))
+    c, case, casefile = gen_golden.write_case("box_walls_visc", "box_walls_visc_overlay")
+    env = dict(os.environ, ADFVM_DROPIN_LIB=hostsim.path)
+    runner = os.path.join(root, "oracle", "ref_harness", "run_overlay.py")
+    for app in ("problem", "adjoint"):
+        out = subprocess.run([sys.executable, runner, app, "--", casefile], cwd=case, env=env, capture_output=True, text=True, timeout=900)
+        assert out.returncode == 0, out.stdout[-1500:] + out.stderr[-3000:]
+    served = [ln for ln in out.stdout.split("\n") if ln.startswith("[overlay]")][-1]
+    assert int(served.split()[-1]) == c["nSteps"], served          # every adjoint step went through primal_grad_viscous
+    got = {ln.split()[0]: float(ln.split()[3]) for ln in open(os.path.join(case, "objective.txt")).read().strip().split("\n")}
+    # the same steps replayed from the recording of the stock reference run (states, options), adjoint fields chained
+    g = Golden("box_walls")
+    cf = g.meta["casefile"]
+    cc = g.mesh_array("adjoint", "cellCentres")
+    C_ = len(next(g.calls("adjoint", "primal_grad"))[2][0])
+    G = float(cf["amp"]) * np.exp(-float(cf["width"]) * np.linalg.norm(cc[:C_] - np.array(json.loads(cf["mid"])), axis=1, keepdims=True) ** 2)
+    pert = [G, np.concatenate([G * 100, 0 * G, 0 * G], axis=1), G * 2e5]
+    fa = function.PrimalFunction(g.spec, np.float64, lib=hostsim).grad().viscous(vt)
+    adj, total = None, 0.0
+    for ci, nm, inp, opt, o in g.calls("adjoint", "primal_grad"):
+        inp = list(inp)
+        if adj is not None:
+            inp[-6:-3] = adj
+        inp[-1] = np.array([[scaling]])
+        r = fa(*inp, **opt)
+        adj = [np.array(a, copy=True) for a in r[:3]]
+        total += sum(float((a * b).sum()) for a, b in zip(r[3:6], pert))
+    expect = total / c["nSteps"]
+    ref_plain = {ln.split()[0]: float(ln.split()[3]) for ln in g.meta["objective_txt"]}["adjoint"]
+    assert abs(expect - ref_plain) > 1e-3 * abs(ref_plain)
+    assert abs(got["adjoint"] - expect) <= 1e-10 * abs(expect), (got, expect)
