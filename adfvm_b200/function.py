@@ -454,6 +454,14 @@ class PrimalFunction:
         c._arr(rho, (1,), "rho", C_); c._arr(rhoU, (3,), "rhoU", C_); c._arr(rhoE, (1,), "rhoE", C_)
         c.lib.check(c.lib.dll.adfvm_set_state(c.ctx, _ptr(rho), _ptr(rhoU), _ptr(rhoE)))
 
+    def state(self):
+        """(rho, rhoU, rhoE) currently resident (what the next call without replace_reusable continues from)"""
+        c = self.c
+        C_ = c.sizes[2]
+        outs = [c.pool.empty((C_, 1), c.dtype), c.pool.empty((C_, 3), c.dtype), c.pool.empty((C_, 1), c.dtype)]
+        c.lib.check(c.lib.dll.adfvm_get_state(c.ctx, _ptr(outs[0]), _ptr(outs[1]), _ptr(outs[2])))
+        return tuple(outs)
+
     def run_block(self, dts):
         """len(dts) resident primal steps; the state at the start of every step stays on the device for
         AdjointFunction.run_block (replaces the host-side `solutions` list of Solver.run(mode='forward'),
