@@ -123,5 +123,5 @@ def default_lib():
     """The CUDA product library; raises if it has not been built."""
     global _default
     if _default is None:
-        _default = Lib(DEFAULT_LIB)
+        _default = Lib(os.environ.get("ADFVM_B200_LIB") or DEFAULT_LIB)     # (override: kernel experiments with a second build of the same sources)
     return _default

@@ -107,6 +107,18 @@ for grp in (slice(0, 3), slice(3, 6)):
     num = max(np.abs(x - y[idw]).max() * s for x, y, s in zip(gwr[grp], gradw[grp], scw))
     den = max(np.abs(y).max() * s for y, s in zip(gradw[grp], scw))
     errs.append(num / den)
+# ---- adjoint artificial viscosity on the decomposed walled mesh: all-reduced normalisation of M_2norm, its halo, the diffusion
+# solve across processor patches with the dot products all-reduced on the device (the walled mesh: the reference does not couple
+# cells across cyclic patches, so on periodic meshes its own result depends on the decomposition - tests/test_viscosity.py)
+SCAL = 3e4
+def _scaled(inp):
+    inp = list(inp); inp[-1] = np.array([[SCAL]], np.float64); return inp
+vis_ref = fw.grad().viscous("abarbanel")(*_scaled(gw.adjoint_inputs(gw.state, adjw)))
+vis_r = fwr.grad().viscous("abarbanel")(*_scaled(cw.adjoint_inputs(cw.state, [np.ascontiguousarray(x[idw]) for x in adjw])))
+num = max(np.abs(x - y[idw]).max() * s for x, y, s in zip(vis_r[:3], vis_ref[:3], scw))
+den = max(np.abs(y).max() * s for y, s in zip(vis_ref[:3], scw))
+errs.append(num / den)
+assert max(np.abs(x - y).max() * s for x, y, s in zip(vis_ref[:3], gradw[:3], scw)) > 1e-3 * den      # the smoothing acted
 # ---- BASELINE.json config 4: the vane cascade of cases/vane_optim (spline-edged multi-block mesh, 4 spanwise layers = 40 000 cells)
 # with the reference's design objective, decomposed like decomposePar (decompose.rank_cases: plane cells and weights per rank)
 gv = cases.vane_cascade(nz=4)
