@@ -747,13 +747,15 @@ public:
     // reverse sweep over the block stored by the last primal_block: the adjoint of the block's final state is resident
     // (A[0], from adjoint_step or a previous adjoint_block); afterwards A[0] holds the adjoint of the block's first state,
     // Sb the accumulated source-term gradient. The resident primal state is left at the block's first state.
-    void adjoint_block(int nsteps, const double* dt, R obja) {
+    // viscous: the adjoint artificial viscosity is applied after every step (viscousInterval = 1, apps/adjoint.py:250,288-289)
+    void adjoint_block(int nsteps, const double* dt, R obja, bool viscous = false) {
         if (nsteps > (int)block.size()) throw std::runtime_error("adjoint_block: no stored primal block of that length");
         ensure_adjoint_buffers();
         const size_t bytes = (size_t)5 * m.sC * sizeof(R);
         for (int k = nsteps - 1; k >= 0; k--) {
             ex.copy(W[0], block[k], bytes);
             adjoint_step_resident((R)dt[k], obja, true);
+            if (viscous) adjoint_viscous((R)dt[k]);
         }
     }
     // ---- adjoint artificial viscosity (fvm_viscosity.h): what `primal_grad_viscous` adds to

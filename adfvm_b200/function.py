@@ -628,12 +628,17 @@ class AdjointFunction:
         c._arr(rhoa, (1,), "rhoa", C_); c._arr(rhoUa, (3,), "rhoUa", C_); c._arr(rhoEa, (1,), "rhoEa", C_)
         c.lib.check(c.lib.dll.adfvm_set_adjoint(c.ctx, _ptr(rhoa), _ptr(rhoUa), _ptr(rhoEa)))
 
-    def run_block(self, dts, obja=1.0):
+    def run_block(self, dts, obja=1.0, scaling=0.0):
         """reverse sweep over the block stored by PrimalFunction.run_block(dts) (the step loop of Adjoint.run,
         apps/adjoint.py:250-291, without the host round trips): adjoint fields and source-term gradient stay resident"""
         n = len(dts)
         dt = (C.c_double * max(n, 1))(*[float(x) for x in dts])
-        self.c.lib.check(self.c.lib.dll.adfvm_adjoint_block(self.c.ctx, n, dt, float(obja)))
+        c = self.c
+        if self.viscosity is None:
+            c.lib.check(c.lib.dll.adfvm_adjoint_block(c.ctx, n, dt, float(obja)))
+        else:                                       # this object is `viscousMap`: the smoothing follows every step of the block
+            c.lib.check(c.lib.dll.adfvm_set_adjoint_viscosity(c.ctx, L.VISC[self.viscosity], float(scaling), self.visc_rtol, self.visc_maxit))
+            c.lib.check(c.lib.dll.adfvm_adjoint_block_viscous(c.ctx, n, dt, float(obja)))
 
     def fields(self, return_static=True, zero_static=False):
         """(rhoa, rhoUa, rhoEa[, dJ/dS_rho, dJ/dS_rhoU, dJ/dS_rhoE]) currently resident"""

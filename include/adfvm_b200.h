@@ -145,6 +145,8 @@ int adfvm_primal_step_resident(adfvm_ctx* ctx, double dt);
 int adfvm_set_adjoint_viscosity(adfvm_ctx* ctx, int32_t type, double scaling, double rtol, int32_t maxit);
 /* the same smoothing applied to the resident adjoint fields (after adfvm_adjoint_step_resident / adfvm_adjoint_block) */
 int adfvm_adjoint_viscous_resident(adfvm_ctx* ctx, double dt);
+/* adfvm_adjoint_block with the smoothing applied after every step (viscousInterval = 1, apps/adjoint.py:250,288-289) */
+int adfvm_adjoint_block_viscous(adfvm_ctx* ctx, int32_t nsteps, const double* dt, double obja);
 /* diagnostic (write_M_2norm, apps/adjoint.py:26,139): M_2norm [nCells][1] of a host state, ghost rows filled; reference numbering */
 int adfvm_get_adjoint_viscosity(adfvm_ctx* ctx, const void* rho, const void* rhoU, const void* rhoE, void* M_2norm);
 /* conjugate-gradient iterations of the last diffusion solve */

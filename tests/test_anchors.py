@@ -95,33 +95,20 @@ def test_anchor_on_device(name, cudalib):
 # path of the same library): Solver.run(mode='forward') + the backward loop of Adjoint.run with every state, the adjoint fields
 # and the source-gradient accumulator resident; the host sees one state per checkpoint and the accumulated gradient per block
 def replay_blocks(a, case, f, tol_obj=1e-10, tol_adj=1e-9, tol_field=1e-10):
+    from adfvm_b200 import blocks
     nSteps, wi = a.cf["nSteps"], a.cf["writeInterval"]
-    pert = case.source
     C = case.mesh.nInternalCells
-    fa = f.grad()
+    pert = case.source                                   # (the context below zeroes the case's source terms)
     with minidriver.source_terms(case, None):
-        f.set_state(*case.inputs())
-        series, checkpoints = [], [list(case.state)]
-        for b in range(nSteps // wi):                      # problem.py `orig`: states written every writeInterval steps
-            dtc, obj = f.run_block([case.dt] * wi)
-            series += list(obj)
-            checkpoints.append([np.array(x, copy=True) for x in f.state()])
+        series, checkpoints = blocks.forward_blocks(f, case.inputs(), nSteps, wi, case.dt)
         orig = sum(series) / nSteps
         assert abs(orig - a.objective["orig"]) <= tol_obj * abs(a.objective["orig"])
         assert np.allclose(series, a.z["timeSeries_orig"], rtol=tol_obj, atol=0)
         a.check_fields("orig", NAMES, checkpoints[-1], tol_field)
-        fa.set_fields(np.zeros((C, 1)), np.zeros((C, 3)), np.zeros((C, 1)))
-        result = 0.0
-        for checkpoint in range(nSteps // wi):
-            k = nSteps // wi - 1 - checkpoint
-            f.set_state(*case.inputs(checkpoints[k]))
-            f.run_block([case.dt] * wi)
-            fa.run_block([case.dt] * wi)
-            out = fa.fields(return_static=True, zero_static=True)
-            result += sum(float((np.asarray(g) * np.asarray(p)).sum()) for g, p in zip(out[3:6], pert))
-        adj = result / nSteps
+        zero = [np.zeros((C, 1)), np.zeros((C, 3)), np.zeros((C, 1))]
+        adj, fields = blocks.adjoint_blocks(f, f.grad(), case.inputs, checkpoints, nSteps, wi, case.dt, zero, pert)
         assert abs(adj - a.objective["adjoint"]) <= tol_adj * abs(a.objective["adjoint"]), (adj, a.objective["adjoint"])
-        a.check_fields("adjoint", ANAMES, out[:3], tol_field, [float(np.abs(s).max()) for s in case.state])
+        a.check_fields("adjoint", ANAMES, fields, tol_field, [float(np.abs(s).max()) for s in case.state])
 
 
 @pytest.mark.parametrize("name", ["anchor_tube500", "anchor_box48"])

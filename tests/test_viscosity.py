@@ -185,6 +185,28 @@ def test_adjoint_run_with_viscosity_oracle_vs_device_code(hostsim):
     assert group_relerr(gfields, rfields, [float(np.abs(s).max()) for s in case.state]) < TOL
 
 
+def test_viscous_blocks_equal_stepwise_driver_loop(hostsim):
+    """adfvm_b200.blocks with the viscous function (states, adjoint fields and gradient accumulator resident, the smoothing after
+    every step) against the step-wise loop with host round trips"""
+    import minidriver
+    from adfvm_b200 import blocks, cases
+    case = cases.walled_box((6, 5, 4))
+    vt, scaling, nSteps, wi = "turkel", 1e5, 4, 2
+    f = function.PrimalFunction(case.spec, np.float64, lib=hostsim)
+    ref, rfields, _ = minidriver.run_adjoint(f, f.grad().viscous(vt), case, nSteps, wi, case.source, scaling=scaling)
+    C_ = case.mesh.nInternalCells
+    pert = case.source
+    with minidriver.source_terms(case, None):
+        f2 = function.PrimalFunction(case.spec, np.float64, lib=hostsim)
+        series, checkpoints = blocks.forward_blocks(f2, case.inputs(), nSteps, wi, case.dt)
+        zero = [np.zeros((C_, 1)), np.zeros((C_, 3)), np.zeros((C_, 1))]
+        fa2 = f2.grad()
+        got, gfields = blocks.adjoint_blocks(f2, fa2, case.inputs, checkpoints, nSteps, wi, case.dt, zero, pert,
+                                             viscous=fa2.viscous(vt), scaling=scaling)
+    assert abs(got - ref) <= 1e-12 * abs(ref)
+    assert group_relerr(gfields, rfields, [float(np.abs(s).max()) for s in case.state]) < 1e-12
+
+
 # ---- the unmodified apps/adjoint.py with a case file that sets adjParams, served through the adpy overlay
 REF = os.environ.get("ADFVM_REFERENCE", "/root/reference")
 
