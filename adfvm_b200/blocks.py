@@ -16,11 +16,11 @@ def forward_blocks(f, inputs, nSteps, writeInterval, dt):
     objectives and the states at every multiple of writeInterval (index 0 = the initial state). dt: scalar or per-step sequence."""
     dts = [float(dt)] * nSteps if np.isscalar(dt) else [float(x) for x in dt]
     f.set_state(*inputs)
-    series, checkpoints = [], [[np.array(x, copy=True) for x in inputs[:3]]]
+    series, checkpoints = [], [list(inputs[:3])]
     for b in range(nSteps // writeInterval):
         _, obj = f.run_block(dts[b * writeInterval:(b + 1) * writeInterval])
         series += [float(x) for x in obj]
-        checkpoints.append([np.array(x, copy=True) for x in f.state()])
+        checkpoints.append(list(f.state()))              # fresh host arrays (page-locked), owned by the caller
     return series, checkpoints
 
 

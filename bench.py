@@ -439,6 +439,27 @@ def measure(case, dtype, rank, world, local, stream, K, W, want_kernels=True, wa
         # up, adjoint down, source gradient down once per block
         res["h2d"] = (5 * C * s) / B + s + (10 * C * s + 4 * s)
         res["d2h"] = (5 * C * s + 2 * s) + (5 * C * s) + (5 * C * s) / B
+        # ---- the same block through adfvm_b200.blocks: the block's states, the adjoint fields and the gradient
+        # accumulator stay in HBM; per block the host sends the start state + the adjoint fields and reads back the end state, the
+        # adjoint fields and the accumulated source gradient
+        from adfvm_b200 import blocks
+        C0 = case.mesh.nInternalCells
+        zero_pert = [np.zeros((1, 1), dtype)] * 3                  # (sensitivity = sum(gradient * perturbation) is host work of the driver)
+
+        def block2():
+            series, cps = blocks.forward_blocks(f, case.inputs(hstate), B, B, case.dt)
+            return blocks.adjoint_blocks(f, fa, case.inputs, cps, B, B, case.dt, hadj0, zero_pert)
+        block2()
+        barrier()
+        t0 = time.perf_counter()
+        block2()
+        barrier()
+        tb = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(tb, op=dist.ReduceOp.MAX)
+        res["e2e_blocks_s_per_step"] = tb.item() / B
+        res["e2e_blocks_h2d"] = (2 * 5 * C0 * s + 5 * C0 * s) / B      # start state (forward) + start state again + adjoint fields (adjoint)
+        res["e2e_blocks_d2h"] = (5 * C0 * s + 10 * C0 * s) / B         # end state; adjoint fields + source gradient
     f.c.close()
     return res
 
@@ -612,6 +633,12 @@ def main():
                     "note": "PrimalFunction/AdjointFunction.__call__ with pinned host buffers, one checkpoint block of %d steps driven like "
                             "the reference's Adjoint.run (forward-mode primal calls returning every state, then primal_grad backwards: state + "
                             "adjoint up, adjoint down every call, source gradient once per block)" % m["e2e_block"]},
+            "e2e_blocks": {"value": 2 * 3 * cells_total / m["e2e_blocks_s_per_step"] / 1e6, "unit": UNIT,
+                           "h2d_bytes_per_step": int(m["e2e_blocks_h2d"]), "d2h_bytes_per_step": int(m["e2e_blocks_d2h"]),
+                           "ms_per_step": m["e2e_blocks_s_per_step"] * 1e3,
+                           "note": "not the headline: the same block of %d steps through adfvm_b200.blocks (SURVEY 8(f)-1: states, adjoint fields "
+                                   "and gradient accumulator resident; host traffic once per block) - what the drivers' loops cost when they call "
+                                   "run_block instead of one Function call per step" % m["e2e_block"]} if "e2e_blocks_s_per_step" in m else None,
             "gpu_launches": int(m["launches"]), "clocks": m["clocks"], "roofline": roof, "kernels": kernels, "cpu_baseline": cpu,
             "parity": parity, "parity_maxerr": parity["maxerr"] if parity else None, "early_tiles": parity["early_tiles"] if parity else None,
             "fp32": fp32, "strong": strong, "wall_s": round(time.time() - T0, 1)}
