@@ -81,6 +81,16 @@ def relerr(a, b):
     return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-300))
 
 
+def relerr_cols(a, b, floor=1e-3):
+    """column by column: each component against its OWN largest value, but not below `floor` times the array's largest - a
+    component that is small everywhere (rhoU_z of a 2-D case) is the sum of terms of the size of the large ones, whose rounding
+    sets its error floor; below that a relative error has no meaning. With floor = 1e-3 a component 1000 times smaller than the
+    largest is still checked to the full tolerance of its own size."""
+    a = np.asarray(a, np.float64).reshape(len(a), -1); b = np.asarray(b, np.float64).reshape(len(b), -1)
+    top = max(float(np.abs(b).max()), 1e-300)
+    return max(float(np.abs(a[:, k] - b[:, k]).max()) / max(float(np.abs(b[:, k]).max()), floor * top) for k in range(b.shape[1]))
+
+
 def group_relerr(arrs, refs, scales=None):
     """Largest error over a group of arrays that share one physical unit after scaling
     (e.g. adjoints of rho, rhoU, rhoE scaled by typical rho, rhoU, rhoE), relative to the group's max."""

@@ -6,7 +6,7 @@ gap is ~1e-6)."""
 import numpy as np
 import pytest
 
-from golden_util import Golden, available, relerr, group_relerr, state_scales
+from golden_util import Golden, available, relerr, relerr_cols, group_relerr, state_scales
 from adfvm_b200 import function, cases
 from oracle import adfvm_oracle as O
 
@@ -24,6 +24,7 @@ def test_golden_primal(name, cudalib):
             r = f(*inp, **opt)
             for a, b in zip(r, out):
                 assert relerr(a, b) < TOL64
+                assert relerr_cols(a, b) < 10 * TOL64        # every component against its own size (1e-9)
 
 
 @pytest.mark.parametrize("name", CASES)

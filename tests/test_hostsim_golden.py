@@ -5,7 +5,7 @@ through the CUDA library in test_gpu_parity.py (-m gpu). fp64 tolerance 1e-10 (n
 import numpy as np
 import pytest
 
-from golden_util import Golden, available, relerr, group_relerr, state_scales
+from golden_util import Golden, available, relerr, relerr_cols, group_relerr, state_scales
 from adfvm_b200 import function
 
 CASES = [c for c in available() if not c.endswith("_fp32")]
@@ -21,6 +21,7 @@ def test_primal_calls(name, hostsim):
             r = f(*inp, **opt)
             for a, b in zip(r, out):
                 assert relerr(a, b) < TOL
+                assert relerr_cols(a, b) < 10 * TOL          # every component against its own size (1e-9)
 
 
 @pytest.mark.parametrize("name", CASES)
