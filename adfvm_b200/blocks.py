@@ -28,17 +28,19 @@ def adjoint_blocks(f, fa, make_inputs, checkpoints, nSteps, writeInterval, dt, a
                    viscous=None, scaling=0.0):
     """`apps/adjoint.py` Adjoint.run: checkpoints backwards, each block recomputed forward on the device and swept in reverse.
     make_inputs(state) -> `primal` positional list for that state; adjoint0: the adjoint fields of the final state;
-    perturbation: arrays shaped like the parameter gradient (source terms). viscous: an `AdjointFunction.viscous(type)` object -
+    perturbation: arrays shaped like the parameter gradient (source terms), or None to skip the sensitivity sum. viscous: an `AdjointFunction.viscous(type)` object -
     the smoothing is then applied after every step (viscousInterval = 1). Returns (sum of sensitivities / nSteps, adjoint fields)."""
     dts = [float(dt)] * nSteps if np.isscalar(dt) else [float(x) for x in dt]
-    fa.set_fields(*adjoint0)
     total, out = 0.0, None
     for checkpoint in range(nSteps // writeInterval):
         k = nSteps // writeInterval - 1 - checkpoint
         blk = dts[k * writeInterval:(k + 1) * writeInterval]
-        f.set_state(*make_inputs(checkpoints[k]))
+        f.set_state(*make_inputs(checkpoints[k]))       # (also loads the static inputs on a fresh context)
+        if checkpoint == 0:
+            fa.set_fields(*adjoint0)
         f.run_block(blk)
         (viscous or fa).run_block(blk, obja, scaling)
         out = fa.fields(return_static=True, zero_static=True)
-        total += sum(float((np.asarray(g, np.float64) * np.asarray(p, np.float64)).sum()) for g, p in zip(out[3:6], perturbation))
+        if perturbation is not None:                    # cmesh.computeSensitivity (host work of the driver, apps/adjoint.py:341)
+            total += sum(float((np.asarray(g, np.float64) * np.asarray(p, np.float64)).sum()) for g, p in zip(out[3:6], perturbation))
     return total / nSteps, list(out[:3])
