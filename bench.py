@@ -609,6 +609,17 @@ def main():
                             "primal_GBs": B_p * 3 * C / (tp_ms / K * 1e-3) / 1e9, "adjoint_GBs": B_a * 3 * C / (ta_ms / K * 1e-3) / 1e9,
                             "primal_frac": B_p * 3 * C / (tp_ms / K * 1e-3) / 1e9 / peak,
                             "adjoint_frac": B_a * 3 * C / (ta_ms / K * 1e-3) / 1e9 / peak}}
+    # the dominant kernel's other ceiling: the fp64 pipe (SASS count of fp64 instructions per face evaluation, DESIGN.md section 5;
+    # an fp64 warp instruction holds one of the 4 x 148 sub-partition pipes for two cycles)
+    FP64_PER_EVAL = {"flux_grad_tile": 953}
+    if dom in FP64_PER_EVAL and args.dtype == "f64":
+        mhz = (m["clocks"] or {}).get("sm_mhz") or 1965.0
+        floor_ms = FP64_PER_EVAL[dom] * 4.0 * C / 32 * 2 / (4 * 148 * mhz * 1e6) * 1e3
+        roof["fp64_pipe"] = {"fp64_instructions_per_face_evaluation": FP64_PER_EVAL[dom], "evaluations_per_cell": 4.0,
+                             "floor_ms_per_pass": floor_ms, "pipe_busy_frac": floor_ms / kernels[dom]["ms_per_pass"],
+                             "hbm_floor_ms_per_pass": kb[dom] * C / peak / 1e6,
+                             "note": "this kernel is bound by fp64 issue (two warps per scheduler at 254 registers), not by HBM: with the "
+                                     "pipe saturated it would reach hbm_floor/floor of the HBM peak"}
     cpu = None
     if not args.no_cpu_baseline and world == 1:
         log("cpu baseline ...")
