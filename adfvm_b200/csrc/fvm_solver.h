@@ -12,6 +12,8 @@
 #include <vector>
 #include <cstring>
 #include <cstdlib>
+#include <chrono>
+#include <cstdio>
 #include "fvm_bodies.h"
 #include "fvm_tile_bodies.h"
 #include "fvm_tiles.h"
@@ -114,6 +116,10 @@ public:
                   const int* owner, const int* neighbour, const int* cellFaces, const int* cellNeighbours, const int* cellOwner,
                   const std::vector<PatchHost>& patches_in) {
         if (have_mesh) throw std::runtime_error("mesh already set (create a new context)");
+        const bool verbose = std::getenv("ADFVM_TILE_TIMING") != nullptr;
+        auto t_lap = std::chrono::steady_clock::now();
+        auto lap = [&](const char* what) { if (verbose) { ex.sync(); auto now = std::chrono::steady_clock::now();
+            std::fprintf(stderr, "[set_mesh] %-26s %.2f s\n", what, std::chrono::duration<double>(now - t_lap).count()); t_lap = now; } };
         m.nCells = sizes[0]; m.nFaces = sizes[1]; m.nInternalCells = sizes[2]; m.nInternalFaces = sizes[3];
         m.nLocalCells = sizes[4]; m.nRemoteCells = sizes[5]; m.nLocalFaces = sizes[6]; m.nGhostCells = sizes[7];
         const int C = m.nInternalCells, F = m.nFaces, Fi = m.nInternalFaces, N = m.nCells;
@@ -126,6 +132,7 @@ public:
         for (long f = 0; f < F; f++) if (volumesL[f] != volumes[owner[f]]) throw std::runtime_error("volumesL != volumes[owner] (perturbed volume arrays are not supported)");
         for (long f = 0; f < Fi; f++) if (volumesR[f] != volumes[neighbour[f]]) throw std::runtime_error("volumesR != volumes[neighbour]");
         m.sC = pad32(C); m.sN = pad32(N); m.sF = pad32(F);
+        lap("validation");
         // ---- tile plan: renumber internal cells and internal faces (fvm_tiles.h); ghosts and boundary faces keep their ids
         // 128-cell tiles with room for 256 halo slots; meshes with many ghost cells per cell (1-D / 2-D cases, whose
         // "empty" patches give every cell 2-4 boundary faces) fall back to 64-cell tiles, whose halo always fits
@@ -142,6 +149,7 @@ public:
         if (plan.T == 64 && plan.maxHalo > kHalo64) throw std::runtime_error("tile halo exceeds the kernel's capacity");
         // kernel variant (T, TS): 0 = (128, 288) regular 4x4x8 tiles of a hex block (halo = its 160 face neighbours: three fp64 CTAs per
         // SM forward AND reverse), 1 = (128, 320) compact 3-D tiles (halo <= 192), 2 = (128, 384), 3 = (64, 448)
+        lap("tile plan");
         tile_variant = plan.T == 64 ? 3 : (plan.maxHalo <= kHalo128r ? 0 : (plan.maxHalo <= kHalo128s ? 1 : 2));
         m.T = plan.T; m.nTiles = plan.nTiles; nEarlyTiles = plan.nEarly;
         int* d_cperm = dalloc<int>(m.sC); ex.upload(d_cperm, plan.cell_new2old.data(), (size_t)C * 4); m.cell_perm = d_cperm;
@@ -165,14 +173,17 @@ public:
             else { ex.free(t_dunit); ex.free(t_linw); ex.free(t_quadw); }
         }
         ex.sync(); ex.free(d_fperm);
+        lap("metric upload + chunks");
         auto newcell = [&](int c) { return c < C ? plan.cell_old2new[c] : c; };
         {
             std::vector<int> ow(m.sF, 0), nb(m.sF, 0);
-            for (long f = 0; f < F; f++) {
-                const int of = plan.face_new2old[f];
-                if (owner[of] < 0 || owner[of] >= C || neighbour[of] < 0 || neighbour[of] >= N) throw std::runtime_error("owner/neighbour out of range");
-                ow[f] = newcell(owner[of]); nb[f] = newcell(neighbour[of]);
-            }
+            detail::parallel_for(F, 1 << 16, [&](long f_lo, long f_hi) {
+                for (long f = f_lo; f < f_hi; f++) {
+                    const int of = plan.face_new2old[f];
+                    if (owner[of] < 0 || owner[of] >= C || neighbour[of] < 0 || neighbour[of] >= N) throw std::runtime_error("owner/neighbour out of range");
+                    ow[f] = newcell(owner[of]); nb[f] = newcell(neighbour[of]);
+                }
+            });
             int* d_owner = dalloc<int>(m.sF); ex.upload(d_owner, ow.data(), (size_t)F * 4); m.owner = d_owner;
             int* d_neigh = dalloc<int>(m.sF); ex.upload(d_neigh, nb.data(), (size_t)F * 4); m.neigh = d_neigh;
             ex.sync();
@@ -181,19 +192,26 @@ public:
         std::vector<int> cf((size_t)6 * m.sC, 0), cn((size_t)6 * m.sC, 0);
         std::vector<unsigned char> co(m.sC, 0);
         std::vector<int> bc_list;
-        for (long c = 0; c < C; c++) {
-            const long oc = plan.cell_new2old[c];
-            bool b = false; unsigned bits = 0;
-            for (int j = 0; j < 6; j++) {
-                int f = cellFaces[oc * 6 + j], nb = cellNeighbours[oc * 6 + j];
-                if (f < 0 || f >= F || nb < 0 || nb >= N) throw std::runtime_error("cellFaces/cellNeighbours out of range");
-                cf[(size_t)j * m.sC + c] = plan.face_old2new[f]; cn[(size_t)j * m.sC + c] = newcell(nb);
-                if (cellOwner[oc * 6 + j]) bits |= 1u << j;
-                if (nb >= C) b = true;
-            }
-            co[c] = (unsigned char)bits;
-            if (b) bc_list.push_back((int)c);
+        {
+            std::vector<unsigned char> isb(C, 0);
+            detail::parallel_for(C, 1 << 16, [&](long c_lo, long c_hi) {
+                for (long c = c_lo; c < c_hi; c++) {
+                    const long oc = plan.cell_new2old[c];
+                    bool b = false; unsigned bits = 0;
+                    for (int j = 0; j < 6; j++) {
+                        int f = cellFaces[oc * 6 + j], nb = cellNeighbours[oc * 6 + j];
+                        if (f < 0 || f >= F || nb < 0 || nb >= N) throw std::runtime_error("cellFaces/cellNeighbours out of range");
+                        cf[(size_t)j * m.sC + c] = plan.face_old2new[f]; cn[(size_t)j * m.sC + c] = newcell(nb);
+                        if (cellOwner[oc * 6 + j]) bits |= 1u << j;
+                        if (nb >= C) b = true;
+                    }
+                    co[c] = (unsigned char)bits;
+                    isb[c] = b;
+                }
+            });
+            for (long c = 0; c < C; c++) if (isb[c]) bc_list.push_back((int)c);
         }
+        lap("connectivity transpose");
         int* d_cf = dalloc<int>(cf.size()); ex.upload(d_cf, cf.data(), cf.size() * 4); m.cellFaces = d_cf;
         int* d_cn = dalloc<int>(cn.size()); ex.upload(d_cn, cn.data(), cn.size() * 4); m.cellNbr = d_cn;
         unsigned char* d_co = dalloc<unsigned char>(co.size()); ex.upload(d_co, co.data(), co.size()); m.cellOwner = d_co;
@@ -209,6 +227,7 @@ public:
             unsigned short* d_ns = dalloc<unsigned short>((size_t)6 * m.sC); run(C, NbrSlotBody<R>{m, d_ns}); m.nbrSlot = d_ns;
             ex.sync();
         }
+        lap("connectivity upload + slots");
         if (mesh_param) { face_new2old_h = plan.face_new2old; cell_new2old_h = plan.cell_new2old; }
         tile_evals_per_cell = plan.evals_per_cell(); tile_colours = plan.maxColours; tile_max_halo = plan.maxHalo;
         tile_rounds_total = (long)(plan.ent_face.size() / kRound);
@@ -253,6 +272,7 @@ public:
         stage_aos = dalloc<R>((size_t)5 * m.sC);
         if (m.nRemoteCells > 0) { sendbuf = dalloc<R>((size_t)15 * m.nRemoteCells); recvbuf = dalloc<R>((size_t)15 * m.nRemoteCells); }
         ex.sync();
+        lap("patches + buffers");
         have_mesh = true;
     }
     PatchDev<R>* patches_dev = nullptr;

@@ -33,6 +33,9 @@
 #include <numeric>
 #include <stdexcept>
 #include <unordered_map>
+#include <thread>
+#include <atomic>
+#include <exception>
 #include <vector>
 #include <chrono>
 #include <cstdio>
@@ -68,6 +71,30 @@ struct TilePlan {
 };
 
 namespace detail {
+
+// host threads for the one-off plan (ADFVM_PLAN_THREADS overrides; 1 = the sequential code path, which gives the identical plan)
+inline int plan_threads() {
+    if (const char* e = std::getenv("ADFVM_PLAN_THREADS")) return std::max(1, std::atoi(e));
+    const unsigned hw = std::thread::hardware_concurrency();
+    return (int)std::max(1u, std::min(hw ? hw : 1u, 16u));
+}
+// fn(lo, hi) over [0, n) split into contiguous chunks, one per thread; exceptions are rethrown in the caller
+template <class F> inline void parallel_for(long n, long grain, F&& fn) {
+    int nt = plan_threads();
+    if (n < 2 * grain) nt = 1;
+    nt = (int)std::min<long>(nt, std::max<long>(1, n / std::max<long>(1, grain)));
+    if (nt <= 1) { fn(0L, n); return; }
+    std::vector<std::thread> th;
+    std::vector<std::exception_ptr> err(nt);
+    const long chunk = (n + nt - 1) / nt;
+    for (int t = 0; t < nt; t++) {
+        const long lo = t * chunk, hi = std::min(n, lo + chunk);
+        if (lo >= hi) break;
+        th.emplace_back([&, t, lo, hi] { try { fn(lo, hi); } catch (...) { err[t] = std::current_exception(); } });
+    }
+    for (auto& x : th) x.join();
+    for (auto& e : err) if (e) std::rethrow_exception(e);
+}
 
 // cell centres up to a translation per connected component: x[nbr] = x[owner] + delta * deltaUnit
 template <typename R>
@@ -111,33 +138,49 @@ inline bool detect_lattice(const std::vector<float>& pos, int C, std::vector<int
     long cap = 2000000;
     if (const char* e = std::getenv("ADFVM_LATTICE_SAMPLE")) cap = std::max(64L, std::atol(e));     // tests exercise the sampling path on small meshes
     const long nsample = std::min<long>(C, cap);
-    std::vector<float> sample, planes;
-    for (int d = 0; d < 3; d++) {
-        sample.clear();
+    std::atomic<bool> off(false);
+    // the three directions are independent: one thread each, the per-cell pass of each split further when threads are left
+    const int inner = std::max(1, plan_threads() / 3);
+    auto one_dim = [&](int d) {
+        std::vector<float> sample, planes;
+        sample.reserve(nsample);
         // scattered sample (a regular stride would alias with the lattice and miss whole planes); a missed plane is
         // caught by the verification pass below, which then rejects the lattice
         for (long i = 0; i < nsample; i++) sample.push_back(pos[3 * (size_t)(nsample == C ? i : (long)(((unsigned long long)i * 2654435761ull) % (unsigned long long)C)) + d]);
         std::sort(sample.begin(), sample.end());
         const float span = sample.back() - sample.front();
         const float tol = std::max(span * 1e-5f, 1e-30f);
-        planes.clear();
         for (size_t i = 0; i < sample.size();) {              // clusters of values closer than tol = one plane
-            size_t j = i; double sum = 0;
-            while (j < sample.size() && sample[j] - sample[i] <= tol) sum += sample[j++];
-            planes.push_back((float)(sum / (double)(j - i)));
-            i = j;
-            if (planes.size() > 8192) return false;
+            size_t k = i; double sum = 0;
+            while (k < sample.size() && sample[k] - sample[i] <= tol) sum += sample[k++];
+            planes.push_back((float)(sum / (double)(k - i)));
+            i = k;
+            if (planes.size() > 8192) { off = true; return; }
         }
-        if ((double)planes.size() * planes.size() * planes.size() > 64.0 * C && planes.size() > 64) return false;   // not a lattice
-        for (long c = 0; c < C; c++) {
-            const float x = pos[3 * (size_t)c + d];
-            size_t k = std::lower_bound(planes.begin(), planes.end(), x) - planes.begin();
-            if (k == planes.size() || (k > 0 && x - planes[k - 1] < planes[k] - x)) k--;
-            if (std::fabs(x - planes[k]) > 2 * tol) return false;
-            lat[3 * (size_t)c + d] = (int)k;
-        }
+        if ((double)planes.size() * planes.size() * planes.size() > 64.0 * C && planes.size() > 64) { off = true; return; }   // not a lattice
+        auto cells = [&](long lo, long hi) {
+            for (long c = lo; c < hi && !off; c++) {
+                const float x = pos[3 * (size_t)c + d];
+                size_t k = std::lower_bound(planes.begin(), planes.end(), x) - planes.begin();
+                if (k == planes.size() || (k > 0 && x - planes[k - 1] < planes[k] - x)) k--;
+                if (std::fabs(x - planes[k]) > 2 * tol) { off = true; return; }
+                lat[3 * (size_t)c + d] = (int)k;
+            }
+        };
+        if (inner <= 1 || C < (1 << 18)) { cells(0, C); return; }
+        std::vector<std::thread> th;
+        const long chunk = ((long)C + inner - 1) / inner;
+        for (int t = 0; t < inner; t++) { const long lo = t * chunk, hi = std::min<long>(C, lo + chunk); if (lo < hi) th.emplace_back(cells, lo, hi); }
+        for (auto& x : th) x.join();
+    };
+    if (plan_threads() >= 3) {
+        std::thread t1(one_dim, 1), t2(one_dim, 2);
+        one_dim(0);
+        t1.join(); t2.join();
+    } else {
+        for (int d = 0; d < 3 && !off; d++) one_dim(d);
     }
-    return true;
+    return !off;
 }
 
 // Recursive bisection of idx[lo,hi) into leaves of T cells, always splitting at a multiple of T so that every leaf but
@@ -146,59 +189,82 @@ inline bool detect_lattice(const std::vector<float>& pos, int C, std::vector<int
 // multiples of 4 / 8 then decompose into exact 4x4x8 tiles and 4x4x2 sub-tiles whatever the block size (a plain
 // halving of 368 = 16*23 planes ends in 23-plane slabs and ragged tiles). Ranges without such a plane, and meshes
 // without a lattice, are cut by cell count at the median coordinate (nth_element).
-inline void rcb(std::vector<int>& idx, const std::vector<float>& pos, const int* lat, long lo, long hi, int T) {
-    struct Range { long lo, hi; };
-    std::vector<Range> stack; stack.push_back({lo, hi});
-    std::vector<long> hist;
-    while (!stack.empty()) {
-        Range r = stack.back(); stack.pop_back();
-        const long n = r.hi - r.lo;
-        if (n <= T) continue;
-        if (lat) {
-            int mn[3] = {1 << 30, 1 << 30, 1 << 30}, mx[3] = {-1, -1, -1};
-            for (long i = r.lo; i < r.hi; i++)
-                for (int k = 0; k < 3; k++) { const int v = lat[3 * (size_t)idx[i] + k]; mn[k] = std::min(mn[k], v); mx[k] = std::max(mx[k], v); }
-            int order[3] = {0, 1, 2};
-            std::sort(order, order + 3, [&](int a, int b) { return (mx[a] - mn[a]) != (mx[b] - mn[b]) ? (mx[a] - mn[a]) > (mx[b] - mn[b]) : a < b; });
-            bool done = false;
-            for (int oi = 0; oi < 3 && !done; oi++) {
-                const int dim = order[oi], ext = mx[dim] - mn[dim] + 1;
-                if (ext < 2) break;
-                hist.assign(ext + 1, 0);
-                for (long i = r.lo; i < r.hi; i++) hist[lat[3 * (size_t)idx[i] + dim] - mn[dim] + 1]++;
-                for (int p = 1; p <= ext; p++) hist[p] += hist[p - 1];           // hist[p] = cells on planes < mn+p
-                int best = -1, bestClass = -1; long bestDist = 0;
-                for (int p = 1; p < ext; p++) {
-                    if (hist[p] % T || hist[p] == 0 || hist[p] == n) continue;
-                    if (hist[p] * 5 < n || hist[p] * 5 > 4 * n) continue;          // keep the two sides within 1:4
-                    const int cls = (p % 8 == 0) ? 3 : (p % 4 == 0) ? 2 : (p % 2 == 0) ? 1 : 0;
-                    const long dist = std::labs(2 * hist[p] - n);
-                    if (cls > bestClass || (cls == bestClass && dist < bestDist)) { best = p; bestClass = cls; bestDist = dist; }
-                }
-                if (best < 0) continue;
-                const int cut = mn[dim] + best;
-                auto mid = std::stable_partition(idx.begin() + r.lo, idx.begin() + r.hi, [&](int c) { return lat[3 * (size_t)c + dim] < cut; });
-                const long left = mid - (idx.begin() + r.lo);
-                stack.push_back({r.lo + left, r.hi});
-                stack.push_back({r.lo, r.lo + left});
-                done = true;
-            }
-            if (done) continue;
-        }
-        float mn[3] = {1e30f, 1e30f, 1e30f}, mx[3] = {-1e30f, -1e30f, -1e30f};
+// one cut of idx[r.lo, r.hi): false when the range is a leaf (<= T cells); else the two halves in a, b
+struct RcbRange { long lo, hi; };
+inline bool rcb_split(std::vector<int>& idx, const std::vector<float>& pos, const int* lat, RcbRange r, int T, std::vector<long>& hist,
+                      RcbRange& a, RcbRange& b) {
+    const long n = r.hi - r.lo;
+    if (n <= T) return false;
+    if (lat) {
+        int mn[3] = {1 << 30, 1 << 30, 1 << 30}, mx[3] = {-1, -1, -1};
         for (long i = r.lo; i < r.hi; i++)
-            for (int k = 0; k < 3; k++) { const float v = pos[3 * (size_t)idx[i] + k]; mn[k] = std::min(mn[k], v); mx[k] = std::max(mx[k], v); }
-        int dim = 0;
-        for (int k = 1; k < 3; k++) if (mx[k] - mn[k] > (mx[dim] - mn[dim]) * 1.0001f) dim = k;
-        const long tiles = (n + T - 1) / T;
-        const long left = (tiles / 2) * T;
-        // order by (coordinate, index): deterministic under ties
-        std::nth_element(idx.begin() + r.lo, idx.begin() + r.lo + left, idx.begin() + r.hi, [&](int a, int b) {
-            const float pa = pos[3 * (size_t)a + dim], pb = pos[3 * (size_t)b + dim];
-            return pa != pb ? pa < pb : a < b; });
-        stack.push_back({r.lo + left, r.hi});
-        stack.push_back({r.lo, r.lo + left});
+            for (int k = 0; k < 3; k++) { const int v = lat[3 * (size_t)idx[i] + k]; mn[k] = std::min(mn[k], v); mx[k] = std::max(mx[k], v); }
+        int order[3] = {0, 1, 2};
+        std::sort(order, order + 3, [&](int x, int y) { return (mx[x] - mn[x]) != (mx[y] - mn[y]) ? (mx[x] - mn[x]) > (mx[y] - mn[y]) : x < y; });
+        for (int oi = 0; oi < 3; oi++) {
+            const int dim = order[oi], ext = mx[dim] - mn[dim] + 1;
+            if (ext < 2) break;
+            hist.assign(ext + 1, 0);
+            for (long i = r.lo; i < r.hi; i++) hist[lat[3 * (size_t)idx[i] + dim] - mn[dim] + 1]++;
+            for (int p = 1; p <= ext; p++) hist[p] += hist[p - 1];           // hist[p] = cells on planes < mn+p
+            int best = -1, bestClass = -1; long bestDist = 0;
+            for (int p = 1; p < ext; p++) {
+                if (hist[p] % T || hist[p] == 0 || hist[p] == n) continue;
+                if (hist[p] * 5 < n || hist[p] * 5 > 4 * n) continue;          // keep the two sides within 1:4
+                const int cls = (p % 8 == 0) ? 3 : (p % 4 == 0) ? 2 : (p % 2 == 0) ? 1 : 0;
+                const long dist = std::labs(2 * hist[p] - n);
+                if (cls > bestClass || (cls == bestClass && dist < bestDist)) { best = p; bestClass = cls; bestDist = dist; }
+            }
+            if (best < 0) continue;
+            const int cut = mn[dim] + best;
+            auto mid = std::stable_partition(idx.begin() + r.lo, idx.begin() + r.hi, [&](int c) { return lat[3 * (size_t)c + dim] < cut; });
+            const long left = mid - (idx.begin() + r.lo);
+            a = {r.lo, r.lo + left}; b = {r.lo + left, r.hi};
+            return true;
+        }
     }
+    float mn[3] = {1e30f, 1e30f, 1e30f}, mx[3] = {-1e30f, -1e30f, -1e30f};
+    for (long i = r.lo; i < r.hi; i++)
+        for (int k = 0; k < 3; k++) { const float v = pos[3 * (size_t)idx[i] + k]; mn[k] = std::min(mn[k], v); mx[k] = std::max(mx[k], v); }
+    int dim = 0;
+    for (int k = 1; k < 3; k++) if (mx[k] - mn[k] > (mx[dim] - mn[dim]) * 1.0001f) dim = k;
+    const long tiles = (n + T - 1) / T;
+    const long left = (tiles / 2) * T;
+    // order by (coordinate, index): deterministic under ties
+    std::nth_element(idx.begin() + r.lo, idx.begin() + r.lo + left, idx.begin() + r.hi, [&](int x, int y) {
+        const float pa = pos[3 * (size_t)x + dim], pb = pos[3 * (size_t)y + dim];
+        return pa != pb ? pa < pb : x < y; });
+    a = {r.lo, r.lo + left}; b = {r.lo + left, r.hi};
+    return true;
+}
+inline void rcb(std::vector<int>& idx, const std::vector<float>& pos, const int* lat, long lo, long hi, int T) {
+    std::vector<RcbRange> stack; stack.push_back({lo, hi});
+    std::vector<long> hist;
+    RcbRange a, b;
+    while (!stack.empty()) {
+        const RcbRange r = stack.back(); stack.pop_back();
+        if (rcb_split(idx, pos, lat, r, T, hist, a, b)) { stack.push_back(b); stack.push_back(a); }
+    }
+}
+// the same cuts (a range's cut depends on nothing outside it): the first levels one after the other, then the sub-ranges on threads
+inline void rcb_parallel(std::vector<int>& idx, const std::vector<float>& pos, const int* lat, long lo, long hi, int T) {
+    const int nt = plan_threads();
+    if (nt <= 1 || hi - lo < (1L << 18)) { rcb(idx, pos, lat, lo, hi, T); return; }
+    std::vector<RcbRange> work; work.push_back({lo, hi});
+    std::vector<long> hist;
+    while ((int)work.size() < 4 * nt) {
+        std::vector<RcbRange> next; bool any = false;
+        // the ranges of one level are disjoint: cut them on threads too (two at the second level, four at the third, ...)
+        std::vector<RcbRange> as(work.size()), bs(work.size()); std::vector<char> ok(work.size(), 0);
+        parallel_for((long)work.size(), 1, [&](long l0, long l1) {
+            std::vector<long> h;
+            for (long i = l0; i < l1; i++) ok[i] = rcb_split(idx, pos, lat, work[i], T, h, as[i], bs[i]) ? 1 : 0;
+        });
+        for (size_t i = 0; i < work.size(); i++) { if (ok[i]) { next.push_back(as[i]); next.push_back(bs[i]); any = true; } }
+        if (!any) return;
+        work.swap(next);            // (leaves drop out: nothing left to do for them)
+    }
+    parallel_for((long)work.size(), 1, [&](long l0, long l1) { for (long i = l0; i < l1; i++) rcb(idx, pos, lat, work[i].lo, work[i].hi, T); });
 }
 
 }  // namespace detail
@@ -336,11 +402,15 @@ TilePlan build_tile_plan(int C, int Fi, int F, const int* owner, const int* neig
     std::vector<int> lattice;
     const int* lat = detail::detect_lattice(pos, C, lattice) ? lattice.data() : nullptr;
     lap("lattice detection");
-    detail::rcb(P.cell_new2old, pos, lat, 0, C, T);
+    detail::rcb_parallel(P.cell_new2old, pos, lat, 0, C, T);
     lap("bisection into tiles");
-    for (int t = 0; t < P.nTiles; t++) detail::rcb(P.cell_new2old, pos, lat, (long)t * T, std::min<long>((long)(t + 1) * T, C), kRound);
-    for (long b = 0; b < C; b += kRound)
-        std::sort(P.cell_new2old.begin() + b, P.cell_new2old.begin() + std::min<long>(b + kRound, C));
+    detail::parallel_for(P.nTiles, 256, [&](long t0, long t1) {
+        for (long t = t0; t < t1; t++) {
+            detail::rcb(P.cell_new2old, pos, lat, t * T, std::min<long>((t + 1) * T, C), kRound);
+            for (long b = t * T; b < std::min<long>((t + 1) * T, C); b += kRound)
+                std::sort(P.cell_new2old.begin() + b, P.cell_new2old.begin() + std::min<long>(b + kRound, C));
+        }
+    });
     lap("sub-tiles");
     P.nEarly = P.nTiles;
     if (nLocalFaces < F) {
@@ -368,100 +438,171 @@ TilePlan build_tile_plan(int C, int Fi, int F, const int* owner, const int* neig
     }
     P.cell_old2new.assign(C, -1);
     for (int i = 0; i < C; i++) P.cell_old2new[P.cell_new2old[i]] = i;
-    // ---- per sub-tile: entries (faces touching it) and their (round, lane) schedule
-    P.round_start.assign((size_t)P.nTiles * NW + 1, 0);
-    P.halo_round.assign((size_t)P.nTiles * NW, 0);
+    // ---- per sub-tile: entries (faces touching it) and their (round, lane) schedule. A tile's entries, schedules and halo list
+    // depend on nothing outside the tile: contiguous chunks of tiles are planned on threads; the numbering of the internal faces
+    // (in the order the sub-tiles first list them: a face is first listed by the tile of its lower-numbered cell) and the offsets
+    // of the per-tile lists follow from prefix sums, so the plan is the same for any number of threads.
     P.face_old2new.assign(F, -1);
     P.face_new2old.assign(F, -1);
     for (int f = Fi; f < F; f++) { P.face_old2new[f] = f; P.face_new2old[f] = f; }
-    int nextFace = 0;
-    std::vector<int> faces;
-    detail::SubTileSchedule sch;
-    std::unordered_map<uint64_t, std::vector<detail::SubTileSchedule>> memo;
     const int N = C + (F - Fi);
-    std::vector<int> slot_of(N, -1), slot_tile(N, -1);
-    P.halo_start.assign(P.nTiles + 1, 0);
-    for (int t = 0; t < P.nTiles; t++) {
-        const int c0 = t * T, c1 = std::min(C, c0 + T);
-        int nHalo = 0;
-        auto slot = [&](int cell) {           // cell: NEW index (ghosts >= C)
-            if (cell >= c0 && cell < c1) return cell - c0;
-            if (slot_tile[cell] != t) { slot_tile[cell] = t; slot_of[cell] = T + nHalo++; P.halo_cell.push_back(cell); }
-            return slot_of[cell];
-        };
-        for (int w = 0; w < NW; w++) {
-            const int s0 = c0 + w * kRound, s1 = std::min(c1, s0 + kRound);
-            faces.clear(); sch.E.clear();
-            for (int c = s0; c < s1; c++) {
-                const int oc = P.cell_new2old[c];
-                for (int j = 0; j < 6; j++) {
-                    const int f = cellFaces[(size_t)oc * 6 + j];
-                    if (f < 0 || f >= F) throw std::runtime_error("cellFaces out of range");
-                    int a = P.cell_old2new[owner[f]], b = -1;
-                    if (f < Fi) {
-                        b = P.cell_old2new[neigh[f]];
-                        if (a == b) throw std::runtime_error("face with identical owner and neighbour");
+    struct ChunkOut {
+        std::vector<int> ent_face_old; std::vector<uint32_t> ent_loc; std::vector<int> halo_cell, rounds, halo_round, halo_count, firsts;
+        int maxColours = 0, maxHalo = 0; long nEntries = 0;
+    };
+    const int nChunks = (int)std::max<long>(1, std::min<long>((long)detail::plan_threads() * 4, (P.nTiles + 63) / 64));
+    std::vector<ChunkOut> outs(nChunks);
+    auto chunk_lo = [&](int c) { return (int)((long)P.nTiles * c / nChunks); };
+    detail::parallel_for(nChunks, 1, [&](long k0, long k1) {
+        std::vector<int> faces;
+        detail::SubTileSchedule sch;
+        std::unordered_map<uint64_t, std::vector<detail::SubTileSchedule>> memo;
+        // small open-addressing maps, cleared per tile: halo cell -> slot, internal face -> seen
+        enum { kMap = 8192 };
+        std::vector<int> hkey(kMap, -1), hval(kMap, 0), hused, fkey(kMap, -1), fused;
+        for (long k = k0; k < k1; k++) {
+            ChunkOut& o = outs[k];
+            for (int t = chunk_lo((int)k); t < chunk_lo((int)k + 1); t++) {
+                const int c0 = t * T, c1 = std::min(C, c0 + T);
+                int nHalo = 0;
+                for (int u : hused) hkey[u] = -1;
+                hused.clear();
+                for (int u : fused) fkey[u] = -1;
+                fused.clear();
+                auto slot = [&](int cell) {           // cell: NEW index (ghosts >= C)
+                    if (cell >= c0 && cell < c1) return cell - c0;
+                    unsigned h = ((unsigned)cell * 2654435761u) & (kMap - 1);
+                    while (hkey[h] >= 0 && hkey[h] != cell) h = (h + 1) & (kMap - 1);
+                    if (hkey[h] < 0) {
+                        if ((int)hused.size() >= kMap / 2) throw std::runtime_error("tile halo too large");
+                        hkey[h] = cell; hval[h] = T + nHalo++; hused.push_back((int)h); o.halo_cell.push_back(cell);
                     }
-                    const bool ain = a >= s0 && a < s1, bin = b >= s0 && b < s1;
-                    // inner face of the sub-tile: list once (when reached from its lower cell)
-                    if (ain && bin && c != std::min(a, b)) continue;
-                    const bool atile = a >= c0 && a < c1, btile = b >= c0 && b < c1;
-                    detail::SubTileSchedule::Ent e;
-                    e.both = ain && bin;
-                    e.a = ain ? a - s0 : b - s0; e.b = e.both ? b - s0 : -1;
-                    e.pref = (atile && btile) ? 0 : 1;      // entries that read a halo slot go to the late rounds (overlap of the halo gather)
-                    faces.push_back(f); sch.E.push_back(e);
+                    return hval[h];
+                };
+                auto first_seen = [&](int f) {        // true the first time this tile lists internal face f
+                    unsigned h = ((unsigned)f * 2654435761u) & (kMap - 1);
+                    while (fkey[h] >= 0 && fkey[h] != f) h = (h + 1) & (kMap - 1);
+                    if (fkey[h] == f) return false;
+                    if ((int)fused.size() >= kMap / 2) throw std::runtime_error("tile with too many faces");
+                    fkey[h] = f; fused.push_back((int)h);
+                    return true;
+                };
+                const size_t firsts0 = o.firsts.size();
+                for (int w = 0; w < NW; w++) {
+                    const int s0 = c0 + w * kRound, s1 = std::min(c1, s0 + kRound);
+                    faces.clear(); sch.E.clear();
+                    for (int c = s0; c < s1; c++) {
+                        const int oc = P.cell_new2old[c];
+                        for (int j = 0; j < 6; j++) {
+                            const int f = cellFaces[(size_t)oc * 6 + j];
+                            if (f < 0 || f >= F) throw std::runtime_error("cellFaces out of range");
+                            int a = P.cell_old2new[owner[f]], b = -1;
+                            if (f < Fi) {
+                                b = P.cell_old2new[neigh[f]];
+                                if (a == b) throw std::runtime_error("face with identical owner and neighbour");
+                            }
+                            const bool ain = a >= s0 && a < s1, bin = b >= s0 && b < s1;
+                            // inner face of the sub-tile: list once (when reached from its lower cell)
+                            if (ain && bin && c != std::min(a, b)) continue;
+                            const bool atile = a >= c0 && a < c1, btile = b >= c0 && b < c1;
+                            detail::SubTileSchedule::Ent e;
+                            e.both = ain && bin;
+                            e.a = ain ? a - s0 : b - s0; e.b = e.both ? b - s0 : -1;
+                            e.pref = (atile && btile) ? 0 : 1;      // entries that read a halo slot go to the late rounds (overlap of the halo gather)
+                            faces.push_back(f); sch.E.push_back(e);
+                        }
+                    }
+                    {   // sub-tiles with the same local face graph (all interior sub-tiles of a structured block) share one schedule
+                        uint64_t key = 1469598103934665603ull;
+                        for (const auto& e : sch.E) { key ^= (uint64_t)(e.a | (e.b + 1) << 6 | (int)e.both << 13 | e.pref << 14); key *= 1099511628211ull; }
+                        auto& bucket = memo[key];
+                        const detail::SubTileSchedule* hit = nullptr;
+                        for (const auto& m_ : bucket) {
+                            if (m_.E.size() != sch.E.size()) continue;
+                            bool same = true;
+                            for (size_t i = 0; i < sch.E.size() && same; i++)
+                                same = m_.E[i].a == sch.E[i].a && m_.E[i].b == sch.E[i].b && m_.E[i].both == sch.E[i].both && m_.E[i].pref == sch.E[i].pref;
+                            if (same) { hit = &m_; break; }
+                        }
+                        if (hit) { sch.home = hit->home; sch.other = hit->other; sch.round = hit->round; sch.R = hit->R; }
+                        else { sch.solve(); if (memo.size() < 8192) bucket.push_back(sch); }
+                    }
+                    const int Rw = faces.empty() ? 0 : sch.R;
+                    o.maxColours = std::max(o.maxColours, Rw);
+                    std::vector<int> at((size_t)Rw * kRound, -1), from((size_t)Rw * kRound, -1);
+                    for (size_t i = 0; i < faces.size(); i++) {
+                        at[(size_t)sch.round[i] * kRound + sch.home[i]] = (int)i;
+                        if (sch.other[i] >= 0) from[(size_t)sch.round[i] * kRound + sch.other[i]] = sch.home[i];
+                    }
+                    int firstHaloRound = -1;
+                    for (int r = 0; r < Rw; r++) for (int l = 0; l < kRound; l++) {
+                        const int i = at[(size_t)r * kRound + l], src = from[(size_t)r * kRound + l];
+                        if (i < 0) { o.ent_face_old.push_back(-1); o.ent_loc.push_back(tile_pack(0, 0, 0, 0, 0, 0, src >= 0, src >= 0 ? src : 0)); continue; }
+                        const int f = faces[i];
+                        const int a = P.cell_old2new[owner[f]];
+                        const int b = f < Fi ? P.cell_old2new[neigh[f]] : neigh[f];
+                        if (b < 0 || b >= N) throw std::runtime_error("neighbour out of range");
+                        // numbered by the tile of the face's lower-numbered cell, in the order that tile first lists it
+                        if (f < Fi && std::min(a, b) / T == t && first_seen(f)) o.firsts.push_back(f);
+                        const bool flip = (a - s0) != l;                 // the home cell is the face's neighbour
+                        if (flip && (f >= Fi || b - s0 != l)) throw std::runtime_error("tile schedule: home cell is not a cell of the face");
+                        const int lo = slot(flip ? b : a), ln = slot(flip ? a : b);
+                        if (lo != w * kRound + l) throw std::runtime_error("tile schedule: home slot mismatch");
+                        if (ln >= 1024) throw std::runtime_error("tile halo too large");
+                        if (ln >= T && firstHaloRound < 0) firstHaloRound = r;
+                        o.ent_face_old.push_back(f);
+                        o.ent_loc.push_back(tile_pack(ln, f < Fi ? 0 : (int)bkind[f - Fi], 1, sch.other[i] >= 0, b >= C, flip, src >= 0, src >= 0 ? src : 0));
+                        o.nEntries++;
+                    }
+                    o.halo_round.push_back(firstHaloRound < 0 ? Rw : firstHaloRound);
+                    o.rounds.push_back(Rw);
                 }
+                o.maxHalo = std::max(o.maxHalo, nHalo);
+                o.halo_count.push_back(nHalo);
+                (void)firsts0;
             }
-            {   // sub-tiles with the same local face graph (all interior sub-tiles of a structured block) share one schedule
-                uint64_t key = 1469598103934665603ull;
-                for (const auto& e : sch.E) { key ^= (uint64_t)(e.a | (e.b + 1) << 6 | (int)e.both << 13 | e.pref << 14); key *= 1099511628211ull; }
-                auto& bucket = memo[key];
-                const detail::SubTileSchedule* hit = nullptr;
-                for (const auto& m_ : bucket) {
-                    if (m_.E.size() != sch.E.size()) continue;
-                    bool same = true;
-                    for (size_t i = 0; i < sch.E.size() && same; i++)
-                        same = m_.E[i].a == sch.E[i].a && m_.E[i].b == sch.E[i].b && m_.E[i].both == sch.E[i].both && m_.E[i].pref == sch.E[i].pref;
-                    if (same) { hit = &m_; break; }
-                }
-                if (hit) { sch.home = hit->home; sch.other = hit->other; sch.round = hit->round; sch.R = hit->R; }
-                else { sch.solve(); if (memo.size() < 8192) bucket.push_back(sch); }
-            }
-            const int Rw = faces.empty() ? 0 : sch.R;
-            P.maxColours = std::max(P.maxColours, Rw);
-            std::vector<int> at((size_t)Rw * kRound, -1), from((size_t)Rw * kRound, -1);
-            for (size_t i = 0; i < faces.size(); i++) {
-                at[(size_t)sch.round[i] * kRound + sch.home[i]] = (int)i;
-                if (sch.other[i] >= 0) from[(size_t)sch.round[i] * kRound + sch.other[i]] = sch.home[i];
-            }
-            int firstHaloRound = -1;
-            for (int r = 0; r < Rw; r++) for (int l = 0; l < kRound; l++) {
-                const int i = at[(size_t)r * kRound + l], src = from[(size_t)r * kRound + l];
-                if (i < 0) { P.ent_face.push_back(-1); P.ent_loc.push_back(tile_pack(0, 0, 0, 0, 0, 0, src >= 0, src >= 0 ? src : 0)); continue; }
-                const int f = faces[i];
-                if (f < Fi && P.face_old2new[f] < 0) { P.face_old2new[f] = nextFace; P.face_new2old[nextFace] = f; nextFace++; }
-                const int a = P.cell_old2new[owner[f]];
-                const int b = f < Fi ? P.cell_old2new[neigh[f]] : neigh[f];
-                if (b < 0 || b >= N) throw std::runtime_error("neighbour out of range");
-                const bool flip = (a - s0) != l;                 // the home cell is the face's neighbour
-                if (flip && (f >= Fi || b - s0 != l)) throw std::runtime_error("tile schedule: home cell is not a cell of the face");
-                const int lo = slot(flip ? b : a), ln = slot(flip ? a : b);
-                if (lo != w * kRound + l) throw std::runtime_error("tile schedule: home slot mismatch");
-                if (ln >= 1024) throw std::runtime_error("tile halo too large");
-                if (ln >= T && firstHaloRound < 0) firstHaloRound = r;
-                P.ent_face.push_back(P.face_old2new[f]);
-                P.ent_loc.push_back(tile_pack(ln, f < Fi ? 0 : (int)bkind[f - Fi], 1, sch.other[i] >= 0, b >= C, flip, src >= 0, src >= 0 ? src : 0));
-                P.nEntries++;
-            }
-            P.halo_round[(size_t)t * NW + w] = firstHaloRound < 0 ? Rw : firstHaloRound;
-            P.round_start[(size_t)t * NW + w + 1] = (int)(P.ent_face.size() / (size_t)kRound);
         }
-        P.maxHalo = std::max(P.maxHalo, nHalo);
-        P.halo_start[t + 1] = (int)P.halo_cell.size();
+    });
+    // offsets of the chunks' lists; face numbers
+    std::vector<size_t> entOff(nChunks + 1, 0), haloOff(nChunks + 1, 0), faceOff(nChunks + 1, 0);
+    for (int k = 0; k < nChunks; k++) {
+        entOff[k + 1] = entOff[k] + outs[k].ent_face_old.size(); haloOff[k + 1] = haloOff[k] + outs[k].halo_cell.size();
+        faceOff[k + 1] = faceOff[k] + outs[k].firsts.size();
+        P.maxColours = std::max(P.maxColours, outs[k].maxColours); P.maxHalo = std::max(P.maxHalo, outs[k].maxHalo); P.nEntries += outs[k].nEntries;
+    }
+    const int nextFace = (int)faceOff[nChunks];
+    if (nextFace != Fi) throw std::runtime_error("internal face not reachable from any cell (broken cellFaces)");
+    detail::parallel_for(nChunks, 1, [&](long k0, long k1) {
+        for (long k = k0; k < k1; k++)
+            for (size_t i = 0; i < outs[k].firsts.size(); i++) {
+                const int f = outs[k].firsts[i], nf = (int)(faceOff[k] + i);
+                P.face_old2new[f] = nf; P.face_new2old[nf] = f;
+            }
+    });
+    P.ent_face.resize(entOff[nChunks]); P.ent_loc.resize(entOff[nChunks]); P.halo_cell.resize(haloOff[nChunks]);
+    detail::parallel_for(nChunks, 1, [&](long k0, long k1) {
+        for (long k = k0; k < k1; k++) {
+            const ChunkOut& o = outs[k];
+            for (size_t i = 0; i < o.ent_face_old.size(); i++) {
+                const int f = o.ent_face_old[i];
+                P.ent_face[entOff[k] + i] = f < 0 ? -1 : P.face_old2new[f];
+                P.ent_loc[entOff[k] + i] = o.ent_loc[i];
+            }
+            std::copy(o.halo_cell.begin(), o.halo_cell.end(), P.halo_cell.begin() + haloOff[k]);
+        }
+    });
+    P.round_start.assign((size_t)P.nTiles * NW + 1, 0);
+    P.halo_round.assign((size_t)P.nTiles * NW, 0);
+    P.halo_start.assign(P.nTiles + 1, 0);
+    {
+        size_t sw = 0, st = 0; int rounds = 0, halo = 0;
+        for (int k = 0; k < nChunks; k++) {
+            for (size_t i = 0; i < outs[k].rounds.size(); i++, sw++) { P.halo_round[sw] = outs[k].halo_round[i]; rounds += outs[k].rounds[i]; P.round_start[sw + 1] = rounds; }
+            for (size_t i = 0; i < outs[k].halo_count.size(); i++, st++) { halo += outs[k].halo_count[i]; P.halo_start[st + 1] = halo; }
+            outs[k] = ChunkOut();             // release as we go
+        }
     }
     lap("entries + schedules");
-    if (nextFace != Fi) throw std::runtime_error("internal face not reachable from any cell (broken cellFaces)");
     return P;
 }
 

@@ -1,1 +1,2 @@
-VARIANTS="pf0 pf1" SIZES="256" bash tools/gpu_exp.sh
+mkdir -p gpurun_out
+ADFVM_TILE_TIMING=1 python tools/setup_time.py --n 256 > gpurun_out/s8_setup256.log 2>&1; cat gpurun_out/s8_setup256.log; nproc
