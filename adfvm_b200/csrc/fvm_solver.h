@@ -793,7 +793,7 @@ public:
     void ensure_visc_buffers() {
         if (vlam) return;
         vlam = dalloc<R>((size_t)m.sC); vM = dalloc<R>((size_t)m.sN); vcf = dalloc<R>((size_t)6 * m.sC); vdg = dalloc<R>((size_t)m.sC);
-        vx = dalloc<R>((size_t)5 * m.sN); vp = dalloc<R>((size_t)5 * m.sN); vr = dalloc<R>((size_t)5 * m.sC); vq = dalloc<R>((size_t)5 * m.sC);
+        vx = dalloc<R>((size_t)5 * m.sN); vp = dalloc<R>((size_t)5 * m.sN + kRowSlack /* the tile kernel bulk-copies whole T-cell rows of vp */); vr = dalloc<R>((size_t)5 * m.sC); vq = dalloc<R>((size_t)5 * m.sC);
         vs = dalloc<R>(VS_SIZE);
     }
     // M_2norm (vM [nCells], ghost rows filled with the default boundary + halo) of the state whose primitives (ghost rows
@@ -835,7 +835,7 @@ public:
             if (it >= visc_maxit) throw std::runtime_error("adjoint viscosity: the diffusion solve did not converge");
             for (int inner = 0; inner < 4; inner++, it++) {            // host looks at the residual every fourth iteration
                 halo_begin(vp, 5); halo_end();
-                ex.reduce_sum5(C, ViscSpmvBody<R>{m, vcf, vdg, vp, vq}, vs + VS_PQ);
+                visc_spmv();
                 if (comm) comm->allreduce_sum_device(vs + VS_PQ, 5, ex.stream_handle());
                 ex.reduce_sum5(C, ViscUpdateBody<R>{m, vdg, vp, vq, rz, vs + VS_PQ, vx, vr}, rzn); launches += 4;
                 if (comm) comm->allreduce_sum_device(rzn, 5, ex.stream_handle());
@@ -846,6 +846,17 @@ public:
         }
         visc_iterations = it;
         run(C, ViscFinishBody<R>{m, vx, Aio});
+    }
+    // q = A p and the five dot products p . q: tile kernel (search direction staged in shared memory) + sum of the per-tile partials
+    R* vpart = nullptr;
+    template <int T, int TS> void run_visc_spmv_tile() { run_tiles_range(0, m.nTiles, ViscSpmvTileBody<R, T, TS>{m, vcf, vdg, vp, vq, vpart}); }
+    void visc_spmv() {
+        if (!vpart) vpart = dalloc<R>((size_t)5 * m.nTiles + 8);
+        if (tile_variant == 0) run_visc_spmv_tile<128, 128 + kHalo128r>();
+        else if (tile_variant == 1) run_visc_spmv_tile<128, 128 + kHalo128s>();
+        else if (tile_variant == 2) run_visc_spmv_tile<128, 128 + kHalo128>();
+        else run_visc_spmv_tile<64, 64 + kHalo64>();
+        ex.reduce_sum5(m.nTiles, ViscPartialBody<R>{vpart}, vs + VS_PQ);
     }
     void adjoint_viscous(R dt) { viscosity_field(Q[0], G[0]); viscosity_apply(A[0], dt); }
     // diagnostic (the reference's write_M_2norm, apps/adjoint.py:26,139): M_2norm [nCells][1] of a host state, reference numbering

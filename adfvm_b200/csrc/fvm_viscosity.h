@@ -16,6 +16,7 @@
 // field instead (matop_cuda.cpp:205), its CPU build GMRES + hypre; all three approximate the same linear system.
 #pragma once
 #include "fvm_bodies.h"
+#include "fvm_tile_bodies.h"
 
 namespace fvm {
 
@@ -232,6 +233,127 @@ template <typename R> struct ViscSpmvBody {
         for (int k = 0; k < 5; k++) { q[(long)k * m.sC + c] = y[k]; o.v[k] = y[k] * p[(long)k * m.sN + c]; }
         return o;
     }
+};
+// The same product as a tile kernel (one CTA per tile of the flux kernels' plan, one thread per cell): the search direction of the
+// tile's own cells arrives by bulk copy, that of its halo cells (face neighbours in other tiles, processor ghost rows) by the
+// asynchronous gather, and the six-neighbour gather of five fields reads shared memory through the precomputed neighbour slots -
+// the staging of GradAdjTileBody. Writes q and the tile's five partial dot products p . q (fixed-order tree over the CTA) to
+// part [nTiles][5]; ViscPartialBody sums them.
+template <typename R, int T, int TS> struct ViscSpmvTileBody {
+    static constexpr const char* kName = "visc_cg_spmv";
+    static constexpr int kThreads = T;
+    static constexpr int kMinBlocks = 4;
+    static constexpr int kPrefetchDistance = 148 * kMinBlocks;
+    MeshDev<R> m; const R *cf, *dg, *p; R *q, *part;
+#if defined(__CUDACC__)
+    static constexpr size_t kRedOff = ((size_t)5 * TS * sizeof(R) + 15) / 16 * 16;
+    static constexpr size_t kBarOff = kRedOff + (size_t)5 * (T / 32) * sizeof(R);
+    static size_t smem_bytes() { return kBarOff + 16; }
+#endif
+    FVM_HD void cell(int c, int lo, const R* ps, R* y) const {
+        const R d = dg[c];
+        for (int k = 0; k < 5; k++) y[k] = d * ps[k * TS + lo];
+        for (int j = 0; j < 6; j++) {
+            const R v = cf[(long)j * m.sC + c];
+            if (v == R(0)) continue;                       // uncoupled face (local boundary): its slot is never read
+            const int sl = m.nbrSlot[(long)j * m.sC + c] & 0x7fff;
+            for (int k = 0; k < 5; k++) y[k] -= v * ps[k * TS + sl];
+        }
+    }
+#if !defined(__CUDACC__)
+    void host_tile(int t) const {
+        const int c0 = t * T, nc = (m.nInternalCells - c0 < T) ? m.nInternalCells - c0 : T;
+        std::vector<R> ps((size_t)5 * TS, std::numeric_limits<R>::quiet_NaN());
+        for (int l = 0; l < nc; l++) for (int k = 0; k < 5; k++) ps[(size_t)k * TS + l] = p[(long)k * m.sN + c0 + l];
+        for (int h = m.halo_start[t]; h < m.halo_start[t + 1]; h++)
+            for (int k = 0; k < 5; k++) ps[(size_t)k * TS + T + h - m.halo_start[t]] = p[(long)k * m.sN + m.halo_cell[h]];
+        // the CTA's tree: per warp a shuffle tree over 32 lanes, then the warps in order
+        R tot[5] = {0, 0, 0, 0, 0};
+        for (int w = 0; w < T / 32; w++) {
+            R lane[32][5];
+            for (int l = 0; l < 32; l++) {
+                const int i = w * 32 + l;
+                for (int k = 0; k < 5; k++) lane[l][k] = R(0);
+                if (i >= nc) continue;
+                R y[5]; cell(c0 + i, i, ps.data(), y);
+                for (int k = 0; k < 5; k++) { q[(long)k * m.sC + c0 + i] = y[k]; lane[l][k] = y[k] * ps[(size_t)k * TS + i]; }
+            }
+            for (int o = 16; o > 0; o >>= 1) for (int l = 0; l < o; l++) for (int k = 0; k < 5; k++) lane[l][k] += lane[l + o][k];
+            for (int k = 0; k < 5; k++) tot[k] += lane[0][k];
+        }
+        for (int k = 0; k < 5; k++) part[(long)t * 5 + k] = tot[k];
+    }
+#else
+    __device__ __forceinline__ void device_tile(int t, unsigned char* smem) const {
+        const int c0 = t * T, nc = min(T, m.nInternalCells - c0);
+        const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+        R* ps = reinterpret_cast<R*>(smem);
+        R* red = reinterpret_cast<R*>(smem + kRedOff);
+        unsigned long long* bars = reinterpret_cast<unsigned long long*>(smem + kBarOff);
+        unsigned long long *bar_rows = &bars[0], *bar_halo = &bars[1];
+        const int h0 = m.halo_start[t], nh = m.halo_start[t + 1] - h0;
+        constexpr unsigned kRow = T * (unsigned)sizeof(R);
+        if (tid == 0) { mbar_init(bar_rows, 1); mbar_init(bar_halo, T); mbar_fence_init(); }
+        __syncthreads();
+        if (tid == 0) {
+            mbar_expect_tx(bar_rows, 5u * kRow);
+            for (int k = 0; k < 5; k++) bulk_g2s(ps + k * TS, p + (long)k * m.sN + c0, kRow, bar_rows);
+        }
+        {
+            constexpr int kIter = (TS - T + T - 1) / T;
+            int hc[kIter];
+            #pragma unroll
+            for (int i = 0; i < kIter; i++) { const int h = tid + i * T; hc[i] = h < nh ? m.halo_cell[h0 + h] : -1; }
+            #pragma unroll
+            for (int i = 0; i < kIter; i++) {
+                const int cellh = hc[i], slot = T + tid + i * T;
+                if (cellh < 0) continue;
+                for (int k = 0; k < 5; k++) cp_async_elem<sizeof(R)>(ps + k * TS + slot, p + (long)k * m.sN + cellh);
+            }
+        }
+        cp_async_arrive(bar_halo);
+        {   // L2 prefetch of the rows of the tile that runs in this CTA slot one wave later
+            const int tn = t + kPrefetchDistance;
+            if (tn < m.nTiles && tid < 5) bulk_prefetch_l2(p + (long)tid * m.sN + (long)tn * T, kRow);
+        }
+        // per-cell inputs that do not depend on the staged rows, loaded before the wait
+        R v[6], d = R(0); int sl[6];
+        if (tid < nc) {
+            d = dg[c0 + tid];
+            #pragma unroll
+            for (int j = 0; j < 6; j++) { v[j] = cf[(long)j * m.sC + c0 + tid]; sl[j] = m.nbrSlot[(long)j * m.sC + c0 + tid] & 0x7fff; }
+        }
+        mbar_wait(bar_rows, 0);
+        mbar_wait(bar_halo, 0);
+        R dot[5] = {R(0), R(0), R(0), R(0), R(0)};
+        if (tid < nc) {
+            R y[5];
+            #pragma unroll
+            for (int k = 0; k < 5; k++) y[k] = d * ps[k * TS + tid];
+            #pragma unroll
+            for (int j = 0; j < 6; j++) {
+                if (v[j] == R(0)) continue;
+                #pragma unroll
+                for (int k = 0; k < 5; k++) y[k] -= v[j] * ps[k * TS + sl[j]];
+            }
+            #pragma unroll
+            for (int k = 0; k < 5; k++) { q[(long)k * m.sC + c0 + tid] = y[k]; dot[k] = y[k] * ps[k * TS + tid]; }
+        }
+        #pragma unroll
+        for (int k = 0; k < 5; k++) {
+            R x = dot[k];
+            for (int o = 16; o > 0; o >>= 1) x += __shfl_down_sync(0xffffffffu, x, o);
+            if (lane == 0) red[w * 5 + k] = x;
+        }
+        __syncthreads();
+        if (tid < 5) { R x = R(0); for (int i = 0; i < T / 32; i++) x += red[i * 5 + tid]; part[(long)t * 5 + tid] = x; }
+    }
+#endif
+};
+template <typename R> struct ViscPartialBody {
+    static constexpr const char* kName = "visc_cg_dot";
+    const R* part;
+    FVM_HD V5<R> operator()(int t) const { V5<R> o; for (int k = 0; k < 5; k++) o.v[k] = part[(long)t * 5 + k]; return o; }
 };
 // alpha = rz / pq (device scalars); x += alpha p, r -= alpha q; returns r . r/dg
 template <typename R> struct ViscUpdateBody {
