@@ -837,7 +837,9 @@ public:
                 halo_begin(vp, 5); halo_end();
                 visc_spmv();
                 if (comm) comm->allreduce_sum_device(vs + VS_PQ, 5, ex.stream_handle());
-                ex.reduce_sum5(C, ViscUpdateBody<R>{m, vdg, vp, vq, rz, vs + VS_PQ, vx, vr}, rzn); launches += 4;
+                if (m.T == 128) run_tiles_range(0, m.nTiles, ViscUpdateTileBody<R, 128>{m, vdg, vp, vq, rz, vs + VS_PQ, vx, vr, vpart});
+                else run_tiles_range(0, m.nTiles, ViscUpdateTileBody<R, 64>{m, vdg, vp, vq, rz, vs + VS_PQ, vx, vr, vpart});
+                ex.reduce_sum5(m.nTiles, ViscPartialBody<R>{vpart}, rzn); launches += 4;
                 if (comm) comm->allreduce_sum_device(rzn, 5, ex.stream_handle());
                 run(C, ViscDirBody<R>{m, vdg, vr, rz, rzn, vp});
                 std::swap(rz, rzn);

@@ -370,6 +370,58 @@ template <typename R> struct ViscUpdateBody {
         return o;
     }
 };
+// the same update as a tile kernel (one CTA per tile, one thread per cell, nothing staged): every SM streams its own cells with
+// all loads of a cell in flight at once, the five dot products leave as per-tile partial sums (fixed-order tree) in part [nTiles][5]
+template <typename R, int T> struct ViscUpdateTileBody {
+    static constexpr const char* kName = "visc_cg_update";
+    static constexpr int kThreads = T;
+    static constexpr int kMinBlocks = 8;
+    MeshDev<R> m; const R *dg, *p, *q, *rz, *pq; R *x, *r, *part;
+#if defined(__CUDACC__)
+    static size_t smem_bytes() { return (size_t)5 * (T / 32) * sizeof(R); }
+#endif
+    FVM_HD void cell(int c, R* o) const {
+        const R id = R(1) / dg[c];
+        for (int k = 0; k < 5; k++) {
+            const R al = pq[k] != R(0) ? rz[k] / pq[k] : R(0);
+            x[(long)k * m.sN + c] += al * p[(long)k * m.sN + c];
+            const R rr = r[(long)k * m.sC + c] - al * q[(long)k * m.sC + c];
+            r[(long)k * m.sC + c] = rr; o[k] = rr * rr * id;
+        }
+    }
+#if !defined(__CUDACC__)
+    void host_tile(int t) const {
+        const int c0 = t * T, nc = (m.nInternalCells - c0 < T) ? m.nInternalCells - c0 : T;
+        R tot[5] = {0, 0, 0, 0, 0};
+        for (int w = 0; w < T / 32; w++) {
+            R lane[32][5];
+            for (int l = 0; l < 32; l++) {
+                for (int k = 0; k < 5; k++) lane[l][k] = R(0);
+                if (w * 32 + l < nc) cell(c0 + w * 32 + l, lane[l]);
+            }
+            for (int o = 16; o > 0; o >>= 1) for (int l = 0; l < o; l++) for (int k = 0; k < 5; k++) lane[l][k] += lane[l + o][k];
+            for (int k = 0; k < 5; k++) tot[k] += lane[0][k];
+        }
+        for (int k = 0; k < 5; k++) part[(long)t * 5 + k] = tot[k];
+    }
+#else
+    __device__ __forceinline__ void device_tile(int t, unsigned char* smem) const {
+        const int c0 = t * T, nc = min(T, m.nInternalCells - c0);
+        const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+        R* red = reinterpret_cast<R*>(smem);
+        R o[5] = {R(0), R(0), R(0), R(0), R(0)};
+        if (tid < nc) cell(c0 + tid, o);
+        #pragma unroll
+        for (int k = 0; k < 5; k++) {
+            R v = o[k];
+            for (int s = 16; s > 0; s >>= 1) v += __shfl_down_sync(0xffffffffu, v, s);
+            if (lane == 0) red[w * 5 + k] = v;
+        }
+        __syncthreads();
+        if (tid < 5) { R v = R(0); for (int i = 0; i < T / 32; i++) v += red[i * 5 + tid]; part[(long)t * 5 + tid] = v; }
+    }
+#endif
+};
 // beta = rz_new / rz; p = r/dg + beta p
 template <typename R> struct ViscDirBody {
     static constexpr const char* kName = "visc_cg_dir";
