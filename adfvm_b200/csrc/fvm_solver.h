@@ -641,6 +641,15 @@ public:
         pb.s1 = (R)RK_BETA[0] * dt; pb.s2 = (R)RK_BETA[1] * dt; pb.s3 = (R)RK_BETA[2] * dt;
         run_tiles_range(t0, nt, pb);
     }
+    // the reverse flux kernel specialised for the physics of the context (Roe + Sutherland / constant viscosity at compile time)
+    template <int T, int TS> void run_flux_grad_tile(int s, R coef, int t0, int nt) {
+        if (ph.riemann == RIEMANN_ROE && ph.mu_law == MU_SUTHERLAND)
+            run_tiles_range(t0, nt, FluxGradTileBody<R, T, TS, SPEC_ROE_SUTHERLAND>{ph, m, Q[s], G[s], A[s + 1], coef, Qb, Gb});
+        else if (ph.riemann == RIEMANN_ROE && ph.mu_law == MU_CONSTANT)
+            run_tiles_range(t0, nt, FluxGradTileBody<R, T, TS, SPEC_ROE_CONSTANT>{ph, m, Q[s], G[s], A[s + 1], coef, Qb, Gb});
+        else
+            run_tiles_range(t0, nt, FluxGradTileBody<R, T, TS, SPEC_GENERIC>{ph, m, Q[s], G[s], A[s + 1], coef, Qb, Gb});
+    }
     void adjoint_reverse(R dt, R obja) {
         const int C = m.nInternalCells;
         for (int s = 2; s >= 0; s--) {
@@ -649,10 +658,10 @@ public:
             // late tiles first: they produce the ghost-row adjoints that travel; the early tiles overlap the exchange
             for (int part = 1; part >= 0; part--) {
                 const int t0 = part ? Te : 0, nt = part ? m.nTiles - Te : Te;
-                if (tile_variant == 0) run_tiles_range(t0, nt, FluxGradTileBody<R, 128, 128 + kHalo128r>{ph, m, Q[s], G[s], A[s + 1], coef, Qb, Gb});
-                else if (tile_variant == 1) run_tiles_range(t0, nt, FluxGradTileBody<R, 128, 128 + kHalo128s>{ph, m, Q[s], G[s], A[s + 1], coef, Qb, Gb});
-                else if (tile_variant == 2) run_tiles_range(t0, nt, FluxGradTileBody<R, 128, 128 + kHalo128>{ph, m, Q[s], G[s], A[s + 1], coef, Qb, Gb});
-                else run_tiles_range(t0, nt, FluxGradTileBody<R, 64, 64 + kHalo64>{ph, m, Q[s], G[s], A[s + 1], coef, Qb, Gb});
+                if (tile_variant == 0) run_flux_grad_tile<128, 128 + kHalo128r>(s, coef, t0, nt);
+                else if (tile_variant == 1) run_flux_grad_tile<128, 128 + kHalo128s>(s, coef, t0, nt);
+                else if (tile_variant == 2) run_flux_grad_tile<128, 128 + kHalo128>(s, coef, t0, nt);
+                else run_flux_grad_tile<64, 64 + kHalo64>(s, coef, t0, nt);
                 if (part) halo_reverse_begin(Gb, 15);
             }
             const R* rG = halo_reverse_end();

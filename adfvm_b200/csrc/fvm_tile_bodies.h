@@ -360,7 +360,11 @@ template <typename R, int T, int TS> struct FluxTileBody {
 //   abar = adjoint of the stage OUTPUT state [5][sC]; coef = -beta_ii*dt (d W_new / d residual)
 //   outputs Qb [5][sN], Gb [15][sN]: rows of internal cells (Gb divided by the cell volume, see GradAdjUpdateBody)
 //   and of the ghost cells of ALL boundary faces
-template <typename R, int T, int TS> struct FluxGradTileBody {
+// SPEC: 0 = Riemann solver and viscosity law read from Phys at run time; 1 = Roe + Sutherland, 2 = Roe + constant viscosity as
+// compile-time constants (the device code works on a copy of Phys with those fields overwritten: the branches on them fold, the
+// coupled-face VJP loses its dead Lax-Friedrichs / other-law code; measured -6 % on the kernel at 256^3, profiles/README.md)
+enum { SPEC_GENERIC = 0, SPEC_ROE_SUTHERLAND = 1, SPEC_ROE_CONSTANT = 2 };
+template <typename R, int T, int TS, int SPEC = 0> struct FluxGradTileBody {
     static constexpr const char* kName = "flux_grad_tile";
     static constexpr int kThreads = T, NW = T / 32;
     // fp64: 254 registers, 2 CTAs per SM. A third CTA (168 registers; the compact variant fits three in shared memory) was
@@ -389,7 +393,7 @@ template <typename R, int T, int TS> struct FluxGradTileBody {
     // one entry of the lane whose cell sits in slot lo: own[20] += the home cell's input adjoints; snd[20] = the other
     // cell's (set when e.sn; zero otherwise); ghost >= 0: global row of the other cell when it is a ghost cell, whose
     // adjoints are stored straight to Qb/Gb
-    FVM_HD void face(const Geom<R>& gm, const TileEntry& e, int lo, int ghost, const R* qg, const R* ab, const R* volh, R* own, R* snd) const {
+    FVM_HD void face(const Phys<R>& ph, const Geom<R>& gm, const TileEntry& e, int lo, int ghost, const R* qg, const R* ab, const R* volh, R* own, R* snd) const {
         Prim<R> qL, qR; Grad<R> gL, gR;
         tile_load_cell<R, TS>(qg, lo, qL, gL); tile_load_cell<R, TS>(qg, e.ln, qR, gR);
         const R sO = gm.area * coef;
@@ -445,7 +449,7 @@ template <typename R, int T, int TS> struct FluxGradTileBody {
                     if (e[i].ghost != (e[i].ln >= T && m.halo_cell[m.halo_start[t] + e[i].ln - T] >= m.nInternalCells)) throw std::runtime_error("ghost flag inconsistent");
                     if (e[i].kind != FACE_COUPLED && !e[i].ghost) throw std::runtime_error("boundary-kind entry without a ghost cell");
                     Geom<R> gm; tile_load_geom<R, 32>(chunk, i, gm);
-                    face(gm, e[i], w * 32 + i, ghost_of(t, e[i]), qg.data(), ab.data(), volh.data(), acc[i], snd[i]);
+                    face(ph, gm, e[i], w * 32 + i, ghost_of(t, e[i]), qg.data(), ab.data(), volh.data(), acc[i], snd[i]);
                 }
                 for (int i = 0; i < 32; i++) if (e[i].has_src) for (int k = 0; k < 20; k++) acc[i][k] += snd[e[i].src][k];
             }
@@ -518,6 +522,9 @@ template <typename R, int T, int TS> struct FluxGradTileBody {
         for (int k = 0; k < 5; k++) ab[k * TS + tid] *= ivh;
         __syncthreads();
         if (nr == 0) return;
+        Phys<R> phs = ph;
+        if (SPEC == SPEC_ROE_SUTHERLAND) { phs.riemann = RIEMANN_ROE; phs.mu_law = MU_SUTHERLAND; }
+        if (SPEC == SPEC_ROE_CONSTANT) { phs.riemann = RIEMANN_ROE; phs.mu_law = MU_CONSTANT; }
         R acc[20];
         for (int k = 0; k < 20; k++) acc[k] = R(0);
         for (int r = 0; r < nr; r++) {
@@ -533,7 +540,7 @@ template <typename R, int T, int TS> struct FluxGradTileBody {
             }
             R snd[20];
             for (int k = 0; k < 20; k++) snd[k] = R(0);
-            if (e.valid) face(gm, e, tid, ghost_of(t, e), qg, ab, volh, acc, snd);
+            if (e.valid) face(phs, gm, e, tid, ghost_of(t, e), qg, ab, volh, acc, snd);
             if (__any_sync(0xffffffffu, e.has_src)) {
                 for (int k = 0; k < 20; k++) { const R v = __shfl_sync(0xffffffffu, snd[k], e.src); if (e.has_src) acc[k] += v; }
             }

@@ -1,4 +1,6 @@
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "visc" > gpurun_out/s12_pytest.log 2>&1; tail -2 gpurun_out/s12_pytest.log
-timeout 300 python tools/visc_bench.py --n 256 > gpurun_out/s12_visc256.json 2> gpurun_out/s12_visc256.err; cat gpurun_out/s12_visc256.json; tail -3 gpurun_out/s12_visc256.err
-timeout 300 python tools/visc_bench.py --n 256 --dtype f32 --type turkel > gpurun_out/s12_visc256_f32.json 2> gpurun_out/s12_visc256_f32.err; cat gpurun_out/s12_visc256_f32.json
+timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/s13_pytest.log 2>&1; tail -2 gpurun_out/s13_pytest.log
+timeout 600 python bench.py --steps 6 --warmup 3 --size 256 --no-cpu-baseline > gpurun_out/s13_bench256.json 2> gpurun_out/s13_bench256.err
+python tools/bench_summary.py gpurun_out/s13_bench256.json | head -7
+timeout 600 python bench.py --steps 10 --warmup 3 --size 128 --no-cpu-baseline > gpurun_out/s13_bench128.json 2> gpurun_out/s13_bench128.err
+python tools/bench_summary.py gpurun_out/s13_bench128.json | head -7
