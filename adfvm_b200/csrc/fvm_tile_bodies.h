@@ -674,17 +674,29 @@ template <typename R, int T, int TS> struct GradAdjTileBody {
             mbar_expect_tx(bar_rows, 15u * kRow);
             for (int k = 0; k < 15; k++) bulk_g2s(gbs + k * TS, Gb + (long)k * m.sN + c0, kRow, bar_rows);
         }
-        {
-            constexpr int kIter = (TS - T + T - 1) / T;
-            int hc[kIter];
-            #pragma unroll
-            for (int i = 0; i < kIter; i++) { const int h = tid + i * T; hc[i] = h < nh ? m.halo_cell[h0 + h] : -1; }
-            #pragma unroll
-            for (int i = 0; i < kIter; i++) {
-                const int cellh = hc[i], slot = T + tid + i * T;
-                if (cellh < 0 || cellh >= m.nInternalCells) continue;
-                for (int k = 0; k < 15; k++) cp_async_elem<sizeof(R)>(gbs + k * TS + slot, Gb + (long)k * m.sN + cellh);
+        constexpr int kIter = (TS - T + T - 1) / T;
+        int hc[kIter];
+        #pragma unroll
+        for (int i = 0; i < kIter; i++) { const int h = tid + i * T; hc[i] = h < nh ? m.halo_cell[h0 + h] : -1; }
+        // the cell's own inputs do not depend on anything: issue their loads BEFORE the gather below stalls on the halo cell list,
+        // and pull the lines the tail of cell() reads (stage state, later-stage adjoints, gradient accumulator) into L2 meanwhile
+        Pre p;
+        if (tid < nc) preload(c0 + tid, p);
+        if ((tid & 15) == 0 && tid < nc) {
+            const long c = c0 + tid;
+            for (int k = 0; k < 5; k++) {
+                prefetch_l2(W + (long)k * m.sC + c);
+                if (A1) prefetch_l2(A1 + (long)k * m.sC + c);
+                if (A2) prefetch_l2(A2 + (long)k * m.sC + c);
+                if (A3) prefetch_l2(A3 + (long)k * m.sC + c);
+                if (Sb) prefetch_l2(Sb + (long)k * m.sC + c);
             }
+        }
+        #pragma unroll
+        for (int i = 0; i < kIter; i++) {
+            const int cellh = hc[i], slot = T + tid + i * T;
+            if (cellh < 0 || cellh >= m.nInternalCells) continue;
+            for (int k = 0; k < 15; k++) cp_async_elem<sizeof(R)>(gbs + k * TS + slot, Gb + (long)k * m.sN + cellh);
         }
         cp_async_arrive(bar_halo);
         {   // L2 prefetch of the rows of the tile that runs in this CTA slot one wave later
@@ -692,8 +704,6 @@ template <typename R, int T, int TS> struct GradAdjTileBody {
             if (tn < m.nTiles && tid < 15) bulk_prefetch_l2(Gb + (long)tid * m.sN + (long)tn * T, kRow);
             if (tn < m.nTiles && tid >= 32 && tid < 39) { const int* p = m.halo_cell + m.halo_start[tn] + 32 * (tid - 32); if (p < m.halo_cell + m.halo_start[tn + 1]) prefetch_l2(p); }
         }
-        Pre p;
-        if (tid < nc) preload(c0 + tid, p);
         mbar_wait(bar_rows, 0);
         mbar_wait(bar_halo, 0);
         if (tid < nc) cell(t, c0 + tid, tid, gbs, p);

@@ -1,1 +1,1 @@
-NO_TESTS=1 VARIANTS="co0 co1" SIZES="256" bash tools/gpu_exp.sh
+VARIANTS="ep0 ep1" SIZES="256" bash tools/gpu_exp.sh
