@@ -1,6 +1,6 @@
 #!/usr/bin/env python
-"""Throughput on the shipped cases' meshes (BASELINE.json configs 1-3 at their own sizes: shockTube 500 cells,
-cylinder 46 250, forwardStep 16 128): device-resident primal and adjoint steps, CUDA-event timing, one JSON line per
+"""Throughput on the shipped cases' own meshes (BASELINE.json configs 1-4: shockTube 500 cells, forwardStep 16 128 and cylinder
+46 250 from their blockMeshDicts, the vane cascade with 4 spanwise layers = 40 000 cells): device-resident primal and adjoint steps, CUDA-event timing, one JSON line per
 case and precision. These meshes are far too small to fill a B200 (launch-latency bound): the numbers are reported
 for completeness next to the 368^3 headline of bench.py.
 Usage: python tools/case_bench.py [--steps 200]"""
@@ -21,28 +21,13 @@ ap.add_argument("--steps", type=int, default=100)
 a = ap.parse_args()
 
 
-def tube(dtype):
-    """cases/shockTube geometry at its own size (500 cells), smoothed Sod initial condition"""
-    from adfvm_b200.cases import Case, _spec, conservative, gaussian_source
-    lo, hi = (-5., -1., -1.), (5., 1., 1.)
-    poly = hexmesh.box_mesh((500, 1, 1), lo, hi, patches=[("sides", "patch", ["x+", "x-"], {}),
-                                                          ("empty", "empty", ["y-", "z+", "y+", "z-"], {})])
-    m = build_mesh(poly)
-    x = m.cellCentres[:m.nInternalCells, 0]
-    sig = 0.5 * (1 - np.tanh(x / 0.3))
-    pr, rho = 1e4 + 9e4 * sig, 0.125 + 0.875 * sig
-    T = (pr / (rho * (1004.5 - 1004.5 / 1.4))).reshape(-1, 1)
-    k0 = {"keys": []}
-    bcs = {f: {"sides": dict(type="zeroGradient", **k0), "empty": dict(type="zeroGradient", **k0)} for f in ("U", "T", "p")}
-    spec = _spec(m, bcs, {"kind": "patch_pA", "patch": "sides"}, mu={"law": "constant", "value": 0.})
-    return Case(m, spec, conservative(np.zeros((len(x), 3)), T, pr.reshape(-1, 1)),
-                gaussian_source(m.cellCentres[:m.nInternalCells], (-4.5, 0., 0.), 1e3, 25.), {}, 1e-5, dtype)
-
-
 stream = torch.cuda.Stream()          # an explicit stream: whole steps replay as CUDA graphs (not possible on the legacy stream)
 torch.cuda.set_stream(stream)
-for name, make in (("shockTube_500", tube), ("forwardStep_16128", lambda d: cases.forward_step(dtype=d, dt=2e-5)),
-                   ("cylinder_46250", lambda d: cases.cylinder2d(dtype=d))):
+# the meshes of the shipped blockMeshDicts (adfvm_b200.blockmesh; parity on them: tests/test_anchors.py) - BASELINE.json configs 1-4
+for name, make in (("shockTube_500", lambda d: cases.shock_tube(500, dtype=d)),
+                   ("forwardStep_16128_shipped_mesh", lambda d: cases.forward_step_shipped(dtype=d)),
+                   ("cylinder_46250_shipped_mesh", lambda d: cases.cylinder_shipped(dtype=d)),
+                   ("vane_cascade_40000", lambda d: cases.vane_cascade(nz=4, dtype=d))):
     for dtype, tag in ((np.float64, "f64"), (np.float32, "f32")):
         case = make(dtype)
         C = case.mesh.nInternalCells
