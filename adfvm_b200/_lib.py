@@ -47,7 +47,8 @@ EXPORTS = ["adfvm_last_error", "adfvm_version", "adfvm_is_cuda", "adfvm_create",
            "adfvm_set_state", "adfvm_mesh_metrics", "adfvm_set_objective_plane", "adfvm_set_parameter_bc", "adfvm_set_parameter_mesh", "adfvm_get_mesh_grad", "adfvm_primal_block", "adfvm_adjoint_block", "adfvm_set_adjoint", "adfvm_get_adjoint",
            "adfvm_set_objective_callback", "adfvm_get_cell_perm", "adfvm_init_fields", "adfvm_get_dtc_global",
            "adfvm_set_adjoint_viscosity", "adfvm_adjoint_viscous_resident", "adfvm_get_adjoint_viscosity", "adfvm_viscosity_iterations",
-           "adfvm_adjoint_block_viscous"]
+           "adfvm_adjoint_block_viscous", "adfvm_state_cache_reserve", "adfvm_state_cache_put", "adfvm_state_cache_select",
+           "adfvm_state_cache_hits"]
 
 
 class Lib:
@@ -77,6 +78,11 @@ class Lib:
         d.adfvm_primal_step_resident.argtypes = [vp, f64]
         d.adfvm_set_adjoint_viscosity.argtypes = [vp, i32, f64, f64, i32]
         d.adfvm_adjoint_viscous_resident.argtypes = [vp, f64]
+        d.adfvm_state_cache_reserve.argtypes = [vp, i32]
+        d.adfvm_state_cache_put.argtypes = [vp, C.c_int64]
+        d.adfvm_state_cache_select.argtypes = [vp, C.c_int64, C.POINTER(i32)]
+        d.adfvm_state_cache_hits.argtypes = [vp]
+        d.adfvm_state_cache_hits.restype = C.c_int64
         d.adfvm_adjoint_block_viscous.argtypes = [vp, i32, C.POINTER(f64), f64]
         d.adfvm_get_adjoint_viscosity.argtypes = [vp, vp, vp, vp, vp]
         d.adfvm_viscosity_iterations.argtypes = [vp]

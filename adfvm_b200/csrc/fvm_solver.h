@@ -423,6 +423,39 @@ public:
         have_state = true;
     }
     void adjoint_state_end() { if (adj_had_state) std::swap(W[0], Wspare); have_state = adj_had_state; }
+    // ---- opt-in cache of states handed out to the host (adfvm_state_cache_*): a state the host layer can PROVE unchanged (the very
+    // array objects it returned, still read-only) is taken from its device copy instead of travelling up again. The reference
+    // re-uploads it at every `primal_grad` call (apps/adjoint.py:268-280: no reuse ids on that function).
+    struct CacheSlot { R* buf; long long key; long stamp; };
+    std::vector<CacheSlot> scache; int scache_cap = 0; long scache_clock = 0, scache_hits = 0; R* scache_pending = nullptr;
+    void state_cache_reserve(int n) { if (n < 0) throw std::runtime_error("bad cache size"); scache_cap = n; }
+    void state_cache_put(long long key) {             // the resident state W[0] under `key`
+        if (scache_cap == 0 || !have_state) return;
+        CacheSlot* s = nullptr;
+        for (auto& c : scache) if (c.key == key) s = &c;
+        if (!s && (int)scache.size() < scache_cap) { scache.push_back({dalloc<R>((size_t)5 * m.sC + kRowSlack), key, 0}); s = &scache.back(); }
+        if (!s) { s = &scache[0]; for (auto& c : scache) if (c.stamp < s->stamp) s = &c; }          // least recently used
+        s->key = key; s->stamp = ++scache_clock;
+        ex.copy(s->buf, W[0], (size_t)5 * m.sC * sizeof(R));
+    }
+    bool state_cache_select(long long key) {          // the next call whose state arrays are NULL takes this copy
+        scache_pending = nullptr;
+        for (auto& c : scache) if (c.key == key) { c.stamp = ++scache_clock; scache_pending = c.buf; }
+        return scache_pending != nullptr;
+    }
+    R* state_cache_take() {
+        if (!scache_pending) throw std::runtime_error("state arrays required (no cached state selected)");
+        R* b = scache_pending; scache_pending = nullptr; scache_hits++;
+        return b;
+    }
+    void set_state_cached() { ex.copy(W[0], state_cache_take(), (size_t)5 * m.sC * sizeof(R)); have_state = true; }
+    void adjoint_state_begin_cached() {
+        R* src = state_cache_take();
+        adj_had_state = have_state;
+        if (have_state) { if (!Wspare) Wspare = dalloc<R>((size_t)5 * m.sC + kRowSlack); std::swap(W[0], Wspare); }
+        ex.copy(W[0], src, (size_t)5 * m.sC * sizeof(R));
+        have_state = true;
+    }
     void get_state(R* rho, R* rhoU, R* rhoE) { get5(W[0], rho, rhoU, rhoE); }
     // host (rho[C][1], rhoU[C][3], rhoE[C][1]) in reference cell order <-> device [5][sC] in tile order
     void put5(R* dst, const R* a, const R* b, const R* c) {

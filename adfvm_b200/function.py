@@ -348,6 +348,37 @@ class _Context:
             self._arr(arr, (dim,), "BC %s.%s.%s" % (field, pid, key), self.patch[pid]["nFaces"])
             self.lib.check(d.adfvm_set_bc_value(self.ctx, self.patch_index[pid], kid, _ptr(arr)))
 
+    # ---- opt-in state cache (PrimalFunction(state_cache=n)): which returned array objects have a device copy
+    def cache_register(self, arrs):
+        """arrs: the three state arrays just returned (the resident state is theirs): make them read-only and file the copy"""
+        import weakref
+        if not self.state_cache:
+            return
+        if self.cache_next == 1:
+            self.lib.check(self.lib.dll.adfvm_state_cache_reserve(self.ctx, self.state_cache))
+        key, self.cache_next = self.cache_next, self.cache_next + 1
+        self.lib.check(self.lib.dll.adfvm_state_cache_put(self.ctx, key))
+        for a in arrs:
+            a.flags.writeable = False
+        ident = id(arrs[0])
+        keys = self.cache_keys
+
+        def gone(_ref, ident=ident, key=key):
+            if keys.get(ident, (None,))[0] == key:
+                keys.pop(ident, None)
+        self.cache_keys[ident] = (key, [weakref.ref(arrs[0], gone), weakref.ref(arrs[1]), weakref.ref(arrs[2])])
+
+    def cache_select(self, state):
+        """True if `state` (rho, rhoU, rhoE) are exactly the array objects of a cached copy, untouched; the copy is then selected"""
+        if not self.state_cache:
+            return False
+        ent = self.cache_keys.get(id(state[0]))
+        if ent is None or any(r() is not a for r, a in zip(ent[1], state)) or any(a.flags.writeable for a in state):
+            return False
+        found = C.c_int32(0)
+        self.lib.check(self.lib.dll.adfvm_state_cache_select(self.ctx, ent[0], C.byref(found)))
+        return bool(found.value)
+
     def attach_comm(self, unique_id: bytes, rank: int, nranks: int):
         buf = C.create_string_buffer(unique_id, 128)
         self.lib.check(self.lib.dll.adfvm_comm_init(self.ctx, buf, rank, nranks))
@@ -359,8 +390,15 @@ class PrimalFunction:
     defaultOptions = {"return_static": True, "zero_static": False, "replace_static": False,
                       "return_reusable": True, "replace_reusable": False}   # adpy/adpy/variable.py:282-287
 
-    def __init__(self, spec, precision=np.float64, device=0, stream=None, lib=None, tile_cells=None):
+    def __init__(self, spec, precision=np.float64, device=0, stream=None, lib=None, tile_cells=None, state_cache=0):
+        """state_cache = n > 0 (opt-in, NOT the reference's semantics): the state arrays this function returns are READ-ONLY numpy
+        arrays, and the library keeps device copies of the last n of them. When the very same array objects come back as the
+        state of a `primal` (replace_reusable) or `primal_grad` call - what `Solver.run(mode='forward')` + `Adjoint.run` do with
+        their `solutions` list (adFVM/solver.py:376-382, apps/adjoint.py:250-280) - and are still read-only, the device copy is
+        used and the 5 C scalars do not travel up again. Anything else (other arrays, arrays made writeable again) is uploaded."""
         self.c = _Context(spec, precision, device, stream, lib, tile_cells)
+        self.c.state_cache = int(state_cache)
+        self.c.cache_keys, self.c.cache_next = {}, 1
 
     def tile_stats(self):
         """(flux evaluations per cell, most rounds of a sub-tile, tiles, cells per tile) of the device layout"""
@@ -410,10 +448,13 @@ class PrimalFunction:
         if opts["return_reusable"]:
             outs = [c.pool.empty((C_, 1), c.dtype), c.pool.empty((C_, 3), c.dtype), c.pool.empty((C_, 1), c.dtype)]
         dtc, obj = np.zeros((1, 1), c.dtype), np.zeros((1, 1), c.dtype)
-        rc = c.lib.dll.adfvm_primal(c.ctx, _ptr(rho), _ptr(rhoU), _ptr(rhoE), float(dt[0, 0]), flags,
-                                    _ptr(outs[0]), _ptr(outs[1]), _ptr(outs[2]), _ptr(dtc), _ptr(obj))
+        cached = opts["replace_reusable"] and c.cache_select((rho, rhoU, rhoE))
+        rc = c.lib.dll.adfvm_primal(c.ctx, None if cached else _ptr(rho), None if cached else _ptr(rhoU), None if cached else _ptr(rhoE),
+                                    float(dt[0, 0]), flags, _ptr(outs[0]), _ptr(outs[1]), _ptr(outs[2]), _ptr(dtc), _ptr(obj))
         c.check_traced()
         c.lib.check(rc)
+        if opts["return_reusable"]:
+            c.cache_register(outs)
         return (outs[0], outs[1], outs[2], dtc, obj)
 
     def init_fields(self, *inputs):
@@ -505,6 +546,11 @@ class PrimalFunction:
         return out
 
     @property
+    def state_cache_hits(self):
+        """calls that started from a cached device copy instead of an upload"""
+        return int(self.c.lib.dll.adfvm_state_cache_hits(self.c.ctx))
+
+    @property
     def launches(self):
         return int(self.c.lib.dll.adfvm_launch_count(self.c.ctx))
 
@@ -588,8 +634,10 @@ class AdjointFunction:
             grads = [c.pool.empty(c.param_bc, c.dtype) if opts["return_static"] else None, None, None]
         elif opts["return_static"]:
             grads = [c.pool.empty((C_, 1), c.dtype), c.pool.empty((C_, 3), c.dtype), c.pool.empty((C_, 1), c.dtype)]
+        cached = c.cache_select((rho, rhoU, rhoE))
         rc = c.lib.dll.adfvm_primal_grad(
-            c.ctx, _ptr(rho), _ptr(rhoU), _ptr(rhoE), float(dt[0, 0]), _ptr(ra), _ptr(rUa), _ptr(rEa), dtca, obja, flags,
+            c.ctx, None if cached else _ptr(rho), None if cached else _ptr(rhoU), None if cached else _ptr(rhoE), float(dt[0, 0]),
+            _ptr(ra), _ptr(rUa), _ptr(rEa), dtca, obja, flags,
             _ptr(outs[0]), _ptr(outs[1]), _ptr(outs[2]), _ptr(grads[0]), _ptr(grads[1]), _ptr(grads[2]))
         c.check_traced()
         c.lib.check(rc)

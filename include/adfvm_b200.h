@@ -151,6 +151,15 @@ int adfvm_adjoint_block_viscous(adfvm_ctx* ctx, int32_t nsteps, const double* dt
 int adfvm_get_adjoint_viscosity(adfvm_ctx* ctx, const void* rho, const void* rhoU, const void* rhoE, void* M_2norm);
 /* conjugate-gradient iterations of the last diffusion solve */
 int64_t adfvm_viscosity_iterations(adfvm_ctx* ctx);
+/* == opt-in: device copies of states handed out to the host (new; the reference uploads the state at every primal_grad call,
+ * apps/adjoint.py:268-280) == reserve n slots; adfvm_state_cache_put(key) files the resident state under `key` (least recently
+ * used slot replaced); adfvm_state_cache_select(key, &found) makes the NEXT adfvm_primal (with ADFVM_REPLACE_REUSABLE) or
+ * adfvm_primal_grad call that passes rho = rhoU = rhoE = NULL start from that copy. The host layer (PrimalFunction(state_cache=n))
+ * selects a key only for the very array objects it returned, which it hands out read-only. */
+int adfvm_state_cache_reserve(adfvm_ctx* ctx, int32_t nslots);
+int adfvm_state_cache_put(adfvm_ctx* ctx, int64_t key);
+int adfvm_state_cache_select(adfvm_ctx* ctx, int64_t key, int32_t* found);
+int64_t adfvm_state_cache_hits(adfvm_ctx* ctx);
 /* adjoint step on resident data; chain!=0 feeds the previous call's output adjoint back in as this call's input */
 int adfvm_adjoint_step_resident(adfvm_ctx* ctx, double dt, double obja, int32_t chain);
 int adfvm_get_dtc_obj(adfvm_ctx* ctx, double* dtc, double* obj);
