@@ -626,7 +626,9 @@ def main():
                             "adjoint_frac": B_a * 3 * C / (ta_ms / K * 1e-3) / 1e9 / peak}}
     # the dominant kernel's other ceiling: the fp64 pipe (SASS count of fp64 instructions per face evaluation, DESIGN.md section 5;
     # an fp64 warp instruction holds one of the 4 x 148 sub-partition pipes for two cycles)
-    FP64_PER_EVAL = {"flux_grad_tile": 953}
+    # 904 = ncu of the specialised (Roe + Sutherland) kernel at 128^3: fp64 pipe active 56.0 % of 727 us x 1.965 GHz x 592 sub-partitions
+    # / 2 cycles per instruction / 262 144 warp-evaluations (profiles/r2f_tiles_f64.summary.txt); the generic instantiation: 953
+    FP64_PER_EVAL = {"flux_grad_tile": 904}
     if dom in FP64_PER_EVAL and args.dtype == "f64":
         mhz = (m["clocks"] or {}).get("sm_mhz") or 1965.0
         floor_ms = FP64_PER_EVAL[dom] * 4.0 * C / 32 * 2 / (4 * 148 * mhz * 1e6) * 1e3
