@@ -349,3 +349,15 @@ def test_viscous_adjoint_large_against_oracle(dtype, tol, cudalib):
     assert group_relerr(expect, plain[:3], sc) > 1e-3
     assert group_relerr(r[:3], expect, sc) < tol
     assert 1 <= fa.viscosity_iterations <= 200
+
+
+def test_state_cache_on_device(cudalib):
+    """PrimalFunction(state_cache=n) on the device: cached device copies give bitwise the results of the upload path"""
+    import test_block
+    test_block.test_state_cache_opt_in(cudalib)
+
+
+def test_viscous_blocks_on_device(cudalib):
+    """adfvm_b200.blocks with the adjoint viscosity after every step (adfvm_adjoint_block_viscous) against the step-wise loop"""
+    import test_viscosity as tv
+    tv.test_viscous_blocks_equal_stepwise_driver_loop(cudalib)
