@@ -271,9 +271,10 @@ def uniform_box(n, lo=(0., 0., 0.), hi=(1., 1., 1.), patches=None):
     m.boundary = boundary
     m.nFaces, m.nInternalFaces, m.nInternalCells, m.nGhostCells, m.nCells, m.nBoundaryFaces = F, Fi, C, G, C + G, G
     owner = np.empty(F, np.int64); neigh = np.empty(F, np.int64); fdim = np.empty(F, np.int8)
-    for d in range(3):
-        sel = has[d]
-        owner[fid[d][sel]] = c[sel]; neigh[fid[d][sel]] = c[sel] + stride[d]; fdim[fid[d][sel]] = d
+    # the internal faces are numbered cell by cell, +x, +y, +z: the (cell, direction) pairs of the existing ones, in row-major order
+    cells_idx, dirs = np.nonzero(np.stack(has, axis=1))
+    owner[:Fi] = cells_idx; neigh[:Fi] = cells_idx + stride[dirs]; fdim[:Fi] = dirs
+    del cells_idx, dirs
     owner[Fi:] = b_owner; neigh[Fi:] = C + np.arange(G); fdim[Fi:] = b_dim
     sign = np.ones(F); sign[Fi:] = b_sign
     coupled = np.ones(F, bool); coupled[Fi:] = b_coupled
@@ -293,19 +294,17 @@ def uniform_box(n, lo=(0., 0., 0.), hi=(1., 1., 1.), patches=None):
     # geometry
     hf = h[fdim]                                                  # spacing normal to the face
     area = (h[0] * h[1] * h[2]) / hf
-    normals = np.zeros((F, 3)); normals[np.arange(F), fdim] = sign
+    normals = np.eye(3)[fdim] * sign[:, None]
     cc = np.empty((C + G, 3))
     cc[:C, 0] = lo[0] + (I + 0.5) * h[0]; cc[:C, 1] = lo[1] + (J + 0.5) * h[1]; cc[:C, 2] = lo[2] + (K + 0.5) * h[2]
-    fc = cc[owner].copy(); fc[np.arange(F), fdim] += 0.5 * hf * sign
+    fc = cc[owner]; fc += (0.5 * hf)[:, None] * normals
     gh = fc[Fi:].copy()
     bc = coupled[Fi:]
     gh[bc, b_dim[bc]] += 0.5 * hf[Fi:][bc] * b_sign[bc]           # coupled: the image cell's centre; else the face centre
     cc[C:] = gh
     dist = np.where(coupled, hf, 0.5 * hf)
     w1 = np.where(coupled, 0.5, 1.0); w2 = np.where(coupled, 0.5, 0.0)
-    pFv = 0.5 * hf[:, None] * normals
-    nFv = np.where(coupled[:, None], -pFv, 0.0)
-    dvec = -dist[:, None] * normals                               # P - N
+    # F - P = (hf/2) n, F - N = -(hf/2) n on coupled faces (0 elsewhere), P - N = -dist n: every vector below is a scalar times n
     m.owner = np.ascontiguousarray(owner, np.int32); m.neighbour = np.ascontiguousarray(neigh, np.int32)
     m.normals = normals; m.faceCentres = fc; m.cellCentres = cc
     m.areas = area.reshape(-1, 1)
@@ -314,18 +313,34 @@ def uniform_box(n, lo=(0., 0., 0.), hi=(1., 1., 1.), patches=None):
     m.deltas = dist.reshape(-1, 1); m.deltasUnit = normals.copy()
     m.weights = np.where(coupled, 0.5, 0.0).reshape(-1, 1)
     m.linearWeights = np.stack([w1 / 3, w2 / 3], axis=1)
-    m.quadraticWeights = np.ascontiguousarray(np.stack([2. / 3 * pFv + 1. / 3 * (pFv + w1[:, None] * dvec),
-                                                        2. / 3 * nFv + 1. / 3 * (nFv - w2[:, None] * dvec)], axis=1))
+    qw = np.empty((F, 2, 3))
+    np.multiply((0.5 * hf - (w1 / 3) * dist)[:, None], normals, out=qw[:, 0, :])                 # (F-P) + (w1/3)(P-N)
+    np.multiply((np.where(coupled, -0.5 * hf, 0.0) + (w2 / 3) * dist)[:, None], normals, out=qw[:, 1, :])   # (F-N) - (w2/3)(P-N)
+    m.quadraticWeights = qw
     # cellFaces: owned faces ascending (internal +x,+y,+z, then boundary in face order), then neighbour-side faces ascending
     cellFaces = np.full((C, 6), -1, np.int64); fill = np.zeros(C, np.int64)
     def put(cells, faces):
         cellFaces[cells, fill[cells]] = faces; fill[cells] += 1
+    # cells that touch no side of the box (all but O(n^2)): [+x, +y, +z, -z, -y, -x] by strided copies of the face-id arrays
+    inner = np.zeros((nz, ny, nx), bool)
+    if min(nx, ny, nz) > 2:
+        inner[1:-1, 1:-1, 1:-1] = True
+        cf4 = cellFaces.reshape(nz, ny, nx, 6)
+        f3 = [fid[d].reshape(nz, ny, nx) for d in range(3)]
+        for d in range(3):
+            cf4[1:-1, 1:-1, 1:-1, d] = f3[d][1:-1, 1:-1, 1:-1]
+        cf4[1:-1, 1:-1, 1:-1, 3] = f3[2][0:-2, 1:-1, 1:-1]
+        cf4[1:-1, 1:-1, 1:-1, 4] = f3[1][1:-1, 0:-2, 1:-1]
+        cf4[1:-1, 1:-1, 1:-1, 5] = f3[0][1:-1, 1:-1, 0:-2]
+        fill[inner.ravel()] = 6
+    rim = ~inner.ravel()
     for d in range(3):
-        put(c[has[d]], fid[d][has[d]])
+        sel = has[d] & rim
+        put(c[sel], fid[d][sel])
     for s0, cells in side_list:
         put(cells, s0 + np.arange(len(cells)))
     for d in (2, 1, 0):
-        sel = idx[d] > 0
+        sel = (idx[d] > 0) & rim
         put(c[sel], fid[d][c[sel] - stride[d]])
     assert np.all(fill == 6)
     fo = owner[cellFaces]; fn = neigh[cellFaces]
